@@ -1,0 +1,386 @@
+"""CPU restatement of the reference's sampling hot path -- TEST INFRASTRUCTURE ONLY.
+
+Never imported by flowmol_b200/ (the product path fails loudly without its CUDA library); used by tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs as the checker / CPU baseline.
+
+Parity status: PINNED.  The reference has no tests or golden vectors of its own, so this
+restatement is pinned against the reference's own modules executed verbatim in the build container
+(oracle/ref_loader.py -> oracle/make_golden.py -> tests/golden/*.npz, checked by tests/test_oracle_golden.py and,
+when /root/reference is present, directly by tests/test_oracle_vs_reference.py).
+
+Every function cites the reference lines it restates (paths relative to the reference root).
+Weights are addressed by the reference's own state_dict key names (`vector_field.` prefix stripped).
+All arithmetic is torch on CPU in `dtype` (fp32 = the reference's precision; fp64 = the accuracy yardstick).
+"""
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import philox
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# graph contract
+# ----------------------------------------------------------------------------------------------------------------
+@dataclass
+class Batch:
+    """Batched complete graphs in the reference's edge order.
+
+    flowmol/data_processing/utils.py:4-17 (build_edge_idxs: upper triangle row-major, then the same list with
+    src/dst swapped), :19-28 (upper-edge mask), :30-46 (batch indices); batching by concatenation with node
+    offsets as dgl.batch does (flowmol/models/flowmol.py:509-523).
+    """
+    n_atoms: torch.Tensor      # int64 [B]
+    src: torch.Tensor          # int64 [E]
+    dst: torch.Tensor          # int64 [E]
+    upper: torch.Tensor        # bool  [E]
+    node_mol: torch.Tensor     # int64 [N]
+    upper_mol: torch.Tensor    # int64 [U]   molecule of each upper edge
+    node_item: torch.Tensor    # int64 [N]   atom index inside its molecule
+    upper_item: torch.Tensor   # int64 [U]   upper-edge index inside its molecule
+    up_idx: torch.Tensor       # int64 [U]   positions of upper edges in the E-list
+    lo_idx: torch.Tensor       # int64 [U]   positions of the mirrored lower edges
+
+    @property
+    def B(self):
+        return int(self.n_atoms.shape[0])
+
+    @property
+    def N(self):
+        return int(self.node_mol.shape[0])
+
+    @property
+    def E(self):
+        return int(self.src.shape[0])
+
+    @property
+    def U(self):
+        return int(self.up_idx.shape[0])
+
+
+def make_batch(n_atoms):
+    n_atoms = torch.as_tensor(n_atoms, dtype=torch.int64).reshape(-1)
+    srcs, dsts, ups, node_mol, upper_mol, node_item, upper_item = [], [], [], [], [], [], []
+    off = 0
+    for b, n in enumerate(n_atoms.tolist()):
+        iu = torch.triu_indices(n, n, offset=1)
+        u = iu.shape[1]
+        srcs.append(torch.cat([iu[0], iu[1]]) + off)
+        dsts.append(torch.cat([iu[1], iu[0]]) + off)
+        ups.append(torch.cat([torch.ones(u, dtype=torch.bool), torch.zeros(u, dtype=torch.bool)]))
+        node_mol.append(torch.full((n,), b, dtype=torch.int64))
+        upper_mol.append(torch.full((u,), b, dtype=torch.int64))
+        node_item.append(torch.arange(n))
+        upper_item.append(torch.arange(u))
+        off += n
+    upper = torch.cat(ups)
+    return Batch(n_atoms=n_atoms, src=torch.cat(srcs), dst=torch.cat(dsts), upper=upper,
+                 node_mol=torch.cat(node_mol), upper_mol=torch.cat(upper_mol),
+                 node_item=torch.cat(node_item), upper_item=torch.cat(upper_item),
+                 up_idx=torch.nonzero(upper).squeeze(1), lo_idx=torch.nonzero(~upper).squeeze(1))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# small ops
+# ----------------------------------------------------------------------------------------------------------------
+def norm_no_nan(x, keepdims=False, sqrt=True):
+    """flowmol/models/gvp.py:14-21 -- clamp INSIDE the sqrt."""
+    out = torch.clamp(torch.sum(torch.square(x), -1, keepdims), min=1e-8)
+    return torch.sqrt(out) if sqrt else out
+
+
+def rbf(d, d_max, count):
+    """flowmol/utils/embedding.py:19-34 (D_min = 0)."""
+    mu = torch.linspace(0.0, d_max, count, dtype=d.dtype).view(1, -1)
+    sigma = d_max / count
+    return torch.exp(-((d.unsqueeze(-1) - mu) / sigma) ** 2)
+
+
+def time_embedding(t, dim, max_positions=1000):
+    """flowmol/utils/embedding.py:5-17. t: [B] -> [B, dim]. The frequency table is always fp32 in the reference."""
+    half = dim // 2
+    e = math.log(max_positions) / (half - 1)
+    freq = torch.exp(torch.arange(half, dtype=torch.float32) * -e).to(t.dtype)
+    arg = (t * max_positions)[:, None] * freq[None, :]
+    return torch.cat([torch.sin(arg), torch.cos(arg)], dim=1)
+
+
+def layer_norm(x, w, b):
+    return F.layer_norm(x, (x.shape[-1],), w, b, 1e-5)
+
+
+class OracleModel:
+    """Functional restatement of CTMCVectorField (live parts only, eval mode, CTMC parameterisation)."""
+
+    def __init__(self, cfg, state_dict, dtype=torch.float32):
+        self.cfg = cfg
+        self.dtype = dtype
+        self.W = {k: v.detach().to(dtype) for k, v in state_dict.items()}
+        self.A = cfg.n_atom_types          # incl. the fake-atom type; mask token index == A
+        self.C = cfg.n_charges
+        self.Eb = cfg.n_bond_types
+
+    # -- building blocks -----------------------------------------------------------------------------------------
+    def linear(self, name, x):
+        return F.linear(x, self.W[name + ".weight"], self.W[name + ".bias"])
+
+    def gvp(self, p, s, v, vec_act_sigmoid=True):
+        """flowmol/models/gvp.py:90-133 with vector gating; `p` is the parameter prefix."""
+        W = self.W
+        Vh = torch.einsum('bvc,vh->bhc', v, W[p + ".Wh"])
+        if (p + ".Wcp") in W:
+            Vcp = torch.einsum('bvc,vp->bpc', v, W[p + ".Wcp"])
+            ncp = Vcp.shape[1] // 2
+            cp = torch.linalg.cross(Vcp[:, :ncp], Vcp[:, ncp:], dim=-1)
+            Vh = torch.cat((Vh, cp), dim=1)
+        Vu = torch.einsum('bhc,hu->buc', Vh, W[p + ".Wu"])
+        sh = norm_no_nan(Vh)
+        s_out = F.silu(self.linear(p + ".to_feats_out.0", torch.cat((s, sh), dim=1)))
+        gate = self.linear(p + ".scalar_to_vector_gates", s_out).unsqueeze(-1)
+        if vec_act_sigmoid:
+            gate = torch.sigmoid(gate)
+        return s_out, gate * Vu
+
+    def gvp_layer_norm(self, p, s, v):
+        """flowmol/models/gvp.py:169-184."""
+        s = layer_norm(s, self.W[p + ".feat_norm.weight"], self.W[p + ".feat_norm.bias"])
+        vn = norm_no_nan(v, keepdims=True, sqrt=False)
+        vn = torch.sqrt(torch.mean(vn, dim=-2, keepdim=True) + 1e-5) + 1e-5
+        return s, v / vn
+
+    def distances(self, bt, x):
+        """flowmol/models/vector_field.py:371-386 (precompute_distances)."""
+        cfg = self.cfg
+        diff = x[bt.src] - x[bt.dst]
+        dij = norm_no_nan(diff, keepdims=True) + 1e-8
+        return diff / dij, rbf(dij.squeeze(1), cfg.rbf_dmax, cfg.rbf_dim)
+
+    def conv(self, l, bt, s, v, ef, x_diff, d, taps=None):
+        """flowmol/models/gvp.py:435-543 (GVPConv.forward + message), message_norm='sum', eval mode."""
+        cfg = self.cfg
+        p = f"conv_layers.{l}"
+        vec_in = [x_diff.unsqueeze(1), v[bt.src]]
+        sc_in = [s[bt.src], d, ef]
+        if cfg.use_dst_feats:
+            sd, vd = self.gvp(p + ".dst_feat_msg_projection", s, v)
+            vec_in.append(vd[bt.dst])
+            sc_in.append(sd[bt.dst])
+        ms, mv = torch.cat(sc_in, dim=1), torch.cat(vec_in, dim=1)
+        for i in range(cfg.n_message_gvps):
+            ms, mv = self.gvp(f"{p}.edge_message.{i}", ms, mv)
+        agg_s = torch.zeros((bt.N, ms.shape[1]), dtype=s.dtype).index_add_(0, bt.dst, ms)
+        agg_v = torch.zeros((bt.N,) + tuple(mv.shape[1:]), dtype=s.dtype).index_add_(0, bt.dst, mv)
+        if taps is not None:
+            taps[f"conv{l}.msg_s"] = agg_s
+            taps[f"conv{l}.msg_v"] = agg_v
+        if not isinstance(cfg.message_norm, str):
+            agg_s, agg_v = agg_s / cfg.message_norm, agg_v / cfg.message_norm
+        elif cfg.message_norm == 'mean':
+            deg = torch.zeros(bt.N, dtype=s.dtype).index_add_(0, bt.dst, torch.ones(bt.E, dtype=s.dtype)).clamp(min=1)
+            agg_s, agg_v = agg_s / deg[:, None], agg_v / deg[:, None, None]
+        s, v = self.gvp_layer_norm(p + ".message_layer_norm", s + agg_s, v + agg_v)
+        rs, rv = s, v
+        for i in range(cfg.n_update_gvps):
+            rs, rv = self.gvp(f"{p}.node_update.{i}", rs, rv)
+        return self.gvp_layer_norm(p + ".update_layer_norm", s + rs, v + rv)
+
+    def position_update(self, u, s, x, v):
+        """flowmol/models/vector_field.py:813-842: three GVPs, the last with 1 output vector and identity gate."""
+        p = f"node_position_updaters.{u}.gvps"
+        s, v = self.gvp(p + ".0", s, v)
+        s, v = self.gvp(p + ".1", s, v)
+        _, dv = self.gvp(p + ".2", s, v, vec_act_sigmoid=False)
+        return x + dv.squeeze(1)
+
+    def edge_update(self, u, bt, s, ef, d):
+        """flowmol/models/vector_field.py:844-880."""
+        p = f"edge_updaters.{u}"
+        inp = [s[bt.src], s[bt.dst], ef]
+        if self.cfg.update_edge_w_distance:
+            inp.append(d)
+        h = F.silu(self.linear(p + ".edge_update_fn.0", torch.cat(inp, dim=-1)))
+        h = F.silu(self.linear(p + ".edge_update_fn.2", h))
+        return layer_norm(ef + h, self.W[p + ".edge_norm.weight"], self.W[p + ".edge_norm.bias"])
+
+    def denoise(self, bt, s, v, x, ef, remove_com, taps=None):
+        """flowmol/models/vector_field.py:296-369 (denoise_graph), apply_softmax=True, n_recycles=1."""
+        cfg = self.cfg
+        x_diff, d = self.distances(bt, x)
+        for l in range(cfg.n_convs):
+            s, v = self.conv(l, bt, s, v, ef, x_diff, d, taps)
+            if taps is not None:
+                taps[f"conv{l}.s"], taps[f"conv{l}.v"] = s, v
+            if l != 0 and (l + 1) % cfg.convs_per_update == 0:
+                u = l // cfg.convs_per_update if cfg.separate_mol_updaters else 0
+                x = self.position_update(u, s, x, v)
+                x_diff, d = self.distances(bt, x)
+                ef = self.edge_update(u, bt, s, ef, d)
+                if taps is not None:
+                    taps[f"upd{l}.x"], taps[f"upd{l}.ef"] = x, ef
+        h = self.linear("node_output_head.2", F.silu(self.linear("node_output_head.0", s)))
+        a_logits, c_logits = h[:, :self.A], h[:, self.A:]
+        e_in = ef[bt.up_idx] + ef[bt.lo_idx]
+        e_logits = self.linear("to_edge_logits.2", F.silu(self.linear("to_edge_logits.0", e_in)))
+        if remove_com:
+            com = torch.zeros((bt.B, 3), dtype=x.dtype).index_add_(0, bt.node_mol, x) / bt.n_atoms.to(x.dtype)[:, None]
+            x = x - com[bt.node_mol]
+        return {'x': x, 'a': torch.softmax(a_logits, -1), 'c': torch.softmax(c_logits, -1),
+                'e': torch.softmax(e_logits, -1)}
+
+    def self_condition(self, bt, s, x, ef, prev):
+        """flowmol/models/self_conditioning.py:37-85."""
+        cfg = self.cfg
+        d_node = rbf(norm_no_nan(x - prev['x']), cfg.rbf_dmax, cfg.rbf_dim)
+        p = "self_conditioning_residual_layer"
+        h = torch.cat([s, prev['a'], prev['c'], d_node], dim=-1)
+        h = F.silu(self.linear(p + ".node_residual_mlp.0", h))
+        s = s + F.silu(self.linear(p + ".node_residual_mlp.2", h))
+
+        def edge_d(pos):  # self_conditioning.py:88-103
+            diff = pos[bt.src] - pos[bt.dst]
+            return rbf((norm_no_nan(diff, keepdims=True) + 1e-8).squeeze(1), cfg.rbf_dmax, cfg.rbf_dim)
+        d_t = edge_d(x)[bt.up_idx]
+        d_1 = edge_d(prev['x'])[bt.up_idx]
+        h = torch.cat([ef[bt.up_idx], prev['e'], d_1 - d_t], dim=-1)
+        h = F.silu(self.linear(p + ".edge_residual_mlp.0", h))
+        res = F.silu(self.linear(p + ".edge_residual_mlp.2", h))
+        one = ef[bt.up_idx] + res
+        ef_out = torch.zeros_like(ef)
+        ef_out[bt.up_idx] = one
+        ef_out[bt.lo_idx] = one
+        return s, ef_out
+
+    def embed(self, bt, a_idx, c_idx, e_idx_upper, t):
+        """flowmol/models/vector_field.py:227-261. Categorical state given as token indices (argmax of one-hots)."""
+        cfg = self.cfg
+        W = self.W
+        tt = torch.full((bt.B,), float(t), dtype=self.dtype)
+        feats = [W["token_embeddings.a.weight"][a_idx], W["token_embeddings.c.weight"][c_idx],
+                 time_embedding(tt, cfg.time_embedding_dim)[bt.node_mol]]
+        h = torch.cat(feats, dim=-1)
+        h = F.silu(self.linear("scalar_embedding.0", h))
+        h = F.silu(self.linear("scalar_embedding.2", h))
+        s = layer_norm(h, W["scalar_embedding.4.weight"], W["scalar_embedding.4.bias"])
+        e_idx = torch.zeros(bt.E, dtype=torch.int64)
+        e_idx[bt.up_idx] = e_idx_upper
+        e_idx[bt.lo_idx] = e_idx_upper
+        h = W["token_embeddings.e.weight"][e_idx]
+        h = F.silu(self.linear("edge_embedding.0", h))
+        h = F.silu(self.linear("edge_embedding.2", h))
+        ef = layer_norm(h, W["edge_embedding.4.weight"], W["edge_embedding.4.bias"])
+        v = torch.zeros((bt.N, cfg.n_vec_channels, 3), dtype=self.dtype)
+        return s, v, ef
+
+    def forward(self, bt, x_t, a_idx, c_idx, e_idx_upper, t, prev=None, taps=None):
+        """flowmol/models/vector_field.py:212-293 in eval mode with apply_softmax=True, remove_com=True.
+
+        `t` is a python float / 0-dim tensor (all molecules share it at sampling time, ctmc_vector_field.py:320).
+        On the first step (prev is None and t == 0) the self-conditioning pre-pass runs with remove_com=False
+        (vector_field.py:269-282)."""
+        x_t = x_t.to(self.dtype)
+        s, v, ef = self.embed(bt, a_idx, c_idx, e_idx_upper, t)
+        if self.cfg.self_conditioning and prev is None and float(t) == 0.0:
+            prev = self.denoise(bt, s.clone(), v.clone(), x_t.clone(), ef.clone(), remove_com=False)
+            if taps is not None:
+                taps["prepass"] = prev
+        if self.cfg.self_conditioning and prev is not None:
+            prev = {k: p.to(self.dtype) for k, p in prev.items()}
+            s, ef = self.self_condition(bt, s, x_t, ef, prev)
+        if taps is not None:
+            taps["in.s"], taps["in.ef"] = s, ef
+        return self.denoise(bt, s, v, x_t, ef, remove_com=True, taps=taps)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CTMC integrator
+# ----------------------------------------------------------------------------------------------------------------
+def sample_categorical(p, u):
+    """Inverse-CDF draw shared with the CUDA kernel: k = #{j : cumsum(p)[j] <= u * cumsum(p)[-1]}, clamped.
+
+    Replaces torch.distributions.Categorical(p).sample() at flowmol/models/ctmc_vector_field.py:428."""
+    c = torch.cumsum(p, dim=-1)
+    k = (c <= (u * c[:, -1]).unsqueeze(-1)).sum(-1)
+    return torch.clamp(k, max=p.shape[1] - 1)
+
+
+def purity_unmask_prob(xt, p, unmask_prob, mask_index, counts_per_mol, item_mol, hc_thresh):
+    """flowmol/utils/ctmc_utils.py:4-32 -- per-item unmask probability (the final `rand <` is done by the caller)."""
+    masked = xt == mask_index
+    pur = p.max(-1)[0]
+    hc = (pur >= hc_thresh) & masked
+    B = counts_per_mol.shape[0]
+    h = torch.zeros(B, dtype=torch.int64).index_add_(0, item_mol, hc.long())
+    m = torch.zeros(B, dtype=torch.int64).index_add_(0, item_mol, masked.long())
+    ph_max = unmask_prob * m / h
+    ph_max[h == 0] = torch.inf
+    ph = torch.minimum(ph_max, torch.full_like(ph_max, 1.0))
+    pl = (unmask_prob * m - ph * h) / (m - h)
+    prob = torch.zeros(xt.shape[0], dtype=torch.float32)
+    prob[hc] = ph[item_mol[hc]]
+    lc = (pur < hc_thresh) & masked
+    prob[lc] = pl[item_mol[lc]]
+    return prob
+
+
+def campbell_step(p, xt, eta, hc_thresh, alpha_t, alpha_t_prime, dt, counts, item_mol, mask_index, last_step, u3):
+    """flowmol/models/ctmc_vector_field.py:414-461 on token indices; u3 = (u_cat, u_unmask, u_remask)."""
+    x1 = sample_categorical(p, u3[0])
+    unmask_prob = torch.clamp(dt * (alpha_t_prime + eta * alpha_t) / (1 - alpha_t), min=0, max=1)
+    mask_prob = torch.clamp(dt * eta, min=0, max=1)
+    if hc_thresh > 0:
+        prob = purity_unmask_prob(xt, p, unmask_prob, mask_index, counts, item_mol, hc_thresh)
+        will_unmask = u3[1] < prob
+    else:
+        will_unmask = (u3[1] < unmask_prob) & (xt == mask_index)
+    xt = xt.clone()
+    if not last_step:
+        will_mask = (u3[2] < mask_prob) & (xt != mask_index)
+        xt[will_mask] = mask_index
+    xt[will_unmask] = x1[will_unmask]
+    return xt, x1
+
+
+def integrate(model, bt, x0, a0, c0, e0_upper, n_timesteps, seed, eta=None, hc_thresh=None, tau=0.05,
+              mol_id_offset=0, record=None):
+    """flowmol/models/ctmc_vector_field.py:145-411 (integrate + step), dfm_type='campbell', linear schedule
+    (alpha_t = t, alpha_t' = 1: flowmol/models/interpolant_scheduler.py:148-154), inv_temp = 1.
+
+    State: x_t fp32 [N,3]; a_t, c_t int64 [N]; e_t int64 [U] (upper edges; both triangles always equal,
+    ctmc_vector_field.py:397-406).  Noise: oracle/philox.py.  Returns dict(x, a, c, e) final state."""
+    cfg = model.cfg
+    eta = cfg.stochasticity if eta is None else eta
+    hc_thresh = cfg.high_confidence_threshold if hc_thresh is None else hc_thresh
+    t = torch.linspace(0, 1, n_timesteps)              # fp32, as the reference
+    x_t = x0.clone().float()
+    a_t, c_t, e_t = a0.clone(), c0.clone(), e0_upper.clone()
+    prev = None
+    node_item, node_mol = bt.node_item.numpy().astype(np.uint32), (bt.node_mol.numpy() + mol_id_offset).astype(np.uint32)
+    up_item, up_mol = bt.upper_item.numpy().astype(np.uint32), (bt.upper_mol.numpy() + mol_id_offset).astype(np.uint32)
+    n_up = bt.n_atoms * (bt.n_atoms - 1) // 2
+    for s_idx in range(1, n_timesteps):
+        s_i, t_i = t[s_idx], t[s_idx - 1]
+        last = s_idx == n_timesteps - 1
+        dst = model.forward(bt, x_t, a_t, c_t, e_t, t_i, prev)
+        dst = {k: v.float() for k, v in dst.items()}
+        dt = s_i - t_i
+        alpha_t, alpha_tp = t_i, torch.ones(())
+        vf = alpha_tp / (1 - alpha_t) * (dst['x'] - x_t)              # vector_field.py:567-569
+        x_t = x_t + dt * vf * 1.0
+        new = {}
+        for m, (name, cur, items, mols, item_mol, counts, mask_index) in enumerate((
+                ('a', a_t, node_item, node_mol, bt.node_mol, bt.n_atoms, model.A),
+                ('c', c_t, node_item, node_mol, bt.node_mol, bt.n_atoms, model.C),
+                ('e', e_t, up_item, up_mol, bt.upper_mol, n_up, model.Eb))):
+            p = F.softmax(torch.log(dst[name]) / tau, dim=-1)          # ctmc_vector_field.py:354-356
+            u3 = tuple(torch.from_numpy(u) for u in philox.uniforms(items, mols, s_idx, m, seed))
+            new[name], x1s = campbell_step(p, cur, eta, hc_thresh, alpha_t, alpha_tp, dt, counts, item_mol,
+                                           mask_index, last, u3)
+        a_t, c_t, e_t = new['a'], new['c'], new['e']
+        prev = dst
+        if record is not None:
+            record.append({'x': x_t.clone(), 'a': a_t.clone(), 'c': c_t.clone(), 'e': e_t.clone(),
+                           'x1': dst['x'].clone(), 'pa': dst['a'].clone(), 'pc': dst['c'].clone(), 'pe': dst['e'].clone()})
+    return {'x': x_t, 'a': a_t, 'c': c_t, 'e': e_t}

@@ -1,0 +1,229 @@
+"""User-facing surface of the reference kept for the sampling path.
+
+    flowmol.load_pretrained(model_name)                       flowmol/__init__.py:30-56
+    model.sample_random_sizes(n_molecules, n_timesteps=...)   flowmol/models/flowmol.py:473-486
+    model.sample(n_atoms, n_timesteps, prior=...)             flowmol/models/flowmol.py:489-589
+    SampledMolecule                                           flowmol/analysis/molecule_builder.py:17-85,217-297
+
+Out of scope: training, losses, metrics, dataset processing.
+"""
+import json
+import os
+from pathlib import Path
+
+import numpy as np
+import torch
+from torch.nn.functional import one_hot
+
+from . import weights as WT
+from .config import GEOM_ATOM_MAP, QM9_ATOM_MAP, ModelConfig
+from .graph import MolGraphBatch
+from .vector_field import CTMCVectorFieldB200
+
+# flowmol/__init__.py:5-28
+pretrained_model_names = [
+    'flowmol3', 'fm3_nodistort', 'fm3_none', 'fm3_ahigh', 'fm3_alow', 'fm3_chigh', 'fm3_clow', 'fm3_distort_extreme',
+    'fm3_distort_highp', 'fm3_distort_hight', 'fm3_distort_lowp', 'fm3_distort_lowt', 'fm3_ehigh', 'fm3_elow',
+    'fm3_fa_highp', 'fm3_fa_highstd', 'fm3_fa_lowp', 'fm3_fa_lowstd', 'fm3_scprop_high', 'fm3_scprop_low', 'fm3_xhigh',
+    'fm3_xlow']
+
+_HERE = Path(__file__).parent
+
+
+def n_atoms_histogram(dataset):
+    """(n_atoms int64[K], counts float64[K]) of the training set (data/<dataset>/train_data_n_atoms_histogram.pt)."""
+    with open(_HERE / "data" / "n_atoms_hist.json") as f:
+        h = json.load(f)[dataset]
+    return torch.tensor(h["n_atoms"], dtype=torch.int64), torch.tensor(h["counts"], dtype=torch.float64)
+
+
+class SampledMolecule:
+    """A sampled molecule: decoded arrays always; an rdkit Mol when rdkit is importable (molecule_builder.py:17-85).
+
+    Decode rules (molecule_builder.py:217-265): atom type = argmax a_1 with fake atoms dropped, charge = argmax c_1 - 2,
+    bond order = argmax e_1 on upper-triangle edges with the mask token mapped to 0, zero-order bonds dropped."""
+
+    def __init__(self, x, a_idx, c_idx, e_idx_upper, atom_type_map, fake_atoms=True, explicit_aromaticity=False):
+        atom_type_map = list(atom_type_map)
+        n = int(x.shape[0])
+        keep = np.ones(n, dtype=bool)
+        if fake_atoms:
+            keep = a_idx != len(atom_type_map)              # the fake-atom token sits right after the real types
+        symbols_all = atom_type_map + (['Sn'] if fake_atoms else []) + ['Se']     # 'Se' marks a still-masked atom
+        new_index = np.cumsum(keep) - 1
+        iu = np.triu_indices(n, k=1)
+        bond = e_idx_upper.copy()
+        bond[bond == (5 if explicit_aromaticity else 4)] = 0
+        sel = (bond != 0) & keep[iu[0]] & keep[iu[1]]
+        self.positions = torch.from_numpy(np.ascontiguousarray(x[keep]))
+        self.atom_types = [symbols_all[int(t)] for t in a_idx[keep]]
+        self.atom_charges = torch.from_numpy((c_idx[keep].astype(np.int64) - 2))
+        self.bond_types = torch.from_numpy(bond[sel].astype(np.int64))
+        self.bond_src_idxs = torch.from_numpy(new_index[iu[0][sel]].astype(np.int64))
+        self.bond_dst_idxs = torch.from_numpy(new_index[iu[1][sel]].astype(np.int64))
+        self.num_atoms = int(keep.sum())
+        self.atom_type_map = atom_type_map
+        self.rdkit_mol = self.build_molecule()
+
+    def build_molecule(self):
+        try:
+            from rdkit import Chem
+            from rdkit.Geometry import Point3D
+        except ImportError:
+            return None
+        order = [None, Chem.rdchem.BondType.SINGLE, Chem.rdchem.BondType.DOUBLE, Chem.rdchem.BondType.TRIPLE,
+                 Chem.rdchem.BondType.AROMATIC]
+        mol = Chem.RWMol()
+        for sym, ch in zip(self.atom_types, self.atom_charges.tolist()):
+            at = Chem.Atom(sym)
+            if ch != 0:
+                at.SetFormalCharge(int(ch))
+            mol.AddAtom(at)
+        for bt, s, d in zip(self.bond_types.tolist(), self.bond_src_idxs.tolist(), self.bond_dst_idxs.tolist()):
+            mol.AddBond(int(s), int(d), order[bt])
+        try:
+            mol = mol.GetMol()
+        except Exception:
+            return None
+        conf = Chem.Conformer(mol.GetNumAtoms())
+        for i, p in enumerate(self.positions.tolist()):
+            conf.SetAtomPosition(i, Point3D(*map(float, p)))
+        mol.AddConformer(conf)
+        return mol
+
+
+class FlowMolB200:
+    """Sampling-only counterpart of `FlowMol` (flowmol/models/flowmol.py:23)."""
+    canonical_feat_order = ['x', 'a', 'c', 'e']
+
+    def __init__(self, atom_type_map, vector_field_config, state_dict, n_atoms_hist=None, dataset="geom",
+                 default_n_timesteps=250, fake_atom_p=0.3, explicit_aromaticity=False, device="cuda:0"):
+        self.atom_type_map = list(atom_type_map)
+        self.fake_atoms = fake_atom_p > 0
+        self.explicit_aromaticity = explicit_aromaticity
+        self.n_atom_types = len(self.atom_type_map) + int(self.fake_atoms)          # flowmol.py:58,78-80
+        self.n_bond_types = 5 if explicit_aromaticity else 4
+        self.default_n_timesteps = default_n_timesteps
+        self.cfg = ModelConfig.from_vector_field_block(vector_field_config, self.n_atom_types, 6, self.n_bond_types)
+        self._state_dict = state_dict
+        self._device = device
+        self.vector_field = None
+        self.n_atoms_map, counts = n_atoms_hist if n_atoms_hist is not None else n_atoms_histogram(dataset)
+        self.n_atoms_dist = torch.distributions.Categorical(probs=counts / counts.sum())       # flowmol.py:461-466
+        if torch.cuda.is_available():
+            self._materialise(device)
+
+    # -- construction ------------------------------------------------------------------------------------------------------
+    @classmethod
+    def from_checkpoint(cls, ckpt_path, device="cuda:0", **load_kwargs):
+        sd, hp = WT.state_dict_from_checkpoint(ckpt_path)
+        hist = None
+        if load_kwargs.get("n_atoms_hist_file"):
+            n, c = torch.load(load_kwargs["n_atoms_hist_file"])
+            hist = (n, c.double())
+        dataset = "qm9" if "qm9" in str(hp.get("n_atoms_hist_file", "")) else "geom"
+        return cls(hp["atom_type_map"], hp["vector_field_config"], sd, n_atoms_hist=hist, dataset=dataset,
+                   default_n_timesteps=hp.get("default_n_timesteps", 250), fake_atom_p=hp.get("fake_atom_p", 0.0),
+                   explicit_aromaticity=hp.get("explicit_aromaticity", False), device=device)
+
+    @classmethod
+    def from_config(cls, name="flowmol3", dataset="geom", seed=0, device="cuda:0"):
+        """Random-init weights of a named reference config (no checkpoint is reachable offline)."""
+        from .config import NAMED_VECTOR_FIELDS
+        amap = GEOM_ATOM_MAP if dataset == "geom" else QM9_ATOM_MAP
+        cfg = ModelConfig.named(name, len(amap) + 1)
+        return cls(amap, NAMED_VECTOR_FIELDS[name], WT.init_state_dict(cfg, seed), dataset=dataset, device=device)
+
+    def _materialise(self, device):
+        self.vector_field = CTMCVectorFieldB200(self.cfg, self._state_dict, device=device)
+        self._device = str(self.vector_field.device)
+
+    def cuda(self, device=None):
+        dev = "cuda:0" if device is None else (f"cuda:{device}" if isinstance(device, int) else str(device))
+        if self.vector_field is None or str(self.vector_field.device) != str(torch.device(dev)):
+            self._materialise(dev)
+        return self
+
+    def to(self, device):
+        return self.cuda(device)
+
+    def eval(self):
+        return self
+
+    # -- sampling ----------------------------------------------------------------------------------------------------------------
+    def sample_n_atoms(self, n_molecules, **kwargs):
+        return self.n_atoms_map[self.n_atoms_dist.sample((n_molecules,), **kwargs)]            # flowmol.py:468-471
+
+    def sample_random_sizes(self, n_molecules, device="cuda:0", stochasticity=None, high_confidence_threshold=None,
+                            xt_traj=False, ep_traj=False, **kwargs):
+        return self.sample(self.sample_n_atoms(n_molecules), device=device, stochasticity=stochasticity,
+                           high_confidence_threshold=high_confidence_threshold, xt_traj=xt_traj, ep_traj=ep_traj, **kwargs)
+
+    def sample_prior(self, g):
+        """flowmol.py:417-448 with the CTMC priors: COM-free N(0,1) positions (priors.py:27-35, `std` ignored there too),
+        all-mask categorical state (priors.py:101-107,305-316)."""
+        N, E = g.num_nodes(), g.num_edges()
+        nbi = g.node_batch_idx().cpu()
+        x = torch.randn(N, 3)
+        com = torch.zeros(g.batch_size, 3).index_add_(0, nbi, x) / g.n_atoms[:, None].float()
+        g.ndata['x_0'] = (x - com[nbi]).to(g.device)
+        g.ndata['a_0'] = one_hot(torch.full((N,), self.n_atom_types), self.n_atom_types + 1).float().to(g.device)
+        g.ndata['c_0'] = one_hot(torch.full((N,), 6), 7).float().to(g.device)
+        g.edata['e_0'] = one_hot(torch.full((E,), self.n_bond_types), self.n_bond_types + 1).float().to(g.device)
+        return g
+
+    @torch.no_grad()
+    def sample(self, n_atoms, n_timesteps=None, device="cuda:0", stochasticity=None, high_confidence_threshold=None,
+               xt_traj=False, ep_traj=False, prior=None, **kwargs):
+        if self.vector_field is None:
+            self._materialise(device)
+        if n_timesteps is None:
+            n_timesteps = self.default_n_timesteps
+        if xt_traj or ep_traj:
+            raise NotImplementedError("trajectory capture (xt_traj / ep_traj) is not implemented yet")
+        dev = self.vector_field.device
+        g = MolGraphBatch(torch.as_tensor(n_atoms).cpu(), device=dev)
+        if prior is None:
+            g = self.sample_prior(g)
+        else:                                                                                  # flowmol.py:532-545
+            g.ndata['x_0'], g.ndata['c_0'] = prior['x_0'].to(dev), prior['c_0'].to(dev)
+            g.edata['e_0'] = prior['e_0'].to(dev)
+            a0 = prior['a_0'].to(dev)
+            if prior['fake_atoms'] and not self.fake_atoms:
+                a0 = a0[:, 1:]
+            elif not prior['fake_atoms'] and self.fake_atoms:
+                a0 = torch.cat([torch.zeros(a0.shape[0], 1, device=dev), a0], dim=-1)
+            g.ndata['a_0'] = a0
+        g = self.vector_field.integrate(g, g.node_batch_idx(), upper_edge_mask=g.upper_edge_mask(), n_timesteps=n_timesteps,
+                                        visualize=False, stochasticity=stochasticity,
+                                        high_confidence_threshold=high_confidence_threshold, **kwargs)
+        g.edata['ue_mask'] = g.upper_edge_mask()
+        g = g.to('cpu')                                                                        # flowmol.py:564 (device -> host)
+        uem = g.edata['ue_mask']
+        mols, no, eo = [], 0, 0
+        a_idx = g.ndata['a_1'].argmax(-1).numpy()
+        c_idx = g.ndata['c_1'].argmax(-1).numpy()
+        e_idx = g.edata['e_1'].argmax(-1).numpy()
+        x = g.ndata['x_1'].numpy()
+        uem = uem.numpy()
+        for n in g.n_atoms.tolist():
+            e = n * (n - 1)
+            mols.append(SampledMolecule(x[no:no + n], a_idx[no:no + n], c_idx[no:no + n], e_idx[eo:eo + e][uem[eo:eo + e]],
+                                        self.atom_type_map, fake_atoms=self.fake_atoms,
+                                        explicit_aromaticity=self.explicit_aromaticity))
+            no += n
+            eo += e
+        return mols
+
+
+def load_pretrained(model_name="flowmol3", device="cuda:0", models_dir=None):
+    """flowmol.load_pretrained: the checkpoint must already be on disk (`<models_dir>/<name>/checkpoints/last.ckpt`,
+    default models_dir = $FLOWMOL_B200_MODELS or flowmol_b200/trained_models); this build has no downloader."""
+    if model_name not in pretrained_model_names:
+        raise ValueError(f"Model {model_name} not found. Supported models: {pretrained_model_names}")
+    root = Path(models_dir or os.environ.get("FLOWMOL_B200_MODELS", _HERE / "trained_models"))
+    ckpt = root / model_name / "checkpoints" / "last.ckpt"
+    if not ckpt.exists():
+        raise FileNotFoundError(f"{ckpt} not found. Copy the reference's trained_models/{model_name}/ directory there "
+                                "(the reference fetches it with wget, flowmol/__init__.py:58-77; no network here).")
+    return FlowMolB200.from_checkpoint(ckpt, device=device)

@@ -1,0 +1,443 @@
+// C ABI of the B200-native FlowMol sampling path (see include/flowmol_b200.h for the contract).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/flowmol_b200.h"
+#include "ctmc.cuh"
+#include "kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+int fail(const std::string& msg) {
+  g_err = msg;
+  return -1;
+}
+#define CUDA_OK(expr)                                                                                      \
+  do {                                                                                                     \
+    cudaError_t e__ = (expr);                                                                              \
+    if (e__ != cudaSuccess) return fail(std::string(#expr) + ": " + cudaGetErrorString(e__));              \
+  } while (0)
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// byte offsets of everything inside a workspace
+struct Layout {
+  int B = 0, N = 0, U = 0, nET = 0, nUT = 0, nNT = 0;
+  long long EP = 0;
+  size_t mol_n, mol_node, mol_u, mol_etile, mol_utile, etile_mol, utile_mol, node_mol;
+  size_t s, v, x, P, Q, vd, EAB, M, partF, partL, ef;
+  size_t pred[3][4];     // [buffer][x,a,c,e]
+  size_t total = 0;
+};
+
+struct Dyn {           // model dimensions known at run time
+  int S, V, F, SD, VD, A, C, EB, MW;
+};
+
+Layout make_layout(const Dyn& d, const int32_t* n_atoms, int B) {
+  Layout L;
+  L.B = B;
+  long long N = 0, U = 0, et = 0, ut = 0;
+  for (int b = 0; b < B; ++b) {
+    const long long n = n_atoms[b];
+    N += n;
+    U += n * (n - 1) / 2;
+    et += (n * (n - 1) + fm::TM - 1) / fm::TM;
+    ut += (n * (n - 1) / 2 + fm::TM - 1) / fm::TM;
+  }
+  L.N = (int)N; L.U = (int)U; L.nET = (int)et; L.nUT = (int)ut; L.nNT = (int)((N + fm::TM - 1) / fm::TM);
+  L.EP = et * fm::TM;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  L.mol_n = take(4ull * B); L.mol_node = take(4ull * B); L.mol_u = take(4ull * B);
+  L.mol_etile = take(4ull * B); L.mol_utile = take(4ull * B);
+  L.etile_mol = take(4ull * L.nET); L.utile_mol = take(4ull * L.nUT); L.node_mol = take(4ull * N);
+  L.s = take(4ull * N * d.S); L.v = take(4ull * N * 3 * d.V); L.x = take(4ull * N * 3);
+  L.P = take(4ull * N * d.S); L.Q = take(4ull * N * d.S * (d.SD > 0)); L.vd = take(4ull * N * 3 * d.VD);
+  L.EAB = take(4ull * N * 2 * d.F); L.M = take(4ull * N * d.MW);
+  L.partF = take(4ull * L.nET * d.MW); L.partL = take(4ull * L.nET * d.MW);
+  L.ef = take(4ull * (size_t)L.EP * d.F);
+  for (int k = 0; k < 3; ++k) {
+    L.pred[k][0] = take(4ull * N * 3); L.pred[k][1] = take(4ull * N * d.A); L.pred[k][2] = take(4ull * N * d.C);
+    L.pred[k][3] = take(4ull * (size_t)U * d.EB);
+  }
+  L.total = off;
+  return L;
+}
+
+}  // namespace
+
+struct FmHandle {
+  FmConfig cfg;
+  int device = 0;
+  int variant = 0;             // 0: flowmol3 dims, 1: dev dims
+  Dyn dyn;
+  float* d_w = nullptr;
+  long long* d_off = nullptr;
+  float* d_table = nullptr;
+  fm::ModelRT rt;
+  std::unordered_map<void*, Layout> batches;
+  int64_t launches = 0;
+};
+
+namespace {
+
+template <class T>
+T* at(void* ws, size_t off) { return reinterpret_cast<T*>(static_cast<char*>(ws) + off); }
+
+fm::BatchRT batch_rt(void* ws, const Layout& L) {
+  fm::BatchRT b;
+  b.B = L.B; b.N = L.N; b.U = L.U; b.n_edge_tiles = L.nET; b.n_upper_tiles = L.nUT; b.n_node_tiles = L.nNT; b.EP = L.EP;
+  b.mol_n = at<int>(ws, L.mol_n); b.mol_node = at<int>(ws, L.mol_node); b.mol_u = at<int>(ws, L.mol_u);
+  b.mol_etile = at<int>(ws, L.mol_etile); b.mol_utile = at<int>(ws, L.mol_utile);
+  b.etile_mol = at<int>(ws, L.etile_mol); b.utile_mol = at<int>(ws, L.utile_mol); b.node_mol = at<int>(ws, L.node_mol);
+  return b;
+}
+
+fm::PredPtr pred_ptr(void* ws, const Layout& L, int k) {
+  return fm::PredPtr{at<float>(ws, L.pred[k][0]), at<float>(ws, L.pred[k][1]), at<float>(ws, L.pred[k][2]),
+                     at<float>(ws, L.pred[k][3])};
+}
+
+template <class D>
+int set_smem_attrs() {
+  const int bytes = (int)D::SMEM_BYTES;
+  CUDA_OK(cudaFuncSetAttribute(fm::k_node_embed<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_OK(cudaFuncSetAttribute(fm::k_edge_init<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_OK(cudaFuncSetAttribute(fm::k_conv_edge<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_OK(cudaFuncSetAttribute(fm::k_node_update<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_OK(cudaFuncSetAttribute(fm::k_dst_proj<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_OK(cudaFuncSetAttribute(fm::k_edge_update<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_OK(cudaFuncSetAttribute(fm::k_node_head<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_OK(cudaFuncSetAttribute(fm::k_edge_head<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return 0;
+}
+
+#define LAUNCH_OK(h)                                                                                       \
+  do {                                                                                                     \
+    ++(h)->launches;                                                                                       \
+    cudaError_t e__ = cudaGetLastError();                                                                  \
+    if (e__ != cudaSuccess) return fail(std::string("kernel launch failed: ") + cudaGetErrorString(e__)); \
+  } while (0)
+
+// one denoise_graph pass (embedding + optional self-conditioning residual + convs + heads)
+template <class D>
+int run_pass(FmHandle* h, void* ws, const Layout& L, const float* x_t, const uint8_t* a_t, const uint8_t* c_t,
+             const uint8_t* e_t, float t, const fm::PredPtr prev, int has_prev, const fm::PredPtr out, int remove_com,
+             int stop_after, cudaStream_t st) {
+  const fm::BatchRT bt = batch_rt(ws, L);
+  const fm::ModelRT& m = h->rt;
+  const size_t smem = D::SMEM_BYTES;
+  float *s = at<float>(ws, L.s), *v = at<float>(ws, L.v), *x = at<float>(ws, L.x), *P = at<float>(ws, L.P);
+  float *Q = at<float>(ws, L.Q), *vd = at<float>(ws, L.vd), *EAB = at<float>(ws, L.EAB), *M = at<float>(ws, L.M);
+  float *partF = at<float>(ws, L.partF), *partL = at<float>(ws, L.partL), *ef = at<float>(ws, L.ef);
+  fm::k_node_embed<D><<<L.nNT, fm::NT, smem, st>>>(m, bt, x_t, a_t, c_t, t, prev, has_prev, s, v, P);
+  LAUNCH_OK(h);
+  if (m.use_dst) { fm::k_dst_proj<D><<<L.nNT, fm::NT, smem, st>>>(m, bt, 0, s, v, Q, vd); LAUNCH_OK(h); }
+  fm::k_edge_init<D><<<L.nUT, fm::NT, smem, st>>>(m, bt, x_t, e_t, prev, has_prev, ef);
+  LAUNCH_OK(h);
+  CUDA_OK(cudaMemcpyAsync(x, x_t, sizeof(float) * 3 * L.N, cudaMemcpyDeviceToDevice, st));
+  for (int l = 0; l < m.L; ++l) {
+    fm::k_conv_edge<D><<<L.nET, fm::NT, smem, st>>>(m, bt, l, x, v, ef, P, Q, vd, M, partF, partL);
+    LAUNCH_OK(h);
+    int upd = -1;
+    if (l != 0 && (l + 1) % m.convs_per_update == 0) upd = m.separate_updaters ? l / m.convs_per_update : 0;   // vector_field.py:321-326
+    const int has_next = l + 1 < m.L;
+    fm::k_node_update<D><<<L.nNT, fm::NT, smem, st>>>(m, bt, l, upd, has_next, s, v, x, M, partF, partL, P, EAB);
+    LAUNCH_OK(h);
+    if (m.use_dst && has_next) { fm::k_dst_proj<D><<<L.nNT, fm::NT, smem, st>>>(m, bt, l + 1, s, v, Q, vd); LAUNCH_OK(h); }
+    if (upd >= 0) { fm::k_edge_update<D><<<L.nET, fm::NT, smem, st>>>(m, bt, upd, x, EAB, ef); LAUNCH_OK(h); }
+    if (l == stop_after) return 0;
+  }
+  fm::k_node_head<D><<<L.nNT, fm::NT, smem, st>>>(m, bt, s, out.a, out.c);
+  LAUNCH_OK(h);
+  fm::k_edge_head<D><<<L.nUT, fm::NT, smem, st>>>(m, bt, ef, out.e);
+  LAUNCH_OK(h);
+  fm::k_com<<<(L.B + 7) / 8, 256, 0, st>>>(bt, x, out.x, remove_com);
+  LAUNCH_OK(h);
+  return 0;
+}
+
+template <class D>
+int forward_impl(FmHandle* h, void* ws, const Layout& L, const float* x_t, const uint8_t* a_t, const uint8_t* c_t,
+                 const uint8_t* e_t, float t, const fm::PredPtr* prev, const fm::PredPtr out, int stop_after, cudaStream_t st) {
+  const fm::PredPtr none{nullptr, nullptr, nullptr, nullptr};
+  fm::PredPtr pv = prev ? *prev : none;
+  int has_prev = (h->cfg.self_conditioning && prev) ? 1 : 0;
+  if (h->cfg.self_conditioning && !prev && t == 0.0f) {     // first sampling step: vector_field.py:269-282
+    const fm::PredPtr tmp = pred_ptr(ws, L, 2);
+    int rc = run_pass<D>(h, ws, L, x_t, a_t, c_t, e_t, t, none, 0, tmp, /*remove_com=*/0, -1, st);
+    if (rc) return rc;
+    pv = tmp;
+    has_prev = 1;
+  }
+  return run_pass<D>(h, ws, L, x_t, a_t, c_t, e_t, t, pv, has_prev, out, /*remove_com=*/1, stop_after, st);
+}
+
+int dispatch_forward(FmHandle* h, void* ws, const Layout& L, const float* x_t, const uint8_t* a_t, const uint8_t* c_t,
+                     const uint8_t* e_t, float t, const fm::PredPtr* prev, const fm::PredPtr out, int stop_after,
+                     cudaStream_t st) {
+  if (h->variant == 0) return forward_impl<fm::DimsFlowmol3>(h, ws, L, x_t, a_t, c_t, e_t, t, prev, out, stop_after, st);
+  return forward_impl<fm::DimsDev>(h, ws, L, x_t, a_t, c_t, e_t, t, prev, out, stop_after, st);
+}
+
+// torch.linspace(0, 1, n) in fp32 (ATen RangeFactories: step = (end-start)/(steps-1); first half start + i*step,
+// second half end - (steps-1-i)*step)
+void time_grid(int n, float* t) {
+  if (n == 1) { t[0] = 0.f; return; }
+  const float step = (1.0f - 0.0f) / (float)(n - 1);
+  const int half = n / 2;
+  for (int i = 0; i < n; ++i) t[i] = i < half ? 0.0f + step * (float)i : 1.0f - step * (float)(n - 1 - i);
+}
+
+float clamp01(float v) { return v < 0.f ? 0.f : (v > 1.f ? 1.f : v); }
+
+int find_batch(FmHandle* h, void* ws, const Layout** L) {
+  auto it = h->batches.find(ws);
+  if (it == h->batches.end()) return fail("workspace has no batch: call fm_batch_init first");
+  *L = &it->second;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fm_abi_version(void) { return FM_ABI_VERSION; }
+const char* fm_last_error(void) { return g_err.c_str(); }
+
+void fm_debug_time_grid(int n, float* out_host) { time_grid(n, out_host); }
+
+int fm_create(const FmConfig* cfg, const float* w_host, size_t n_floats, const int64_t* off_host, size_t n_off, int device,
+              FmHandle** out) {
+  if (!cfg || !w_host || !off_host || !out) return fail("fm_create: null argument");
+  const FmConfig& c = *cfg;
+  int variant = -1;
+  using F3 = fm::DimsFlowmol3;
+  using DV = fm::DimsDev;
+  auto matches = [&](int S, int V, int F, int R, int CP, int SD, int VD, int TOK, int TD) {
+    return c.n_hidden_scalars == S && c.n_vec_channels == V && c.n_hidden_edge_feats == F && c.rbf_dim == R &&
+           c.n_cp_feats == CP && (c.use_dst_feats ? c.s_dst : 0) == SD && (c.use_dst_feats ? c.v_dst : 0) == VD &&
+           c.token_dim == TOK && c.time_embedding_dim == TD;
+  };
+  if (matches(F3::S, F3::V, F3::F, F3::R, F3::CP, F3::SD, F3::VD, F3::TOK, F3::TD)) variant = 0;
+  else if (matches(DV::S, DV::V, DV::F, DV::R, DV::CP, DV::SD, DV::VD, DV::TOK, DV::TD)) variant = 1;
+  if (variant < 0)
+    return fail("fm_create: no kernel instantiation for these dimensions (built: flowmol3 = S256/V32/F128/R32/cp4, "
+                "dev = S64/V16/F64/R32/cp4 + dst feats 16/4); add a Dims<> alias in csrc/model.cuh");
+  if (c.n_atom_types + 1 > fm::AMAX || c.n_atom_types + c.n_charges > 32 || c.n_bond_types + 1 > fm::KMAXC ||
+      c.n_charges + 1 > fm::KMAXC || c.n_atom_types + 1 > fm::KMAXC)
+    return fail("fm_create: too many categories for the kernels' fixed-size buffers");
+  const size_t expect = (size_t)fm::G_COUNT + (size_t)c.n_convs * fm::C_COUNT + (size_t)c.n_updaters * fm::U_COUNT;
+  if (n_off != expect) return fail("fm_create: offset table has the wrong number of entries (weight_layout mismatch)");
+  for (size_t i = 0; i < n_off; ++i)
+    if (off_host[i] >= (int64_t)n_floats || (off_host[i] >= 0 && off_host[i] % 4 != 0)) return fail("fm_create: bad offset table");
+  if (c.n_convs < 1 || c.convs_per_update < 1) return fail("fm_create: bad layer counts");
+  CUDA_OK(cudaSetDevice(device));
+  FmHandle* h = new FmHandle();
+  h->cfg = c; h->device = device; h->variant = variant;
+  h->dyn = Dyn{c.n_hidden_scalars, c.n_vec_channels, c.n_hidden_edge_feats, c.use_dst_feats ? c.s_dst : 0,
+               c.use_dst_feats ? c.v_dst : 0, c.n_atom_types, c.n_charges, c.n_bond_types,
+               c.n_hidden_scalars + 3 * c.n_vec_channels};
+  CUDA_OK(cudaMalloc(&h->d_w, n_floats * sizeof(float)));
+  CUDA_OK(cudaMalloc(&h->d_off, n_off * sizeof(long long)));
+  CUDA_OK(cudaMalloc(&h->d_table, sizeof(float) * (c.n_bond_types + 1) * c.n_hidden_edge_feats));
+  CUDA_OK(cudaMemcpy(h->d_w, w_host, n_floats * sizeof(float), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(h->d_off, off_host, n_off * sizeof(long long), cudaMemcpyHostToDevice));
+  fm::ModelRT& m = h->rt;
+  m.w = h->d_w; m.off = h->d_off; m.eemb_table = h->d_table;
+  m.A = c.n_atom_types; m.C = c.n_charges; m.EB = c.n_bond_types; m.L = c.n_convs; m.NU = c.n_updaters;
+  m.convs_per_update = c.convs_per_update; m.separate_updaters = c.separate_mol_updaters;
+  m.self_cond = c.self_conditioning; m.use_dst = c.use_dst_feats; m.rbf_dmax = c.rbf_dmax; m.msg_norm = c.message_norm;
+  int rc = variant == 0 ? set_smem_attrs<F3>() : set_smem_attrs<DV>();
+  if (rc) { fm_destroy(h); return rc; }
+  if (variant == 0) fm::k_edge_table<F3><<<c.n_bond_types + 1, 128>>>(m, h->d_table);
+  else fm::k_edge_table<DV><<<c.n_bond_types + 1, 128>>>(m, h->d_table);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaDeviceSynchronize());
+  *out = h;
+  return 0;
+}
+
+void fm_destroy(FmHandle* h) {
+  if (!h) return;
+  cudaFree(h->d_w); cudaFree(h->d_off); cudaFree(h->d_table);
+  delete h;
+}
+
+int fm_workspace_bytes(FmHandle* h, const int32_t* n_atoms, int32_t B, size_t* bytes) {
+  if (!h || !n_atoms || !bytes || B <= 0) return fail("fm_workspace_bytes: bad argument");
+  for (int b = 0; b < B; ++b)
+    if (n_atoms[b] < 2 || n_atoms[b] > 2000) return fail("fm_workspace_bytes: every molecule needs 2..2000 atoms");
+  *bytes = make_layout(h->dyn, n_atoms, B).total;
+  return 0;
+}
+
+int fm_batch_init(FmHandle* h, const int32_t* n_atoms, int32_t B, void* ws, size_t ws_bytes, void* stream) {
+  if (!h || !n_atoms || !ws || B <= 0) return fail("fm_batch_init: bad argument");
+  for (int b = 0; b < B; ++b)
+    if (n_atoms[b] < 2 || n_atoms[b] > 2000) return fail("fm_batch_init: every molecule needs 2..2000 atoms");
+  const Layout L = make_layout(h->dyn, n_atoms, B);
+  if (L.total > ws_bytes) return fail("fm_batch_init: workspace too small");
+  if (reinterpret_cast<uintptr_t>(ws) % 256) return fail("fm_batch_init: workspace must be 256-byte aligned");
+  if ((long long)L.EP * h->dyn.F >= (1ll << 40) || L.EP >= (1ll << 31)) return fail("fm_batch_init: batch too large");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::vector<int> mol_n(B), mol_node(B), mol_u(B), mol_et(B), mol_ut(B), et_mol(L.nET), ut_mol(L.nUT), node_mol(L.N);
+  int node = 0, u = 0, et = 0, ut = 0;
+  for (int b = 0; b < B; ++b) {
+    const int n = n_atoms[b];
+    mol_n[b] = n; mol_node[b] = node; mol_u[b] = u; mol_et[b] = et; mol_ut[b] = ut;
+    for (int i = 0; i < n; ++i) node_mol[node + i] = b;
+    const int ne = (n * (n - 1) + fm::TM - 1) / fm::TM, nu = (n * (n - 1) / 2 + fm::TM - 1) / fm::TM;
+    for (int k = 0; k < ne; ++k) et_mol[et + k] = b;
+    for (int k = 0; k < nu; ++k) ut_mol[ut + k] = b;
+    node += n; u += n * (n - 1) / 2; et += ne; ut += nu;
+  }
+  CUDA_OK(cudaSetDevice(h->device));
+  auto up = [&](size_t off, const std::vector<int>& v) {
+    return cudaMemcpyAsync(at<char>(ws, off), v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice, st);
+  };
+  CUDA_OK(up(L.mol_n, mol_n)); CUDA_OK(up(L.mol_node, mol_node)); CUDA_OK(up(L.mol_u, mol_u));
+  CUDA_OK(up(L.mol_etile, mol_et)); CUDA_OK(up(L.mol_utile, mol_ut)); CUDA_OK(up(L.etile_mol, et_mol));
+  CUDA_OK(up(L.utile_mol, ut_mol)); CUDA_OK(up(L.node_mol, node_mol));
+  CUDA_OK(cudaStreamSynchronize(st));      // the host vectors die here
+  h->batches[ws] = L;
+  return 0;
+}
+
+int fm_forward(FmHandle* h, void* ws, const float* x_t, const uint8_t* a_t, const uint8_t* c_t, const uint8_t* e_t, float t,
+               const FmPred* prev, const FmPred* out, int32_t stop_after_conv, void* stream) {
+  if (!h || !ws || !x_t || !a_t || !c_t || !e_t) return fail("fm_forward: null argument");
+  if (stop_after_conv < 0 && !out) return fail("fm_forward: out is required for a full evaluation");
+  const Layout* L;
+  if (find_batch(h, ws, &L)) return -1;
+  CUDA_OK(cudaSetDevice(h->device));
+  h->launches = 0;
+  fm::PredPtr pv, po{nullptr, nullptr, nullptr, nullptr};
+  if (prev) pv = fm::PredPtr{prev->x, prev->a, prev->c, prev->e};
+  if (out) po = fm::PredPtr{out->x, out->a, out->c, out->e};
+  return dispatch_forward(h, ws, *L, x_t, a_t, c_t, e_t, t, prev ? &pv : nullptr, po, stop_after_conv,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int fm_integrate(FmHandle* h, void* ws, float* x, uint8_t* a, uint8_t* c, uint8_t* e, const FmSampleOpts* o, void* stream) {
+  if (!h || !ws || !x || !a || !c || !e || !o) return fail("fm_integrate: null argument");
+  if (o->n_timesteps < 2) return fail("fm_integrate: n_timesteps must be >= 2");
+  const Layout* Lp;
+  if (find_batch(h, ws, &Lp)) return -1;
+  const Layout& L = *Lp;
+  CUDA_OK(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  h->launches = 0;
+  const int T = o->n_timesteps;
+  std::vector<float> t(T);
+  if (o->tspan_host) memcpy(t.data(), o->tspan_host, sizeof(float) * T);
+  else time_grid(T, t.data());
+  const fm::BatchRT bt = batch_rt(ws, L);
+  cudaGraph_t graph = nullptr;
+  if (o->use_cuda_graph) CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  int rc = 0;
+  for (int k = 1; k < T && rc == 0; ++k) {                        // ctmc_vector_field.py:205-232
+    const float t_i = t[k - 1], s_i = t[k];
+    const fm::PredPtr cur = pred_ptr(ws, L, k & 1), prv = pred_ptr(ws, L, (k - 1) & 1);
+    rc = dispatch_forward(h, ws, L, x, a, c, e, t_i, k == 1 ? nullptr : &prv, cur, -1, st);
+    if (rc) break;
+    fm::StepScalars sc;
+    sc.t_i = t_i;
+    sc.dt = s_i - t_i;
+    const float eta = o->stochasticity;
+    for (int m = 0; m < 3; ++m) {                                   // linear schedule: alpha_t = t, alpha_t' = 1
+      volatile float num = 1.0f + eta * t_i;
+      volatile float q = sc.dt * num;
+      volatile float den = 1.0f - t_i;
+      sc.unmask_prob[m] = clamp01(q / den);
+      volatile float qm = sc.dt * eta;
+      sc.mask_prob[m] = clamp01(qm);
+    }
+    sc.hc_thresh = o->high_confidence_threshold;
+    sc.tau = o->cat_temperature;
+    sc.last_step = k == T - 1;
+    sc.step_index = k;
+    sc.seed_lo = (uint32_t)(o->seed & 0xffffffffull);
+    sc.seed_hi = (uint32_t)(o->seed >> 32);
+    sc.mol_id_offset = o->mol_id_offset;
+    fm::k_ctmc_step<<<L.B, 256, 0, st>>>(bt, h->rt.A, h->rt.C, h->rt.EB, cur.x, cur.a, cur.c, cur.e, x, a, c, e, sc);
+    ++h->launches;
+    if (cudaGetLastError() != cudaSuccess) rc = fail("k_ctmc_step launch failed");
+  }
+  if (o->use_cuda_graph) {
+    cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) return fail(std::string("stream capture failed: ") + cudaGetErrorString(ce));
+    cudaGraphExec_t exec = nullptr;
+    CUDA_OK(cudaGraphInstantiate(&exec, graph, 0));
+    cudaError_t le = cudaGraphLaunch(exec, st);
+    cudaGraphDestroy(graph);
+    if (le != cudaSuccess) { cudaGraphExecDestroy(exec); return fail(std::string("graph launch failed: ") + cudaGetErrorString(le)); }
+    CUDA_OK(cudaStreamSynchronize(st));
+    cudaGraphExecDestroy(exec);
+  }
+  return rc;
+}
+
+int fm_sample_host(FmHandle* h, const int32_t* n_atoms, int32_t B, float* x_host, uint8_t* a_host, uint8_t* c_host,
+                   uint8_t* e_host, const FmSampleOpts* o, void* ws, size_t ws_bytes, void* stream) {
+  if (!h || !n_atoms || !x_host || !a_host || !c_host || !e_host || !o || !ws) return fail("fm_sample_host: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = fm_batch_init(h, n_atoms, B, ws, ws_bytes, stream);
+  if (rc) return rc;
+  const Layout& L = h->batches[ws];
+  // the state lives in the (otherwise unused until the first ping-pong) tail of the workspace: reuse pred buffer 2's
+  // neighbours is unsafe, so state gets its own small device allocation for the duration of the call
+  float* dx = nullptr; uint8_t *da = nullptr, *dc = nullptr, *de = nullptr;
+  CUDA_OK(cudaMallocAsync(&dx, sizeof(float) * 3 * L.N, st));
+  CUDA_OK(cudaMallocAsync(&da, L.N, st));
+  CUDA_OK(cudaMallocAsync(&dc, L.N, st));
+  CUDA_OK(cudaMallocAsync(&de, L.U > 0 ? L.U : 1, st));
+  CUDA_OK(cudaMemcpyAsync(dx, x_host, sizeof(float) * 3 * L.N, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(da, a_host, L.N, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(dc, c_host, L.N, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(de, e_host, L.U, cudaMemcpyHostToDevice, st));
+  rc = fm_integrate(h, ws, dx, da, dc, de, o, stream);
+  if (rc == 0) {
+    CUDA_OK(cudaMemcpyAsync(x_host, dx, sizeof(float) * 3 * L.N, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(a_host, da, L.N, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(c_host, dc, L.N, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(e_host, de, L.U, cudaMemcpyDeviceToHost, st));
+  }
+  cudaFreeAsync(dx, st); cudaFreeAsync(da, st); cudaFreeAsync(dc, st); cudaFreeAsync(de, st);
+  CUDA_OK(cudaStreamSynchronize(st));
+  return rc;
+}
+
+int fm_workspace_tensor(FmHandle* h, void* ws, const char* name, void** ptr, size_t* n_floats) {
+  if (!h || !ws || !name || !ptr || !n_floats) return fail("fm_workspace_tensor: null argument");
+  const Layout* Lp;
+  if (find_batch(h, ws, &Lp)) return -1;
+  const Layout& L = *Lp;
+  const Dyn& d = h->dyn;
+  const std::string n(name);
+  size_t off, cnt;
+  if (n == "s") { off = L.s; cnt = (size_t)L.N * d.S; }
+  else if (n == "v") { off = L.v; cnt = (size_t)L.N * 3 * d.V; }
+  else if (n == "x") { off = L.x; cnt = (size_t)L.N * 3; }
+  else if (n == "P") { off = L.P; cnt = (size_t)L.N * d.S; }
+  else if (n == "M") { off = L.M; cnt = (size_t)L.N * d.MW; }
+  else if (n == "EAB") { off = L.EAB; cnt = (size_t)L.N * 2 * d.F; }
+  else if (n == "ef") { off = L.ef; cnt = (size_t)L.EP * d.F; }
+  else return fail("fm_workspace_tensor: unknown tensor name");
+  *ptr = at<char>(ws, off);
+  *n_floats = cnt;
+  return 0;
+}
+
+int64_t fm_last_launch_count(FmHandle* h) { return h ? h->launches : -1; }
+
+}  // extern "C"

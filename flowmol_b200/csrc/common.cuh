@@ -1,0 +1,92 @@
+// Common device helpers for the FlowMol B200 sampling kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fm {
+
+constexpr int NT = 256;     // threads per CTA for every tile kernel
+constexpr int NWARP = 8;
+constexpr int TM = 64;      // rows (edges / upper edges / nodes) per CTA tile
+constexpr int RPW = 8;      // rows owned by one warp inside a tile
+constexpr int KC = 16;      // K-chunk of the weight stream staged through shared memory
+constexpr int WSTAGE_FLOATS = 2 * KC * 256;   // double buffer, widest weight matrix has 256 columns
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
+
+__host__ __device__ __forceinline__ int pad4(int x) { return (x + 3) & ~3; }
+__host__ __device__ __forceinline__ int pad32(int x) { return (x + 31) & ~31; }
+
+// ---- async copy (LDGSTS) -------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// ---- math (accurate versions: the parity bar is the reference's fp32 noise floor) ---------------------------------
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }          // torch.nn.SiLU
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }    // torch.sigmoid
+
+// flowmol/models/gvp.py:14-21 -- sqrt(clamp(x^2+y^2+z^2, 1e-8))
+__device__ __forceinline__ float norm_no_nan3(float x, float y, float z) {
+  float q = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+  return sqrtf(fmaxf(q, 1e-8f));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- Philox4x32-10 (same function as oracle/philox.py) -------------------------------------------------------------
+struct Philox4 { uint32_t x, y, z, w; };
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                                 uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+    uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += W0; k1 += W1;
+  }
+  return Philox4{c0, c1, c2, c3};
+}
+__device__ __forceinline__ float u24(uint32_t r) { return (float)(r >> 8) * 5.9604644775390625e-08f; }  // 2^-24
+
+// ---- complete-graph index algebra ---------------------------------------------------------------------------------
+// Internal directed-edge order inside a molecule with n atoms: local edge le = j*(n-1) + i', dst = j,
+// src = i' + (i' >= j).  (The reference order -- upper triangle row-major, then its mirror,
+// flowmol/data_processing/utils.py:4-17 -- is only used at the C-ABI boundary for the upper-edge arrays.)
+__device__ __forceinline__ void edge_src_dst(int le, int n, int& i, int& j) {
+  j = le / (n - 1);
+  int ip = le - j * (n - 1);
+  i = ip + (ip >= j ? 1 : 0);
+}
+__device__ __forceinline__ int edge_pos(int i, int j, int n) {  // local index of directed edge src i -> dst j
+  return j * (n - 1) + (i < j ? i : i - 1);
+}
+// upper-triangle index lu (row-major over i<j) -> (i, j)
+__device__ __forceinline__ void upper_ij(int lu, int n, int& i, int& j) {
+  float b = (float)(2 * n - 1);
+  int ii = (int)floorf((b - sqrtf(fmaxf(b * b - 8.0f * (float)lu, 0.0f))) * 0.5f);
+  ii = max(0, min(ii, n - 2));
+  // offset(i) = i*(2n-i-1)/2 ; fix rounding of the float sqrt
+  while (ii > 0 && (ii * (2 * n - ii - 1)) / 2 > lu) --ii;
+  while (((ii + 1) * (2 * n - ii - 2)) / 2 <= lu) ++ii;
+  i = ii;
+  j = lu - (ii * (2 * n - ii - 1)) / 2 + ii + 1;
+}
+
+}  // namespace fm

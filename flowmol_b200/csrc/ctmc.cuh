@@ -1,0 +1,117 @@
+// One integrator step after the network call (CTMCVectorField.step / campbell_step / purity_sampling:
+// flowmol/models/ctmc_vector_field.py:328-409,414-461, flowmol/utils/ctmc_utils.py:4-35) -- one CTA per molecule.
+//
+// The reference does this with ~60 ATen launches per step, boolean-mask indexing (host syncs), torch_scatter
+// segment_csr for the per-molecule purity counts and the global torch RNG.  Here: one launch per step, per-molecule
+// counts by a block reduction, counter-based Philox noise keyed by (item, global molecule id, step, modality).
+// Memory-bound: per upper edge 16 B (p_hat) + 1 B state read, 1 B written.
+#pragma once
+#include "model.cuh"
+
+namespace fm {
+
+constexpr int KMAXC = 16;   // max categories of one modality
+
+struct StepScalars {
+  float t_i, dt;
+  float unmask_prob[3], mask_prob[3];    // per modality a, c, e   (clamped, ctmc_vector_field.py:430-434)
+  float hc_thresh, tau;
+  int last_step, step_index;
+  uint32_t seed_lo, seed_hi;
+  int mol_id_offset;
+};
+
+// p = softmax(log(p_hat) / tau); returns max_k p_k ("purity")          (ctmc_vector_field.py:354-356)
+__device__ __forceinline__ float sharpen(const float* __restrict__ phat, int K, float tau, float* p) {
+  float mx = -INFINITY;
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) { p[k] = __fdiv_rn(logf(phat[k]), tau); mx = fmaxf(mx, p[k]); }
+  float sum = 0.f;
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) { p[k] = expf(__fsub_rn(p[k], mx)); sum = __fadd_rn(sum, p[k]); }
+  float pur = 0.f;
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) { p[k] = __fdiv_rn(p[k], sum); pur = fmaxf(pur, p[k]); }
+  return pur;
+}
+
+__device__ __forceinline__ int block_sum_int(int v, int* scratch /*NWARP ints*/) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  int t = 0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += scratch[w];
+  return t;
+}
+
+// one modality of one molecule: `cnt` items, categories K (mask index == K)
+__device__ __forceinline__ void campbell_modality(const float* __restrict__ phat /*[cnt][K]*/, uint8_t* __restrict__ state,
+                                                  int cnt, int K, int modality, uint32_t mol_gid, const StepScalars& sc,
+                                                  int* scratch) {
+  const float q_u = sc.unmask_prob[modality], q_m = sc.mask_prob[modality];
+  float p[KMAXC];
+  // pass 1: per-molecule counts of masked / high-confidence masked items      (ctmc_utils.py:6-18)
+  int m_loc = 0, h_loc = 0;
+  if (sc.hc_thresh > 0.f) {
+    for (int it = threadIdx.x; it < cnt; it += blockDim.x) {
+      if (state[it] == K) {
+        ++m_loc;
+        if (sharpen(phat + (size_t)it * K, K, sc.tau, p) >= sc.hc_thresh) ++h_loc;
+      }
+    }
+  }
+  const int m_cnt = block_sum_int(m_loc, scratch);
+  const int h_cnt = block_sum_int(h_loc, scratch);
+  float ph = 0.f, pl = 0.f;
+  if (sc.hc_thresh > 0.f) {
+    const float qm = __fmul_rn(q_u, (float)m_cnt);
+    const float ph_max = h_cnt == 0 ? INFINITY : __fdiv_rn(qm, (float)h_cnt);   // ctmc_utils.py:21-22
+    ph = fminf(ph_max, 1.0f);
+    pl = __fdiv_rn(__fsub_rn(qm, __fmul_rn(ph, (float)h_cnt)), (float)(m_cnt - h_cnt));   // ctmc_utils.py:26 (unused if m == h)
+  }
+  // pass 2: draw x1, decide unmask / re-mask                                      (ctmc_vector_field.py:428-457)
+  for (int it = threadIdx.x; it < cnt; it += blockDim.x) {
+    const int z = state[it];
+    const float pur = sharpen(phat + (size_t)it * K, K, sc.tau, p);
+    const Philox4 rnd = philox4x32_10((uint32_t)it, mol_gid, (uint32_t)sc.step_index, (uint32_t)modality, sc.seed_lo, sc.seed_hi);
+    // inverse-CDF categorical draw (shared definition with oracle/flowmol_oracle.py:sample_categorical)
+    float c = 0.f, cum[KMAXC];
+    for (int k = 0; k < K; ++k) { c = __fadd_rn(c, p[k]); cum[k] = c; }
+    const float thr = __fmul_rn(u24(rnd.x), c);
+    int x1 = 0;
+    for (int k = 0; k < K; ++k) x1 += (cum[k] <= thr) ? 1 : 0;
+    x1 = min(x1, K - 1);
+    const bool masked = z == K;
+    float prob;
+    if (sc.hc_thresh > 0.f) prob = masked ? (pur >= sc.hc_thresh ? ph : pl) : 0.f;
+    else prob = masked ? q_u : 0.f;
+    const bool will_unmask = u24(rnd.y) < prob;
+    int zn = z;
+    if (!sc.last_step && (u24(rnd.z) < q_m) && !masked) zn = K;
+    if (will_unmask) zn = x1;
+    state[it] = (uint8_t)zn;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_ctmc_step(const BatchRT bt, int A, int C, int EB, const float* __restrict__ px, const float* __restrict__ pa,
+            const float* __restrict__ pc, const float* __restrict__ pe, float* __restrict__ x_t,
+            uint8_t* __restrict__ a_t, uint8_t* __restrict__ c_t, uint8_t* __restrict__ e_t, const StepScalars sc) {
+  __shared__ int scratch[32];
+  const int mol = blockIdx.x;
+  const int n = bt.mol_n[mol], nb = bt.mol_node[mol], ub = bt.mol_u[mol], ucount = n * (n - 1) / 2;
+  // positions: x_t += dt * (alpha'/(1-alpha)) * (x1_hat - x_t), linear schedule alpha = t  (ctmc_vector_field.py:331-334)
+  const float coef = __fdiv_rn(1.0f, __fsub_rn(1.0f, sc.t_i));
+  for (int i = threadIdx.x; i < n * 3; i += blockDim.x) {
+    const int g = nb * 3 + i;
+    const float vf = __fmul_rn(coef, __fsub_rn(px[g], x_t[g]));
+    x_t[g] = __fadd_rn(x_t[g], __fmul_rn(sc.dt, vf));
+  }
+  const uint32_t gid = (uint32_t)(mol + sc.mol_id_offset);
+  campbell_modality(pa + (size_t)nb * A, a_t + nb, n, A, 0, gid, sc, scratch);
+  campbell_modality(pc + (size_t)nb * C, c_t + nb, n, C, 1, gid, sc, scratch);
+  campbell_modality(pe + (size_t)ub * EB, e_t + ub, ucount, EB, 2, gid, sc, scratch);
+}
+
+}  // namespace fm

@@ -1,0 +1,254 @@
+"""CTMCVectorFieldB200 -- host-side mirror of the reference's `CTMCVectorField` for the sampling path.
+
+Same method names and argument meaning as flowmol/models/ctmc_vector_field.py (`integrate`, `forward`) and
+flowmol/models/vector_field.py:212 (`forward(g, t, node_batch_idx, upper_edge_mask, apply_softmax, remove_com,
+prev_dst_dict)`), so `model.vector_field = CTMCVectorFieldB200(...)` is a drop-in at the seam
+flowmol/models/flowmol.py:557.  Everything numerical happens in libflowmol_b200.so (CUDA, sm_100a) through the C ABI
+of include/flowmol_b200.h; PyTorch is only the container for device memory and the stream.  No autograd, no DGL
+message passing, no CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+from torch.nn.functional import one_hot
+
+from . import _lib
+from . import weights as WT
+from .config import ModelConfig
+from .graph import MolGraphBatch, n_atoms_of
+
+
+def _require_cuda(device):
+    if not torch.cuda.is_available():
+        raise RuntimeError("flowmol_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError(f"flowmol_b200 runs on CUDA devices only, got {dev}")
+    return torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+
+
+class CTMCVectorFieldB200:
+    canonical_feat_order = ['x', 'a', 'c', 'e']
+
+    def __init__(self, cfg: ModelConfig, state_dict, device="cuda:0"):
+        self.cfg = cfg
+        self.device = _require_cuda(device)
+        self.lib = _lib.load()
+        self.n_atom_types, self.n_charges, self.n_bond_types = cfg.n_atom_types, cfg.n_charges, cfg.n_bond_types
+        self.mask_idxs = {'a': cfg.n_atom_types, 'c': cfg.n_charges, 'e': cfg.n_bond_types}   # ctmc_vector_field.py:64-68
+        self.eta = cfg.stochasticity
+        self.hc_thresh = cfg.high_confidence_threshold
+        self.cat_temperature = cfg.cat_temperature
+        blob, offsets = WT.pack(cfg, state_dict)
+        self._blob, self._offsets = np.ascontiguousarray(blob), np.ascontiguousarray(offsets)
+        if not (cfg.a_token_dim == cfg.c_token_dim == cfg.e_token_dim):
+            raise NotImplementedError("token embedding dims must be equal")
+        mn = cfg.message_norm
+        c = _lib.FmConfig(
+            n_atom_types=cfg.n_atom_types, n_charges=cfg.n_charges, n_bond_types=cfg.n_bond_types,
+            n_hidden_scalars=cfg.n_hidden_scalars, n_vec_channels=cfg.n_vec_channels,
+            n_hidden_edge_feats=cfg.n_hidden_edge_feats, n_cp_feats=cfg.n_cp_feats, rbf_dim=cfg.rbf_dim,
+            time_embedding_dim=cfg.time_embedding_dim, token_dim=cfg.a_token_dim, n_convs=cfg.n_convs,
+            n_updaters=cfg.n_updaters, convs_per_update=cfg.convs_per_update,
+            separate_mol_updaters=int(cfg.separate_mol_updaters), self_conditioning=int(cfg.self_conditioning),
+            use_dst_feats=int(cfg.use_dst_feats), s_dst=cfg.s_dst, v_dst=cfg.v_dst, rbf_dmax=float(cfg.rbf_dmax),
+            message_norm=(0.0 if mn == 'sum' else -1.0 if mn == 'mean' else float(mn)))
+        h = C.c_void_p()
+        _lib.check(self.lib.fm_create(C.byref(c), self._blob.ctypes.data, self._blob.size, self._offsets.ctypes.data,
+                                      self._offsets.size, self.device.index, C.byref(h)))
+        self._h = h
+        self._ws = None
+        self._ws_key = None
+        self.last_launches = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self.lib.fm_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # -- nn.Module-ish surface (readme.md:46-47 chains .cuda().eval()) -----------------------------------------------------
+    def eval(self):
+        return self
+
+    def cuda(self, device=None):
+        return self
+
+    def to(self, device):
+        if _require_cuda(device) != self.device:
+            raise RuntimeError("a CTMCVectorFieldB200 is bound to the device it was created on")
+        return self
+
+    # -- workspace ---------------------------------------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _prepare(self, n_atoms):
+        n = np.ascontiguousarray(np.asarray(n_atoms, dtype=np.int32).reshape(-1))
+        key = n.tobytes()
+        if self._ws_key != key:
+            nbytes = C.c_size_t()
+            _lib.check(self.lib.fm_workspace_bytes(self._h, n.ctypes.data, len(n), C.byref(nbytes)))
+            if self._ws is None or self._ws.numel() < nbytes.value:
+                self._ws = None
+                self._ws = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.fm_batch_init(self._h, n.ctypes.data, len(n), self._ws.data_ptr(), self._ws.numel(),
+                                                  self._stream()))
+            self._ws_key = key
+        return n
+
+    def workspace_tensor(self, name):
+        """Device view of a named workspace tensor (tests / debugging)."""
+        ptr, cnt = C.c_void_p(), C.c_size_t()
+        _lib.check(self.lib.fm_workspace_tensor(self._h, self._ws.data_ptr(), name.encode(), C.byref(ptr), C.byref(cnt)))
+        off = ptr.value - self._ws.data_ptr()
+        return self._ws[off:off + 4 * cnt.value].view(torch.float32)
+
+    def _pred_buffers(self, N, U):
+        dev = self.device
+        return {'x': torch.empty(N, 3, device=dev), 'a': torch.empty(N, self.n_atom_types, device=dev),
+                'c': torch.empty(N, self.n_charges, device=dev), 'e': torch.empty(U, self.n_bond_types, device=dev)}
+
+    @staticmethod
+    def _pred_struct(d):
+        return _lib.FmPred(x=d['x'].data_ptr(), a=d['a'].data_ptr(), c=d['c'].data_ptr(), e=d['e'].data_ptr())
+
+    # -- token-level API (what the C ABI takes) -----------------------------------------------------------------------------
+    def forward_tokens(self, n_atoms, x_t, a_idx, c_idx, e_idx_upper, t, prev=None, stop_after_conv=-1):
+        """One network evaluation on token-index state.  Returns the dst dict {'x','a','c','e'} (e on upper edges)."""
+        n = self._prepare(n_atoms)
+        N, U = int(n.sum()), int((n.astype(np.int64) * (n - 1) // 2).sum())
+        dev = self.device
+        x_t = x_t.to(dev, torch.float32).contiguous()
+        a = a_idx.to(dev, torch.uint8).contiguous()
+        c = c_idx.to(dev, torch.uint8).contiguous()
+        e = e_idx_upper.to(dev, torch.uint8).contiguous()
+        assert x_t.shape == (N, 3) and a.shape == (N,) and c.shape == (N,) and e.shape == (U,)
+        out = self._pred_buffers(N, U)
+        pv = None
+        if prev is not None:
+            prev = {k: prev[k].to(dev, torch.float32).contiguous() for k in 'xace'}
+            pv = self._pred_struct(prev)
+        po = self._pred_struct(out)
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.fm_forward(self._h, self._ws.data_ptr(), x_t.data_ptr(), a.data_ptr(), c.data_ptr(),
+                                           e.data_ptr(), float(t), C.byref(pv) if pv is not None else None, C.byref(po),
+                                           int(stop_after_conv), self._stream()))
+        self.last_launches = int(self.lib.fm_last_launch_count(self._h))
+        return out
+
+    def _opts(self, n_timesteps, stochasticity, high_confidence_threshold, seed, mol_id_offset, tspan, cuda_graph):
+        if tspan is None:
+            tspan = torch.linspace(0, 1, n_timesteps)                # ctmc_vector_field.py:170 (fp32, evaluated by torch)
+        ts = np.ascontiguousarray(tspan.detach().cpu().float().numpy())
+        o = _lib.FmSampleOpts(
+            n_timesteps=len(ts), stochasticity=float(self.eta if stochasticity is None else stochasticity),
+            high_confidence_threshold=float(self.hc_thresh if high_confidence_threshold is None else high_confidence_threshold),
+            cat_temperature=float(self.cat_temperature), seed=int(seed) & (2 ** 64 - 1), mol_id_offset=int(mol_id_offset),
+            tspan_host=ts.ctypes.data_as(C.POINTER(C.c_float)), use_cuda_graph=int(bool(cuda_graph)))
+        return o, ts
+
+    def integrate_tokens(self, n_atoms, x0, a0, c0, e0_upper, n_timesteps, seed, stochasticity=None,
+                         high_confidence_threshold=None, mol_id_offset=0, tspan=None, cuda_graph=False):
+        """Full trajectory on device-resident token state; returns final {'x','a','c','e'} (new tensors)."""
+        n = self._prepare(n_atoms)
+        dev = self.device
+        x = x0.to(dev, torch.float32).contiguous().clone()
+        a = a0.to(dev, torch.uint8).contiguous().clone()
+        c = c0.to(dev, torch.uint8).contiguous().clone()
+        e = e0_upper.to(dev, torch.uint8).contiguous().clone()
+        o, ts = self._opts(n_timesteps, stochasticity, high_confidence_threshold, seed, mol_id_offset, tspan, cuda_graph)
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.fm_integrate(self._h, self._ws.data_ptr(), x.data_ptr(), a.data_ptr(), c.data_ptr(),
+                                             e.data_ptr(), C.byref(o), self._stream()))
+        self.last_launches = int(self.lib.fm_last_launch_count(self._h))
+        return {'x': x, 'a': a, 'c': c, 'e': e}
+
+    def sample_host(self, n_atoms, x0, a0, c0, e0_upper, n_timesteps, seed, stochasticity=None,
+                    high_confidence_threshold=None, mol_id_offset=0, tspan=None, cuda_graph=False):
+        """Host (pinned) buffers in, host buffers out: H2D + batch descriptor + trajectory + D2H inside one C call.
+        x0 float32 [N,3], a0/c0 uint8 [N], e0_upper uint8 [U] are CPU tensors updated IN PLACE."""
+        n = np.ascontiguousarray(np.asarray(n_atoms, dtype=np.int32).reshape(-1))
+        for t_, dt_ in ((x0, torch.float32), (a0, torch.uint8), (c0, torch.uint8), (e0_upper, torch.uint8)):
+            assert t_.device.type == "cpu" and t_.dtype == dt_ and t_.is_contiguous()
+        nbytes = C.c_size_t()
+        _lib.check(self.lib.fm_workspace_bytes(self._h, n.ctypes.data, len(n), C.byref(nbytes)))
+        if self._ws is None or self._ws.numel() < nbytes.value:
+            self._ws = None
+            self._ws = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+        self._ws_key = n.tobytes()
+        o, ts = self._opts(n_timesteps, stochasticity, high_confidence_threshold, seed, mol_id_offset, tspan, cuda_graph)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.fm_sample_host(self._h, n.ctypes.data, len(n), x0.data_ptr(), a0.data_ptr(), c0.data_ptr(),
+                                               e0_upper.data_ptr(), C.byref(o), self._ws.data_ptr(), self._ws.numel(),
+                                               self._stream()))
+        self.last_launches = int(self.lib.fm_last_launch_count(self._h))
+        return {'x': x0, 'a': a0, 'c': c0, 'e': e0_upper}
+
+    # -- graph-level API (the reference's signatures) --------------------------------------------------------------------------
+    def _tokens_from_graph(self, g, suffix):
+        uem = g.upper_edge_mask() if isinstance(g, MolGraphBatch) else None
+        return (g.ndata[f'a_{suffix}'].argmax(-1), g.ndata[f'c_{suffix}'].argmax(-1), g.edata[f'e_{suffix}'], uem)
+
+    def forward(self, g, t, node_batch_idx=None, upper_edge_mask=None, apply_softmax=True, remove_com=True,
+                prev_dst_dict=None):
+        """EndpointVectorField.forward at sampling time (vector_field.py:212-293).  `t` is the [B] tensor of (equal) times."""
+        if not (apply_softmax and remove_com):
+            raise NotImplementedError("the sampling path always calls forward(apply_softmax=True, remove_com=True)")
+        n_atoms = n_atoms_of(g)
+        tt = torch.as_tensor(t, dtype=torch.float32).reshape(-1)
+        if not bool((tt == tt[0]).all()):
+            raise NotImplementedError("all molecules share one time during sampling (ctmc_vector_field.py:320)")
+        a_idx, c_idx, e_oh, uem = self._tokens_from_graph(g, 't')
+        uem = upper_edge_mask if upper_edge_mask is not None else uem
+        e_idx = e_oh[uem.to(e_oh.device)].argmax(-1)
+        return self.forward_tokens(n_atoms, g.ndata['x_t'], a_idx, c_idx, e_idx, float(tt[0]), prev_dst_dict)
+
+    __call__ = forward
+
+    def integrate(self, g, node_batch_idx=None, upper_edge_mask=None, n_timesteps=None, visualize=False,
+                  dfm_type='campbell', stochasticity=None, high_confidence_threshold=None, cat_temp_func=None,
+                  forward_weight_func=None, tspan=None, seed=None, mol_id_offset=0, cuda_graph=False, **kwargs):
+        """CTMCVectorField.integrate (ctmc_vector_field.py:145-285): reads x_0/a_0/c_0/e_0 from the graph, writes
+        x_1/a_1/c_1/e_1 (and *_t).  `seed` selects the Philox noise stream (default: drawn from torch's global RNG so
+        `torch.manual_seed` / seed_everything still controls reproducibility, cf. test.py:70-71)."""
+        if dfm_type not in (None, 'campbell'):
+            raise NotImplementedError("only dfm_type='campbell' (the reference default) is implemented")
+        if cat_temp_func is not None or forward_weight_func is not None or kwargs.get('inv_temp_func') is not None:
+            raise NotImplementedError("custom temperature / forward-weight schedules are not implemented")
+        if visualize:
+            raise NotImplementedError("trajectory capture (xt_traj / ep_traj) is not implemented yet")
+        if n_timesteps is None and tspan is None:
+            raise ValueError("n_timesteps is required")
+        n_atoms = n_atoms_of(g)
+        uem = upper_edge_mask if upper_edge_mask is not None else g.upper_edge_mask()
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        e0 = g.edata['e_0']
+        uem_d = uem.to(e0.device)
+        out = self.integrate_tokens(n_atoms, g.ndata['x_0'], g.ndata['a_0'].argmax(-1), g.ndata['c_0'].argmax(-1),
+                                    e0[uem_d].argmax(-1), n_timesteps, seed, stochasticity, high_confidence_threshold,
+                                    mol_id_offset, tspan, cuda_graph)
+        a1 = one_hot(out['a'].long(), self.n_atom_types + 1).float()
+        c1 = one_hot(out['c'].long(), self.n_charges + 1).float()
+        eu = one_hot(out['e'].long(), self.n_bond_types + 1).float()
+        e1 = torch.zeros(uem.shape[0], self.n_bond_types + 1, device=eu.device)
+        um = uem.to(eu.device)
+        e1[um] = eu
+        e1[~um] = eu                                                  # both triangles carry the same state (:397-406)
+        for k, val in (('x', out['x']), ('a', a1), ('c', c1)):
+            g.ndata[f'{k}_t'] = val
+            g.ndata[f'{k}_1'] = val
+        g.edata['e_t'] = e1
+        g.edata['e_1'] = e1
+        return g
+
+
+def from_named_config(name, n_atom_types, seed=0, device="cuda:0"):
+    """Random-weight model with one of the embedded reference configs ('flowmol3', 'dev') -- tests and benchmarks."""
+    cfg = ModelConfig.named(name, n_atom_types)
+    return CTMCVectorFieldB200(cfg, WT.init_state_dict(cfg, seed), device=device)

@@ -159,101 +159,149 @@ def state_dict_from_checkpoint(path):
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# packing for the CUDA library
+# packing for the CUDA library  (layout: flowmol_b200/weight_layout.py)
 # ----------------------------------------------------------------------------------------------------------------
+from . import weight_layout as WL
+
+
 def _pad4(n):
     return (n + 3) // 4 * 4
 
 
-class Packer:
-    """Appends [K, Npad] row-major fp32 matrices / vectors to one blob; every entry starts 16-byte aligned."""
+def _pad32(n):
+    return (n + 31) // 32 * 32
 
-    def __init__(self):
+
+class Packer:
+    def __init__(self, n_entries):
         self.chunks = []
         self.size = 0
-        self.index = OrderedDict()
+        self.offsets = np.full(n_entries, -1, dtype=np.int64)
 
-    def add(self, name, arr):
+    def _append(self, idx, arr):
         arr = np.ascontiguousarray(arr, dtype=np.float32).reshape(-1)
         pad = (-self.size) % 4
         if pad:
             self.chunks.append(np.zeros(pad, np.float32))
             self.size += pad
-        self.index[name] = (self.size, arr.size)
+        assert self.offsets[idx] == -1, f"entry {idx} packed twice"
+        self.offsets[idx] = self.size
         self.chunks.append(arr)
         self.size += arr.size
 
-    def add_matrix_kn(self, name, w_kn):
-        """w_kn: [K, N] -> stored [K, pad4(N)] (zero padded columns)."""
+    def raw(self, idx, arr):
+        self._append(idx, arr)
+
+    def gemm(self, idx, w_kn):
+        """w_kn [K, N] -> [pad4(K), pad32(N)] zero padded."""
         w = np.asarray(w_kn, dtype=np.float32)
         K, N = w.shape
-        out = np.zeros((K, _pad4(N)), np.float32)
-        out[:, :N] = w
-        self.add(name, out)
+        out = np.zeros((_pad4(K), _pad32(N)), np.float32)
+        out[:K, :N] = w
+        self._append(idx, out)
+
+    def vec(self, idx, b):
+        b = np.asarray(b, dtype=np.float32).reshape(-1)
+        out = np.zeros(_pad32(b.size), np.float32)
+        out[:b.size] = b
+        self._append(idx, out)
 
     def blob(self):
-        return np.concatenate(self.chunks) if self.chunks else np.zeros(0, np.float32)
+        return np.concatenate(self.chunks)
 
 
-def _gvp_pack(P, name, sd, p, n_node_rows=0):
-    """One GVP: [Wh | Wcp] fused as a single [v_in, h+2cp] matrix, Wu, W (transposed, optional node-side rows split
-    off: rows [0, n_node_rows) of the transposed to_feats_out weight multiply per-node inputs), b, Wg (transposed), bg."""
-    wh = sd[p + ".Wh"].numpy()
-    parts = [wh]
+def _np(sd, k):
+    return sd[k].detach().float().cpu().numpy()
+
+
+def _pack_gvp(P, base, sd, p, w_rows=None):
+    """GVP under state_dict prefix `p` -> 6 consecutive entries starting at id `base`.
+    [Wh | Wcp] are fused into one operand (they multiply the same input); `w_rows` selects/reorders the rows of the
+    transposed to_feats_out weight that stay on the per-row path."""
+    parts = [_np(sd, p + ".Wh")]
     if (p + ".Wcp") in sd:
-        parts.append(sd[p + ".Wcp"].numpy())
-    P.add_matrix_kn(name + ".whcp", np.concatenate(parts, axis=1))
-    P.add_matrix_kn(name + ".wu", sd[p + ".Wu"].numpy())
-    w = sd[p + ".to_feats_out.0.weight"].numpy().T            # [in, out]
-    P.add_matrix_kn(name + ".w", w)
-    P.add(name + ".b", sd[p + ".to_feats_out.0.bias"].numpy())
-    P.add_matrix_kn(name + ".wg", sd[p + ".scalar_to_vector_gates.weight"].numpy().T)
-    P.add(name + ".bg", sd[p + ".scalar_to_vector_gates.bias"].numpy())
+        parts.append(_np(sd, p + ".Wcp"))
+    P.gemm(base + 0, np.concatenate(parts, axis=1))
+    P.gemm(base + 1, _np(sd, p + ".Wu"))
+    w = _np(sd, p + ".to_feats_out.0.weight").T                     # [in, out]
+    P.gemm(base + 2, w if w_rows is None else w[w_rows])
+    P.vec(base + 3, _np(sd, p + ".to_feats_out.0.bias"))
+    P.gemm(base + 4, _np(sd, p + ".scalar_to_vector_gates.weight").T)
+    P.vec(base + 5, _np(sd, p + ".scalar_to_vector_gates.bias"))
 
 
-def _lin_pack(P, name, sd, p):
-    P.add_matrix_kn(name + ".w", sd[p + ".weight"].numpy().T)
-    P.add(name + ".b", sd[p + ".bias"].numpy())
+def _pack_linear(P, iw, ib, sd, p):
+    P.gemm(iw, _np(sd, p + ".weight").T)
+    P.vec(ib, _np(sd, p + ".bias"))
 
 
 def pack(cfg: ModelConfig, sd):
-    """Returns (blob float32[n], index {name: (offset, size)}) in the fixed order the C library expects
-    (flowmol_b200/csrc/weights.h walks the same sequence; a layout hash guards against drift)."""
+    """state_dict -> (blob float32[n], offsets int64[n_entries]).
+
+    Algebraic restructuring done here (DESIGN.md "node-side folding"): the rows of the first message linear that
+    multiply s_src (and, with use_dst_feats, s_dst_msg) and the rows of the first edge-update linear that multiply
+    s_src / s_dst are split off; the kernels apply them once per NODE and gather the result per edge."""
     check_state_dict(cfg, sd)
-    sd = {k: v.detach().float().cpu() for k, v in sd.items()}
-    P = Packer()
-    P.add("emb.a", sd["token_embeddings.a.weight"].numpy())
-    P.add("emb.c", sd["token_embeddings.c.weight"].numpy())
-    P.add("emb.e", sd["token_embeddings.e.weight"].numpy())
-    _lin_pack(P, "semb.0", sd, "scalar_embedding.0")
-    _lin_pack(P, "semb.2", sd, "scalar_embedding.2")
-    P.add("semb.ln.w", sd["scalar_embedding.4.weight"].numpy()); P.add("semb.ln.b", sd["scalar_embedding.4.bias"].numpy())
-    _lin_pack(P, "eemb.0", sd, "edge_embedding.0")
-    _lin_pack(P, "eemb.2", sd, "edge_embedding.2")
-    P.add("eemb.ln.w", sd["edge_embedding.4.weight"].numpy()); P.add("eemb.ln.b", sd["edge_embedding.4.bias"].numpy())
+    S, V, F, R, cp = cfg.n_hidden_scalars, cfg.n_vec_channels, cfg.n_hidden_edge_feats, cfg.rbf_dim, cfg.n_cp_feats
+    L, NU = cfg.n_convs, cfg.n_updaters
+    P = Packer(WL.n_entries(L, NU))
+    g = WL.gid
+    P.raw(g("EMB_A"), _np(sd, "token_embeddings.a.weight"))
+    P.raw(g("EMB_C"), _np(sd, "token_embeddings.c.weight"))
+    P.raw(g("EMB_E"), _np(sd, "token_embeddings.e.weight"))
+    # constant tables evaluated with torch so they are bit-identical to flowmol/utils/embedding.py:5-34
+    P.raw(g("RBF_MU"), torch.linspace(0.0, float(cfg.rbf_dmax), R).numpy())
+    half = cfg.time_embedding_dim // 2
+    freq = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(1000) / (half - 1)))
+    P.raw(g("TIME_FREQ"), freq.numpy())
+    _pack_linear(P, g("SEMB0_W"), g("SEMB0_B"), sd, "scalar_embedding.0")
+    _pack_linear(P, g("SEMB2_W"), g("SEMB2_B"), sd, "scalar_embedding.2")
+    P.vec(g("SEMB_LN_W"), _np(sd, "scalar_embedding.4.weight")); P.vec(g("SEMB_LN_B"), _np(sd, "scalar_embedding.4.bias"))
+    _pack_linear(P, g("EEMB0_W"), g("EEMB0_B"), sd, "edge_embedding.0")
+    _pack_linear(P, g("EEMB2_W"), g("EEMB2_B"), sd, "edge_embedding.2")
+    P.vec(g("EEMB_LN_W"), _np(sd, "edge_embedding.4.weight")); P.vec(g("EEMB_LN_B"), _np(sd, "edge_embedding.4.bias"))
     if cfg.self_conditioning:
         p = "self_conditioning_residual_layer"
-        _lin_pack(P, "sc.n0", sd, p + ".node_residual_mlp.0"); _lin_pack(P, "sc.n2", sd, p + ".node_residual_mlp.2")
-        _lin_pack(P, "sc.e0", sd, p + ".edge_residual_mlp.0"); _lin_pack(P, "sc.e2", sd, p + ".edge_residual_mlp.2")
-    for l in range(cfg.n_convs):
+        _pack_linear(P, g("SCN0_W"), g("SCN0_B"), sd, p + ".node_residual_mlp.0")
+        _pack_linear(P, g("SCN2_W"), g("SCN2_B"), sd, p + ".node_residual_mlp.2")
+        _pack_linear(P, g("SCE0_W"), g("SCE0_B"), sd, p + ".edge_residual_mlp.0")
+        _pack_linear(P, g("SCE2_W"), g("SCE2_B"), sd, p + ".edge_residual_mlp.2")
+    _pack_linear(P, g("NHEAD0_W"), g("NHEAD0_B"), sd, "node_output_head.0")
+    _pack_linear(P, g("NHEAD2_W"), g("NHEAD2_B"), sd, "node_output_head.2")
+    _pack_linear(P, g("EHEAD0_W"), g("EHEAD0_B"), sd, "to_edge_logits.0")
+    _pack_linear(P, g("EHEAD2_W"), g("EHEAD2_B"), sd, "to_edge_logits.2")
+    sdst, vdst = cfg.s_dst, cfg.v_dst
+    for l in range(L):
         p = f"conv_layers.{l}"
+        c = lambda n: WL.cid(l, n)
         if cfg.use_dst_feats:
-            _gvp_pack(P, f"conv{l}.dst", sd, p + ".dst_feat_msg_projection")
+            _pack_gvp(P, c("DST_WHCP"), sd, p + ".dst_feat_msg_projection")
+        # message GVP 0: input scalars are cat[s_src(S) | d(R) | ef(F) | s_dst_msg(sdst) | sh(H0+cp)]  (gvp.py:523-539)
+        h0 = max(V + 1 + vdst, V)
+        w0 = _np(sd, f"{p}.edge_message.0.to_feats_out.0.weight").T                       # [in, S]
+        rows_edge = list(range(S, S + R + F)) + list(range(S + R + F + sdst, S + R + F + sdst + h0 + cp))
+        _pack_gvp(P, c("MSG0_WHCP"), sd, f"{p}.edge_message.0", w_rows=rows_edge)
+        P.gemm(c("WSRC"), w0[:S])
+        P.vec(c("BSRC"), _np(sd, f"{p}.edge_message.0.to_feats_out.0.bias"))
+        if cfg.use_dst_feats:
+            P.gemm(c("WDST"), w0[S + R + F:S + R + F + sdst])
+        _pack_gvp(P, c("MSG1_WHCP"), sd, f"{p}.edge_message.1")
+        _pack_gvp(P, c("MSG2_WHCP"), sd, f"{p}.edge_message.2")
         for i in range(3):
-            _gvp_pack(P, f"conv{l}.msg{i}", sd, f"{p}.edge_message.{i}")
+            _pack_gvp(P, c(f"UPD{i}_WHCP"), sd, f"{p}.node_update.{i}")
+        P.vec(c("LN_MSG_W"), _np(sd, f"{p}.message_layer_norm.feat_norm.weight"))
+        P.vec(c("LN_MSG_B"), _np(sd, f"{p}.message_layer_norm.feat_norm.bias"))
+        P.vec(c("LN_UPD_W"), _np(sd, f"{p}.update_layer_norm.feat_norm.weight"))
+        P.vec(c("LN_UPD_B"), _np(sd, f"{p}.update_layer_norm.feat_norm.bias"))
+    for u in range(NU):
+        c = lambda n: WL.uid(L, u, n)
         for i in range(3):
-            _gvp_pack(P, f"conv{l}.upd{i}", sd, f"{p}.node_update.{i}")
-        for nm, q in (("ln_msg", "message_layer_norm"), ("ln_upd", "update_layer_norm")):
-            P.add(f"conv{l}.{nm}.w", sd[f"{p}.{q}.feat_norm.weight"].numpy())
-            P.add(f"conv{l}.{nm}.b", sd[f"{p}.{q}.feat_norm.bias"].numpy())
-    for u in range(cfg.n_updaters):
-        for i in range(3):
-            _gvp_pack(P, f"pos{u}.gvp{i}", sd, f"node_position_updaters.{u}.gvps.{i}")
-    for u in range(cfg.n_updaters):
+            _pack_gvp(P, c(f"POS{i}_WHCP"), sd, f"node_position_updaters.{u}.gvps.{i}")
         p = f"edge_updaters.{u}"
-        _lin_pack(P, f"eupd{u}.0", sd, p + ".edge_update_fn.0")
-        _lin_pack(P, f"eupd{u}.2", sd, p + ".edge_update_fn.2")
-        P.add(f"eupd{u}.ln.w", sd[p + ".edge_norm.weight"].numpy()); P.add(f"eupd{u}.ln.b", sd[p + ".edge_norm.bias"].numpy())
-    _lin_pack(P, "nhead.0", sd, "node_output_head.0"); _lin_pack(P, "nhead.2", sd, "node_output_head.2")
-    _lin_pack(P, "ehead.0", sd, "to_edge_logits.0"); _lin_pack(P, "ehead.2", sd, "to_edge_logits.2")
-    return P.blob(), P.index
+        w1 = _np(sd, p + ".edge_update_fn.0.weight").T      # [2S+F+R, F], rows: s_src | s_dst | ef | d  (vector_field.py:866-875)
+        P.gemm(c("EUPD_WN"), np.concatenate([w1[:S], w1[S:2 * S]], axis=1))          # [S, 2F]: per-node EA | EB
+        P.vec(c("EUPD_BN"), np.concatenate([_np(sd, p + ".edge_update_fn.0.bias"), np.zeros(F, np.float32)]))
+        P.gemm(c("EUPD_WE"), w1[2 * S:])                                              # rows ef | d
+        _pack_linear(P, c("EUPD_W2"), c("EUPD_B2"), sd, p + ".edge_update_fn.2")
+        P.vec(c("EUPD_LN_W"), _np(sd, p + ".edge_norm.weight")); P.vec(c("EUPD_LN_B"), _np(sd, p + ".edge_norm.bias"))
+    return P.blob(), P.offsets

@@ -1,0 +1,111 @@
+/* flowmol_b200 -- C ABI of the B200-native FlowMol sampling hot path.
+ *
+ * The reference (Dunni3/FlowMol) is pure Python and has no FFI; its seam for this path is an attribute call on an
+ * nn.Module.  Each entry point below names the reference interface it replaces (paths relative to the reference root):
+ *
+ *   fm_create / fm_destroy   weights of `FlowMol.vector_field` (CTMCVectorField.__init__, flowmol/models/
+ *                            ctmc_vector_field.py:23-69 + vector_field.py:16-197) as loaded by
+ *                            FlowMol.load_from_checkpoint (flowmol/__init__.py:30-56)
+ *   fm_batch_init            graph construction in FlowMol.sample (flowmol/models/flowmol.py:509-529:
+ *                            build_edge_idxs / dgl.batch / get_upper_edge_mask / get_batch_idxs)
+ *   fm_forward               CTMCVectorField.forward == EndpointVectorField.forward(g, t, node_batch_idx, upper_edge_mask,
+ *                            apply_softmax=True, remove_com=True, prev_dst_dict)      (vector_field.py:212-293), the fine seam
+ *                            at ctmc_vector_field.py:318
+ *   fm_integrate             CTMCVectorField.integrate(g, node_batch_idx, upper_edge_mask, n_timesteps, stochasticity,
+ *                            high_confidence_threshold, ...)  (ctmc_vector_field.py:145-285), the coarse seam at
+ *                            flowmol/models/flowmol.py:557
+ *   fm_sample_host           FlowMol.sample(n_atoms, n_timesteps, prior=...) from host buffers to host buffers
+ *                            (flowmol.py:489-589 minus rdkit), i.e. integrate + the H2D / D2H around it
+ *
+ * Conventions
+ *   - plain C types only; every array is caller-owned; device pointers unless the name ends in `_host`.
+ *   - categorical state is carried as token indices (uint8): the argmax of the reference's one-hot tensors; the mask
+ *     token is index n_classes (ctmc_vector_field.py:64-68).  Edge state / edge predictions are per UPPER-triangle
+ *     edge in the reference's order (flowmol/data_processing/utils.py:4-17): molecule-major, (i<j) row-major.
+ *   - all calls are asynchronous on `stream` (a cudaStream_t passed as void*) except fm_create / fm_sample_host.
+ *   - return 0 on success, negative on error; fm_last_error() gives the message.  No C++ exception crosses the ABI.
+ *   - a handle is bound to one device; one in-flight call per workspace.
+ */
+#ifndef FLOWMOL_B200_H
+#define FLOWMOL_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FM_ABI_VERSION 1
+
+typedef struct FmHandle FmHandle;
+
+typedef struct FmConfig {
+  int32_t n_atom_types;      /* incl. fake-atom type; mask token index == n_atom_types */
+  int32_t n_charges, n_bond_types;
+  int32_t n_hidden_scalars, n_vec_channels, n_hidden_edge_feats, n_cp_feats;
+  int32_t rbf_dim, time_embedding_dim, token_dim;      /* a/c/e token dims must be equal */
+  int32_t n_convs, n_updaters, convs_per_update, separate_mol_updaters;
+  int32_t self_conditioning, use_dst_feats, s_dst, v_dst;
+  float rbf_dmax;
+  float message_norm;        /* 0: 'sum', -1: 'mean', >0: divide aggregated messages by this */
+} FmConfig;
+
+typedef struct FmPred {      /* predicted endpoint, the reference's dst_dict (softmaxed, COM-free) */
+  float* x;                  /* [N,3] */
+  float* a;                  /* [N,n_atom_types] */
+  float* c;                  /* [N,n_charges] */
+  float* e;                  /* [U,n_bond_types] upper edges */
+} FmPred;
+
+typedef struct FmSampleOpts {
+  int32_t n_timesteps;
+  float stochasticity;       /* eta */
+  float high_confidence_threshold;
+  float cat_temperature;     /* tau (0.05) */
+  uint64_t seed;             /* Philox key */
+  int32_t mol_id_offset;     /* global id of molecule 0 of this batch (sharding-invariant noise) */
+  const float* tspan_host;   /* optional [n_timesteps] fp32 time grid; NULL => linspace(0,1,n) evaluated like torch.linspace */
+  int32_t use_cuda_graph;    /* capture the per-step launch sequence once and replay it */
+} FmSampleOpts;
+
+int fm_abi_version(void);
+const char* fm_last_error(void);
+
+/* weights: packed blob + offset table produced by flowmol_b200.weights.pack (layout: flowmol_b200/weight_layout.py) */
+int fm_create(const FmConfig* cfg, const float* packed_weights_host, size_t n_floats, const int64_t* offsets_host,
+              size_t n_offsets, int device, FmHandle** out);
+void fm_destroy(FmHandle* h);
+
+/* workspace sizing for a batch with the given atom counts (host array) */
+int fm_workspace_bytes(FmHandle* h, const int32_t* n_atoms_host, int32_t n_molecules, size_t* bytes);
+/* writes the batch descriptor into the workspace (must be 256-byte aligned device memory of fm_workspace_bytes bytes) */
+int fm_batch_init(FmHandle* h, const int32_t* n_atoms_host, int32_t n_molecules, void* workspace, size_t workspace_bytes,
+                  void* stream);
+
+/* one network evaluation.  prev == NULL and t == 0 runs the self-conditioning pre-pass first (vector_field.py:269-282).
+ * stop_after_conv >= 0 stops after that conv layer (+ its molecule update) for layer-wise parity tests; -1 = full. */
+int fm_forward(FmHandle* h, void* workspace, const float* x_t, const uint8_t* a_t, const uint8_t* c_t,
+               const uint8_t* e_t_upper, float t, const FmPred* prev, const FmPred* out, int32_t stop_after_conv,
+               void* stream);
+
+/* full trajectory: state arrays are updated in place from (x_0, a_0, c_0, e_0) to (x_1, a_1, c_1, e_1) */
+int fm_integrate(FmHandle* h, void* workspace, float* x, uint8_t* a, uint8_t* c, uint8_t* e_upper,
+                 const FmSampleOpts* opts, void* stream);
+
+/* host-to-host convenience: H2D of the prior, fm_batch_init, fm_integrate, D2H of the result (synchronous) */
+int fm_sample_host(FmHandle* h, const int32_t* n_atoms_host, int32_t n_molecules, float* x_host, uint8_t* a_host,
+                   uint8_t* c_host, uint8_t* e_upper_host, const FmSampleOpts* opts, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* introspection for tests: device pointer + size (floats) of a named workspace tensor after fm_batch_init:
+ * "s" [N,S], "v" [N,3,V], "x" [N,3], "ef" [EP,F] (internal padded dst-major order), "P", "M" */
+int fm_workspace_tensor(FmHandle* h, void* workspace, const char* name, void** ptr, size_t* n_floats);
+/* host-only helper: the fallback time grid used when tspan_host == NULL (torch.linspace-like fp32 grid) */
+void fm_debug_time_grid(int32_t n, float* out_host);
+/* number of kernels launched by the last fm_forward / fm_integrate call on this handle */
+int64_t fm_last_launch_count(FmHandle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,224 @@
+"""GPU parity tests: CUDA path (through the C ABI) vs golden vectors produced by the reference's own code, and vs the
+CPU oracle on fresh seeded inputs.  Run on the B200 box with `pytest -m gpu`.
+
+Tolerances (fp32 path; the yardstick is the reference's own fp32-vs-fp64 noise floor, SURVEY.md section 8c:
+max|dx| 6e-7, max|dp| 3e-7 per forward):
+    per forward : |dx| <= 5e-6, |dp| <= 3e-6, argmax(a, c, e) exact
+    hidden state: rtol 1e-5 / atol 1e-5 per layer (summation order differs: per-node folding of the s_src / s_dst rows)
+    trajectory  : final categorical state identical for every molecule, |dx| <= 1e-4
+"""
+import numpy as np
+import pytest
+import torch
+
+from flowmol_b200 import graph as G
+from flowmol_b200 import weights as WT
+from flowmol_b200.config import ModelConfig
+from oracle import flowmol_oracle as O
+from tests.helpers import load_golden, model_from_golden, t
+
+pytestmark = pytest.mark.gpu
+
+FWD = ["fwd_dev_taps", "fwd_flowmol3_taps", "fwd_flowmol3_geom", "fwd_dev_qm9"]
+ITG = ["itg_dev_T10", "itg_dev_T50", "itg_flowmol3_T10", "itg_flowmol3_T25"]
+TOL_X, TOL_P, TOL_H = 5e-6, 3e-6, 1e-5
+
+_models = {}
+
+
+def cuda_model(cfg_name, A, wseed):
+    from flowmol_b200.vector_field import CTMCVectorFieldB200
+    key = (cfg_name, A, wseed)
+    if key not in _models:
+        cfg = ModelConfig.named(cfg_name, A)
+        _models[key] = (cfg, CTMCVectorFieldB200(cfg, WT.init_state_dict(cfg, wseed), device="cuda:0"))
+    return _models[key]
+
+
+def model_for(gd):
+    return cuda_model(str(gd["config"]), int(gd["n_atom_types"]), int(gd["weight_seed"]))
+
+
+def check_pred(d, want, tag):
+    d = {k: v.cpu().numpy() for k, v in d.items()}
+    assert np.isfinite(d["x"]).all(), tag
+    np.testing.assert_allclose(d["x"], want["x"], rtol=0, atol=TOL_X, err_msg=f"{tag} x")
+    for k in "ace":
+        np.testing.assert_allclose(d[k], want[k], rtol=0, atol=TOL_P, err_msg=f"{tag} {k}")
+        assert np.array_equal(d[k].argmax(-1), want[k].argmax(-1)), f"{tag} argmax {k}"
+
+
+@pytest.mark.parametrize("name", FWD)
+def test_forward_vs_reference_golden(name):
+    gd = load_golden(name)
+    cfg, vf = model_for(gd)
+    n_atoms = gd["n_atoms"]
+    d0 = vf.forward_tokens(n_atoms, t(gd["c0.x_t"]), t(gd["c0.a"]), t(gd["c0.c"]), t(gd["c0.e"]), float(gd["c0.t"]), None)
+    check_pred(d0, {k: gd[f"c0.out.{k}"] for k in "xace"}, f"{name} first step")
+    prev = {k: t(gd[f"c0.out.{k}"]) for k in "xace"}
+    d1 = vf.forward_tokens(n_atoms, t(gd["c1.x_t"]), t(gd["c1.a"]), t(gd["c1.c"]), t(gd["c1.e"]), float(gd["c1.t"]), prev)
+    check_pred(d1, {k: gd[f"c1.out.{k}"] for k in "xace"}, f"{name} mid trajectory")
+    assert vf.last_launches > 0
+
+
+@pytest.mark.parametrize("name", ["fwd_dev_taps", "fwd_flowmol3_taps"])
+def test_layerwise_hidden_state_vs_reference_golden(name):
+    gd = load_golden(name)
+    cfg, vf = model_for(gd)
+    n_atoms = gd["n_atoms"]
+    perm = torch.from_numpy(G.ref_edge_to_internal(n_atoms))
+    prev = {k: t(gd[f"c0.out.{k}"]) for k in "xace"}
+    args = (n_atoms, t(gd["c1.x_t"]), t(gd["c1.a"]), t(gd["c1.c"]), t(gd["c1.e"]), float(gd["c1.t"]), prev)
+    N = int(np.sum(n_atoms))
+    for l in range(cfg.n_convs):
+        vf.forward_tokens(*args, stop_after_conv=l)
+        s = vf.workspace_tensor("s").view(N, cfg.n_hidden_scalars).cpu().numpy()
+        v = vf.workspace_tensor("v").view(N, 3, cfg.n_vec_channels).permute(0, 2, 1).cpu().numpy()
+        np.testing.assert_allclose(s, gd[f"c1.tap.conv{l}.s"], rtol=TOL_H, atol=TOL_H, err_msg=f"conv{l} s")
+        np.testing.assert_allclose(v, gd[f"c1.tap.conv{l}.v"], rtol=TOL_H, atol=TOL_H, err_msg=f"conv{l} v")
+        if l >= 1:
+            x = vf.workspace_tensor("x").view(N, 3).cpu().numpy()
+            ef = vf.workspace_tensor("ef").view(-1, cfg.n_hidden_edge_feats).cpu()[perm].numpy()
+            np.testing.assert_allclose(x, gd[f"c1.tap.pos{l}"], rtol=0, atol=TOL_X, err_msg=f"pos{l}")
+            np.testing.assert_allclose(ef, gd[f"c1.tap.eupd{l}"], rtol=TOL_H, atol=TOL_H, err_msg=f"eupd{l}")
+
+
+@pytest.mark.parametrize("name", ITG)
+def test_trajectory_vs_reference_golden(name):
+    gd = load_golden(name)
+    cfg, vf = model_for(gd)
+    n_atoms = gd["n_atoms"]
+    N, U = int(n_atoms.sum()), int((n_atoms * (n_atoms - 1) // 2).sum())
+    A = cfg.n_atom_types
+    out = vf.integrate_tokens(n_atoms, t(gd["x_0"]), torch.full((N,), A), torch.full((N,), 6), torch.full((U,), 4),
+                              int(gd["T"]), seed=int(gd["noise_seed"]))
+    out = {k: v.cpu().numpy() for k, v in out.items()}
+    assert np.array_equal(out["a"], gd["a_1"]), name
+    assert np.array_equal(out["c"], gd["c_1"]), name
+    assert np.array_equal(out["e"], gd["e_1"]), name
+    np.testing.assert_allclose(out["x"], gd["x_1"], rtol=0, atol=1e-4)
+
+
+def _oracle_vs_cuda_forward(cfg_name, A, n_atoms, wseed, seed):
+    cfg, vf = cuda_model(cfg_name, A, wseed)
+    om = O.OracleModel(cfg, WT.init_state_dict(cfg, wseed))
+    bt = O.make_batch(n_atoms)
+    gen = torch.Generator().manual_seed(seed)
+    x = torch.randn(bt.N, 3, generator=gen)
+    a = torch.randint(0, A + 1, (bt.N,), generator=gen)
+    c = torch.randint(0, 7, (bt.N,), generator=gen)
+    e = torch.randint(0, 5, (bt.U,), generator=gen)
+    with torch.no_grad():
+        w0 = om.forward(bt, x, torch.full_like(a, A), torch.full_like(c, 6), torch.full_like(e, 4), 0.0, None)
+        w1 = om.forward(bt, x, a, c, e, 0.5, w0)
+    d0 = vf.forward_tokens(n_atoms, x, torch.full_like(a, A), torch.full_like(c, 6), torch.full_like(e, 4), 0.0, None)
+    check_pred(d0, {k: v.numpy() for k, v in w0.items()}, f"{cfg_name} {n_atoms} first")
+    d1 = vf.forward_tokens(n_atoms, x, a, c, e, 0.5, w0)
+    check_pred(d1, {k: v.numpy() for k, v in w1.items()}, f"{cfg_name} {n_atoms} mid")
+
+
+def test_forward_edge_cases_vs_oracle_small_and_ragged():
+    # n = 2 (one edge pair), n = 3, one 64-edge-exact molecule boundary (n = 9: 72 edges), ragged mix
+    _oracle_vs_cuda_forward("dev", 6, [2, 3, 9, 2, 17, 5], wseed=21, seed=1)
+    _oracle_vs_cuda_forward("flowmol3", 11, [2, 3, 9, 12], wseed=22, seed=2)
+
+
+def test_forward_large_molecules_multi_tile_segments_vs_oracle():
+    # n - 1 > 64: every dst's in-edge list spans 2..3 tiles (partial-sum path); 181 = GEOM maximum
+    _oracle_vs_cuda_forward("dev", 6, [70, 130, 4], wseed=21, seed=3)
+    _oracle_vs_cuda_forward("flowmol3", 11, [66, 181], wseed=22, seed=4)
+
+
+def test_trajectory_vs_oracle_fresh_inputs():
+    for cfg_name, A, n_atoms, T in (("dev", 6, [6, 2, 29, 18, 3], 30), ("flowmol3", 11, [5, 24, 9], 12)):
+        cfg, vf = cuda_model(cfg_name, A, 31)
+        om = O.OracleModel(cfg, WT.init_state_dict(cfg, 31))
+        bt = O.make_batch(n_atoms)
+        x0 = torch.randn(bt.N, 3, generator=torch.Generator().manual_seed(9))
+        a0, c0, e0 = torch.full((bt.N,), A), torch.full((bt.N,), 6), torch.full((bt.U,), 4)
+        with torch.no_grad():
+            want = O.integrate(om, bt, x0, a0, c0, e0, T, seed=4242, mol_id_offset=100)
+        got = vf.integrate_tokens(n_atoms, x0, a0, c0, e0, T, seed=4242, mol_id_offset=100)
+        for k in "ace":
+            assert torch.equal(got[k].cpu().long(), want[k]), (cfg_name, k)
+        assert (got["x"].cpu() - want["x"]).abs().max() <= 1e-4
+        assert (got["a"] != A).all() and (got["c"] != 6).all() and (got["e"] != 4).all()
+
+
+def test_results_do_not_depend_on_batch_composition_or_sharding():
+    """Per-molecule Philox noise + molecule-aligned tiles => bit-identical molecules however the batch is cut."""
+    cfg, vf = cuda_model("flowmol3", 11, 41)
+    n_atoms = np.array([7, 30, 3, 70, 12, 19])
+    bt = O.make_batch(n_atoms)
+    x0 = torch.randn(bt.N, 3, generator=torch.Generator().manual_seed(3))
+    A = 11
+    full = vf.integrate_tokens(n_atoms, x0, torch.full((bt.N,), A), torch.full((bt.N,), 6), torch.full((bt.U,), 4), 8, seed=7)
+    full = {k: v.cpu() for k, v in full.items()}
+    noff = np.concatenate([[0], np.cumsum(n_atoms)])
+    uoff = np.concatenate([[0], np.cumsum(n_atoms * (n_atoms - 1) // 2)])
+    for lo, hi in ((0, 2), (2, 3), (3, 6)):          # three "ranks"
+        sub = n_atoms[lo:hi]
+        N, U = int(sub.sum()), int((sub * (sub - 1) // 2).sum())
+        part = vf.integrate_tokens(sub, x0[noff[lo]:noff[hi]], torch.full((N,), A), torch.full((N,), 6), torch.full((U,), 4), 8,
+                                   seed=7, mol_id_offset=lo)
+        assert torch.equal(part["x"].cpu(), full["x"][noff[lo]:noff[hi]])
+        assert torch.equal(part["a"].cpu(), full["a"][noff[lo]:noff[hi]])
+        assert torch.equal(part["c"].cpu(), full["c"][noff[lo]:noff[hi]])
+        assert torch.equal(part["e"].cpu(), full["e"][uoff[lo]:uoff[hi]])
+
+
+def test_host_entry_point_and_cuda_graph_match_device_entry_point():
+    cfg, vf = cuda_model("dev", 6, 51)
+    n_atoms = np.array([9, 4, 21])
+    bt = O.make_batch(n_atoms)
+    x0 = torch.randn(bt.N, 3, generator=torch.Generator().manual_seed(5))
+    a0, c0, e0 = torch.full((bt.N,), 6), torch.full((bt.N,), 6), torch.full((bt.U,), 4)
+    ref = vf.integrate_tokens(n_atoms, x0, a0, c0, e0, 15, seed=11)
+    gr = vf.integrate_tokens(n_atoms, x0, a0, c0, e0, 15, seed=11, cuda_graph=True)
+    hx, ha, hc, he = x0.clone().pin_memory(), a0.to(torch.uint8).pin_memory(), c0.to(torch.uint8).pin_memory(), e0.to(torch.uint8).pin_memory()
+    vf.sample_host(n_atoms, hx, ha, hc, he, 15, seed=11)
+    for k, hv in zip("xace", (hx, ha, hc, he)):
+        assert torch.equal(ref[k].cpu(), gr[k].cpu()), k
+        assert torch.equal(ref[k].cpu(), hv), k
+
+
+def test_reference_api_surface_sample_random_sizes():
+    import flowmol_b200 as flowmol
+    model = flowmol.FlowMolB200.from_config("dev", dataset="qm9", seed=3).cuda().eval()
+    torch.manual_seed(0)
+    mols = model.sample_random_sizes(6, n_timesteps=20)
+    assert len(mols) == 6
+    for m in mols:
+        assert m.positions.shape[1] == 3 and len(m.atom_types) == m.num_atoms == m.positions.shape[0]
+        assert (m.bond_src_idxs < m.bond_dst_idxs).all() and (m.bond_types > 0).all()
+        assert "Se" not in m.atom_types                       # no masked atom survives t = 1
+    torch.manual_seed(0)
+    again = model.sample_random_sizes(6, n_timesteps=20)
+    assert all(torch.equal(p.positions, q.positions) and p.atom_types == q.atom_types for p, q in zip(mols, again))
+
+
+@pytest.mark.parametrize("cfg_name,dataset,B,T", [("flowmol3", "qm9", 1024, 250), ("flowmol3", "geom", 512, 20)])
+def test_full_size_batches_size_independent_properties(cfg_name, dataset, B, T):
+    """BASELINE configs 2 and 3 at full batch size: properties that do not need the (hours-long) CPU oracle."""
+    from flowmol_b200.api import n_atoms_histogram
+    A = 6 if dataset == "qm9" else 11
+    cfg, vf = cuda_model(cfg_name, A, 0)
+    nmap, counts = n_atoms_histogram(dataset)
+    gen = torch.Generator().manual_seed(1234)
+    n_atoms = nmap[torch.multinomial(counts / counts.sum(), B, replacement=True, generator=gen)].numpy()
+    N, U = int(n_atoms.sum()), int((n_atoms * (n_atoms - 1) // 2).sum())
+    x0 = torch.randn(N, 3, generator=gen)
+    nbi = torch.arange(B).repeat_interleave(torch.from_numpy(n_atoms))
+    x0 = x0 - (torch.zeros(B, 3).index_add_(0, nbi, x0) / torch.from_numpy(n_atoms)[:, None].float())[nbi]
+    out = vf.integrate_tokens(n_atoms, x0, torch.full((N,), A), torch.full((N,), 6), torch.full((U,), 4), T, seed=99)
+    x = out["x"].cpu()
+    assert torch.isfinite(x).all()
+    assert (out["a"] != A).all() and (out["c"] != 6).all() and (out["e"] != 4).all()      # every mask resolved at t = 1
+    com = torch.zeros(B, 3).index_add_(0, nbi, x) / torch.from_numpy(n_atoms)[:, None].float()
+    assert com.abs().max() < 1e-3                                                           # trajectories stay COM-free
+    # re-running the first 8 molecules alone reproduces them bit for bit
+    k = 8
+    Nk, Uk = int(n_atoms[:k].sum()), int((n_atoms[:k] * (n_atoms[:k] - 1) // 2).sum())
+    sub = vf.integrate_tokens(n_atoms[:k], x0[:Nk], torch.full((Nk,), A), torch.full((Nk,), 6), torch.full((Uk,), 4), T, seed=99)
+    assert torch.equal(sub["x"].cpu(), x[:Nk]) and torch.equal(sub["a"].cpu(), out["a"].cpu()[:Nk])
+    assert torch.equal(sub["e"].cpu(), out["e"].cpu()[:Uk])

@@ -1,0 +1,292 @@
+"""bench.py -- molecules/s of the FlowMol sampling hot path on B200 (contract: see the task brief / DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload geom512|qm9_1024|dev_qm9_32]
+
+One "step" = ONE PASS OF THE HOT PATH OVER ONE BATCH: a complete `integrate` of the batch (all `timesteps` Euler/CTMC
+steps: T-1 network evaluations + the self-conditioning pre-pass + T-1 CTMC updates).  Default workload = BASELINE.json
+configs[2], the configuration the metric is quoted on: GEOM-drugs sized molecules (n ~ train_data_n_atoms_histogram,
+torch.Generator().manual_seed(1234)), flowmol3 dims, 512 molecules PER GPU, 250 timesteps, random-init weights
+(seed 0), all-mask CTMC prior + COM-free N(0,1) positions.  N > 1: torchrun, one rank per GPU, each rank samples its own
+512 molecules (weak scaling; global molecule ids => noise independent of the sharding); the only collective is the final
+NCCL gather of the results to rank 0, inside the timed region.
+
+Printed JSON line (rank 0): metric/value/unit/..., `e2e` (same metric through fm_sample_host with pinned HOST buffers:
+H2D of the prior + batch descriptor + trajectory + D2H of the result inside the timed region), `roofline` for the dominant
+kernel (k_conv_edge, timed live with CUDA events on its stream), `cpu_baseline` (the CPU oracle port on a bounded sample),
+`clocks`, `gpu_launches`.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (config, dataset, molecules per GPU, timesteps, BASELINE.json config index)
+    "geom512": ("flowmol3", "geom", 512, 250, 2),
+    "qm9_1024": ("flowmol3", "qm9", 1024, 250, 1),
+    "dev_qm9_32": ("dev", "qm9", 32, 50, 0),
+}
+# matmul FLOPs of the reference per directed edge of one GVPConv message phase (624 502, flowmol3)
+CONV_EDGE_FLOP_PER_EDGE = {"flowmol3": 624502, "dev": 2 * (201 * 64 + 84 * 64 * 2 + 3 * 64 * 16) + 6 * (21 * 29 + 25 * 16 + 2 * (16 * 24 + 20 * 16))}
+# matmul FLOPs of one full network evaluation, flowmol3: per edge / per node
+FWD_FLOP = {"flowmol3": (4874436, 6499384), "dev": (308680, 324660)}
+
+
+def draw_sizes(dataset, B, seed=1234, rank=0):
+    from flowmol_b200.api import n_atoms_histogram
+    nmap, counts = n_atoms_histogram(dataset)
+    gen = torch.Generator().manual_seed(seed + 7919 * rank)
+    return nmap[torch.multinomial(counts / counts.sum(), B, replacement=True, generator=gen)].numpy().astype(np.int64)
+
+
+def make_prior(n_atoms, A, seed):
+    """x_0 COM-free N(0,1) (flowmol/data_processing/priors.py:27-35), all-mask tokens (priors.py:101-107)."""
+    gen = torch.Generator().manual_seed(seed)
+    n = torch.from_numpy(n_atoms)
+    N, U = int(n.sum()), int((n * (n - 1) // 2).sum())
+    x0 = torch.randn(N, 3, generator=gen)
+    nbi = torch.arange(len(n)).repeat_interleave(n)
+    x0 = x0 - (torch.zeros(len(n), 3).index_add_(0, nbi, x0) / n[:, None].float())[nbi]
+    return x0, torch.full((N,), A, dtype=torch.uint8), torch.full((N,), 6, dtype=torch.uint8), torch.full((U,), 4, dtype=torch.uint8)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            self.th.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_port_throughput(cfg_name, dataset, timesteps, budget_s=20.0, rank_seed=0):
+    """CPU baseline: the oracle port (oracle/flowmol_oracle.py == the reference's algorithm restated, pinned bit-exactly
+    to the reference run verbatim) on all host cores, on a bounded sample of the same workload, extrapolated linearly in
+    network evaluations to `timesteps` (state the extrapolation: value = molecules / (sec_per_eval * timesteps))."""
+    from flowmol_b200 import weights as WT
+    from flowmol_b200.config import ModelConfig
+    from oracle import flowmol_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    A = 11 if dataset == "geom" else 6
+    cfg = ModelConfig.named(cfg_name, A)
+    sd = WT.init_state_dict(cfg, 0)
+    om = O.OracleModel(cfg, sd)
+    nb = 8 if cfg_name == "flowmol3" else 32
+    n_atoms = draw_sizes(dataset, nb, rank=rank_seed)
+    bt = O.make_batch(n_atoms)
+    x0, a0, c0, e0 = make_prior(n_atoms, A, 1)
+    a0, c0, e0 = a0.long(), c0.long(), e0.long()
+    with torch.no_grad():
+        d = om.forward(bt, x0, a0, c0, e0, 0.0, None)          # warm-up (also the pre-pass shape)
+        evals, t0 = 0, time.perf_counter()
+        while True:
+            d = om.forward(bt, x0, a0, c0, e0, 0.3, d)
+            evals += 1
+            if time.perf_counter() - t0 > budget_s or evals >= 50:
+                break
+        sec_per_eval = (time.perf_counter() - t0) / evals
+    value = nb / (sec_per_eval * timesteps)
+    return {"value": value, "unit": "molecules/s", "cores": cores, "kind": "port",
+            "sample": f"{nb} {dataset}-sized molecules (N={bt.N}, E={bt.E}), {evals} network evaluations timed "
+                      f"({sec_per_eval:.3f} s each), extrapolated linearly to {timesteps} evaluations per molecule"}
+
+
+def run_reference_arm(args, wl):
+    cfg_name, dataset, B, T, _ = wl
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_port_throughput(cfg_name, dataset, T, budget_s=max(3.0, 60.0 / max(1, args.warmup + args.steps)), rank_seed=0)
+        if i >= args.warmup:
+            vals.append(r)
+    v = float(np.mean([r["value"] for r in vals]))
+    cb = dict(vals[-1], value=v)
+    line = {"impl": "reference", "metric": f"molecules/sec @{T} steps ({dataset.upper()} batch)", "value": v,
+            "unit": "molecules/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * B / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config_dict(args.workload, wl, args.gpus),
+            "cpu_baseline": cb, "e2e": {"value": v, "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def config_dict(name, wl, gpus):
+    cfg_name, dataset, B, T, idx = wl
+    return {"workload": f"BASELINE.json configs[{idx}]: {dataset} sized molecules, {cfg_name} dims, {B} molecules per GPU, "
+                        f"{T} timesteps", "name": name, "molecules_per_gpu": B, "global_molecules": B * gpus, "timesteps": T,
+            "sizes": "n_atoms ~ train_data_n_atoms_histogram, torch.Generator().manual_seed(1234 + 7919*rank)",
+            "weights": "random init (reference constructors' distributions), seed 0", "parallelism": f"molecule sharding x{gpus}",
+            "l2": "inputs larger than L2 (edge hidden state alone is ~0.6 GB per evaluation at geom512); no flush needed"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="geom512", choices=sorted(WORKLOADS))
+    ap.add_argument("--timesteps", type=int, default=None, help="override the workload's timesteps (experiments only)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cuda-graph", type=int, default=0)
+    args = ap.parse_args()
+    wl = list(WORKLOADS[args.workload])
+    if args.timesteps:
+        wl[3] = args.timesteps
+    wl = tuple(wl)
+    cfg_name, dataset, B, T, _ = wl
+    if args.impl == "reference":
+        return run_reference_arm(args, wl)
+
+    import torch.distributed as dist
+    from flowmol_b200 import weights as WT
+    from flowmol_b200.config import ModelConfig
+    from flowmol_b200.vector_field import CTMCVectorFieldB200
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    A = 11 if dataset == "geom" else 6
+    cfg = ModelConfig.named(cfg_name, A)
+    vf = CTMCVectorFieldB200(cfg, WT.init_state_dict(cfg, 0), device=dev)
+    n_atoms = draw_sizes(dataset, B, rank=rank)
+    N, U, E = int(n_atoms.sum()), int((n_atoms * (n_atoms - 1) // 2).sum()), int((n_atoms * (n_atoms - 1)).sum())
+    x0, a0, c0, e0 = make_prior(n_atoms, A, 100 + rank)
+    hx, ha, hc, he = x0.pin_memory(), a0.pin_memory(), c0.pin_memory(), e0.pin_memory()
+    dx, da, dc, de = x0.to(dev), a0.to(dev), c0.to(dev), e0.to(dev)
+    # result gather buffers (padded to the max over ranks): x fp32[N,3] | a u8[N] | c u8[N] | e u8[U]
+    if world > 1:
+        sizes = torch.tensor([N, U], device=dev)
+        mx = sizes.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        Nm, Um = int(mx[0]), int(mx[1])
+        send = torch.zeros(Nm * 12 + 2 * Nm + Um, dtype=torch.uint8, device=dev)
+        recv = [torch.zeros_like(send) for _ in range(world)] if rank == 0 else None
+
+    def one_pass_device(seed):
+        out = vf.integrate_tokens(n_atoms, dx, da, dc, de, T, seed=seed, mol_id_offset=rank * B, cuda_graph=bool(args.cuda_graph))
+        if world > 1:                                     # the one exchange step: results to rank 0 over NCCL / NVLink
+            send[:N * 12] = out["x"].view(torch.uint8).reshape(-1)
+            send[Nm * 12:Nm * 12 + N] = out["a"]
+            send[Nm * 13:Nm * 13 + N] = out["c"]
+            send[Nm * 14:Nm * 14 + U] = out["e"]
+            dist.gather(send, recv, dst=0)
+        return out
+
+    def one_pass_host(seed):
+        bx, ba, bc, be = hx.clone().pin_memory(), ha.clone().pin_memory(), hc.clone().pin_memory(), he.clone().pin_memory()
+        vf.sample_host(n_atoms, bx, ba, bc, be, T, seed=seed, mol_id_offset=rank * B, cuda_graph=bool(args.cuda_graph))
+        return bx
+
+    def timed(fn, k):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0_.record()
+        for i in range(k):
+            fn(1000 + i)
+        e1_.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0_.elapsed_time(e1_)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms[0])
+
+    for i in range(args.warmup):
+        one_pass_device(i)
+    with ClockSampler(local) as clk:
+        ms_total = timed(one_pass_device, args.steps)
+    launches = vf.last_launches * args.steps
+    ms_per_step = ms_total / args.steps
+    value = world * B / (ms_per_step / 1000.0)
+    one_pass_host(0)
+    ms_e2e = timed(one_pass_host, args.steps) / args.steps
+    e2e_value = world * B / (ms_e2e / 1000.0)
+    # roofline of the dominant kernel, timed live on its own stream after a forward left valid state in the workspace
+    ms_conv = vf.time_conv_edge(layer=1, iters=5)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    bf16 = peaks.get("bf16_tflops_sustained") or 1400.0
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback (B200_PROFILING.md 1.4 PF sustained)"
+    tf32_peak = bf16 / 2.0
+    flops = CONV_EDGE_FLOP_PER_EDGE[cfg_name] * E
+    achieved = flops / (ms_conv * 1e-3) / 1e12
+    ffma_peak = 148 * 128 * 2 * (peaks.get("sm_max_mhz", 1965.0) * 1e6) / 1e12
+    roofline = {"kernel": "k_conv_edge (fused gather + rbf + 3 message GVPs + segment-sum, one conv layer)", "bound": "tensor",
+                "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
+                "peak_kind": f"dense TF32 tensor = 1/2 x bf16, {peak_src}; this round's kernel runs on the fp32 CUDA-core path "
+                             f"(FFMA peak {ffma_peak:.1f} TFLOP/s => frac_of_ffma {achieved / ffma_peak:.3f})",
+                "algorithmic_flops_per_launch": flops, "ms_per_launch": ms_conv, "traffic": None,
+                "hbm_gbs_of_kernel": (E * cfg.n_hidden_edge_feats * 4) / (ms_conv * 1e-3) / 1e9}
+    fe, fn_ = FWD_FLOP[cfg_name]
+    total_flops = (fe * E + fn_ * N) * T * world
+    line = {"metric": f"molecules/sec @{T} steps ({dataset.upper()} batch)", "value": value, "unit": "molecules/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(args.workload, wl, world),
+            "e2e": {"value": e2e_value, "unit": "molecules/s", "h2d_bytes_per_step": int(N * 12 + 2 * N + U + 4 * B),
+                    "d2h_bytes_per_step": int(N * 12 + 2 * N + U), "ms_per_step": ms_e2e},
+            "gpu_launches": int(launches), "roofline": roofline,
+            "model_tflops": total_flops / (ms_per_step * 1e-3) / 1e12, "batch": {"N": N, "E": E, "U": U}}
+    if rank == 0:
+        line["clocks"] = clk.summary()
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_port_throughput(cfg_name, dataset, T)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -85,6 +85,7 @@ struct FmHandle {
   fm::ModelRT rt;
   std::unordered_map<void*, Layout> batches;
   int64_t launches = 0;
+  cudaStream_t cap_stream = nullptr;    // private stream for CUDA-graph capture (the legacy default stream cannot capture)
 };
 
 namespace {
@@ -269,6 +270,7 @@ int fm_create(const FmConfig* cfg, const float* w_host, size_t n_floats, const i
 void fm_destroy(FmHandle* h) {
   if (!h) return;
   cudaFree(h->d_w); cudaFree(h->d_off); cudaFree(h->d_table);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   delete h;
 }
 
@@ -342,7 +344,12 @@ int fm_integrate(FmHandle* h, void* ws, float* x, uint8_t* a, uint8_t* c, uint8_
   else time_grid(T, t.data());
   const fm::BatchRT bt = batch_rt(ws, L);
   cudaGraph_t graph = nullptr;
-  if (o->use_cuda_graph) CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  cudaStream_t user_stream = st;
+  if (o->use_cuda_graph) {              // whole-trajectory graph: every launch below is recorded, then replayed once on `stream`
+    if (!h->cap_stream) CUDA_OK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    st = h->cap_stream;
+    CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  }
   int rc = 0;
   for (int k = 1; k < T && rc == 0; ++k) {                        // ctmc_vector_field.py:205-232
     const float t_i = t[k - 1], s_i = t[k];
@@ -378,10 +385,10 @@ int fm_integrate(FmHandle* h, void* ws, float* x, uint8_t* a, uint8_t* c, uint8_
     if (ce != cudaSuccess) return fail(std::string("stream capture failed: ") + cudaGetErrorString(ce));
     cudaGraphExec_t exec = nullptr;
     CUDA_OK(cudaGraphInstantiate(&exec, graph, 0));
-    cudaError_t le = cudaGraphLaunch(exec, st);
+    cudaError_t le = cudaGraphLaunch(exec, user_stream);
     cudaGraphDestroy(graph);
     if (le != cudaSuccess) { cudaGraphExecDestroy(exec); return fail(std::string("graph launch failed: ") + cudaGetErrorString(le)); }
-    CUDA_OK(cudaStreamSynchronize(st));
+    CUDA_OK(cudaStreamSynchronize(user_stream));
     cudaGraphExecDestroy(exec);
   }
   return rc;
@@ -439,5 +446,39 @@ int fm_workspace_tensor(FmHandle* h, void* ws, const char* name, void** ptr, siz
 }
 
 int64_t fm_last_launch_count(FmHandle* h) { return h ? h->launches : -1; }
+
+// Re-launch the hot kernel (k_conv_edge of `layer`) `iters` times on the workspace state left by the last fm_forward and
+// time it with CUDA events on the launching stream (bench.py's roofline line).
+int fm_time_conv_edge(FmHandle* h, void* ws, int32_t layer, int32_t iters, float* ms_avg, void* stream) {
+  if (!h || !ws || !ms_avg || iters < 1 || layer < 0 || layer >= h->cfg.n_convs) return fail("fm_time_conv_edge: bad argument");
+  const Layout* Lp;
+  if (find_batch(h, ws, &Lp)) return -1;
+  const Layout& L = *Lp;
+  CUDA_OK(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const fm::BatchRT bt = batch_rt(ws, L);
+  float *v = at<float>(ws, L.v), *x = at<float>(ws, L.x), *P = at<float>(ws, L.P), *Q = at<float>(ws, L.Q);
+  float *vd = at<float>(ws, L.vd), *M = at<float>(ws, L.M), *partF = at<float>(ws, L.partF), *partL = at<float>(ws, L.partL);
+  float* ef = at<float>(ws, L.ef);
+  cudaEvent_t e0, e1;
+  CUDA_OK(cudaEventCreate(&e0));
+  CUDA_OK(cudaEventCreate(&e1));
+  CUDA_OK(cudaStreamSynchronize(st));
+  CUDA_OK(cudaEventRecord(e0, st));
+  for (int i = 0; i < iters; ++i) {
+    if (h->variant == 0)
+      fm::k_conv_edge<fm::DimsFlowmol3><<<L.nET, fm::NT, fm::DimsFlowmol3::SMEM_BYTES, st>>>(h->rt, bt, layer, x, v, ef, P, Q, vd, M, partF, partL);
+    else
+      fm::k_conv_edge<fm::DimsDev><<<L.nET, fm::NT, fm::DimsDev::SMEM_BYTES, st>>>(h->rt, bt, layer, x, v, ef, P, Q, vd, M, partF, partL);
+  }
+  CUDA_OK(cudaEventRecord(e1, st));
+  CUDA_OK(cudaEventSynchronize(e1));
+  CUDA_OK(cudaGetLastError());
+  float ms = 0.f;
+  CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *ms_avg = ms / (float)iters;
+  return 0;
+}
 
 }  // extern "C"

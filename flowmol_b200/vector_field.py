@@ -108,6 +108,13 @@ class CTMCVectorFieldB200:
         off = ptr.value - self._ws.data_ptr()
         return self._ws[off:off + 4 * cnt.value].view(torch.float32)
 
+    def time_conv_edge(self, layer=1, iters=5):
+        """Mean duration (ms) of the hot kernel re-launched on the state left by the last forward (bench roofline)."""
+        ms = C.c_float()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.fm_time_conv_edge(self._h, self._ws.data_ptr(), int(layer), int(iters), C.byref(ms), self._stream()))
+        return float(ms.value)
+
     def _pred_buffers(self, N, U):
         dev = self.device
         return {'x': torch.empty(N, 3, device=dev), 'a': torch.empty(N, self.n_atom_types, device=dev),

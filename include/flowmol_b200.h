@@ -64,7 +64,7 @@ typedef struct FmSampleOpts {
   float cat_temperature;     /* tau (0.05) */
   uint64_t seed;             /* Philox key */
   int32_t mol_id_offset;     /* global id of molecule 0 of this batch (sharding-invariant noise) */
-  const float* tspan_host;   /* optional [n_timesteps] fp32 time grid; NULL => linspace(0,1,n) evaluated like torch.linspace */
+  const float* tspan_host;   /* optional [n_timesteps] fp32 time grid; NULL => fp32 linspace(0,1,n), within 1 ulp of torch.linspace (pass torch's values for bit parity) */
   int32_t use_cuda_graph;    /* capture the per-step launch sequence once and replay it */
 } FmSampleOpts;
 
@@ -102,6 +102,9 @@ int fm_sample_host(FmHandle* h, const int32_t* n_atoms_host, int32_t n_molecules
 int fm_workspace_tensor(FmHandle* h, void* workspace, const char* name, void** ptr, size_t* n_floats);
 /* host-only helper: the fallback time grid used when tspan_host == NULL (torch.linspace-like fp32 grid) */
 void fm_debug_time_grid(int32_t n, float* out_host);
+/* measurement helper: re-launch the hot kernel (fused gather + 3 message GVPs + segment-sum of conv `layer`) `iters` times on
+ * the workspace state left by the last fm_forward and return its mean duration (CUDA events on `stream`). */
+int fm_time_conv_edge(FmHandle* h, void* workspace, int32_t layer, int32_t iters, float* ms_avg, void* stream);
 /* number of kernels launched by the last fm_forward / fm_integrate call on this handle */
 int64_t fm_last_launch_count(FmHandle* h);
 

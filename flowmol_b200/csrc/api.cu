@@ -11,6 +11,7 @@
 #include "../../include/flowmol_b200.h"
 #include "ctmc.cuh"
 #include "kernels.cuh"
+#include "tc_test.cuh"
 
 namespace {
 
@@ -446,6 +447,26 @@ int fm_workspace_tensor(FmHandle* h, void* ws, const char* name, void** ptr, siz
 }
 
 int64_t fm_last_launch_count(FmHandle* h) { return h ? h->launches : -1; }
+
+// stand-alone tcgen05 check (host buffers): out[128][64] = W[128][K] . X[64][K]^T, passes = 1 (plain TF32) or 3 (3xTF32)
+int fm_debug_tc_gemm(const float* w_host, const float* x_host, int32_t K, float* out_host, int32_t passes, int device) {
+  if (!w_host || !x_host || !out_host || K < 32 || K % 32 || K > 128 || (passes != 1 && passes != 3)) return fail("fm_debug_tc_gemm: bad argument");
+  CUDA_OK(cudaSetDevice(device));
+  float *dw = nullptr, *dx = nullptr, *dout = nullptr;
+  CUDA_OK(cudaMalloc(&dw, sizeof(float) * 128 * K));
+  CUDA_OK(cudaMalloc(&dx, sizeof(float) * 64 * K));
+  CUDA_OK(cudaMalloc(&dout, sizeof(float) * 128 * 64));
+  CUDA_OK(cudaMemcpy(dw, w_host, sizeof(float) * 128 * K, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(dx, x_host, sizeof(float) * 64 * K, cudaMemcpyHostToDevice));
+  const int smem = (K / 32) * 48 * 1024 + 1024;
+  CUDA_OK(cudaFuncSetAttribute(fm::k_tc_gemm_test, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  fm::k_tc_gemm_test<<<1, 128, smem>>>(dw, dx, K, dout, passes);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaDeviceSynchronize());
+  CUDA_OK(cudaMemcpy(out_host, dout, sizeof(float) * 128 * 64, cudaMemcpyDeviceToHost));
+  cudaFree(dw); cudaFree(dx); cudaFree(dout);
+  return 0;
+}
 
 // Re-launch the hot kernel (k_conv_edge of `layer`) `iters` times on the workspace state left by the last fm_forward and
 // time it with CUDA events on the launching stream (bench.py's roofline line).

@@ -1,0 +1,76 @@
+// Stand-alone check of the tcgen05 building blocks: D^T[f][e] = sum_k W[f][k] * X[e][k] with 3xTF32,
+// W: 128 x K (UMMA A operand, M = 128), X: 64 x K (UMMA B operand, N = 64), K a multiple of 32.
+#pragma once
+#include "tc.cuh"
+
+namespace fm {
+
+constexpr int TCT_M = 128, TCT_N = 64;
+
+__global__ void __launch_bounds__(128, 1) k_tc_gemm_test(const float* __restrict__ W, const float* __restrict__ X, int K,
+                                                         float* __restrict__ out /*[128][64]*/, int passes /*1 or 3*/) {
+  extern __shared__ __align__(1024) uint8_t tsm[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int nslab = K / 32;
+  // per slab: W_hi (16 KB) | W_lo (16 KB) | X_hi (8 KB) | X_lo (8 KB)
+  const uint32_t SLAB = 48 * 1024;
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tsm) + 1023) & ~uintptr_t(1023));
+  for (int s = 0; s < nslab; ++s) {
+    uint8_t* sb = base + (size_t)s * SLAB;
+    for (int idx = tid; idx < TCT_M * 32; idx += 128) {
+      const int r = idx >> 5, k = idx & 31;
+      float hi, lo;
+      tc::split_tf32(W[(size_t)r * K + s * 32 + k], hi, lo);
+      *reinterpret_cast<float*>(sb + tc::sw128_off(r, k)) = hi;
+      *reinterpret_cast<float*>(sb + 16384 + tc::sw128_off(r, k)) = lo;
+    }
+    for (int idx = tid; idx < TCT_N * 32; idx += 128) {
+      const int r = idx >> 5, k = idx & 31;
+      float hi, lo;
+      tc::split_tf32(X[(size_t)r * K + s * 32 + k], hi, lo);
+      *reinterpret_cast<float*>(sb + 32768 + tc::sw128_off(r, k)) = hi;
+      *reinterpret_cast<float*>(sb + 40960 + tc::sw128_off(r, k)) = lo;
+    }
+  }
+  if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
+  if (warp == 0) tc::tmem_alloc(&tmem_base, 64);
+  tc::fence_proxy_async();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tm = tmem_base;
+  if (tid == 0) {
+    const uint32_t idesc = tc::idesc_tf32(TCT_M, TCT_N);
+    uint32_t accum = 0;
+    for (int s = 0; s < nslab; ++s) {
+      const uint32_t sb = tc::smem_u32(base + (size_t)s * SLAB);
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t ko = j * 32;            // 8 tf32 = 32 bytes per k-step inside the swizzle atom
+        const uint64_t whi = tc::desc_sw128(sb + ko), wlo = tc::desc_sw128(sb + 16384 + ko);
+        const uint64_t xhi = tc::desc_sw128(sb + 32768 + ko), xlo = tc::desc_sw128(sb + 40960 + ko);
+        if (passes == 3) {
+          tc::umma_tf32(tm, wlo, xhi, idesc, accum); accum = 1;
+          tc::umma_tf32(tm, whi, xlo, idesc, accum);
+        }
+        tc::umma_tf32(tm, whi, xhi, idesc, accum); accum = 1;
+      }
+    }
+    tc::umma_commit(&bar);
+  }
+  tc::mbar_wait(&bar, 0);
+  tc::tc_fence_after();
+  float v[32];
+  for (int c = 0; c < TCT_N; c += 32) {
+    tc::tmem_ld32(tm + ((uint32_t)(warp * 32) << 16) + c, v);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) out[(size_t)tid * TCT_N + c + i] = v[i];
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tm, 64);
+}
+
+}  // namespace fm

@@ -105,6 +105,9 @@ void fm_debug_time_grid(int32_t n, float* out_host);
 /* measurement helper: re-launch the hot kernel (fused gather + 3 message GVPs + segment-sum of conv `layer`) `iters` times on
  * the workspace state left by the last fm_forward and return its mean duration (CUDA events on `stream`). */
 int fm_time_conv_edge(FmHandle* h, void* workspace, int32_t layer, int32_t iters, float* ms_avg, void* stream);
+/* stand-alone check of the tcgen05 building blocks (host buffers): out[128][64] = W[128][K] . X[64][K]^T, K in {32,64,96,128};
+ * passes = 1 (plain TF32) or 3 (error-compensated 3xTF32) */
+int fm_debug_tc_gemm(const float* w_host, const float* x_host, int32_t K, float* out_host, int32_t passes, int device);
 /* number of kernels launched by the last fm_forward / fm_integrate call on this handle */
 int64_t fm_last_launch_count(FmHandle* h);
 

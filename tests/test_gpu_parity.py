@@ -222,3 +222,24 @@ def test_full_size_batches_size_independent_properties(cfg_name, dataset, B, T):
     sub = vf.integrate_tokens(n_atoms[:k], x0[:Nk], torch.full((Nk,), A), torch.full((Nk,), 6), torch.full((Uk,), 4), T, seed=99)
     assert torch.equal(sub["x"].cpu(), x[:Nk]) and torch.equal(sub["a"].cpu(), out["a"].cpu()[:Nk])
     assert torch.equal(sub["e"].cpu(), out["e"].cpu()[:Uk])
+
+
+def test_tcgen05_3xtf32_gemm_building_block():
+    """tcgen05.mma kind::tf32 with hand-built SW128 K-major descriptors: 1xTF32 ~1e-3, 3xTF32 at fp32 accuracy."""
+    import ctypes as C
+    from flowmol_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    for K in (32, 96, 128):
+        W = rng.standard_normal((128, K)).astype(np.float32)
+        X = rng.standard_normal((64, K)).astype(np.float32)
+        want = W.astype(np.float64) @ X.astype(np.float64).T
+        errs = {}
+        for passes in (1, 3):
+            out = np.zeros((128, 64), np.float32)
+            _lib.check(lib.fm_debug_tc_gemm(W.ctypes.data, X.ctypes.data, K, out.ctypes.data, passes, 0))
+            errs[passes] = float(np.abs(out - want).max() / np.abs(want).max())
+        fp32 = float(np.abs((W @ X.T) - want).max() / np.abs(want).max())
+        print(f"K={K} rel err 1xTF32 {errs[1]:.2e} 3xTF32 {errs[3]:.2e} fp32 {fp32:.2e}")
+        assert errs[1] < 5e-3, errs
+        assert errs[3] < 2e-6, errs

@@ -11,6 +11,7 @@
 #include "../../include/flowmol_b200.h"
 #include "ctmc.cuh"
 #include "kernels.cuh"
+#include "conv_tc.cuh"
 #include "tc_test.cuh"
 
 namespace {
@@ -63,7 +64,7 @@ Layout make_layout(const Dyn& d, const int32_t* n_atoms, int B) {
   L.s = take(4ull * N * d.S); L.v = take(4ull * N * 3 * d.V); L.x = take(4ull * N * 3);
   L.P = take(4ull * N * d.S); L.Q = take(4ull * N * d.S * (d.SD > 0)); L.vd = take(4ull * N * 3 * d.VD);
   L.EAB = take(4ull * N * 2 * d.F); L.M = take(4ull * N * d.MW);
-  L.partF = take(4ull * L.nET * d.MW); L.partL = take(4ull * L.nET * d.MW);
+  L.partF = take(8ull * L.nET * d.MW); L.partL = take(8ull * L.nET * d.MW);   // x2: the tensor-core kernel uses 32-row tiles
   L.ef = take(4ull * (size_t)L.EP * d.F);
   for (int k = 0; k < 3; ++k) {
     L.pred[k][0] = take(4ull * N * 3); L.pred[k][1] = take(4ull * N * d.A); L.pred[k][2] = take(4ull * N * d.C);
@@ -86,6 +87,8 @@ struct FmHandle {
   fm::ModelRT rt;
   std::unordered_map<void*, Layout> batches;
   int64_t launches = 0;
+  bool has_tc = false;         // packed weights contain the UMMA operand images
+  int conv_impl = 0;           // 0: fp32 CUDA-core k_conv_edge, 1: tcgen05 3xTF32 k_conv_edge_tc (flowmol3 dims only)
   cudaStream_t cap_stream = nullptr;    // private stream for CUDA-graph capture (the legacy default stream cannot capture)
 };
 
@@ -119,6 +122,8 @@ int set_smem_attrs() {
   CUDA_OK(cudaFuncSetAttribute(fm::k_edge_update<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CUDA_OK(cudaFuncSetAttribute(fm::k_node_head<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CUDA_OK(cudaFuncSetAttribute(fm::k_edge_head<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  if constexpr (D::S == 256 && D::V == 32 && D::SD == 0)
+    CUDA_OK(cudaFuncSetAttribute(fm::k_conv_edge_tc<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::TcPlan<D>::SMEM_BYTES));
   return 0;
 }
 
@@ -147,12 +152,19 @@ int run_pass(FmHandle* h, void* ws, const Layout& L, const float* x_t, const uin
   LAUNCH_OK(h);
   CUDA_OK(cudaMemcpyAsync(x, x_t, sizeof(float) * 3 * L.N, cudaMemcpyDeviceToDevice, st));
   for (int l = 0; l < m.L; ++l) {
-    fm::k_conv_edge<D><<<L.nET, fm::NT, smem, st>>>(m, bt, l, x, v, ef, P, Q, vd, M, partF, partL);
+    int agg_rows = fm::TM;
+    if constexpr (D::S == 256 && D::V == 32 && D::SD == 0) {
+      if (h->conv_impl == 1) {
+        fm::k_conv_edge_tc<D><<<2 * L.nET, fm::NT, fm::TcPlan<D>::SMEM_BYTES, st>>>(m, bt, l, x, v, ef, P, M, partF, partL);
+        agg_rows = fm::TCT;
+      }
+    }
+    if (agg_rows == fm::TM) fm::k_conv_edge<D><<<L.nET, fm::NT, smem, st>>>(m, bt, l, x, v, ef, P, Q, vd, M, partF, partL);
     LAUNCH_OK(h);
     int upd = -1;
     if (l != 0 && (l + 1) % m.convs_per_update == 0) upd = m.separate_updaters ? l / m.convs_per_update : 0;   // vector_field.py:321-326
     const int has_next = l + 1 < m.L;
-    fm::k_node_update<D><<<L.nNT, fm::NT, smem, st>>>(m, bt, l, upd, has_next, s, v, x, M, partF, partL, P, EAB);
+    fm::k_node_update<D><<<L.nNT, fm::NT, smem, st>>>(m, bt, l, upd, has_next, agg_rows, s, v, x, M, partF, partL, P, EAB);
     LAUNCH_OK(h);
     if (m.use_dst && has_next) { fm::k_dst_proj<D><<<L.nNT, fm::NT, smem, st>>>(m, bt, l + 1, s, v, Q, vd); LAUNCH_OK(h); }
     if (upd >= 0) { fm::k_edge_update<D><<<L.nET, fm::NT, smem, st>>>(m, bt, upd, x, EAB, ef); LAUNCH_OK(h); }
@@ -245,6 +257,8 @@ int fm_create(const FmConfig* cfg, const float* w_host, size_t n_floats, const i
   CUDA_OK(cudaSetDevice(device));
   FmHandle* h = new FmHandle();
   h->cfg = c; h->device = device; h->variant = variant;
+  h->has_tc = off_host[fm::G_COUNT + fm::C_MSG0_TCW] >= 0;
+  h->conv_impl = 0;
   h->dyn = Dyn{c.n_hidden_scalars, c.n_vec_channels, c.n_hidden_edge_feats, c.use_dst_feats ? c.s_dst : 0,
                c.use_dst_feats ? c.v_dst : 0, c.n_atom_types, c.n_charges, c.n_bond_types,
                c.n_hidden_scalars + 3 * c.n_vec_channels};
@@ -448,6 +462,24 @@ int fm_workspace_tensor(FmHandle* h, void* ws, const char* name, void** ptr, siz
 
 int64_t fm_last_launch_count(FmHandle* h) { return h ? h->launches : -1; }
 
+int fm_set_option(FmHandle* h, const char* name, int32_t value) {
+  if (!h || !name) return fail("fm_set_option: null argument");
+  const std::string n(name);
+  if (n == "conv_impl") {
+    if (value != 0 && value != 1) return fail("fm_set_option: conv_impl must be 0 (fp32 CUDA cores) or 1 (tcgen05 3xTF32)");
+    if (value == 1 && h->variant != 0) return fail("fm_set_option: the tcgen05 kernel is built for the flowmol3 dimensions only");
+    if (value == 1 && !h->has_tc) return fail("fm_set_option: packed weights carry no tensor-core images");
+    h->conv_impl = value;
+    return 0;
+  }
+  return fail("fm_set_option: unknown option");
+}
+int fm_get_option(FmHandle* h, const char* name, int32_t* value) {
+  if (!h || !name || !value) return fail("fm_get_option: null argument");
+  if (std::string(name) == "conv_impl") { *value = h->conv_impl; return 0; }
+  return fail("fm_get_option: unknown option");
+}
+
 // stand-alone tcgen05 check (host buffers): out[128][64] = W[128][K] . X[64][K]^T, passes = 1 (plain TF32) or 3 (3xTF32)
 int fm_debug_tc_gemm(const float* w_host, const float* x_host, int32_t K, float* out_host, int32_t passes, int device) {
   if (!w_host || !x_host || !out_host || K < 32 || K % 32 || K > 128 || (passes != 1 && passes != 3)) return fail("fm_debug_tc_gemm: bad argument");
@@ -487,7 +519,9 @@ int fm_time_conv_edge(FmHandle* h, void* ws, int32_t layer, int32_t iters, float
   CUDA_OK(cudaStreamSynchronize(st));
   CUDA_OK(cudaEventRecord(e0, st));
   for (int i = 0; i < iters; ++i) {
-    if (h->variant == 0)
+    if (h->variant == 0 && h->conv_impl == 1)
+      fm::k_conv_edge_tc<fm::DimsFlowmol3><<<2 * L.nET, fm::NT, fm::TcPlan<fm::DimsFlowmol3>::SMEM_BYTES, st>>>(h->rt, bt, layer, x, v, ef, P, M, partF, partL);
+    else if (h->variant == 0)
       fm::k_conv_edge<fm::DimsFlowmol3><<<L.nET, fm::NT, fm::DimsFlowmol3::SMEM_BYTES, st>>>(h->rt, bt, layer, x, v, ef, P, Q, vd, M, partF, partL);
     else
       fm::k_conv_edge<fm::DimsDev><<<L.nET, fm::NT, fm::DimsDev::SMEM_BYTES, st>>>(h->rt, bt, layer, x, v, ef, P, Q, vd, M, partF, partL);

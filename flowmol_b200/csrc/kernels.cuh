@@ -483,10 +483,12 @@ __device__ __forceinline__ void tile_gvp_layernorm(float* __restrict__ Xs, float
 // aggregated message of node g, column col: direct or pieces in tile order (see k_conv_edge)
 template <class D>
 __device__ __forceinline__ float gather_message(const BatchRT& bt, const float* __restrict__ M, const float* __restrict__ partF,
-                                                const float* __restrict__ partL, int g, int mol, int col) {
+                                                const float* __restrict__ partL, int g, int mol, int col, int agg_rows) {
+  // agg_rows = rows per tile of the conv-edge kernel that produced the pieces (64: k_conv_edge, 32: k_conv_edge_tc)
   const int n = bt.mol_n[mol], j = g - bt.mol_node[mol];
   const int first = j * (n - 1), last = first + n - 2;
-  const int t0 = bt.mol_etile[mol] + first / TM, t1 = bt.mol_etile[mol] + last / TM;
+  const int tb = bt.mol_etile[mol] * (TM / agg_rows);
+  const int t0 = tb + first / agg_rows, t1 = tb + last / agg_rows;
   if (t0 == t1) return M[(size_t)g * D::MW + col];
   float acc = partL[(size_t)t0 * D::MW + col];
   for (int t = t0 + 1; t <= t1; ++t) acc = __fadd_rn(acc, partF[(size_t)t * D::MW + col]);
@@ -519,7 +521,7 @@ __device__ __forceinline__ void tile_linear_store(const float* __restrict__ Xs, 
 template <class D>
 __global__ void __launch_bounds__(NT, 1)
 k_node_update(const ModelRT m, const BatchRT bt, int layer, int updater /* -1: no molecule update after this conv */,
-              int has_next, float* __restrict__ s, float* __restrict__ v, float* __restrict__ x,
+              int has_next, int agg_rows, float* __restrict__ s, float* __restrict__ v, float* __restrict__ x,
               const float* __restrict__ M, const float* __restrict__ partF, const float* __restrict__ partL,
               float* __restrict__ Pnext, float* __restrict__ EAB) {
   extern __shared__ __align__(16) float smem_raw[];
@@ -533,7 +535,7 @@ k_node_update(const ModelRT m, const BatchRT bt, int layer, int updater /* -1: n
     float val = 0.f;
     if (g < bt.N) {
       const int mol = bt.node_mol[g];
-      float msg = gather_message<D>(bt, M, partF, partL, g, mol, col);
+      float msg = gather_message<D>(bt, M, partF, partL, g, mol, col, agg_rows);
       if (znorm > 0.f) msg = __fdiv_rn(msg, znorm);
       else if (znorm < 0.f) msg = __fdiv_rn(msg, (float)(bt.mol_n[mol] - 1));      // 'mean' over in-edges
       const float cur = col < D::S ? s[(size_t)g * D::S + col] : v[(size_t)g * 3 * D::V + (col - D::S)];

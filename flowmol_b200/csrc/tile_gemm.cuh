@@ -41,7 +41,7 @@ __device__ __forceinline__ void load_w(const float* __restrict__ wrow, int lane,
   }
 }
 
-template <int PLANES, int CPT>
+template <int PLANES, int CPT, int RPW = 8>
 __device__ __forceinline__ void tile_gemm(const float* __restrict__ A, int lda, int plane_stride, int K,
                                           const float* __restrict__ Wg, float* __restrict__ wstage,
                                           float (&acc)[PLANES][RPW][CPT]) {

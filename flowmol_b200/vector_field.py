@@ -108,6 +108,16 @@ class CTMCVectorFieldB200:
         off = ptr.value - self._ws.data_ptr()
         return self._ws[off:off + 4 * cnt.value].view(torch.float32)
 
+    def set_option(self, name, value):
+        """'conv_impl': 0 = fp32 CUDA-core message kernel, 1 = tcgen05 3xTF32 message kernel (flowmol3 dims)."""
+        _lib.check(self.lib.fm_set_option(self._h, name.encode(), int(value)))
+        return self
+
+    def get_option(self, name):
+        v = C.c_int32()
+        _lib.check(self.lib.fm_get_option(self._h, name.encode(), C.byref(v)))
+        return int(v.value)
+
     def time_conv_edge(self, layer=1, iters=5):
         """Mean duration (ms) of the hot kernel re-launched on the state left by the last forward (bench roofline)."""
         ms = C.c_float()

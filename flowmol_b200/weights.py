@@ -214,6 +214,49 @@ def _np(sd, k):
     return sd[k].detach().float().cpu().numpy()
 
 
+# ---- tensor-core operand images ------------------------------------------------------------------------------------------
+def tf32_rna(x):
+    """cvt.rna.tf32.f32: round to nearest (ties away from zero) to 10 explicit mantissa bits, result in an fp32 container."""
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    return ((u + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def split_tf32(x):
+    x = np.asarray(x, dtype=np.float32)
+    hi = tf32_rna(x)
+    return hi, tf32_rna(x - hi)
+
+
+def sw128_image(tile):
+    """[rows, 32] fp32 -> the byte image of a K-major SWIZZLE_128B UMMA operand tile: row r occupies bytes
+    [128 r, 128 r + 128), its 16-byte chunk c is stored at chunk position c ^ (r & 7)  (csrc/tc.cuh:sw128_off)."""
+    rows = tile.shape[0]
+    t = np.asarray(tile, dtype=np.float32).reshape(rows, 8, 4)
+    out = np.empty_like(t)
+    r = np.arange(rows)
+    for c in range(8):
+        out[r, c ^ (r & 7)] = t[r, c]
+    return out.reshape(-1)
+
+
+def tc_units(w_fk, rows_per_unit):
+    """w_fk [features, K] fp32 -> concatenated units in the order the kernel consumes them:
+    for k-slab s (32 columns), for m-tile m (rows_per_unit feature rows): [hi unit | lo unit], each rows_per_unit*128 B."""
+    w = np.asarray(w_fk, dtype=np.float32)
+    Fdim, K = w.shape
+    ns, nm = (K + 31) // 32, (Fdim + rows_per_unit - 1) // rows_per_unit
+    wp = np.zeros((nm * rows_per_unit, ns * 32), np.float32)
+    wp[:Fdim, :K] = w
+    hi, lo = split_tf32(wp)
+    chunks = []
+    for s_ in range(ns):
+        for m in range(nm):
+            sl = (slice(m * rows_per_unit, (m + 1) * rows_per_unit), slice(s_ * 32, s_ * 32 + 32))
+            chunks.append(sw128_image(hi[sl]))
+            chunks.append(sw128_image(lo[sl]))
+    return np.concatenate(chunks)
+
+
 def _pack_gvp(P, base, sd, p, w_rows=None):
     """GVP under state_dict prefix `p` -> 6 consecutive entries starting at id `base`.
     [Wh | Wcp] are fused into one operand (they multiply the same input); `w_rows` selects/reorders the rows of the
@@ -287,6 +330,11 @@ def pack(cfg: ModelConfig, sd):
             P.gemm(c("WDST"), w0[S + R + F:S + R + F + sdst])
         _pack_gvp(P, c("MSG1_WHCP"), sd, f"{p}.edge_message.1")
         _pack_gvp(P, c("MSG2_WHCP"), sd, f"{p}.edge_message.2")
+        if S % 128 == 0 and V <= 32:     # tensor-core images: features on the UMMA M axis (128-row tiles), gates 32-row units
+            for i in range(3):
+                wt = _np(sd, f"{p}.edge_message.{i}.to_feats_out.0.weight")            # [S, in]
+                P.raw(c(f"MSG{i}_TCW"), tc_units(wt[:, rows_edge] if i == 0 else wt, 128))
+                P.raw(c(f"MSG{i}_TCG"), tc_units(_np(sd, f"{p}.edge_message.{i}.scalar_to_vector_gates.weight"), 32))
         for i in range(3):
             _pack_gvp(P, c(f"UPD{i}_WHCP"), sd, f"{p}.node_update.{i}")
         P.vec(c("LN_MSG_W"), _np(sd, f"{p}.message_layer_norm.feat_norm.weight"))

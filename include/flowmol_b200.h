@@ -108,6 +108,10 @@ int fm_time_conv_edge(FmHandle* h, void* workspace, int32_t layer, int32_t iters
 /* stand-alone check of the tcgen05 building blocks (host buffers): out[128][64] = W[128][K] . X[64][K]^T, K in {32,64,96,128};
  * passes = 1 (plain TF32) or 3 (error-compensated 3xTF32) */
 int fm_debug_tc_gemm(const float* w_host, const float* x_host, int32_t K, float* out_host, int32_t passes, int device);
+/* options: "conv_impl" = 0 fp32 CUDA-core message kernel (bit-for-bit the reference's fp32 arithmetic up to summation order),
+ *          1 tcgen05 3xTF32 message kernel (flowmol3 dimensions; fp32-faithful error-compensated tensor-core path) */
+int fm_set_option(FmHandle* h, const char* name, int32_t value);
+int fm_get_option(FmHandle* h, const char* name, int32_t* value);
 /* number of kernels launched by the last fm_forward / fm_integrate call on this handle */
 int64_t fm_last_launch_count(FmHandle* h);
 

@@ -1,0 +1,180 @@
+"""CPU tests of the host-side logic: weight layout, C ABI surface, graph index algebra, decode, config validation."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from flowmol_b200 import graph as G
+from flowmol_b200 import weight_layout as WL
+from flowmol_b200 import weights as WT
+from flowmol_b200.config import ModelConfig, NAMED_VECTOR_FIELDS
+from oracle import flowmol_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_generated_weight_id_header_is_in_sync():
+    with open(WL.HEADER_PATH) as f:
+        assert f.read() == WL.header_text(), "run `python -m flowmol_b200.weight_layout --write`"
+
+
+def test_c_abi_library_loads_and_exports_every_declared_symbol():
+    from flowmol_b200 import _lib
+    lib = _lib.load()
+    with open(os.path.join(ROOT, "include", "flowmol_b200.h")) as f:
+        declared = set(re.findall(r"\b(fm_[a-z0-9_]+)\s*\(", f.read()))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.fm_abi_version() == 1
+    # host-only helper (no GPU needed): fallback time grid is within 1 ulp of torch.linspace
+    for n in (2, 50, 250):
+        out = np.zeros(n, np.float32)
+        lib.fm_debug_time_grid(n, out.ctypes.data)
+        ref = torch.linspace(0, 1, n).numpy()
+        assert np.abs(out - ref).max() <= np.spacing(np.float32(1.0))
+
+
+def test_product_path_fails_loudly_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from flowmol_b200.vector_field import CTMCVectorFieldB200
+    cfg = ModelConfig.named("dev", 6)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        CTMCVectorFieldB200(cfg, WT.init_state_dict(cfg, 0), device="cuda:0")
+    with pytest.raises(RuntimeError):
+        CTMCVectorFieldB200(cfg, WT.init_state_dict(cfg, 0), device="cpu")
+
+
+@pytest.mark.parametrize("n_atoms", [[2], [3, 2, 9], [70, 5, 130]])
+def test_graph_contract_and_internal_edge_order(n_atoms):
+    g = G.MolGraphBatch(n_atoms)
+    bt = O.make_batch(n_atoms)
+    src, dst = g.edges()
+    assert torch.equal(src, bt.src) and torch.equal(dst, bt.dst) and torch.equal(g.upper_edge_mask(), bt.upper)
+    assert torch.equal(g.node_batch_idx(), bt.node_mol)
+    perm = G.ref_edge_to_internal(n_atoms)
+    sizes = G.batch_sizes(n_atoms)
+    assert len(np.unique(perm)) == sizes["E"] and perm.max() < sizes["EP"]
+    # internal order is dst-major inside each molecule: slots of one dst are contiguous and sorted by src
+    ebase, nb = 0, 0
+    for n in n_atoms:
+        m = (bt.dst >= nb) & (bt.dst < nb + n)
+        slots = perm[m.numpy()] - ebase
+        d, s = (bt.dst[m] - nb).numpy(), (bt.src[m] - nb).numpy()
+        order = np.argsort(slots)
+        assert np.array_equal(slots[order], np.arange(n * (n - 1)))
+        assert np.array_equal(d[order], np.repeat(np.arange(n), n - 1))
+        assert all(np.array_equal(s[order][j * (n - 1):(j + 1) * (n - 1)], np.delete(np.arange(n), j)) for j in range(n))
+        ebase += (n * (n - 1) + 63) // 64 * 64
+        nb += n
+    assert torch.equal(G.n_atoms_of(g), torch.tensor(n_atoms))
+
+
+def test_segment_sum_scheme_of_conv_edge_kernel_emulated():
+    """Emulates k_conv_edge's tile-local segment sums + k_node_update's in-order assembly (direct / partL / partF)."""
+    rng = np.random.default_rng(0)
+    for n in (2, 5, 33, 65, 66, 130, 181):
+        ecount, TM = n * (n - 1), 64
+        msg = rng.standard_normal(ecount)
+        ntile = (ecount + TM - 1) // TM
+        M, partF, partL = np.full(n, np.nan), np.full(ntile, np.nan), np.full(ntile, np.nan)
+        for t in range(ntile):
+            le0, acc, seg_first = t * TM, 0.0, t * TM
+            for row in range(TM):
+                le = le0 + row
+                if le >= ecount:
+                    break
+                j = le // (n - 1)
+                acc += msg[le]
+                last = row == TM - 1 or le + 1 >= ecount or (le + 1) // (n - 1) != j
+                if last:
+                    head, tail = seg_first == j * (n - 1), le == j * (n - 1) + n - 2
+                    if head and tail:
+                        M[j] = acc
+                    elif head:
+                        partL[t] = acc
+                    else:
+                        partF[t] = acc
+                    acc, seg_first = 0.0, le + 1
+        for j in range(n):
+            first, last = j * (n - 1), j * (n - 1) + n - 2
+            t0, t1 = first // TM, last // TM
+            got = M[j] if t0 == t1 else partL[t0] + sum(partF[t] for t in range(t0 + 1, t1 + 1))
+            assert abs(got - msg[first:last + 1].sum()) < 1e-9, (n, j)
+
+
+@pytest.mark.parametrize("name,A", [("dev", 6), ("flowmol3", 11)])
+def test_packed_weights_node_side_folding_is_algebraically_exact(name, A):
+    """P[src] (+ Q[dst]) + W_edge . [d | ef | sh] == W . cat[s_src, d, ef, (s_dst_msg), sh] + b   (fp64 check)."""
+    cfg = ModelConfig.named(name, A)
+    sd = WT.init_state_dict(cfg, 3)
+    blob, off = WT.pack(cfg, sd)
+    S, V, F, R, cp = cfg.n_hidden_scalars, cfg.n_vec_channels, cfg.n_hidden_edge_feats, cfg.rbf_dim, cfg.n_cp_feats
+    sdst, h0 = cfg.s_dst, max(V + 1 + cfg.v_dst, V)
+    pad4, pad32 = (lambda x: (x + 3) // 4 * 4), (lambda x: (x + 31) // 32 * 32)
+
+    def mat(idx, K, N):
+        o = off[idx]
+        return blob[o:o + pad4(K) * pad32(N)].reshape(pad4(K), pad32(N))[:K, :N].astype(np.float64)
+    rng = np.random.default_rng(1)
+    s_src, d, ef, sd_, sh = (rng.standard_normal(k) for k in (S, R, F, sdst, h0 + cp))
+    W = sd["conv_layers.1.edge_message.0.to_feats_out.0.weight"].double().numpy()
+    b = sd["conv_layers.1.edge_message.0.to_feats_out.0.bias"].double().numpy()
+    want = W @ np.concatenate([s_src, d, ef, sd_, sh]) + b
+    P = s_src @ mat(WL.cid(1, "WSRC"), S, S) + blob[off[WL.cid(1, "BSRC")]:][:S]
+    got = P + np.concatenate([d, ef, sh]) @ mat(WL.cid(1, "MSG0_W"), R + F + h0 + cp, S)
+    if sdst:
+        got = got + sd_ @ mat(WL.cid(1, "WDST"), sdst, S)
+    np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-6)
+    # EdgeUpdate: EA[src] + EB[dst] + W_e . [ef | d]
+    W1 = sd["edge_updaters.1.edge_update_fn.0.weight"].double().numpy()
+    b1 = sd["edge_updaters.1.edge_update_fn.0.bias"].double().numpy()
+    s_dst = rng.standard_normal(S)
+    want = W1 @ np.concatenate([s_src, s_dst, ef, d]) + b1
+    WN = mat(WL.uid(cfg.n_convs, 1, "EUPD_WN"), S, 2 * F)
+    BN = blob[off[WL.uid(cfg.n_convs, 1, "EUPD_BN")]:][:2 * F]
+    got = (s_src @ WN + BN)[:F] + (s_dst @ WN + BN)[F:] + np.concatenate([ef, d]) @ mat(WL.uid(cfg.n_convs, 1, "EUPD_WE"), F + R, F)
+    np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-6)
+
+
+def test_config_rejects_options_off_the_live_path():
+    base = dict(NAMED_VECTOR_FIELDS["flowmol3"])
+    for bad in (dict(attention=True), dict(s_message_dim=64), dict(n_recycles=2), dict(a_token_dim=0), dict(n_message_gvps=2)):
+        with pytest.raises((NotImplementedError, ValueError)):
+            ModelConfig.from_vector_field_block({**base, **bad}, 11)
+    cfg = ModelConfig.named("flowmol3", 11)
+    assert (cfg.n_convs, cfg.n_updaters, cfg.s_dst) == (6, 6, 0)
+    assert sum(int(np.prod(s)) for _, s in WT.expected_tensors(cfg)) == 5854185          # BASELINE.md parameter count
+
+
+def test_lightning_checkpoint_ingestion_and_molecule_decode(tmp_path):
+    from flowmol_b200.api import FlowMolB200, SampledMolecule, load_pretrained
+    cfg = ModelConfig.named("dev", 11)
+    sd = WT.init_state_dict(cfg, 0)
+    ck = {"state_dict": {"vector_field." + k: v for k, v in sd.items()} | {"loss_fn.weight": torch.zeros(3)},
+          "hyper_parameters": {"atom_type_map": ['C', 'H', 'N', 'O', 'F', 'P', 'S', 'Cl', 'Br', 'I'], "fake_atom_p": 0.3,
+                               "vector_field_config": NAMED_VECTOR_FIELDS["dev"], "default_n_timesteps": 250,
+                               "explicit_aromaticity": False, "n_atoms_hist_file": "data/geom_full_kekulized/x.pt"}}
+    d = tmp_path / "flowmol3" / "checkpoints"
+    d.mkdir(parents=True)
+    torch.save(ck, d / "last.ckpt")
+    model = load_pretrained("flowmol3", models_dir=tmp_path) if not torch.cuda.is_available() else FlowMolB200.from_checkpoint(d / "last.ckpt")
+    assert model.n_atom_types == 11 and model.cfg.n_hidden_scalars == 64
+    assert all(torch.equal(model._state_dict[k], sd[k]) for k in sd)
+    sizes = model.sample_n_atoms(1000)
+    assert sizes.min() >= 3 and sizes.max() <= 181
+    with pytest.raises(ValueError):
+        load_pretrained("nope")
+    # decode: 4 atoms, atom 2 is a fake atom (index 10), bonds 0-1 single, 0-2 (to the fake atom) double, 1-3 masked
+    x = np.arange(12, dtype=np.float32).reshape(4, 3)
+    a = np.array([0, 3, 10, 1])
+    c = np.array([2, 3, 2, 1])
+    e = np.array([1, 2, 0, 0, 4, 3])            # upper edges (0,1) (0,2) (0,3) (1,2) (1,3) (2,3)
+    m = SampledMolecule(x, a, c, e, model.atom_type_map, fake_atoms=True)
+    assert m.atom_types == ['C', 'O', 'H'] and m.atom_charges.tolist() == [0, 1, -1] and m.num_atoms == 3
+    assert m.bond_types.tolist() == [1] and m.bond_src_idxs.tolist() == [0] and m.bond_dst_idxs.tolist() == [1]
+    assert torch.equal(m.positions, torch.from_numpy(x[[0, 1, 3]]))

@@ -87,6 +87,7 @@ struct FmHandle {
   fm::ModelRT rt;
   std::unordered_map<void*, Layout> batches;
   int64_t launches = 0;
+  int tc_debug = 0;            // timing experiments (conv_tc.cuh TcCtx::dbg)
   bool has_tc = false;         // packed weights contain the UMMA operand images
   int conv_impl = 0;           // 0: fp32 CUDA-core k_conv_edge, 1: tcgen05 3xTF32 k_conv_edge_tc (flowmol3 dims only)
   cudaStream_t cap_stream = nullptr;    // private stream for CUDA-graph capture (the legacy default stream cannot capture)
@@ -155,7 +156,7 @@ int run_pass(FmHandle* h, void* ws, const Layout& L, const float* x_t, const uin
     int agg_rows = fm::TM;
     if constexpr (D::S == 256 && D::V == 32 && D::SD == 0) {
       if (h->conv_impl == 1) {
-        fm::k_conv_edge_tc<D><<<2 * L.nET, fm::NT, fm::TcPlan<D>::SMEM_BYTES, st>>>(m, bt, l, x, v, ef, P, M, partF, partL);
+        fm::k_conv_edge_tc<D><<<2 * L.nET, fm::NT, fm::TcPlan<D>::SMEM_BYTES, st>>>(m, bt, l, x, v, ef, P, M, partF, partL, h->tc_debug);
         agg_rows = fm::TCT;
       }
     }
@@ -472,6 +473,7 @@ int fm_set_option(FmHandle* h, const char* name, int32_t value) {
     h->conv_impl = value;
     return 0;
   }
+  if (n == "tc_debug") { h->tc_debug = value; return 0; }
   return fail("fm_set_option: unknown option");
 }
 int fm_get_option(FmHandle* h, const char* name, int32_t* value) {
@@ -520,7 +522,7 @@ int fm_time_conv_edge(FmHandle* h, void* ws, int32_t layer, int32_t iters, float
   CUDA_OK(cudaEventRecord(e0, st));
   for (int i = 0; i < iters; ++i) {
     if (h->variant == 0 && h->conv_impl == 1)
-      fm::k_conv_edge_tc<fm::DimsFlowmol3><<<2 * L.nET, fm::NT, fm::TcPlan<fm::DimsFlowmol3>::SMEM_BYTES, st>>>(h->rt, bt, layer, x, v, ef, P, M, partF, partL);
+      fm::k_conv_edge_tc<fm::DimsFlowmol3><<<2 * L.nET, fm::NT, fm::TcPlan<fm::DimsFlowmol3>::SMEM_BYTES, st>>>(h->rt, bt, layer, x, v, ef, P, M, partF, partL, h->tc_debug);
     else if (h->variant == 0)
       fm::k_conv_edge<fm::DimsFlowmol3><<<L.nET, fm::NT, fm::DimsFlowmol3::SMEM_BYTES, st>>>(h->rt, bt, layer, x, v, ef, P, Q, vd, M, partF, partL);
     else

@@ -57,6 +57,7 @@ struct TcCtx {
   uint32_t tmem;        // TMEM base (lane 0, column 0 of the allocation)
   uint32_t g;           // global unit counter (ring slot / phase bookkeeping), identical in every thread
   uint32_t acc_phase;
+  int dbg;              // timing experiments only: 1 = no weight copies, 2 = no MMA issue, 4 = no vector stages, 8 = no x_store
 };
 
 // C^T[f][e] (TMEM columns [col0 + 32*m, +32) for m-tile m) = sum over k-slabs of W-units x X-slabs, 3xTF32.
@@ -70,6 +71,7 @@ __device__ __forceinline__ void tc_gemm(const TcGemm w, TcCtx& cx, uint32_t col0
     for (uint32_t u = 0; u < nunits; ++u) {
       const uint32_t gi = cx.g + u, slot = gi % TC_RING, use = gi / TC_RING;
       if (use > 0) tc::mbar_wait(&cx.empty[slot], (use - 1) & 1);
+      if (cx.dbg & 1) { tc::mbar_arrive_expect_tx(&cx.full[slot], 0u); continue; }
       tc::mbar_arrive_expect_tx(&cx.full[slot], (uint32_t)w.unit_bytes);
       tc::bulk_g2s(cx.ring + slot * TC_UNIT, reinterpret_cast<const uint8_t*>(w.units) + (size_t)u * w.unit_bytes,
                    (uint32_t)w.unit_bytes, &cx.full[slot]);
@@ -88,7 +90,7 @@ __device__ __forceinline__ void tc_gemm(const TcGemm w, TcCtx& cx, uint32_t col0
           tc::mbar_wait(&cx.full[slot], use & 1);
           tc::tc_fence_after();
           const uint32_t wb = tc::smem_u32(cx.ring + slot * TC_UNIT);
-          for (int j = 0; j < ksteps; ++j) {
+          for (int j = 0; j < ksteps && !(cx.dbg & 2); ++j) {
             const uint64_t dw = tc::desc_sw128(wb + 32 * j);
             tc::umma_tf32(d, dw, tc::desc_sw128(xl + 32 * j), idesc, (s > 0 || j > 0) ? 1u : 0u);
             tc::umma_tf32(d, dw, tc::desc_sw128(xh + 32 * j), idesc, 1u);
@@ -101,7 +103,7 @@ __device__ __forceinline__ void tc_gemm(const TcGemm w, TcCtx& cx, uint32_t col0
           tc::mbar_wait(&cx.full[slot], use & 1);
           tc::tc_fence_after();
           const uint32_t wb = tc::smem_u32(cx.ring + slot * TC_UNIT);
-          for (int j = 0; j < ksteps; ++j)
+          for (int j = 0; j < ksteps && !(cx.dbg & 2); ++j)
             tc::umma_tf32(d, tc::desc_sw128(wb + 32 * j), tc::desc_sw128(xh + 32 * j), idesc, 1u);
           tc::umma_commit(&cx.empty[slot]);
           ++u;
@@ -144,7 +146,7 @@ template <class D>
 __global__ void __launch_bounds__(NT, 1)
 k_conv_edge_tc(const ModelRT m, const BatchRT bt, int layer, const float* __restrict__ x, const float* __restrict__ v,
                const float* __restrict__ ef, const float* __restrict__ P, float* __restrict__ M, float* __restrict__ partF,
-               float* __restrict__ partL) {
+               float* __restrict__ partL, int dbg) {
   using PL = TcPlan<D>;
   static_assert(D::S == 256 && D::V == 32 && D::SD == 0, "k_conv_edge_tc is specialised for the flowmol3 dimensions");
   extern __shared__ uint8_t smem_dyn[];
@@ -161,7 +163,7 @@ k_conv_edge_tc(const ModelRT m, const BatchRT bt, int layer, const float* __rest
   TcCtx cx;
   cx.xhi = base + PL::OFF_XHI; cx.xlo = base + PL::OFF_XLO; cx.ring = base + PL::OFF_RING;
   cx.full = bars; cx.empty = bars + TC_RING; cx.accbar = bars + 2 * TC_RING;
-  cx.g = 0; cx.acc_phase = 0;
+  cx.g = 0; cx.acc_phase = 0; cx.dbg = dbg;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // 32-row tiles are the halves of the 64-slot storage tiles of the batch descriptor
   const int tile = blockIdx.x, tile64 = tile >> 1, mol = bt.etile_mol[tile64];
@@ -236,7 +238,7 @@ k_conv_edge_tc(const ModelRT m, const BatchRT bt, int layer, const float* __rest
     const int hc = h + D::CP;
     const GvpPtr w = gvp_ptr_conv(m, layer, gi == 0 ? C_MSG0_WHCP : (gi == 1 ? C_MSG1_WHCP : C_MSG2_WHCP));
     // -- vector stage 1 (CUDA cores): [Vh | Vcp] = V x [Wh | Wcp], cross products, norms -> k-slabs of the scalar operand
-    {
+    if (!(dbg & 4)) {
       float acc[3][TC_RPW][D::CPT_HC0];
       tile_gemm<3, D::CPT_HC0, TC_RPW>(Va, PL::LDVA, TCT * PL::LDVA, pad4(v_in), w.whcp, wstage, acc);
       const int ncol = h + 2 * D::CP;
@@ -295,7 +297,7 @@ k_conv_edge_tc(const ModelRT m, const BatchRT bt, int layer, const float* __rest
         float pre = bias;
         if (gi == 0) pre = s >= 0 ? P[(size_t)s * D::S + f] : 0.f;     // per-node half of the first linear (bias folded in)
         const float val = silu_f(acc[e] + pre);
-        x_store(cx, e, f, val);                                          // next layer's / the gate GEMM's operand, k = f
+        if (!(dbg & 8)) x_store(cx, e, f, val);                          // next layer's / the gate GEMM's operand, k = f
         if (gi == 2 && s >= 0) {                                         // segment-sum of the scalar message, thread-local
           const int d = s_dst[e];
           run = __fadd_rn(run, val);
@@ -320,7 +322,7 @@ k_conv_edge_tc(const ModelRT m, const BatchRT bt, int layer, const float* __rest
       for (int e = 0; e < TCT; ++e) G[e * 32 + lane] = sigmoid_f(acc[e] + bg);
     }
     // -- vector stage 2 (CUDA cores): V' = gate * (Vh_ext x Wu) --------------------------------------------------------------------------
-    {
+    if (!(dbg & 4)) {
       float acc[3][TC_RPW][1];
       tile_gemm<3, 1, TC_RPW>(Vb, PL::LDVB, TCT * PL::LDVB, pad4(hc), w.wu, wstage, acc);    // entry barrier publishes G
 #pragma unroll

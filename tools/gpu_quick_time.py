@@ -1,0 +1,19 @@
+"""Quick per-forward timing at GEOM-512 (flowmol3) for the current build."""
+import os, sys, time
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from flowmol_b200 import weights as WT
+from flowmol_b200.config import ModelConfig
+from flowmol_b200.vector_field import CTMCVectorFieldB200
+from bench import draw_sizes, make_prior
+cfg = ModelConfig.named("flowmol3", 11)
+vf = CTMCVectorFieldB200(cfg, WT.init_state_dict(cfg, 0))
+n_atoms = draw_sizes("geom", 512)
+x0, a0, c0, e0 = make_prior(n_atoms, 11, 100)
+for impl in [int(a) for a in (sys.argv[1:] or ["0"])]:
+    vf.set_option("conv_impl", impl)
+    d = vf.forward_tokens(n_atoms, x0, a0, c0, e0, 0.0, None); torch.cuda.synchronize()
+    ts = []
+    for _ in range(3):
+        t0 = time.time(); d = vf.forward_tokens(n_atoms, x0, a0, c0, e0, 0.3, d); torch.cuda.synchronize(); ts.append(time.time() - t0)
+    print(f"impl {impl}: forward ms {min(ts)*1e3:.2f}  conv_edge ms {vf.time_conv_edge(1, 3):.3f}")

@@ -12,6 +12,8 @@
 #include "ctmc.cuh"
 #include "kernels.cuh"
 #include "conv_tc.cuh"
+#include "egemm_tc.cuh"
+#include "vec_stages.cuh"
 #include "tc_test.cuh"
 
 namespace {
@@ -35,6 +37,8 @@ struct Layout {
   long long EP = 0;
   size_t mol_n, mol_node, mol_u, mol_etile, mol_utile, etile_mol, utile_mol, node_mol;
   size_t s, v, x, P, Q, vd, EAB, M, partF, partL, ef;
+  size_t SA, SB, VH, SH, GT;   // wide tensor-core pipeline intermediates (per padded edge slot, rounded up to 256 slots)
+  long long EPA = 0;
   size_t pred[3][4];     // [buffer][x,a,c,e]
   size_t total = 0;
 };
@@ -66,6 +70,10 @@ Layout make_layout(const Dyn& d, const int32_t* n_atoms, int B) {
   L.EAB = take(4ull * N * 2 * d.F); L.M = take(4ull * N * d.MW);
   L.partF = take(8ull * L.nET * d.MW); L.partL = take(8ull * L.nET * d.MW);   // x2: the tensor-core kernel uses 32-row tiles
   L.ef = take(4ull * (size_t)L.EP * d.F);
+  L.EPA = (L.EP + 255) / 256 * 256;
+  const size_t wide = d.S == 256 && d.SD == 0 ? (size_t)L.EPA : 0;
+  L.SA = take(4ull * wide * d.S); L.SB = take(4ull * wide * d.S); L.VH = take(4ull * wide * 120); L.SH = take(4ull * wide * 40);
+  L.GT = take(4ull * wide * 32);
   for (int k = 0; k < 3; ++k) {
     L.pred[k][0] = take(4ull * N * 3); L.pred[k][1] = take(4ull * N * d.A); L.pred[k][2] = take(4ull * N * d.C);
     L.pred[k][3] = take(4ull * (size_t)U * d.EB);
@@ -85,6 +93,7 @@ struct FmHandle {
   long long* d_off = nullptr;
   float* d_table = nullptr;
   fm::ModelRT rt;
+  std::vector<long long> off_h;   // host copy of the weight offset table
   std::unordered_map<void*, Layout> batches;
   int64_t launches = 0;
   int tc_debug = 0;            // timing experiments (conv_tc.cuh TcCtx::dbg)
@@ -123,8 +132,15 @@ int set_smem_attrs() {
   CUDA_OK(cudaFuncSetAttribute(fm::k_edge_update<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CUDA_OK(cudaFuncSetAttribute(fm::k_node_head<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CUDA_OK(cudaFuncSetAttribute(fm::k_edge_head<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  if constexpr (D::S == 256 && D::V == 32 && D::SD == 0)
+  if constexpr (D::S == 256 && D::V == 32 && D::SD == 0) {
     CUDA_OK(cudaFuncSetAttribute(fm::k_conv_edge_tc<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::TcPlan<D>::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_MSG0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EG_SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_MSG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EG_SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EG_SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_vec_a<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_vec_b<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_vec_c<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  }
   return 0;
 }
 
@@ -134,6 +150,40 @@ int set_smem_attrs() {
     cudaError_t e__ = cudaGetLastError();                                                                  \
     if (e__ != cudaSuccess) return fail(std::string("kernel launch failed: ") + cudaGetErrorString(e__)); \
   } while (0)
+
+// message pass of conv `l` as the wide tensor-core pipeline (egemm_tc.cuh + vec_stages.cuh): 10 launches
+template <class D>
+int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int l, cudaStream_t st) {
+  if constexpr (D::S == 256 && D::V == 32 && D::SD == 0) {
+    const fm::ModelRT& m = h->rt;
+    auto wptr = [&](int id) { return h->d_w + h->off_h[fm::G_COUNT + l * fm::C_COUNT + id]; };
+    float *v = at<float>(ws, L.v), *x = at<float>(ws, L.x), *P = at<float>(ws, L.P), *M = at<float>(ws, L.M);
+    float *partF = at<float>(ws, L.partF), *partL = at<float>(ws, L.partL), *ef = at<float>(ws, L.ef);
+    float *SA = at<float>(ws, L.SA), *SB = at<float>(ws, L.SB), *VH = at<float>(ws, L.VH), *SH = at<float>(ws, L.SH), *GT = at<float>(ws, L.GT);
+    const size_t smem = D::SMEM_BYTES;
+    const int gt = (int)(L.EPA / fm::EG_T);
+    fm::k_vec_a<D><<<L.nET, fm::NT, smem, st>>>(m, bt, l, x, v, VH, SH);
+    LAUNCH_OK(h);
+    const int tcw[3] = {fm::C_MSG0_TCW, fm::C_MSG1_TCW, fm::C_MSG2_TCW}, tcg[3] = {fm::C_MSG0_TCG, fm::C_MSG1_TCG, fm::C_MSG2_TCG};
+    const int gb[3] = {fm::C_MSG0_WHCP, fm::C_MSG1_WHCP, fm::C_MSG2_WHCP};
+    float* cur = ef;      // input activations of the current scalar linear
+    float* outs[3] = {SA, SB, SA};
+    for (int g = 0; g < 3; ++g) {
+      fm::EgArgs a{wptr(tcw[g]), wptr(gb[g] + fm::GV_B), cur, SH, P, x, outs[g], L.EP};
+      if (g == 0) fm::k_egemm_tc<D, fm::EG_MSG0><<<gt, fm::EG_THREADS, fm::EG_SMEM_BYTES, st>>>(m, bt, a);
+      else fm::k_egemm_tc<D, fm::EG_MSG><<<gt, fm::EG_THREADS, fm::EG_SMEM_BYTES, st>>>(m, bt, a);
+      LAUNCH_OK(h);
+      fm::EgArgs ag{wptr(tcg[g]), wptr(gb[g] + fm::GV_BG), outs[g], nullptr, nullptr, nullptr, GT, L.EP};
+      fm::k_egemm_tc<D, fm::EG_GATE><<<gt, fm::EG_THREADS, fm::EG_SMEM_BYTES, st>>>(m, bt, ag);
+      LAUNCH_OK(h);
+      if (g < 2) { fm::k_vec_b<D><<<L.nET, fm::NT, smem, st>>>(m, bt, l, g + 1, VH, SH, GT); LAUNCH_OK(h); }
+      cur = outs[g];
+    }
+    fm::k_vec_c<D><<<L.nET, fm::NT, smem, st>>>(m, bt, l, VH, GT, SA, M, partF, partL);
+    LAUNCH_OK(h);
+  }
+  return 0;
+}
 
 // one denoise_graph pass (embedding + optional self-conditioning residual + convs + heads)
 template <class D>
@@ -158,10 +208,16 @@ int run_pass(FmHandle* h, void* ws, const Layout& L, const float* x_t, const uin
       if (h->conv_impl == 1) {
         fm::k_conv_edge_tc<D><<<2 * L.nET, fm::NT, fm::TcPlan<D>::SMEM_BYTES, st>>>(m, bt, l, x, v, ef, P, M, partF, partL, h->tc_debug);
         agg_rows = fm::TCT;
+        LAUNCH_OK(h);
       }
     }
-    if (agg_rows == fm::TM) fm::k_conv_edge<D><<<L.nET, fm::NT, smem, st>>>(m, bt, l, x, v, ef, P, Q, vd, M, partF, partL);
-    LAUNCH_OK(h);
+    if (h->conv_impl == 2) {
+      int rc = conv_wide<D>(h, ws, L, bt, l, st);
+      if (rc) return rc;
+    } else if (agg_rows == fm::TM) {
+      fm::k_conv_edge<D><<<L.nET, fm::NT, smem, st>>>(m, bt, l, x, v, ef, P, Q, vd, M, partF, partL);
+      LAUNCH_OK(h);
+    }
     int upd = -1;
     if (l != 0 && (l + 1) % m.convs_per_update == 0) upd = m.separate_updaters ? l / m.convs_per_update : 0;   // vector_field.py:321-326
     const int has_next = l + 1 < m.L;
@@ -259,6 +315,7 @@ int fm_create(const FmConfig* cfg, const float* w_host, size_t n_floats, const i
   FmHandle* h = new FmHandle();
   h->cfg = c; h->device = device; h->variant = variant;
   h->has_tc = off_host[fm::G_COUNT + fm::C_MSG0_TCW] >= 0;
+  h->off_h.assign(off_host, off_host + n_off);
   h->conv_impl = 0;
   h->dyn = Dyn{c.n_hidden_scalars, c.n_vec_channels, c.n_hidden_edge_feats, c.use_dst_feats ? c.s_dst : 0,
                c.use_dst_feats ? c.v_dst : 0, c.n_atom_types, c.n_charges, c.n_bond_types,
@@ -467,9 +524,9 @@ int fm_set_option(FmHandle* h, const char* name, int32_t value) {
   if (!h || !name) return fail("fm_set_option: null argument");
   const std::string n(name);
   if (n == "conv_impl") {
-    if (value != 0 && value != 1) return fail("fm_set_option: conv_impl must be 0 (fp32 CUDA cores) or 1 (tcgen05 3xTF32)");
-    if (value == 1 && h->variant != 0) return fail("fm_set_option: the tcgen05 kernel is built for the flowmol3 dimensions only");
-    if (value == 1 && !h->has_tc) return fail("fm_set_option: packed weights carry no tensor-core images");
+    if (value < 0 || value > 2) return fail("fm_set_option: conv_impl must be 0 (fp32 CUDA cores), 1 (fused tcgen05) or 2 (wide tcgen05 pipeline)");
+    if (value >= 1 && h->variant != 0) return fail("fm_set_option: the tcgen05 kernel is built for the flowmol3 dimensions only");
+    if (value >= 1 && !h->has_tc) return fail("fm_set_option: packed weights carry no tensor-core images");
     h->conv_impl = value;
     return 0;
   }
@@ -521,7 +578,10 @@ int fm_time_conv_edge(FmHandle* h, void* ws, int32_t layer, int32_t iters, float
   CUDA_OK(cudaStreamSynchronize(st));
   CUDA_OK(cudaEventRecord(e0, st));
   for (int i = 0; i < iters; ++i) {
-    if (h->variant == 0 && h->conv_impl == 1)
+    if (h->variant == 0 && h->conv_impl == 2) {
+      int rc = conv_wide<fm::DimsFlowmol3>(h, ws, L, bt, layer, st);
+      if (rc) return rc;
+    } else if (h->variant == 0 && h->conv_impl == 1)
       fm::k_conv_edge_tc<fm::DimsFlowmol3><<<2 * L.nET, fm::NT, fm::TcPlan<fm::DimsFlowmol3>::SMEM_BYTES, st>>>(h->rt, bt, layer, x, v, ef, P, M, partF, partL, h->tc_debug);
     else if (h->variant == 0)
       fm::k_conv_edge<fm::DimsFlowmol3><<<L.nET, fm::NT, fm::DimsFlowmol3::SMEM_BYTES, st>>>(h->rt, bt, layer, x, v, ef, P, Q, vd, M, partF, partL);

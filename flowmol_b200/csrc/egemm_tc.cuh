@@ -1,0 +1,245 @@
+// k_egemm_tc -- per-edge dense layers on the 5th-generation tensor cores, 256 edges per CTA.
+//
+//   OUT[e][f] = act( sum_k W[f][k] * IN[e][k] + pre(e, f) )            error-compensated 3xTF32, fp32 accumulation in TMEM
+//
+// The fused single-CTA chain (conv_tc.cuh) is limited by what fits next to its operands in 227 KB: 32-edge tiles leave
+// tcgen05.mma at its ~64-cycle-per-instruction floor (N = 32 costs the same as N = 128, measured: profiles/r01b) and stream
+// 1.9 MB of weight images per 32 edges.  Here the three scalar linears and the three gate linears of a message pass run as
+// wide tiles instead: N = 2 x 128 edges per CTA (full-rate MMAs, weight images amortised over 256 edges), activations
+// round-trip through HBM between the stages (1 KB per edge) and the small vector-channel stages run in their own
+// CUDA-core kernels (vec_stages.cuh).
+//
+// Orientation "features on M": UMMA A = weight unit [128 features][32 k] (bulk-TMA ring, pre-swizzled hi / lo images),
+// UMMA B = activation k-slab [128 edges][32 k] x 2 halves, converted fp32 -> (hi, lo) SW128 images by the loader warps,
+// D in TMEM: lane = feature, column = edge => epilogue stores are coalesced over features, bias is per thread.
+//
+// Warp roles (10 warps): 0 = weight producer, 1 = MMA issuer, 2..9 = activation loaders (one edge row per thread), then
+// the same 8 warps run the epilogue (TMEM lane quarter = warp % 4, edge half = (warp - 2) / 4).
+#pragma once
+#include "conv_tc.cuh"
+
+namespace fm {
+
+constexpr int EG_T = 256;                       // edges per CTA
+constexpr int EG_THREADS = 320;
+constexpr int EG_RING = 4;
+constexpr int EG_XSTAGE = 65536;                // hi h0 | hi h1 | lo h0 | lo h1, 16 KB each
+constexpr int EG_OFF_X = 0;
+constexpr int EG_OFF_RING = 2 * EG_XSTAGE;
+constexpr int EG_OFF_ROW = EG_OFF_RING + EG_RING * TC_UNIT;     // int src[256], dst[256]; float dist[256]
+constexpr int EG_OFF_BAR = EG_OFF_ROW + 3 * EG_T * 4;
+constexpr int EG_BYTES = EG_OFF_BAR + (2 * EG_RING + 5) * 8 + 16;
+constexpr size_t EG_SMEM_BYTES = EG_BYTES + 1024;
+
+enum EgMode : int { EG_MSG0 = 0, EG_MSG = 1, EG_GATE = 2 };
+
+struct EgArgs {
+  const float* units;        // weight images (weights.py:tc_units)
+  const float* bias;         // MSG: to_feats_out bias; GATE: gate bias (padded to 32)
+  const float* in_s;         // MSG / GATE: [EPA][S] activations of the previous stage; MSG0: edge features ef [EP][F]
+  const float* in_sh;        // MSG0 / MSG: [EPA][40] vector norms of this GVP
+  const float* P;            // MSG0: per-node pre-activations [N][S]
+  const float* x;            // MSG0: positions [N][3]
+  float* out;                // MSG0 / MSG: [EPA][S];  GATE: [EPA][32]
+  long long EP;              // padded edge slots (multiple of 64)
+};
+
+template <class D, int MODE>
+__global__ void __launch_bounds__(EG_THREADS, 1)
+k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
+  constexpr int S = D::S;
+  constexpr int K = MODE == EG_MSG0 ? D::KE0 : (MODE == EG_MSG ? D::K1 : S);
+  constexpr int NSLAB = (K + 31) / 32;
+  constexpr int LAST_KSTEPS = ((K - 1) % 32) / 8 + 1;
+  constexpr int NMT = MODE == EG_GATE ? 1 : S / 128;
+  constexpr int UNIT_BYTES = MODE == EG_GATE ? 32 * 128 : TC_UNIT;
+  constexpr int SH_W = 40;                                     // row pitch of the norm buffer
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  uint8_t* xst = base + EG_OFF_X;
+  uint8_t* ring = base + EG_OFF_RING;
+  int* r_src = reinterpret_cast<int*>(base + EG_OFF_ROW);
+  float* r_dist = reinterpret_cast<float*>(r_src + 2 * EG_T);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + EG_OFF_BAR);
+  uint64_t *w_full = bars, *w_empty = bars + EG_RING, *x_full = bars + 2 * EG_RING, *x_empty = x_full + 2, *acc_full = x_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long slot0 = (long long)blockIdx.x * EG_T;
+  if (tid == 0) {
+    for (int i = 0; i < EG_RING; ++i) { tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1); }
+    tc::mbar_init(&x_full[0], 8); tc::mbar_init(&x_full[1], 8);
+    tc::mbar_init(&x_empty[0], 1); tc::mbar_init(&x_empty[1], 1);
+    tc::mbar_init(acc_full, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
+  // per-row bookkeeping: validity, and for the first message linear the (src, dst) pair and its distance
+  if (tid >= 64) {
+    const int r = tid - 64;
+    const long long slot = slot0 + r;
+    int s = -1;
+    float dist = 0.f;
+    if (slot < a.EP) {
+      const int t64 = (int)(slot >> 6), mol = bt.etile_mol[t64];
+      const int n = bt.mol_n[mol], le = (int)(slot - ((long long)bt.mol_etile[mol] << 6));
+      if (le < n * (n - 1)) {
+        s = 0;
+        if (MODE == EG_MSG0) {
+          int i, j;
+          edge_src_dst(le, n, i, j);
+          const int nb = bt.mol_node[mol];
+          s = nb + i;
+          float dx, dy, dz;
+          dist = pair_dist(a.x, s, nb + j, dx, dy, dz);
+        }
+      }
+    }
+    r_src[r] = s;
+    r_dist[r] = dist;
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ---- weight producer -------------------------------------------------------------------------------------------------
+    if (lane == 0) {
+      constexpr uint32_t NU = NSLAB * NMT * 2;
+      for (uint32_t u = 0; u < NU; ++u) {
+        const uint32_t sl = u % EG_RING, use = u / EG_RING;
+        if (use > 0) tc::mbar_wait(&w_empty[sl], (use - 1) & 1);
+        tc::mbar_arrive_expect_tx(&w_full[sl], UNIT_BYTES);
+        tc::bulk_g2s(ring + sl * TC_UNIT, reinterpret_cast<const uint8_t*>(a.units) + (size_t)u * UNIT_BYTES, UNIT_BYTES, &w_full[sl]);
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer ----------------------------------------------------------------------------------------------------------
+    if (lane == 0) {
+      const uint32_t idesc = tc::idesc_tf32(128, 128);
+      uint32_t u = 0;
+      for (int j = 0; j < NSLAB; ++j) {
+        const int st = j & 1, ksteps = (j == NSLAB - 1) ? LAST_KSTEPS : 4;
+        tc::mbar_wait(&x_full[st], (j >> 1) & 1);
+        tc::tc_fence_after();
+        const uint32_t xb = tc::smem_u32(xst + st * EG_XSTAGE);
+        for (int mt = 0; mt < NMT; ++mt) {
+          {
+            const uint32_t sl = u % EG_RING, use = u / EG_RING;
+            tc::mbar_wait(&w_full[sl], use & 1);
+            tc::tc_fence_after();
+            const uint32_t wb = tc::smem_u32(ring + sl * TC_UNIT);
+            for (int h = 0; h < 2; ++h) {
+              const uint32_t d = tmem + (uint32_t)((mt * 2 + h) * 128);
+              for (int ks = 0; ks < ksteps; ++ks) {
+                const uint64_t dw = tc::desc_sw128(wb + 32 * ks);
+                tc::umma_tf32(d, dw, tc::desc_sw128(xb + 32768 + h * 16384 + 32 * ks), idesc, (j > 0 || ks > 0) ? 1u : 0u);
+                tc::umma_tf32(d, dw, tc::desc_sw128(xb + h * 16384 + 32 * ks), idesc, 1u);
+              }
+            }
+            tc::umma_commit(&w_empty[sl]);
+            ++u;
+          }
+          {
+            const uint32_t sl = u % EG_RING, use = u / EG_RING;
+            tc::mbar_wait(&w_full[sl], use & 1);
+            tc::tc_fence_after();
+            const uint32_t wb = tc::smem_u32(ring + sl * TC_UNIT);
+            for (int h = 0; h < 2; ++h) {
+              const uint32_t d = tmem + (uint32_t)((mt * 2 + h) * 128);
+              for (int ks = 0; ks < ksteps; ++ks)
+                tc::umma_tf32(d, tc::desc_sw128(wb + 32 * ks), tc::desc_sw128(xb + h * 16384 + 32 * ks), idesc, 1u);
+            }
+            tc::umma_commit(&w_empty[sl]);
+            ++u;
+          }
+        }
+        tc::umma_commit(&x_empty[st]);
+      }
+      tc::umma_commit(acc_full);
+    }
+  } else {
+    // ---- activation loaders: one edge row per thread, fp32 -> (hi, lo) SW128 images ------------------------------------------------
+    const int r = tid - 64, h = r >> 7, rr = r & 127;
+    const long long slot = slot0 + r;
+    const bool valid = r_src[r] >= 0;
+    const float sigma = m.rbf_dmax / (float)D::R;
+    const float* mu = m.g(G_RBF_MU);
+    for (int j = 0; j < NSLAB; ++j) {
+      const int st = j & 1;
+      if (j >= 2) tc::mbar_wait(&x_empty[st], ((j >> 1) - 1) & 1);
+      uint8_t* hi = xst + st * EG_XSTAGE + h * 16384;
+      uint8_t* lo = hi + 32768;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) {
+          if (MODE == EG_MSG0) {
+            if (j == 0) {
+              const float dd = r_dist[r];
+              val = make_float4(rbf_f(dd, mu[c * 4], sigma), rbf_f(dd, mu[c * 4 + 1], sigma), rbf_f(dd, mu[c * 4 + 2], sigma),
+                                rbf_f(dd, mu[c * 4 + 3], sigma));
+            } else if (j <= D::F / 32) {
+              val = __ldg(reinterpret_cast<const float4*>(a.in_s + (size_t)slot * D::F + (j - 1) * 32) + c);
+            } else {
+              const int k0 = (j - 1 - D::F / 32) * 32 + c * 4;
+              if (k0 < SH_W) val = *(reinterpret_cast<const float4*>(a.in_sh + (size_t)slot * SH_W + k0));
+            }
+          } else if (MODE == EG_MSG) {
+            if (j < S / 32) val = *(reinterpret_cast<const float4*>(a.in_s + (size_t)slot * S + j * 32) + c);
+            else {
+              const int k0 = (j - S / 32) * 32 + c * 4;
+              if (k0 < SH_W) val = *(reinterpret_cast<const float4*>(a.in_sh + (size_t)slot * SH_W + k0));
+            }
+          } else {
+            val = *(reinterpret_cast<const float4*>(a.in_s + (size_t)slot * S + j * 32) + c);
+          }
+        }
+        float4 vh, vl;
+        tc::split_tf32(val.x, vh.x, vl.x); tc::split_tf32(val.y, vh.y, vl.y);
+        tc::split_tf32(val.z, vh.z, vl.z); tc::split_tf32(val.w, vh.w, vl.w);
+        const uint32_t off = tc::sw128_off(rr, c * 4);
+        *reinterpret_cast<float4*>(hi + off) = vh;
+        *reinterpret_cast<float4*>(lo + off) = vl;
+      }
+      tc::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&x_full[st])) : "memory");
+      }
+    }
+    // ---- epilogue: TMEM -> registers -> bias / gathered pre-activation -> activation -> coalesced global stores ------------------------
+    tc::mbar_wait(acc_full, 0);
+    tc::tc_fence_after();
+    const int q = warp & 3, eh = (warp - 2) >> 2;
+    if (MODE != EG_GATE || q == 0) {
+      for (int mt = 0; mt < NMT; ++mt) {
+        const int f = mt * 128 + q * 32 + lane;
+        const float bias = MODE == EG_MSG0 ? 0.f : a.bias[f];
+        for (int c = 0; c < 4; ++c) {
+          float acc[32];
+          tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((mt * 2 + eh) * 128 + c * 32), acc);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int e = eh * 128 + c * 32 + i;
+            const int s = r_src[e];
+            if (s < 0) continue;
+            const long long row = slot0 + e;
+            if (MODE == EG_GATE) {
+              a.out[(size_t)row * 32 + f] = sigmoid_f(acc[i] + bias);
+            } else {
+              const float pre = MODE == EG_MSG0 ? a.P[(size_t)s * S + f] : bias;
+              a.out[(size_t)row * S + f] = silu_f(acc[i] + pre);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace fm

@@ -1,0 +1,196 @@
+// Vector-channel stages of the message GVPs for the wide tensor-core pipeline (egemm_tc.cuh): fp32 CUDA-core kernels on
+// 64-edge tiles (same molecule-aligned tiling and segment-sum scheme as k_conv_edge).
+//
+//   k_vec_a : gather x / v of src, x_diff;  [Vh | Vcp] = V [Wh | Wcp], cross products, norms     (GVP 0, stage 1)
+//   k_vec_b : V' = gate * (Vh_ext Wu)  (GVP g, stage 2)  then stage 1 of GVP g+1
+//   k_vec_c : V' of GVP 2, then the segment-sum over in-edges of the vector AND scalar messages -> M / partL / partF
+//
+// Global intermediates per padded edge slot: VH [3][40] hidden vectors (Vh | cross), SH [40] their norms (zero padded),
+// GT [32] gates, S [256] scalar activations (written by k_egemm_tc).
+#pragma once
+#include "kernels.cuh"
+
+namespace fm {
+
+constexpr int VHW = 40;   // row pitch of VH planes and SH
+
+template <class D>
+struct EdgeTile {
+  int mol, n, nb, ecount, le0;
+  size_t erow0;
+  __device__ explicit EdgeTile(const BatchRT& bt) {
+    const int tile = blockIdx.x;
+    mol = bt.etile_mol[tile];
+    n = bt.mol_n[mol]; nb = bt.mol_node[mol]; ecount = n * (n - 1);
+    le0 = (tile - bt.mol_etile[mol]) * TM;
+    erow0 = (size_t)tile * TM;
+  }
+};
+
+// stage 1 of a GVP on the tile in shared memory: Va[.., 0:v_in) -> Vb = [Vh | cross] (cols [0, h+cp)), stores VH and SH
+template <class D, int CPT_HC>
+__device__ __forceinline__ void vec_stage1(Smem<D>& sm, const int v_in, const int h, const float* __restrict__ whcp, const size_t erow0,
+                                           float* __restrict__ VH, float* __restrict__ SH) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int hc = h + D::CP;
+  {
+    float acc[3][RPW][CPT_HC];
+    tile_gemm<3, CPT_HC>(sm.Va, D::LDVA, TM * D::LDVA, pad4(v_in), whcp, sm.wstage, acc);
+    const int ncol = h + 2 * D::CP;
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+#pragma unroll
+      for (int r = 0; r < RPW; ++r)
+#pragma unroll
+        for (int c = 0; c < CPT_HC; ++c) {
+          const int col = ColMap<CPT_HC>::col(lane, c);
+          if (col < ncol) sm.Vb[(p * TM + warp * RPW + r) * D::LDVB + col] = acc[p][r][c];
+        }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < TM * D::CP; idx += NT) {
+    const int row = idx / D::CP, j = idx - row * D::CP;
+    float* bx = sm.Vb + (0 * TM + row) * D::LDVB;
+    float* by = sm.Vb + (1 * TM + row) * D::LDVB;
+    float* bz = sm.Vb + (2 * TM + row) * D::LDVB;
+    const int ca = h + j, cb = h + D::CP + j;
+    const float ax = bx[ca], ay = by[ca], az = bz[ca], qx = bx[cb], qy = by[cb], qz = bz[cb];
+    bx[ca] = __fsub_rn(__fmul_rn(ay, qz), __fmul_rn(az, qy));
+    by[ca] = __fsub_rn(__fmul_rn(az, qx), __fmul_rn(ax, qz));
+    bz[ca] = __fsub_rn(__fmul_rn(ax, qy), __fmul_rn(ay, qx));
+  }
+  __syncthreads();
+  for (int idx = tid; idx < TM * VHW; idx += NT) {
+    const int row = idx / VHW, c = idx - row * VHW;
+    const bool ok = sm.src[row] >= 0 && c < hc;
+    const float a = ok ? sm.Vb[(0 * TM + row) * D::LDVB + c] : 0.f, b = ok ? sm.Vb[(1 * TM + row) * D::LDVB + c] : 0.f,
+                cc = ok ? sm.Vb[(2 * TM + row) * D::LDVB + c] : 0.f;
+    float* vh = VH + (erow0 + row) * 3 * VHW;
+    vh[c] = a; vh[VHW + c] = b; vh[2 * VHW + c] = cc;
+    SH[(erow0 + row) * VHW + c] = ok ? norm_no_nan3(a, b, cc) : 0.f;
+  }
+}
+
+// stage 2 of a GVP: Vb (loaded from VH) x Wu, gated by GT -> Va[.., 0:V)
+template <class D>
+__device__ __forceinline__ void vec_stage2(Smem<D>& sm, const int hc, const float* __restrict__ wu, const size_t erow0,
+                                           const float* __restrict__ VH, const float* __restrict__ GT) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int idx = tid; idx < 3 * TM * VHW; idx += NT) {
+    const int pr = idx / VHW, c = idx - pr * VHW;
+    const int p = pr / TM, row = pr - p * TM;
+    sm.Vb[pr * D::LDVB + c] = sm.src[row] >= 0 ? VH[((erow0 + row) * 3 + p) * VHW + c] : 0.f;
+  }
+  for (int idx = tid; idx < TM * 32; idx += NT) {
+    const int row = idx >> 5;
+    sm.G[idx] = sm.src[row] >= 0 ? GT[(erow0 + row) * 32 + (idx & 31)] : 0.f;
+  }
+  float acc[3][RPW][1];
+  tile_gemm<3, 1>(sm.Vb, D::LDVB, TM * D::LDVB, pad4(hc), wu, sm.wstage, acc);
+#pragma unroll
+  for (int p = 0; p < 3; ++p)
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      const int row = warp * RPW + r;
+      if (lane < D::V) sm.Va[(p * TM + row) * D::LDVA + lane] = __fmul_rn(sm.G[row * 32 + lane], acc[p][r][0]);
+    }
+  __syncthreads();
+}
+
+template <class D>
+__device__ __forceinline__ void tile_rows(Smem<D>& sm, const EdgeTile<D>& et) {
+  if (threadIdx.x < TM) {
+    const int le = et.le0 + threadIdx.x;
+    int s = -1, d = -1;
+    if (le < et.ecount) {
+      int i, j;
+      edge_src_dst(le, et.n, i, j);
+      s = et.nb + i; d = et.nb + j;
+    }
+    sm.src[threadIdx.x] = s; sm.dst[threadIdx.x] = d;
+  }
+  __syncthreads();
+}
+
+template <class D>
+__global__ void __launch_bounds__(NT, 1)
+k_vec_a(const ModelRT m, const BatchRT bt, int layer, const float* __restrict__ x, const float* __restrict__ v,
+        float* __restrict__ VH, float* __restrict__ SH) {
+  extern __shared__ __align__(16) float smem_raw[];
+  Smem<D> sm(smem_raw);
+  const int tid = threadIdx.x;
+  const EdgeTile<D> et(bt);
+  tile_rows<D>(sm, et);
+  if (tid < TM) {
+    const int s = sm.src[tid], d = sm.dst[tid];
+    float ux = 0.f, uy = 0.f, uz = 0.f;
+    if (s >= 0) {
+      float dx, dy, dz;
+      const float dist = pair_dist(x, s, d, dx, dy, dz);
+      ux = __fdiv_rn(dx, dist); uy = __fdiv_rn(dy, dist); uz = __fdiv_rn(dz, dist);
+    }
+    sm.Va[(0 * TM + tid) * D::LDVA] = ux;
+    sm.Va[(1 * TM + tid) * D::LDVA] = uy;
+    sm.Va[(2 * TM + tid) * D::LDVA] = uz;
+  }
+  constexpr int VW = D::LDVA - 1;
+  for (int idx = tid; idx < 3 * TM * VW; idx += NT) {
+    const int pr = idx / VW, c = idx - pr * VW;
+    const int p = pr / TM, row = pr - p * TM;
+    float val = 0.f;
+    const int s = sm.src[row];
+    if (s >= 0 && c < D::V) val = v[((size_t)s * 3 + p) * D::V + c];
+    sm.Va[pr * D::LDVA + 1 + c] = val;
+  }
+  vec_stage1<D, D::CPT_HC0>(sm, D::VIN0, D::H0, m.c(layer, C_MSG0_WHCP), et.erow0, VH, SH);
+}
+
+template <class D>
+__global__ void __launch_bounds__(NT, 1)
+k_vec_b(const ModelRT m, const BatchRT bt, int layer, int g_next /* 1 or 2 */, float* __restrict__ VH, float* __restrict__ SH,
+        const float* __restrict__ GT) {
+  extern __shared__ __align__(16) float smem_raw[];
+  Smem<D> sm(smem_raw);
+  const EdgeTile<D> et(bt);
+  tile_rows<D>(sm, et);
+  const int hc_prev = (g_next == 1 ? D::H0 : D::V) + D::CP;
+  const int wu_id = g_next == 1 ? C_MSG0_WU : C_MSG1_WU;
+  vec_stage2<D>(sm, hc_prev, m.c(layer, wu_id), et.erow0, VH, GT);
+  vec_stage1<D, D::CPT_HC>(sm, D::V, D::V, m.c(layer, g_next == 1 ? C_MSG1_WHCP : C_MSG2_WHCP), et.erow0, VH, SH);
+}
+
+template <class D>
+__global__ void __launch_bounds__(NT, 1)
+k_vec_c(const ModelRT m, const BatchRT bt, int layer, const float* __restrict__ VH, const float* __restrict__ GT,
+        const float* __restrict__ Smsg, float* __restrict__ M, float* __restrict__ partF, float* __restrict__ partL) {
+  extern __shared__ __align__(16) float smem_raw[];
+  Smem<D> sm(smem_raw);
+  const int tid = threadIdx.x;
+  const EdgeTile<D> et(bt);
+  tile_rows<D>(sm, et);
+  vec_stage2<D>(sm, D::V + D::CP, m.c(layer, C_MSG2_WU), et.erow0, VH, GT);
+  const int tile = blockIdx.x;
+  for (int col = tid; col < D::MW; col += NT) {
+    float acc = 0.f;
+    int seg_first = et.le0;
+    for (int row = 0; row < TM; ++row) {
+      const int d = sm.dst[row];
+      if (d < 0) break;
+      float val;
+      if (col < D::S) val = Smsg[(et.erow0 + row) * D::S + col];
+      else { const int p = (col - D::S) / D::V, c = (col - D::S) - p * D::V; val = sm.Va[(p * TM + row) * D::LDVA + c]; }
+      acc = __fadd_rn(acc, val);
+      if (row == TM - 1 || sm.dst[row + 1] != d) {
+        const int j = d - et.nb, le_last = et.le0 + row;
+        const bool head = seg_first == j * (et.n - 1), tail = le_last == j * (et.n - 1) + (et.n - 2);
+        if (head && tail) M[(size_t)d * D::MW + col] = acc;
+        else if (head) partL[(size_t)tile * D::MW + col] = acc;
+        else partF[(size_t)tile * D::MW + col] = acc;
+        acc = 0.f;
+        seg_first = le_last + 1;
+      }
+    }
+  }
+}
+
+}  // namespace fm

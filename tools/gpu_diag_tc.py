@@ -14,6 +14,9 @@ def err(a, b):
     return float(np.abs(a - b).max()), float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
 
 
+IMPLS = tuple(int(a) for a in sys.argv[1:]) or (0, 2)
+
+
 def main():
     for name in ("fwd_flowmol3_taps", "fwd_flowmol3_geom"):
         gd = load_golden(name)
@@ -24,7 +27,7 @@ def main():
         perm = torch.from_numpy(G.ref_edge_to_internal(n_atoms))
         prev = {k: t(gd[f"c0.out.{k}"]) for k in "xace"}
         args = (n_atoms, t(gd["c1.x_t"]), t(gd["c1.a"]), t(gd["c1.c"]), t(gd["c1.e"]), float(gd["c1.t"]), prev)
-        for impl in (0, 1):
+        for impl in IMPLS:
             try:
                 vf.set_option("conv_impl", impl)
                 if "c1.tap.conv0.s" in gd:
@@ -46,7 +49,7 @@ def main():
         cfg = ModelConfig.named("flowmol3", 11)
         vf = CTMCVectorFieldB200(cfg, WT.init_state_dict(cfg, int(gd["weight_seed"])))
         n_atoms = gd["n_atoms"]; N, U = int(n_atoms.sum()), int((n_atoms * (n_atoms - 1) // 2).sum())
-        for impl in (0, 1):
+        for impl in IMPLS:
             try:
                 vf.set_option("conv_impl", impl)
                 out = vf.integrate_tokens(n_atoms, t(gd["x_0"]), torch.full((N,), 11), torch.full((N,), 6), torch.full((U,), 4), int(gd["T"]), seed=int(gd["noise_seed"]))
@@ -62,13 +65,13 @@ def main():
     vf = CTMCVectorFieldB200(cfg, WT.init_state_dict(cfg, 0))
     n_atoms = draw_sizes("geom", 512)
     x0, a0, c0, e0 = make_prior(n_atoms, 11, 100)
-    for impl in (0, 1):
+    for impl in IMPLS:
         try:
             vf.set_option("conv_impl", impl)
             d = vf.forward_tokens(n_atoms, x0, a0, c0, e0, 0.0, None); torch.cuda.synchronize()
             t0 = time.time(); d2 = vf.forward_tokens(n_atoms, x0, a0, c0, e0, 0.3, d); torch.cuda.synchronize(); dt = time.time() - t0
             print("GEOM-512 impl", impl, "forward ms", round(dt * 1e3, 2), "conv_edge ms", round(vf.time_conv_edge(1, 3), 3), "finite", bool(torch.isfinite(d2["x"]).all()))
-            if impl == 0: ref = d2
+            if impl == IMPLS[0]: ref = d2
             else: print("   tc vs fp32 forward:", {k: err(d2[k].cpu().numpy(), ref[k].cpu().numpy()) for k in "xace"})
         except Exception:
             traceback.print_exc()

@@ -169,11 +169,11 @@ int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
     float* cur = ef;      // input activations of the current scalar linear
     float* outs[3] = {SA, SB, SA};
     for (int g = 0; g < 3; ++g) {
-      fm::EgArgs a{wptr(tcw[g]), wptr(gb[g] + fm::GV_B), cur, SH, P, x, outs[g], L.EP};
+      fm::EgArgs a{wptr(tcw[g]), wptr(gb[g] + fm::GV_B), cur, SH, P, x, outs[g], L.EP, h->tc_debug};
       if (g == 0) fm::k_egemm_tc<D, fm::EG_MSG0><<<gt, fm::EG_THREADS, fm::EG_SMEM_BYTES, st>>>(m, bt, a);
       else fm::k_egemm_tc<D, fm::EG_MSG><<<gt, fm::EG_THREADS, fm::EG_SMEM_BYTES, st>>>(m, bt, a);
       LAUNCH_OK(h);
-      fm::EgArgs ag{wptr(tcg[g]), wptr(gb[g] + fm::GV_BG), outs[g], nullptr, nullptr, nullptr, GT, L.EP};
+      fm::EgArgs ag{wptr(tcg[g]), wptr(gb[g] + fm::GV_BG), outs[g], nullptr, nullptr, nullptr, GT, L.EP, h->tc_debug};
       fm::k_egemm_tc<D, fm::EG_GATE><<<gt, fm::EG_THREADS, fm::EG_SMEM_BYTES, st>>>(m, bt, ag);
       LAUNCH_OK(h);
       if (g < 2) { fm::k_vec_b<D><<<L.nET, fm::NT, smem, st>>>(m, bt, l, g + 1, VH, SH, GT); LAUNCH_OK(h); }

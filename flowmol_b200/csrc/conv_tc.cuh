@@ -240,7 +240,7 @@ k_conv_edge_tc(const ModelRT m, const BatchRT bt, int layer, const float* __rest
     // -- vector stage 1 (CUDA cores): [Vh | Vcp] = V x [Wh | Wcp], cross products, norms -> k-slabs of the scalar operand
     if (!(dbg & 4)) {
       float acc[3][TC_RPW][D::CPT_HC0];
-      tile_gemm<3, D::CPT_HC0, TC_RPW>(Va, PL::LDVA, TCT * PL::LDVA, pad4(v_in), w.whcp, wstage, acc);
+      tile_gemm<3, D::CPT_HC0, TC_RPW, 2 * KC * 64>(Va, PL::LDVA, TCT * PL::LDVA, pad4(v_in), w.whcp, wstage, acc);
       const int ncol = h + 2 * D::CP;
 #pragma unroll
       for (int p = 0; p < 3; ++p)
@@ -324,7 +324,7 @@ k_conv_edge_tc(const ModelRT m, const BatchRT bt, int layer, const float* __rest
     // -- vector stage 2 (CUDA cores): V' = gate * (Vh_ext x Wu) --------------------------------------------------------------------------
     if (!(dbg & 4)) {
       float acc[3][TC_RPW][1];
-      tile_gemm<3, 1, TC_RPW>(Vb, PL::LDVB, TCT * PL::LDVB, pad4(hc), w.wu, wstage, acc);    // entry barrier publishes G
+      tile_gemm<3, 1, TC_RPW, 2 * KC * 64>(Vb, PL::LDVB, TCT * PL::LDVB, pad4(hc), w.wu, wstage, acc);    // entry barrier publishes G
 #pragma unroll
       for (int p = 0; p < 3; ++p)
 #pragma unroll

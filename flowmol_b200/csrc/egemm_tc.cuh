@@ -42,6 +42,7 @@ struct EgArgs {
   const float* x;            // MSG0: positions [N][3]
   float* out;                // MSG0 / MSG: [EPA][S];  GATE: [EPA][32]
   long long EP;              // padded edge slots (multiple of 64)
+  int dbg;                   // timing experiments: 1 no weight copies, 2 no MMA issue, 4 loaders skip global reads, 8 no epilogue math/stores
 };
 
 template <class D, int MODE>
@@ -109,6 +110,7 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
       for (uint32_t u = 0; u < NU; ++u) {
         const uint32_t sl = u % EG_RING, use = u / EG_RING;
         if (use > 0) tc::mbar_wait(&w_empty[sl], (use - 1) & 1);
+        if (a.dbg & 1) { tc::mbar_arrive_expect_tx(&w_full[sl], 0u); continue; }
         tc::mbar_arrive_expect_tx(&w_full[sl], UNIT_BYTES);
         tc::bulk_g2s(ring + sl * TC_UNIT, reinterpret_cast<const uint8_t*>(a.units) + (size_t)u * UNIT_BYTES, UNIT_BYTES, &w_full[sl]);
       }
@@ -131,7 +133,7 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
             const uint32_t wb = tc::smem_u32(ring + sl * TC_UNIT);
             for (int h = 0; h < 2; ++h) {
               const uint32_t d = tmem + (uint32_t)((mt * 2 + h) * 128);
-              for (int ks = 0; ks < ksteps; ++ks) {
+              for (int ks = 0; ks < ksteps && !(a.dbg & 2); ++ks) {
                 const uint64_t dw = tc::desc_sw128(wb + 32 * ks);
                 tc::umma_tf32(d, dw, tc::desc_sw128(xb + 32768 + h * 16384 + 32 * ks), idesc, (j > 0 || ks > 0) ? 1u : 0u);
                 tc::umma_tf32(d, dw, tc::desc_sw128(xb + h * 16384 + 32 * ks), idesc, 1u);
@@ -147,7 +149,7 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
             const uint32_t wb = tc::smem_u32(ring + sl * TC_UNIT);
             for (int h = 0; h < 2; ++h) {
               const uint32_t d = tmem + (uint32_t)((mt * 2 + h) * 128);
-              for (int ks = 0; ks < ksteps; ++ks)
+              for (int ks = 0; ks < ksteps && !(a.dbg & 2); ++ks)
                 tc::umma_tf32(d, tc::desc_sw128(wb + 32 * ks), tc::desc_sw128(xb + h * 16384 + 32 * ks), idesc, 1u);
             }
             tc::umma_commit(&w_empty[sl]);
@@ -162,14 +164,12 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
     // ---- activation loaders: one edge row per thread, fp32 -> (hi, lo) SW128 images ------------------------------------------------
     const int r = tid - 64, h = r >> 7, rr = r & 127;
     const long long slot = slot0 + r;
-    const bool valid = r_src[r] >= 0;
+    const bool valid = r_src[r] >= 0 && !(a.dbg & 4);
     const float sigma = m.rbf_dmax / (float)D::R;
     const float* mu = m.g(G_RBF_MU);
-    for (int j = 0; j < NSLAB; ++j) {
-      const int st = j & 1;
-      if (j >= 2) tc::mbar_wait(&x_empty[st], ((j >> 1) - 1) & 1);
-      uint8_t* hi = xst + st * EG_XSTAGE + h * 16384;
-      uint8_t* lo = hi + 32768;
+    // fetch of one k-slab of this thread's row into registers (issued one slab ahead of its conversion: the HBM / L2 round
+    // trip overlaps the wait for the stage and the MMAs of the previous slab)
+    auto fetch = [&](int j, float4 (&buf)[8]) {
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -195,6 +195,20 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
             val = *(reinterpret_cast<const float4*>(a.in_s + (size_t)slot * S + j * 32) + c);
           }
         }
+        buf[c] = val;
+      }
+    };
+    float4 cur[8], nxt[8];
+    fetch(0, cur);
+    for (int j = 0; j < NSLAB; ++j) {
+      const int st = j & 1;
+      if (j + 1 < NSLAB) fetch(j + 1, nxt);
+      if (j >= 2) tc::mbar_wait(&x_empty[st], ((j >> 1) - 1) & 1);
+      uint8_t* hi = xst + st * EG_XSTAGE + h * 16384;
+      uint8_t* lo = hi + 32768;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float4 val = cur[c];
         float4 vh, vl;
         tc::split_tf32(val.x, vh.x, vl.x); tc::split_tf32(val.y, vh.y, vl.y);
         tc::split_tf32(val.z, vh.z, vl.z); tc::split_tf32(val.w, vh.w, vl.w);
@@ -207,12 +221,14 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
       if (lane == 0) {
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&x_full[st])) : "memory");
       }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) cur[c] = nxt[c];
     }
     // ---- epilogue: TMEM -> registers -> bias / gathered pre-activation -> activation -> coalesced global stores ------------------------
     tc::mbar_wait(acc_full, 0);
     tc::tc_fence_after();
     const int q = warp & 3, eh = (warp - 2) >> 2;
-    if (MODE != EG_GATE || q == 0) {
+    if ((MODE != EG_GATE || q == 0) && !(a.dbg & 8)) {
       for (int mt = 0; mt < NMT; ++mt) {
         const int f = mt * 128 + q * 32 + lane;
         const float bias = MODE == EG_MSG0 ? 0.f : a.bias[f];
@@ -227,10 +243,11 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
             if (s < 0) continue;
             const long long row = slot0 + e;
             if (MODE == EG_GATE) {
-              a.out[(size_t)row * 32 + f] = sigmoid_f(acc[i] + bias);
+              a.out[(size_t)row * 32 + f] = __frcp_rn(1.0f + __expf(-(acc[i] + bias)));
             } else {
               const float pre = MODE == EG_MSG0 ? a.P[(size_t)s * S + f] : bias;
-              a.out[(size_t)row * S + f] = silu_f(acc[i] + pre);
+              const float z = acc[i] + pre;
+              a.out[(size_t)row * S + f] = z * __frcp_rn(1.0f + __expf(-z));
             }
           }
         }

@@ -41,7 +41,7 @@ __device__ __forceinline__ void load_w(const float* __restrict__ wrow, int lane,
   }
 }
 
-template <int PLANES, int CPT, int RPW = 8>
+template <int PLANES, int CPT, int RPW = 8, int WCAP = WSTAGE_FLOATS>
 __device__ __forceinline__ void tile_gemm(const float* __restrict__ A, int lda, int plane_stride, int K,
                                           const float* __restrict__ Wg, float* __restrict__ wstage,
                                           float (&acc)[PLANES][RPW][CPT]) {
@@ -54,6 +54,37 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ A, int lda, 
 #pragma unroll
       for (int c = 0; c < CPT; ++c) acc[p][r][c] = 0.0f;
 
+  if (K <= 64 && K * NP <= WCAP) {
+    // small operand (the vector-channel GEMMs): stage the whole matrix once -- a chunked pipeline would expose one L2
+    // round trip per 16 rows because there is almost no math to hide it behind
+    __syncthreads();
+    for (int i = tid; i < K * NP / 4; i += NT) cp_async16(wstage + i * 4, Wg + i * 4);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    for (int kk = 0; kk < K; kk += 4) {
+#pragma unroll
+      for (int p = 0; p < PLANES; ++p) {
+        float4 a[RPW];
+        const float* ap = A + p * plane_stride + (warp * RPW) * lda + kk;
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) a[r] = *reinterpret_cast<const float4*>(ap + r * lda);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float w[CPT];
+          load_w<CPT>(wstage + (kk + j) * NP, lane, w);
+#pragma unroll
+          for (int r = 0; r < RPW; ++r) {
+            const float av = j == 0 ? a[r].x : (j == 1 ? a[r].y : (j == 2 ? a[r].z : a[r].w));
+#pragma unroll
+            for (int cc = 0; cc < CPT; ++cc) acc[p][r][cc] = fmaf(av, w[cc], acc[p][r][cc]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    return;
+  }
   const int nchunks = (K + KC - 1) / KC;
   auto issue = [&](int c) {
     const int k0 = c * KC;

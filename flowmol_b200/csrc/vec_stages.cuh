@@ -170,6 +170,14 @@ k_vec_c(const ModelRT m, const BatchRT bt, int layer, const float* __restrict__ 
   tile_rows<D>(sm, et);
   vec_stage2<D>(sm, D::V + D::CP, m.c(layer, C_MSG2_WU), et.erow0, VH, GT);
   const int tile = blockIdx.x;
+  // scalar messages of the tile: one coalesced pass HBM -> shared memory, then the per-column walk reads shared memory
+  for (int idx = tid; idx < TM * (D::S / 4); idx += NT) {
+    const int row = idx / (D::S / 4), c4 = idx - row * (D::S / 4);
+    float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sm.src[row] >= 0) val = __ldg(reinterpret_cast<const float4*>(Smsg + (et.erow0 + row) * D::S) + c4);
+    *reinterpret_cast<float4*>(sm.Xs + row * D::XLD + c4 * 4) = val;
+  }
+  __syncthreads();
   for (int col = tid; col < D::MW; col += NT) {
     float acc = 0.f;
     int seg_first = et.le0;
@@ -177,7 +185,7 @@ k_vec_c(const ModelRT m, const BatchRT bt, int layer, const float* __restrict__ 
       const int d = sm.dst[row];
       if (d < 0) break;
       float val;
-      if (col < D::S) val = Smsg[(et.erow0 + row) * D::S + col];
+      if (col < D::S) val = sm.Xs[row * D::XLD + col];
       else { const int p = (col - D::S) / D::V, c = (col - D::S) - p * D::V; val = sm.Va[(p * TM + row) * D::LDVA + c]; }
       acc = __fadd_rn(acc, val);
       if (row == TM - 1 || sm.dst[row + 1] != d) {

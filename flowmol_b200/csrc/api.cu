@@ -137,8 +137,8 @@ int set_smem_attrs() {
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_MSG0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EG_SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_MSG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EG_SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EG_SMEM_BYTES));
-    CUDA_OK(cudaFuncSetAttribute(fm::k_vec_a<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CUDA_OK(cudaFuncSetAttribute(fm::k_vec_b<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_vec_a<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::VecSmem<D>::BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_vec_b<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::VecSmem<D>::BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_vec_c<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   }
   return 0;
@@ -162,7 +162,8 @@ int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
     float *SA = at<float>(ws, L.SA), *SB = at<float>(ws, L.SB), *VH = at<float>(ws, L.VH), *SH = at<float>(ws, L.SH), *GT = at<float>(ws, L.GT);
     const size_t smem = D::SMEM_BYTES;
     const int gt = (int)(L.EPA / fm::EG_T);
-    fm::k_vec_a<D><<<L.nET, fm::NT, smem, st>>>(m, bt, l, x, v, VH, SH);
+    const size_t vsm = fm::VecSmem<D>::BYTES;
+    fm::k_vec_a<D><<<L.nET, fm::NT, vsm, st>>>(m, bt, l, x, v, VH, SH);
     LAUNCH_OK(h);
     const int tcw[3] = {fm::C_MSG0_TCW, fm::C_MSG1_TCW, fm::C_MSG2_TCW}, tcg[3] = {fm::C_MSG0_TCG, fm::C_MSG1_TCG, fm::C_MSG2_TCG};
     const int gb[3] = {fm::C_MSG0_WHCP, fm::C_MSG1_WHCP, fm::C_MSG2_WHCP};
@@ -176,7 +177,7 @@ int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
       fm::EgArgs ag{wptr(tcg[g]), wptr(gb[g] + fm::GV_BG), outs[g], nullptr, nullptr, nullptr, GT, L.EP, h->tc_debug};
       fm::k_egemm_tc<D, fm::EG_GATE><<<gt, fm::EG_THREADS, fm::EG_SMEM_BYTES, st>>>(m, bt, ag);
       LAUNCH_OK(h);
-      if (g < 2) { fm::k_vec_b<D><<<L.nET, fm::NT, smem, st>>>(m, bt, l, g + 1, VH, SH, GT); LAUNCH_OK(h); }
+      if (g < 2) { fm::k_vec_b<D><<<L.nET, fm::NT, vsm, st>>>(m, bt, l, g + 1, VH, SH, GT); LAUNCH_OK(h); }
       cur = outs[g];
     }
     fm::k_vec_c<D><<<L.nET, fm::NT, smem, st>>>(m, bt, l, VH, GT, SA, M, partF, partL);

@@ -239,8 +239,7 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int e = eh * 128 + c * 32 + i;
-            const int s = r_src[e];
-            if (s < 0) continue;
+            const int s = max(r_src[e], 0);          // padding rows are computed and stored too (their slots exist)
             const long long row = slot0 + e;
             if (MODE == EG_GATE) {
               a.out[(size_t)row * 32 + f] = __frcp_rn(1.0f + __expf(-(acc[i] + bias)));

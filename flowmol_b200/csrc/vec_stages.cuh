@@ -14,6 +14,27 @@ namespace fm {
 
 constexpr int VHW = 40;   // row pitch of VH planes and SH
 
+// compact shared-memory plan for the stages that never touch the scalar tile: 2 CTAs per SM (latency hiding)
+template <class D>
+struct VecSmem {
+  static constexpr int FLOATS = D::SM_VA + D::SM_VB + D::SM_G + WSTAGE_FLOATS / 2 + D::SM_MISC;
+  static constexpr size_t BYTES = (size_t)FLOATS * 4;
+  __device__ static Smem<D> carve(float* base) {
+    Smem<D> sm(base);
+    sm.Xs = nullptr;
+    sm.Va = base;
+    sm.Vb = sm.Va + D::SM_VA;
+    sm.G = sm.Vb + D::SM_VB;
+    sm.wstage = sm.G + D::SM_G;
+    float* misc = sm.wstage + WSTAGE_FLOATS / 2;
+    sm.src = reinterpret_cast<int*>(misc);
+    sm.dst = sm.src + TM;
+    sm.dist = misc + 2 * TM;
+    sm.aux = reinterpret_cast<int*>(misc + 3 * TM);
+    return sm;
+  }
+};
+
 template <class D>
 struct EdgeTile {
   int mol, n, nb, ecount, le0;
@@ -35,7 +56,7 @@ __device__ __forceinline__ void vec_stage1(Smem<D>& sm, const int v_in, const in
   const int hc = h + D::CP;
   {
     float acc[3][RPW][CPT_HC];
-    tile_gemm<3, CPT_HC>(sm.Va, D::LDVA, TM * D::LDVA, pad4(v_in), whcp, sm.wstage, acc);
+    tile_gemm<3, CPT_HC, 8, WSTAGE_FLOATS / 2>(sm.Va, D::LDVA, TM * D::LDVA, pad4(v_in), whcp, sm.wstage, acc);
     const int ncol = h + 2 * D::CP;
 #pragma unroll
     for (int p = 0; p < 3; ++p)
@@ -60,14 +81,24 @@ __device__ __forceinline__ void vec_stage1(Smem<D>& sm, const int v_in, const in
     bz[ca] = __fsub_rn(__fmul_rn(ax, qy), __fmul_rn(ay, qx));
   }
   __syncthreads();
-  for (int idx = tid; idx < TM * VHW; idx += NT) {
-    const int row = idx / VHW, c = idx - row * VHW;
-    const bool ok = sm.src[row] >= 0 && c < hc;
-    const float a = ok ? sm.Vb[(0 * TM + row) * D::LDVB + c] : 0.f, b = ok ? sm.Vb[(1 * TM + row) * D::LDVB + c] : 0.f,
-                cc = ok ? sm.Vb[(2 * TM + row) * D::LDVB + c] : 0.f;
-    float* vh = VH + (erow0 + row) * 3 * VHW;
-    vh[c] = a; vh[VHW + c] = b; vh[2 * VHW + c] = cc;
-    SH[(erow0 + row) * VHW + c] = ok ? norm_no_nan3(a, b, cc) : 0.f;
+  for (int idx = tid; idx < TM * (VHW / 4); idx += NT) {
+    const int row = idx / (VHW / 4), c4 = idx - row * (VHW / 4);
+    const bool okr = sm.src[row] >= 0;
+    float va[4], vb_[4], vc[4], nn[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = c4 * 4 + k;
+      const bool ok = okr && c < hc;
+      va[k] = ok ? sm.Vb[(0 * TM + row) * D::LDVB + c] : 0.f;
+      vb_[k] = ok ? sm.Vb[(1 * TM + row) * D::LDVB + c] : 0.f;
+      vc[k] = ok ? sm.Vb[(2 * TM + row) * D::LDVB + c] : 0.f;
+      nn[k] = ok ? norm_no_nan3(va[k], vb_[k], vc[k]) : 0.f;
+    }
+    float4* vh = reinterpret_cast<float4*>(VH + (erow0 + row) * 3 * VHW);
+    vh[c4] = make_float4(va[0], va[1], va[2], va[3]);
+    vh[VHW / 4 + c4] = make_float4(vb_[0], vb_[1], vb_[2], vb_[3]);
+    vh[2 * (VHW / 4) + c4] = make_float4(vc[0], vc[1], vc[2], vc[3]);
+    reinterpret_cast<float4*>(SH + (erow0 + row) * VHW)[c4] = make_float4(nn[0], nn[1], nn[2], nn[3]);
   }
 }
 
@@ -76,17 +107,34 @@ template <class D>
 __device__ __forceinline__ void vec_stage2(Smem<D>& sm, const int hc, const float* __restrict__ wu, const size_t erow0,
                                            const float* __restrict__ VH, const float* __restrict__ GT) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int idx = tid; idx < 3 * TM * VHW; idx += NT) {
-    const int pr = idx / VHW, c = idx - pr * VHW;
-    const int p = pr / TM, row = pr - p * TM;
-    sm.Vb[pr * D::LDVB + c] = sm.src[row] >= 0 ? VH[((erow0 + row) * 3 + p) * VHW + c] : 0.f;
-  }
-  for (int idx = tid; idx < TM * 32; idx += NT) {
-    const int row = idx >> 5;
-    sm.G[idx] = sm.src[row] >= 0 ? GT[(erow0 + row) * 32 + (idx & 31)] : 0.f;
+  {
+    // the tile's VH block (64 x 120 floats) and GT block (64 x 32) are contiguous in memory: straight float4 streams, all
+    // loads of a thread in flight together (padding slots hold finite garbage or zeros and are masked at the segment-sum)
+    constexpr int NV = TM * 3 * VHW / 4, NG = TM * 32 / 4;
+    const float4* vsrc = reinterpret_cast<const float4*>(VH + erow0 * 3 * VHW);
+    const float4* gsrc = reinterpret_cast<const float4*>(GT + erow0 * 32);
+    float4 vb[(NV + NT - 1) / NT], gb[(NG + NT - 1) / NT];
+#pragma unroll
+    for (int i = 0; i < (NV + NT - 1) / NT; ++i) { const int idx = tid + i * NT; if (idx < NV) vb[i] = vsrc[idx]; }
+#pragma unroll
+    for (int i = 0; i < (NG + NT - 1) / NT; ++i) { const int idx = tid + i * NT; if (idx < NG) gb[i] = gsrc[idx]; }
+#pragma unroll
+    for (int i = 0; i < (NV + NT - 1) / NT; ++i) {
+      const int idx = tid + i * NT;
+      if (idx < NV) {
+        const int row = idx / (3 * VHW / 4), rem = idx - row * (3 * VHW / 4), p = rem / (VHW / 4), c4 = rem - p * (VHW / 4);
+        const bool ok = sm.src[row] >= 0;
+        *reinterpret_cast<float4*>(sm.Vb + (p * TM + row) * D::LDVB + c4 * 4) = ok ? vb[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < (NG + NT - 1) / NT; ++i) {
+      const int idx = tid + i * NT;
+      if (idx < NG) *reinterpret_cast<float4*>(sm.G + idx * 4) = sm.src[idx >> 3] >= 0 ? gb[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
   float acc[3][RPW][1];
-  tile_gemm<3, 1>(sm.Vb, D::LDVB, TM * D::LDVB, pad4(hc), wu, sm.wstage, acc);
+  tile_gemm<3, 1, 8, WSTAGE_FLOATS / 2>(sm.Vb, D::LDVB, TM * D::LDVB, pad4(hc), wu, sm.wstage, acc);
 #pragma unroll
   for (int p = 0; p < 3; ++p)
 #pragma unroll
@@ -113,11 +161,11 @@ __device__ __forceinline__ void tile_rows(Smem<D>& sm, const EdgeTile<D>& et) {
 }
 
 template <class D>
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(NT, 2)
 k_vec_a(const ModelRT m, const BatchRT bt, int layer, const float* __restrict__ x, const float* __restrict__ v,
         float* __restrict__ VH, float* __restrict__ SH) {
   extern __shared__ __align__(16) float smem_raw[];
-  Smem<D> sm(smem_raw);
+  Smem<D> sm = VecSmem<D>::carve(smem_raw);
   const int tid = threadIdx.x;
   const EdgeTile<D> et(bt);
   tile_rows<D>(sm, et);
@@ -146,11 +194,11 @@ k_vec_a(const ModelRT m, const BatchRT bt, int layer, const float* __restrict__ 
 }
 
 template <class D>
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(NT, 2)
 k_vec_b(const ModelRT m, const BatchRT bt, int layer, int g_next /* 1 or 2 */, float* __restrict__ VH, float* __restrict__ SH,
         const float* __restrict__ GT) {
   extern __shared__ __align__(16) float smem_raw[];
-  Smem<D> sm(smem_raw);
+  Smem<D> sm = VecSmem<D>::carve(smem_raw);
   const EdgeTile<D> et(bt);
   tile_rows<D>(sm, et);
   const int hc_prev = (g_next == 1 ? D::H0 : D::V) + D::CP;

@@ -1,7 +1,12 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python tools/gpu_wide_probe.py 0 1 2 4 8 6 14 2>&1 | tail -9 | tee gpurun_out/wide_probe.txt
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_egemm|k_vec" -c 60 --csv --log-file gpurun_out/wide_launches.csv python tools/gpu_wide_probe.py 0 2 4 8 > gpurun_out/wide_ncu1.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_egemm_tc -s 13 -c 2 -f -o gpurun_out/wide_egemm python tools/gpu_wide_probe.py 0 > gpurun_out/wide_ncu2.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_vec_b -s 2 -c 1 -f -o gpurun_out/wide_vecb python tools/gpu_wide_probe.py 0 > gpurun_out/wide_ncu3.log 2>&1
-tail -2 gpurun_out/wide_ncu2.log gpurun_out/wide_ncu3.log
+timeout 600 python tools/gpu_quick_time.py 0 2 2>&1 | tail -3 | tee gpurun_out/wide_probe2.txt
+timeout 600 python tools/gpu_diag_tc.py 2 2>&1 | grep -E "conv5|mid|mismatch|Traceback|Error" | tail -12 | tee -a gpurun_out/wide_probe2.txt
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_egemm|k_vec|k_conv_edge|k_edge_update|k_node_update" -c 40 --csv --log-file gpurun_out/wide_launches2.csv python tools/gpu_wide_probe.py 0 > gpurun_out/wide_ncu1.log 2>&1
+python - <<'PY'
+import csv,re
+lines=[l for l in open('gpurun_out/wide_launches2.csv') if not l.startswith('==')]
+for i,row in enumerate(csv.DictReader(lines)):
+    k=row['Kernel Name']; m=re.search(r'\(int\)(\d)>', k)
+    print(i, k.split('<')[0].replace('void ',''), m.group(1) if m and 'egemm' in k else '', row['Metric Value'])
+PY

@@ -96,6 +96,7 @@ struct FmHandle {
   std::vector<long long> off_h;   // host copy of the weight offset table
   std::unordered_map<void*, Layout> batches;
   int64_t launches = 0;
+  int eg_nh = 2;               // 128-edge halves per CTA of k_egemm_tc (2: 1 CTA/SM, 1: 2 CTAs/SM)
   int tc_debug = 0;            // timing experiments (conv_tc.cuh TcCtx::dbg)
   bool has_tc = false;         // packed weights contain the UMMA operand images
   int conv_impl = 0;           // 0: fp32 CUDA-core k_conv_edge, 1: tcgen05 3xTF32 k_conv_edge_tc (flowmol3 dims only)
@@ -134,12 +135,15 @@ int set_smem_attrs() {
   CUDA_OK(cudaFuncSetAttribute(fm::k_edge_head<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   if constexpr (D::S == 256 && D::V == 32 && D::SD == 0) {
     CUDA_OK(cudaFuncSetAttribute(fm::k_conv_edge_tc<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::TcPlan<D>::SMEM_BYTES));
-    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_MSG0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EG_SMEM_BYTES));
-    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_MSG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EG_SMEM_BYTES));
-    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EG_SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_MSG0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<2>::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_MSG, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<2>::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_GATE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<2>::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_MSG0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<1>::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_MSG, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<1>::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_GATE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<1>::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_vec_a<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::VecSmem<D>::BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_vec_b<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::VecSmem<D>::BYTES));
-    CUDA_OK(cudaFuncSetAttribute(fm::k_vec_c<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_vec_c<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::VecSmem<D>::BYTES));
   }
   return 0;
 }
@@ -161,7 +165,8 @@ int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
     float *partF = at<float>(ws, L.partF), *partL = at<float>(ws, L.partL), *ef = at<float>(ws, L.ef);
     float *SA = at<float>(ws, L.SA), *SB = at<float>(ws, L.SB), *VH = at<float>(ws, L.VH), *SH = at<float>(ws, L.SH), *GT = at<float>(ws, L.GT);
     const size_t smem = D::SMEM_BYTES;
-    const int gt = (int)(L.EPA / fm::EG_T);
+    const int NHsel = h->eg_nh;
+    const int gt = (int)(L.EPA / (128 * NHsel));
     const size_t vsm = fm::VecSmem<D>::BYTES;
     fm::k_vec_a<D><<<L.nET, fm::NT, vsm, st>>>(m, bt, l, x, v, VH, SH);
     LAUNCH_OK(h);
@@ -171,16 +176,22 @@ int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
     float* outs[3] = {SA, SB, SA};
     for (int g = 0; g < 3; ++g) {
       fm::EgArgs a{wptr(tcw[g]), wptr(gb[g] + fm::GV_B), cur, SH, P, x, outs[g], L.EP, h->tc_debug};
-      if (g == 0) fm::k_egemm_tc<D, fm::EG_MSG0><<<gt, fm::EG_THREADS, fm::EG_SMEM_BYTES, st>>>(m, bt, a);
-      else fm::k_egemm_tc<D, fm::EG_MSG><<<gt, fm::EG_THREADS, fm::EG_SMEM_BYTES, st>>>(m, bt, a);
+      if (NHsel == 2) {
+        if (g == 0) fm::k_egemm_tc<D, fm::EG_MSG0, 2><<<gt, fm::EgPlan<2>::THREADS, fm::EgPlan<2>::SMEM_BYTES, st>>>(m, bt, a);
+        else fm::k_egemm_tc<D, fm::EG_MSG, 2><<<gt, fm::EgPlan<2>::THREADS, fm::EgPlan<2>::SMEM_BYTES, st>>>(m, bt, a);
+      } else {
+        if (g == 0) fm::k_egemm_tc<D, fm::EG_MSG0, 1><<<gt, fm::EgPlan<1>::THREADS, fm::EgPlan<1>::SMEM_BYTES, st>>>(m, bt, a);
+        else fm::k_egemm_tc<D, fm::EG_MSG, 1><<<gt, fm::EgPlan<1>::THREADS, fm::EgPlan<1>::SMEM_BYTES, st>>>(m, bt, a);
+      }
       LAUNCH_OK(h);
       fm::EgArgs ag{wptr(tcg[g]), wptr(gb[g] + fm::GV_BG), outs[g], nullptr, nullptr, nullptr, GT, L.EP, h->tc_debug};
-      fm::k_egemm_tc<D, fm::EG_GATE><<<gt, fm::EG_THREADS, fm::EG_SMEM_BYTES, st>>>(m, bt, ag);
+      if (NHsel == 2) fm::k_egemm_tc<D, fm::EG_GATE, 2><<<gt, fm::EgPlan<2>::THREADS, fm::EgPlan<2>::SMEM_BYTES, st>>>(m, bt, ag);
+      else fm::k_egemm_tc<D, fm::EG_GATE, 1><<<gt, fm::EgPlan<1>::THREADS, fm::EgPlan<1>::SMEM_BYTES, st>>>(m, bt, ag);
       LAUNCH_OK(h);
       if (g < 2) { fm::k_vec_b<D><<<L.nET, fm::NT, vsm, st>>>(m, bt, l, g + 1, VH, SH, GT); LAUNCH_OK(h); }
       cur = outs[g];
     }
-    fm::k_vec_c<D><<<L.nET, fm::NT, smem, st>>>(m, bt, l, VH, GT, SA, M, partF, partL);
+    fm::k_vec_c<D><<<L.nET, fm::NT, vsm, st>>>(m, bt, l, VH, GT, SA, M, partF, partL);
     LAUNCH_OK(h);
   }
   return 0;
@@ -532,6 +543,7 @@ int fm_set_option(FmHandle* h, const char* name, int32_t value) {
     return 0;
   }
   if (n == "tc_debug") { h->tc_debug = value; return 0; }
+  if (n == "eg_nh") { if (value != 1 && value != 2) return fail("fm_set_option: eg_nh must be 1 or 2"); h->eg_nh = value; return 0; }
   return fail("fm_set_option: unknown option");
 }
 int fm_get_option(FmHandle* h, const char* name, int32_t* value) {

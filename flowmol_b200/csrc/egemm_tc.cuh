@@ -20,16 +20,22 @@
 
 namespace fm {
 
-constexpr int EG_T = 256;                       // edges per CTA
-constexpr int EG_THREADS = 320;
-constexpr int EG_RING = 4;
-constexpr int EG_XSTAGE = 65536;                // hi h0 | hi h1 | lo h0 | lo h1, 16 KB each
-constexpr int EG_OFF_X = 0;
-constexpr int EG_OFF_RING = 2 * EG_XSTAGE;
-constexpr int EG_OFF_ROW = EG_OFF_RING + EG_RING * TC_UNIT;     // int src[256], dst[256]; float dist[256]
-constexpr int EG_OFF_BAR = EG_OFF_ROW + 3 * EG_T * 4;
-constexpr int EG_BYTES = EG_OFF_BAR + (2 * EG_RING + 5) * 8 + 16;
-constexpr size_t EG_SMEM_BYTES = EG_BYTES + 1024;
+// NH = 128-edge halves per CTA.  NH = 2: 256 edges, 1 CTA / SM (weight images amortised over 256 edges).
+// NH = 1: 128 edges, 6 warps, 2 CTAs / SM -- the MMAs of one CTA overlap the prologue / epilogue of the other.
+template <int NH>
+struct EgPlan {
+  static constexpr int T = 128 * NH;
+  static constexpr int THREADS = 64 + 128 * NH;
+  static constexpr int RING = NH == 2 ? 4 : 3;
+  static constexpr int XSTAGE = 32768 * NH;               // hi halves | lo halves, 16 KB each
+  static constexpr int OFF_X = 0;
+  static constexpr int OFF_RING = 2 * XSTAGE;
+  static constexpr int OFF_ROW = OFF_RING + RING * TC_UNIT;   // int src[T]
+  static constexpr int OFF_BAR = OFF_ROW + T * 4;
+  static_assert(NH == 2 || OFF_BAR + (2 * RING + 5) * 8 + 16 <= 115712, "2 CTAs per SM need <= 113 KB each");
+  static constexpr int BYTES = OFF_BAR + (2 * RING + 5) * 8 + 16;
+  static constexpr size_t SMEM_BYTES = BYTES;             // the dynamic shared-memory base is 1024-byte aligned (declared so)
+};
 
 enum EgMode : int { EG_MSG0 = 0, EG_MSG = 1, EG_GATE = 2 };
 
@@ -45,9 +51,12 @@ struct EgArgs {
   int dbg;                   // timing experiments: 1 no weight copies, 2 no MMA issue, 4 loaders skip global reads, 8 no epilogue math/stores
 };
 
-template <class D, int MODE>
-__global__ void __launch_bounds__(EG_THREADS, 1)
+template <class D, int MODE, int NH>
+__global__ void __launch_bounds__(EgPlan<NH>::THREADS, NH == 1 ? 2 : 1)
 k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
+  using PL = EgPlan<NH>;
+  constexpr int EG_T = PL::T, EG_RING = PL::RING, EG_XSTAGE = PL::XSTAGE;
+  constexpr int LO_OFF = NH * 16384;                          // offset of the lo images inside a stage
   constexpr int S = D::S;
   constexpr int K = MODE == EG_MSG0 ? D::KE0 : (MODE == EG_MSG ? D::K1 : S);
   constexpr int NSLAB = (K + 31) / 32;
@@ -55,26 +64,27 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
   constexpr int NMT = MODE == EG_GATE ? 1 : S / 128;
   constexpr int UNIT_BYTES = MODE == EG_GATE ? 32 * 128 : TC_UNIT;
   constexpr int SH_W = 40;                                     // row pitch of the norm buffer
-  extern __shared__ uint8_t smem_dyn[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  uint8_t* xst = base + EG_OFF_X;
-  uint8_t* ring = base + EG_OFF_RING;
-  int* r_src = reinterpret_cast<int*>(base + EG_OFF_ROW);
-  float* r_dist = reinterpret_cast<float*>(r_src + 2 * EG_T);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(base + EG_OFF_BAR);
+  extern __shared__ __align__(1024) uint8_t smem_dyn[];
+  uint8_t* base = smem_dyn;
+  uint8_t* xst = base + PL::OFF_X;
+  uint8_t* ring = base + PL::OFF_RING;
+  int* r_src = reinterpret_cast<int*>(base + PL::OFF_ROW);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + PL::OFF_BAR);
   uint64_t *w_full = bars, *w_empty = bars + EG_RING, *x_full = bars + 2 * EG_RING, *x_empty = x_full + 2, *acc_full = x_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long slot0 = (long long)blockIdx.x * EG_T;
   if (tid == 0) {
     for (int i = 0; i < EG_RING; ++i) { tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1); }
-    tc::mbar_init(&x_full[0], 8); tc::mbar_init(&x_full[1], 8);
+    tc::mbar_init(&x_full[0], 4 * NH); tc::mbar_init(&x_full[1], 4 * NH);
     tc::mbar_init(&x_empty[0], 1); tc::mbar_init(&x_empty[1], 1);
     tc::mbar_init(acc_full, 1);
     tc::fence_mbar_init();
   }
-  if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
+  constexpr uint32_t TMEM_COLS = NH == 2 ? 512 : 256;
+  if (warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS);
   // per-row bookkeeping: validity, and for the first message linear the (src, dst) pair and its distance
+  float my_dist = 0.f;                        // MSG0: distance of this loader thread's own edge row
   if (tid >= 64) {
     const int r = tid - 64;
     const long long slot = slot0 + r;
@@ -96,7 +106,7 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
       }
     }
     r_src[r] = s;
-    r_dist[r] = dist;
+    my_dist = dist;
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -131,11 +141,11 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
             tc::mbar_wait(&w_full[sl], use & 1);
             tc::tc_fence_after();
             const uint32_t wb = tc::smem_u32(ring + sl * TC_UNIT);
-            for (int h = 0; h < 2; ++h) {
-              const uint32_t d = tmem + (uint32_t)((mt * 2 + h) * 128);
+            for (int h = 0; h < NH; ++h) {
+              const uint32_t d = tmem + (uint32_t)((mt * NH + h) * 128);
               for (int ks = 0; ks < ksteps && !(a.dbg & 2); ++ks) {
                 const uint64_t dw = tc::desc_sw128(wb + 32 * ks);
-                tc::umma_tf32(d, dw, tc::desc_sw128(xb + 32768 + h * 16384 + 32 * ks), idesc, (j > 0 || ks > 0) ? 1u : 0u);
+                tc::umma_tf32(d, dw, tc::desc_sw128(xb + LO_OFF + h * 16384 + 32 * ks), idesc, (j > 0 || ks > 0) ? 1u : 0u);
                 tc::umma_tf32(d, dw, tc::desc_sw128(xb + h * 16384 + 32 * ks), idesc, 1u);
               }
             }
@@ -147,8 +157,8 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
             tc::mbar_wait(&w_full[sl], use & 1);
             tc::tc_fence_after();
             const uint32_t wb = tc::smem_u32(ring + sl * TC_UNIT);
-            for (int h = 0; h < 2; ++h) {
-              const uint32_t d = tmem + (uint32_t)((mt * 2 + h) * 128);
+            for (int h = 0; h < NH; ++h) {
+              const uint32_t d = tmem + (uint32_t)((mt * NH + h) * 128);
               for (int ks = 0; ks < ksteps && !(a.dbg & 2); ++ks)
                 tc::umma_tf32(d, tc::desc_sw128(wb + 32 * ks), tc::desc_sw128(xb + h * 16384 + 32 * ks), idesc, 1u);
             }
@@ -176,7 +186,7 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
         if (valid) {
           if (MODE == EG_MSG0) {
             if (j == 0) {
-              const float dd = r_dist[r];
+              const float dd = my_dist;
               val = make_float4(rbf_f(dd, mu[c * 4], sigma), rbf_f(dd, mu[c * 4 + 1], sigma), rbf_f(dd, mu[c * 4 + 2], sigma),
                                 rbf_f(dd, mu[c * 4 + 3], sigma));
             } else if (j <= D::F / 32) {
@@ -205,7 +215,7 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
       if (j + 1 < NSLAB) fetch(j + 1, nxt);
       if (j >= 2) tc::mbar_wait(&x_empty[st], ((j >> 1) - 1) & 1);
       uint8_t* hi = xst + st * EG_XSTAGE + h * 16384;
-      uint8_t* lo = hi + 32768;
+      uint8_t* lo = hi + LO_OFF;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         const float4 val = cur[c];
@@ -233,21 +243,19 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
         const int f = mt * 128 + q * 32 + lane;
         const float bias = MODE == EG_MSG0 ? 0.f : a.bias[f];
         for (int c = 0; c < 4; ++c) {
-          float acc[32];
-          tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((mt * 2 + eh) * 128 + c * 32), acc);
-          tc::tmem_ld_wait();
+          float acc[32], pre[32];
+          tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((mt * NH + eh) * 128 + c * 32), acc);
+          if (MODE == EG_MSG0) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int e = eh * 128 + c * 32 + i;
-            const int s = max(r_src[e], 0);          // padding rows are computed and stored too (their slots exist)
-            const long long row = slot0 + e;
-            if (MODE == EG_GATE) {
-              a.out[(size_t)row * 32 + f] = __frcp_rn(1.0f + __expf(-(acc[i] + bias)));
-            } else {
-              const float pre = MODE == EG_MSG0 ? a.P[(size_t)s * S + f] : bias;
-              const float z = acc[i] + pre;
-              a.out[(size_t)row * S + f] = z * __frcp_rn(1.0f + __expf(-z));
-            }
+            for (int i = 0; i < 32; ++i) pre[i] = __ldg(a.P + (size_t)max(r_src[eh * 128 + c * 32 + i], 0) * S + f);
+          }
+          tc::tmem_ld_wait();
+          float* op = a.out + (size_t)(slot0 + eh * 128 + c * 32) * (MODE == EG_GATE ? 32 : S) + f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {      // padding rows are computed and stored too (their slots exist)
+            const float z = acc[i] + (MODE == EG_MSG0 ? pre[i] : bias);
+            const float sg = __frcp_rn(1.0f + __expf(-z));
+            op[(size_t)i * (MODE == EG_GATE ? 32 : S)] = MODE == EG_GATE ? sg : z * sg;
           }
         }
       }
@@ -255,7 +263,7 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(tmem, 512);
+  if (warp == 1) tc::tmem_dealloc(tmem, TMEM_COLS);
 }
 
 }  // namespace fm

@@ -208,42 +208,46 @@ k_vec_b(const ModelRT m, const BatchRT bt, int layer, int g_next /* 1 or 2 */, f
 }
 
 template <class D>
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(NT, 2)
 k_vec_c(const ModelRT m, const BatchRT bt, int layer, const float* __restrict__ VH, const float* __restrict__ GT,
         const float* __restrict__ Smsg, float* __restrict__ M, float* __restrict__ partF, float* __restrict__ partL) {
   extern __shared__ __align__(16) float smem_raw[];
-  Smem<D> sm(smem_raw);
+  Smem<D> sm = VecSmem<D>::carve(smem_raw);
   const int tid = threadIdx.x;
   const EdgeTile<D> et(bt);
   tile_rows<D>(sm, et);
   vec_stage2<D>(sm, D::V + D::CP, m.c(layer, C_MSG2_WU), et.erow0, VH, GT);
   const int tile = blockIdx.x;
-  // scalar messages of the tile: one coalesced pass HBM -> shared memory, then the per-column walk reads shared memory
-  for (int idx = tid; idx < TM * (D::S / 4); idx += NT) {
-    const int row = idx / (D::S / 4), c4 = idx - row * (D::S / 4);
-    float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (sm.src[row] >= 0) val = __ldg(reinterpret_cast<const float4*>(Smsg + (et.erow0 + row) * D::S) + c4);
-    *reinterpret_cast<float4*>(sm.Xs + row * D::XLD + c4 * 4) = val;
-  }
-  __syncthreads();
   for (int col = tid; col < D::MW; col += NT) {
     float acc = 0.f;
     int seg_first = et.le0;
-    for (int row = 0; row < TM; ++row) {
-      const int d = sm.dst[row];
-      if (d < 0) break;
-      float val;
-      if (col < D::S) val = sm.Xs[row * D::XLD + col];
-      else { const int p = (col - D::S) / D::V, c = (col - D::S) - p * D::V; val = sm.Va[(p * TM + row) * D::LDVA + c]; }
-      acc = __fadd_rn(acc, val);
-      if (row == TM - 1 || sm.dst[row + 1] != d) {
-        const int j = d - et.nb, le_last = et.le0 + row;
-        const bool head = seg_first == j * (et.n - 1), tail = le_last == j * (et.n - 1) + (et.n - 2);
-        if (head && tail) M[(size_t)d * D::MW + col] = acc;
-        else if (head) partL[(size_t)tile * D::MW + col] = acc;
-        else partF[(size_t)tile * D::MW + col] = acc;
-        acc = 0.f;
-        seg_first = le_last + 1;
+    for (int r0 = 0; r0 < TM; r0 += 16) {
+      // scalar columns stream from HBM: 16 independent coalesced loads in flight per thread (padding slots exist in memory)
+      float buf[16];
+      if (col < D::S) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) buf[k] = __ldg(Smsg + (et.erow0 + r0 + k) * D::S + col);
+      } else {
+        const int p = (col - D::S) / D::V, c = (col - D::S) - p * D::V;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) buf[k] = sm.Va[(p * TM + r0 + k) * D::LDVA + c];
+      }
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const int row = r0 + k;
+        const int d = sm.dst[row];
+        if (d >= 0) {
+          acc = __fadd_rn(acc, buf[k]);
+          if (row == TM - 1 || sm.dst[row + 1] != d) {
+            const int j = d - et.nb, le_last = et.le0 + row;
+            const bool head = seg_first == j * (et.n - 1), tail = le_last == j * (et.n - 1) + (et.n - 2);
+            if (head && tail) M[(size_t)d * D::MW + col] = acc;
+            else if (head) partL[(size_t)tile * D::MW + col] = acc;
+            else partF[(size_t)tile * D::MW + col] = acc;
+            acc = 0.f;
+            seg_first = le_last + 1;
+          }
+        }
       }
     }
   }

@@ -30,6 +30,7 @@ def main():
         for impl in IMPLS:
             try:
                 vf.set_option("conv_impl", impl)
+                vf.set_option("eg_nh", int(os.environ.get("EG_NH", "2")))
                 if "c1.tap.conv0.s" in gd:
                     for l in range(cfg.n_convs):
                         vf.forward_tokens(*args, stop_after_conv=l); torch.cuda.synchronize()
@@ -52,6 +53,7 @@ def main():
         for impl in IMPLS:
             try:
                 vf.set_option("conv_impl", impl)
+                vf.set_option("eg_nh", int(os.environ.get("EG_NH", "2")))
                 out = vf.integrate_tokens(n_atoms, t(gd["x_0"]), torch.full((N,), 11), torch.full((N,), 6), torch.full((U,), 4), int(gd["T"]), seed=int(gd["noise_seed"]))
                 torch.cuda.synchronize()
                 out = {k: v.cpu().numpy() for k, v in out.items()}

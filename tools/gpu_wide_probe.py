@@ -11,6 +11,7 @@ vf = CTMCVectorFieldB200(cfg, WT.init_state_dict(cfg, 0))
 n_atoms = draw_sizes("geom", 512)
 x0, a0, c0, e0 = make_prior(n_atoms, 11, 100)
 vf.set_option("conv_impl", 2)
+vf.set_option("eg_nh", int(os.environ.get("EG_NH", "2")))
 d = vf.forward_tokens(n_atoms, x0, a0, c0, e0, 0.0, None); torch.cuda.synchronize()
 for dbg in [int(a) for a in (sys.argv[1:] or ["0"])]:
     vf.set_option("tc_debug", dbg)

@@ -328,7 +328,8 @@ int fm_create(const FmConfig* cfg, const float* w_host, size_t n_floats, const i
   h->cfg = c; h->device = device; h->variant = variant;
   h->has_tc = off_host[fm::G_COUNT + fm::C_MSG0_TCW] >= 0;
   h->off_h.assign(off_host, off_host + n_off);
-  h->conv_impl = 0;
+  h->conv_impl = (variant == 0 && h->has_tc) ? 2 : 0;   // flowmol3 dims: wide tcgen05 3xTF32 pipeline by default
+  h->eg_nh = 1;
   h->dyn = Dyn{c.n_hidden_scalars, c.n_vec_channels, c.n_hidden_edge_feats, c.use_dst_feats ? c.s_dst : 0,
                c.use_dst_feats ? c.v_dst : 0, c.n_atom_types, c.n_charges, c.n_bond_types,
                c.n_hidden_scalars + 3 * c.n_vec_channels};

@@ -1,10 +1,12 @@
 """GPU parity tests: CUDA path (through the C ABI) vs golden vectors produced by the reference's own code, and vs the
 CPU oracle on fresh seeded inputs.  Run on the B200 box with `pytest -m gpu`.
 
-Tolerances (fp32 path; the yardstick is the reference's own fp32-vs-fp64 noise floor, SURVEY.md section 8c:
-max|dx| 6e-7, max|dp| 3e-7 per forward):
+Tolerances (the yardstick is the reference's own fp32-vs-fp64 noise floor, SURVEY.md section 8c: max|dx| 6e-7,
+max|dp| 3e-7 per forward).  The flowmol3 configuration runs its message linears as error-compensated 3xTF32 on the
+tensor cores by default (measured: hidden state 1.1e-5 abs / 2.5e-6 rel after 6 layers, outputs 2.4e-7; the fp32
+CUDA-core kernels of the dev configuration and of `conv_impl=0` sit at 1.4e-6 / 1.8e-7):
     per forward : |dx| <= 5e-6, |dp| <= 3e-6, argmax(a, c, e) exact
-    hidden state: rtol 1e-5 / atol 1e-5 per layer (summation order differs: per-node folding of the s_src / s_dst rows)
+    hidden state: rtol 1e-5 / atol 3e-5 per layer
     trajectory  : final categorical state identical for every molecule, |dx| <= 1e-4
 """
 import numpy as np
@@ -21,7 +23,7 @@ pytestmark = pytest.mark.gpu
 
 FWD = ["fwd_dev_taps", "fwd_flowmol3_taps", "fwd_flowmol3_geom", "fwd_dev_qm9"]
 ITG = ["itg_dev_T10", "itg_dev_T50", "itg_flowmol3_T10", "itg_flowmol3_T25"]
-TOL_X, TOL_P, TOL_H = 5e-6, 3e-6, 1e-5
+TOL_X, TOL_P, TOL_H, ATOL_H = 5e-6, 3e-6, 1e-5, 3e-5
 
 _models = {}
 
@@ -74,13 +76,13 @@ def test_layerwise_hidden_state_vs_reference_golden(name):
         vf.forward_tokens(*args, stop_after_conv=l)
         s = vf.workspace_tensor("s").view(N, cfg.n_hidden_scalars).cpu().numpy()
         v = vf.workspace_tensor("v").view(N, 3, cfg.n_vec_channels).permute(0, 2, 1).cpu().numpy()
-        np.testing.assert_allclose(s, gd[f"c1.tap.conv{l}.s"], rtol=TOL_H, atol=TOL_H, err_msg=f"conv{l} s")
-        np.testing.assert_allclose(v, gd[f"c1.tap.conv{l}.v"], rtol=TOL_H, atol=TOL_H, err_msg=f"conv{l} v")
+        np.testing.assert_allclose(s, gd[f"c1.tap.conv{l}.s"], rtol=TOL_H, atol=ATOL_H, err_msg=f"conv{l} s")
+        np.testing.assert_allclose(v, gd[f"c1.tap.conv{l}.v"], rtol=TOL_H, atol=ATOL_H, err_msg=f"conv{l} v")
         if l >= 1:
             x = vf.workspace_tensor("x").view(N, 3).cpu().numpy()
             ef = vf.workspace_tensor("ef").view(-1, cfg.n_hidden_edge_feats).cpu()[perm].numpy()
             np.testing.assert_allclose(x, gd[f"c1.tap.pos{l}"], rtol=0, atol=TOL_X, err_msg=f"pos{l}")
-            np.testing.assert_allclose(ef, gd[f"c1.tap.eupd{l}"], rtol=TOL_H, atol=TOL_H, err_msg=f"eupd{l}")
+            np.testing.assert_allclose(ef, gd[f"c1.tap.eupd{l}"], rtol=TOL_H, atol=ATOL_H, err_msg=f"eupd{l}")
 
 
 @pytest.mark.parametrize("name", ITG)
@@ -165,6 +167,30 @@ def test_results_do_not_depend_on_batch_composition_or_sharding():
         assert torch.equal(part["a"].cpu(), full["a"][noff[lo]:noff[hi]])
         assert torch.equal(part["c"].cpu(), full["c"][noff[lo]:noff[hi]])
         assert torch.equal(part["e"].cpu(), full["e"][uoff[lo]:uoff[hi]])
+
+
+def test_fp32_and_tensor_core_message_kernels_agree():
+    """conv_impl 0 (fp32 CUDA cores), 1 (fused tcgen05) and 2 (wide tcgen05 pipeline, default) on the same inputs."""
+    cfg, vf = cuda_model("flowmol3", 11, 61)
+    assert vf.get_option("conv_impl") == 2
+    n_atoms = np.array([9, 70, 3, 33])
+    bt = O.make_batch(n_atoms)
+    gen = torch.Generator().manual_seed(8)
+    x = torch.randn(bt.N, 3, generator=gen)
+    a, c, e = torch.randint(0, 12, (bt.N,), generator=gen), torch.randint(0, 7, (bt.N,), generator=gen), torch.randint(0, 5, (bt.U,), generator=gen)
+    outs = {}
+    try:
+        for impl in (0, 1, 2):
+            vf.set_option("conv_impl", impl)
+            d0 = vf.forward_tokens(n_atoms, x, torch.full_like(a, 11), torch.full_like(c, 6), torch.full_like(e, 4), 0.0, None)
+            outs[impl] = {k: v.cpu() for k, v in vf.forward_tokens(n_atoms, x, a, c, e, 0.4, d0).items()}
+    finally:
+        vf.set_option("conv_impl", 2)
+    for impl in (1, 2):
+        assert (outs[impl]["x"] - outs[0]["x"]).abs().max() <= TOL_X
+        for k in "ace":
+            assert (outs[impl][k] - outs[0][k]).abs().max() <= TOL_P
+            assert torch.equal(outs[impl][k].argmax(-1), outs[0][k].argmax(-1))
 
 
 def test_host_entry_point_and_cuda_graph_match_device_entry_point():

@@ -69,8 +69,8 @@ Layout make_layout(const Dyn& d, const int32_t* n_atoms, int B) {
   L.P = take(4ull * N * d.S); L.Q = take(4ull * N * d.S * (d.SD > 0)); L.vd = take(4ull * N * 3 * d.VD);
   L.EAB = take(4ull * N * 2 * d.F); L.M = take(4ull * N * d.MW);
   L.partF = take(8ull * L.nET * d.MW); L.partL = take(8ull * L.nET * d.MW);   // x2: the tensor-core kernel uses 32-row tiles
-  L.ef = take(4ull * (size_t)L.EP * d.F);
   L.EPA = (L.EP + 255) / 256 * 256;
+  L.ef = take(4ull * (size_t)L.EPA * d.F);       // rounded up: the wide kernels store whole 128-slot tiles
   const size_t wide = d.S == 256 && d.SD == 0 ? (size_t)L.EPA : 0;
   L.SA = take(4ull * wide * d.S); L.SB = take(4ull * wide * d.S); L.VH = take(4ull * wide * 120); L.SH = take(4ull * wide * 40);
   L.GT = take(4ull * wide * 32);
@@ -141,6 +141,8 @@ int set_smem_attrs() {
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_MSG0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<1>::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_MSG, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<1>::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_GATE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<1>::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_EU1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<1>::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_EU2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<1>::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_vec_a<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::VecSmem<D>::BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_vec_b<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::VecSmem<D>::BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_vec_c<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::VecSmem<D>::BYTES));
@@ -175,7 +177,7 @@ int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
     float* cur = ef;      // input activations of the current scalar linear
     float* outs[3] = {SA, SB, SA};
     for (int g = 0; g < 3; ++g) {
-      fm::EgArgs a{wptr(tcw[g]), wptr(gb[g] + fm::GV_B), cur, SH, P, x, outs[g], L.EP, h->tc_debug};
+      fm::EgArgs a{wptr(tcw[g]), wptr(gb[g] + fm::GV_B), cur, SH, P, x, outs[g], nullptr, nullptr, L.EP, h->tc_debug};
       if (NHsel == 2) {
         if (g == 0) fm::k_egemm_tc<D, fm::EG_MSG0, 2><<<gt, fm::EgPlan<2>::THREADS, fm::EgPlan<2>::SMEM_BYTES, st>>>(m, bt, a);
         else fm::k_egemm_tc<D, fm::EG_MSG, 2><<<gt, fm::EgPlan<2>::THREADS, fm::EgPlan<2>::SMEM_BYTES, st>>>(m, bt, a);
@@ -184,7 +186,7 @@ int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
         else fm::k_egemm_tc<D, fm::EG_MSG, 1><<<gt, fm::EgPlan<1>::THREADS, fm::EgPlan<1>::SMEM_BYTES, st>>>(m, bt, a);
       }
       LAUNCH_OK(h);
-      fm::EgArgs ag{wptr(tcg[g]), wptr(gb[g] + fm::GV_BG), outs[g], nullptr, nullptr, nullptr, GT, L.EP, h->tc_debug};
+      fm::EgArgs ag{wptr(tcg[g]), wptr(gb[g] + fm::GV_BG), outs[g], nullptr, nullptr, nullptr, GT, nullptr, nullptr, L.EP, h->tc_debug};
       if (NHsel == 2) fm::k_egemm_tc<D, fm::EG_GATE, 2><<<gt, fm::EgPlan<2>::THREADS, fm::EgPlan<2>::SMEM_BYTES, st>>>(m, bt, ag);
       else fm::k_egemm_tc<D, fm::EG_GATE, 1><<<gt, fm::EgPlan<1>::THREADS, fm::EgPlan<1>::SMEM_BYTES, st>>>(m, bt, ag);
       LAUNCH_OK(h);
@@ -236,7 +238,24 @@ int run_pass(FmHandle* h, void* ws, const Layout& L, const float* x_t, const uin
     fm::k_node_update<D><<<L.nNT, fm::NT, smem, st>>>(m, bt, l, upd, has_next, agg_rows, s, v, x, M, partF, partL, P, EAB);
     LAUNCH_OK(h);
     if (m.use_dst && has_next) { fm::k_dst_proj<D><<<L.nNT, fm::NT, smem, st>>>(m, bt, l + 1, s, v, Q, vd); LAUNCH_OK(h); }
-    if (upd >= 0) { fm::k_edge_update<D><<<L.nET, fm::NT, smem, st>>>(m, bt, upd, x, EAB, ef); LAUNCH_OK(h); }
+    if (upd >= 0) {
+      bool done = false;
+      if constexpr (D::S == 256 && D::V == 32 && D::SD == 0 && D::F == 128) {
+        if (h->conv_impl == 2) {           // EdgeUpdate as two wide tensor-core linears (h round-trips through HBM)
+          auto uptr = [&](int id) { return h->d_w + h->off_h[fm::G_COUNT + m.L * fm::C_COUNT + upd * fm::U_COUNT + id]; };
+          float* H = at<float>(ws, L.SA);
+          const int gt = (int)(L.EPA / 128);
+          fm::EgArgs a1{uptr(fm::U_EUPD_TC1), nullptr, ef, nullptr, EAB, x, H, nullptr, nullptr, L.EP, h->tc_debug};
+          fm::k_egemm_tc<D, fm::EG_EU1, 1><<<gt, fm::EgPlan<1>::THREADS, fm::EgPlan<1>::SMEM_BYTES, st>>>(m, bt, a1);
+          LAUNCH_OK(h);
+          fm::EgArgs a2{uptr(fm::U_EUPD_TC2), uptr(fm::U_EUPD_B2), H, ef, nullptr, nullptr, ef, uptr(fm::U_EUPD_LN_W), uptr(fm::U_EUPD_LN_B), L.EP, h->tc_debug};
+          fm::k_egemm_tc<D, fm::EG_EU2, 1><<<gt, fm::EgPlan<1>::THREADS, fm::EgPlan<1>::SMEM_BYTES, st>>>(m, bt, a2);
+          LAUNCH_OK(h);
+          done = true;
+        }
+      }
+      if (!done) { fm::k_edge_update<D><<<L.nET, fm::NT, smem, st>>>(m, bt, upd, x, EAB, ef); LAUNCH_OK(h); }
+    }
     if (l == stop_after) return 0;
   }
   fm::k_node_head<D><<<L.nNT, fm::NT, smem, st>>>(m, bt, s, out.a, out.c);

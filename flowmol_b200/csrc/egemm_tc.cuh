@@ -30,14 +30,16 @@ struct EgPlan {
   static constexpr int XSTAGE = 32768 * NH;               // hi halves | lo halves, 16 KB each
   static constexpr int OFF_X = 0;
   static constexpr int OFF_RING = 2 * XSTAGE;
-  static constexpr int OFF_ROW = OFF_RING + RING * TC_UNIT;   // int src[T]
-  static constexpr int OFF_BAR = OFF_ROW + T * 4;
+  static constexpr int OFF_ROW = OFF_RING + RING * TC_UNIT;   // int src[T]; int16 (dst - src)[T]
+  static constexpr int OFF_BAR = OFF_ROW + T * 6;
   static_assert(NH == 2 || OFF_BAR + (2 * RING + 5) * 8 + 16 <= 115712, "2 CTAs per SM need <= 113 KB each");
   static constexpr int BYTES = OFF_BAR + (2 * RING + 5) * 8 + 16;
   static constexpr size_t SMEM_BYTES = BYTES;             // the dynamic shared-memory base is 1024-byte aligned (declared so)
 };
 
-enum EgMode : int { EG_MSG0 = 0, EG_MSG = 1, EG_GATE = 2 };
+enum EgMode : int { EG_MSG0 = 0, EG_MSG = 1, EG_GATE = 2, EG_EU1 = 3, EG_EU2 = 4 };
+// EG_EU1 / EG_EU2: the two linears of EdgeUpdate (flowmol/models/vector_field.py:844-880): h = SiLU(We [ef | rbf(d)] + EA[src] +
+// EB[dst]);  ef <- LayerNorm(ef + SiLU(W2 h + b2)).  NH = 1 only.
 
 struct EgArgs {
   const float* units;        // weight images (weights.py:tc_units)
@@ -46,7 +48,9 @@ struct EgArgs {
   const float* in_sh;        // MSG0 / MSG: [EPA][40] vector norms of this GVP
   const float* P;            // MSG0: per-node pre-activations [N][S]
   const float* x;            // MSG0: positions [N][3]
-  float* out;                // MSG0 / MSG: [EPA][S];  GATE: [EPA][32]
+  float* out;                // MSG0 / MSG: [EPA][S];  GATE: [EPA][32];  EU1: h [EPA][F];  EU2: ef [EP][F] (in place)
+  const float* ln_w;         // EU2: LayerNorm gamma / beta
+  const float* ln_b;
   long long EP;              // padded edge slots (multiple of 64)
   int dbg;                   // timing experiments: 1 no weight copies, 2 no MMA issue, 4 loaders skip global reads, 8 no epilogue math/stores
 };
@@ -58,10 +62,13 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
   constexpr int EG_T = PL::T, EG_RING = PL::RING, EG_XSTAGE = PL::XSTAGE;
   constexpr int LO_OFF = NH * 16384;                          // offset of the lo images inside a stage
   constexpr int S = D::S;
-  constexpr int K = MODE == EG_MSG0 ? D::KE0 : (MODE == EG_MSG ? D::K1 : S);
+  constexpr bool IS_EU = MODE == EG_EU1 || MODE == EG_EU2;
+  constexpr int K = MODE == EG_MSG0 ? D::KE0 : (MODE == EG_MSG ? D::K1 : (MODE == EG_EU1 ? D::F + D::R : (MODE == EG_EU2 ? D::F : S)));
   constexpr int NSLAB = (K + 31) / 32;
   constexpr int LAST_KSTEPS = ((K - 1) % 32) / 8 + 1;
-  constexpr int NMT = MODE == EG_GATE ? 1 : S / 128;
+  constexpr int NMT = MODE == EG_GATE ? 1 : (IS_EU ? D::F / 128 : S / 128);
+  constexpr int OW = MODE == EG_GATE ? 32 : (IS_EU ? D::F : S);          // output row width
+  static_assert(!IS_EU || (NH == 1 && D::F == 128), "edge-update modes: one 128-edge half, F = 128");
   constexpr int UNIT_BYTES = MODE == EG_GATE ? 32 * 128 : TC_UNIT;
   constexpr int SH_W = 40;                                     // row pitch of the norm buffer
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
@@ -69,6 +76,7 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
   uint8_t* xst = base + PL::OFF_X;
   uint8_t* ring = base + PL::OFF_RING;
   int* r_src = reinterpret_cast<int*>(base + PL::OFF_ROW);
+  short* r_dd = reinterpret_cast<short*>(r_src + EG_T);        // dst - src (same molecule, |.| < 2000)
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + PL::OFF_BAR);
   uint64_t *w_full = bars, *w_empty = bars + EG_RING, *x_full = bars + 2 * EG_RING, *x_empty = x_full + 2, *acc_full = x_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
@@ -88,24 +96,26 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
   if (tid >= 64) {
     const int r = tid - 64;
     const long long slot = slot0 + r;
-    int s = -1;
+    int s = -1, dd = 0;
     float dist = 0.f;
     if (slot < a.EP) {
       const int t64 = (int)(slot >> 6), mol = bt.etile_mol[t64];
       const int n = bt.mol_n[mol], le = (int)(slot - ((long long)bt.mol_etile[mol] << 6));
       if (le < n * (n - 1)) {
         s = 0;
-        if (MODE == EG_MSG0) {
+        if (MODE == EG_MSG0 || MODE == EG_EU1) {
           int i, j;
           edge_src_dst(le, n, i, j);
           const int nb = bt.mol_node[mol];
           s = nb + i;
+          dd = j - i;
           float dx, dy, dz;
           dist = pair_dist(a.x, s, nb + j, dx, dy, dz);
         }
       }
     }
     r_src[r] = s;
+    r_dd[r] = (short)dd;
     my_dist = dist;
   }
   tc::tc_fence_before();
@@ -201,6 +211,15 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
               const int k0 = (j - S / 32) * 32 + c * 4;
               if (k0 < SH_W) val = *(reinterpret_cast<const float4*>(a.in_sh + (size_t)slot * SH_W + k0));
             }
+          } else if (MODE == EG_EU1) {
+            if (j < D::F / 32) val = *(reinterpret_cast<const float4*>(a.in_s + (size_t)slot * D::F + j * 32) + c);
+            else {
+              const float dd = my_dist;
+              val = make_float4(rbf_f(dd, mu[c * 4], sigma), rbf_f(dd, mu[c * 4 + 1], sigma), rbf_f(dd, mu[c * 4 + 2], sigma),
+                                rbf_f(dd, mu[c * 4 + 3], sigma));
+            }
+          } else if (MODE == EG_EU2) {
+            val = *(reinterpret_cast<const float4*>(a.in_s + (size_t)slot * D::F + j * 32) + c);
           } else {
             val = *(reinterpret_cast<const float4*>(a.in_s + (size_t)slot * S + j * 32) + c);
           }
@@ -241,21 +260,55 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
     if ((MODE != EG_GATE || q == 0) && !(a.dbg & 8)) {
       for (int mt = 0; mt < NMT; ++mt) {
         const int f = mt * 128 + q * 32 + lane;
-        const float bias = MODE == EG_MSG0 ? 0.f : a.bias[f];
+        const float bias = (MODE == EG_MSG0 || MODE == EG_EU1) ? 0.f : a.bias[f];
+        float* red = reinterpret_cast<float*>(xst);            // EU2: cross-warp LayerNorm partials (the stages are idle now)
         for (int c = 0; c < 4; ++c) {
           float acc[32], pre[32];
           tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((mt * NH + eh) * 128 + c * 32), acc);
           if (MODE == EG_MSG0) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) pre[i] = __ldg(a.P + (size_t)max(r_src[eh * 128 + c * 32 + i], 0) * S + f);
+          } else if (MODE == EG_EU1) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int e = c * 32 + i, sn = max(r_src[e], 0);
+              pre[i] = __fadd_rn(__ldg(a.P + (size_t)sn * 2 * D::F + f), __ldg(a.P + (size_t)(sn + r_dd[e]) * 2 * D::F + D::F + f));
+            }
+          } else if (MODE == EG_EU2) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) pre[i] = a.in_sh[(size_t)(slot0 + c * 32 + i) * D::F + f];     // residual: current ef
           }
           tc::tmem_ld_wait();
-          float* op = a.out + (size_t)(slot0 + eh * 128 + c * 32) * (MODE == EG_GATE ? 32 : S) + f;
+          float* op = a.out + (size_t)(slot0 + eh * 128 + c * 32) * OW + f;
+          if (MODE != EG_EU2) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {      // padding rows are computed and stored too (their slots exist)
-            const float z = acc[i] + (MODE == EG_MSG0 ? pre[i] : bias);
-            const float sg = __frcp_rn(1.0f + __expf(-z));
-            op[(size_t)i * (MODE == EG_GATE ? 32 : S)] = MODE == EG_GATE ? sg : z * sg;
+            for (int i = 0; i < 32; ++i) {      // padding rows are computed and stored too (their slots exist)
+              const float z = acc[i] + ((MODE == EG_MSG0 || MODE == EG_EU1) ? pre[i] : bias);
+              const float sg = __frcp_rn(1.0f + __expf(-z));
+              op[(size_t)i * OW] = MODE == EG_GATE ? sg : z * sg;
+            }
+          } else {
+            // y = ef + SiLU(W2 h + b2);  LayerNorm over the 128 features of every edge = over the lanes of the 4 epilogue warps
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float z = acc[i] + bias;
+              acc[i] = __fadd_rn(pre[i], z * __frcp_rn(1.0f + __expf(-z)));
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { const float t = warp_sum(acc[i]); if (lane == i) red[q * 32 + i] = t; }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < 32; ++i) pre[i] = (red[i] + red[32 + i] + red[64 + i] + red[96 + i]) * (1.0f / 128.0f);   // mean
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { const float dlt = acc[i] - pre[i]; const float t = warp_sum(dlt * dlt); if (lane == i) red[128 + q * 32 + i] = t; }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const float gam = a.ln_w[f], bet = a.ln_b[f];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float var = (red[128 + i] + red[160 + i] + red[192 + i] + red[224 + i]) * (1.0f / 128.0f);
+              op[(size_t)i * OW] = (acc[i] - pre[i]) * (1.0f / sqrtf(var + 1e-5f)) * gam + bet;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");     // red[] is rewritten by the next chunk
           }
         }
       }

@@ -352,4 +352,7 @@ def pack(cfg: ModelConfig, sd):
         P.gemm(c("EUPD_WE"), w1[2 * S:])                                              # rows ef | d
         _pack_linear(P, c("EUPD_W2"), c("EUPD_B2"), sd, p + ".edge_update_fn.2")
         P.vec(c("EUPD_LN_W"), _np(sd, p + ".edge_norm.weight")); P.vec(c("EUPD_LN_B"), _np(sd, p + ".edge_norm.bias"))
+        if F == 128 and S % 128 == 0 and V <= 32:        # tensor-core images of the two EdgeUpdate linears (features on M)
+            P.raw(c("EUPD_TC1"), tc_units(w1[2 * S:].T, 128))                                  # [F, F + R], k order ef | d
+            P.raw(c("EUPD_TC2"), tc_units(_np(sd, p + ".edge_update_fn.2.weight"), 128))       # [F, F]
     return P.blob(), P.offsets

@@ -97,6 +97,8 @@ struct FmHandle {
   std::unordered_map<void*, Layout> batches;
   int64_t launches = 0;
   int eg_nh = 2;               // 128-edge halves per CTA of k_egemm_tc (2: 1 CTA/SM, 1: 2 CTAs/SM)
+  long long* d_trace = nullptr;   // clock64 stamps of one egemm CTA (timeline experiments)
+  int trace_cta = 0, trace_mode = 1;
   int tc_debug = 0;            // timing experiments (conv_tc.cuh TcCtx::dbg)
   bool has_tc = false;         // packed weights contain the UMMA operand images
   int conv_impl = 0;           // 0: fp32 CUDA-core k_conv_edge, 1: tcgen05 3xTF32 k_conv_edge_tc (flowmol3 dims only)
@@ -177,7 +179,7 @@ int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
     float* cur = ef;      // input activations of the current scalar linear
     float* outs[3] = {SA, SB, SA};
     for (int g = 0; g < 3; ++g) {
-      fm::EgArgs a{wptr(tcw[g]), wptr(gb[g] + fm::GV_B), cur, SH, P, x, outs[g], nullptr, nullptr, L.EP, h->tc_debug};
+      fm::EgArgs a{wptr(tcw[g]), wptr(gb[g] + fm::GV_B), cur, SH, P, x, outs[g], nullptr, nullptr, L.EP, h->trace_mode == (g == 0 ? 0 : 1) ? h->d_trace : nullptr, h->trace_cta, h->tc_debug};
       if (NHsel == 2) {
         if (g == 0) fm::k_egemm_tc<D, fm::EG_MSG0, 2><<<gt, fm::EgPlan<2>::THREADS, fm::EgPlan<2>::SMEM_BYTES, st>>>(m, bt, a);
         else fm::k_egemm_tc<D, fm::EG_MSG, 2><<<gt, fm::EgPlan<2>::THREADS, fm::EgPlan<2>::SMEM_BYTES, st>>>(m, bt, a);
@@ -186,7 +188,7 @@ int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
         else fm::k_egemm_tc<D, fm::EG_MSG, 1><<<gt, fm::EgPlan<1>::THREADS, fm::EgPlan<1>::SMEM_BYTES, st>>>(m, bt, a);
       }
       LAUNCH_OK(h);
-      fm::EgArgs ag{wptr(tcg[g]), wptr(gb[g] + fm::GV_BG), outs[g], nullptr, nullptr, nullptr, GT, nullptr, nullptr, L.EP, h->tc_debug};
+      fm::EgArgs ag{wptr(tcg[g]), wptr(gb[g] + fm::GV_BG), outs[g], nullptr, nullptr, nullptr, GT, nullptr, nullptr, L.EP, h->trace_mode == 2 ? h->d_trace : nullptr, h->trace_cta, h->tc_debug};
       if (NHsel == 2) fm::k_egemm_tc<D, fm::EG_GATE, 2><<<gt, fm::EgPlan<2>::THREADS, fm::EgPlan<2>::SMEM_BYTES, st>>>(m, bt, ag);
       else fm::k_egemm_tc<D, fm::EG_GATE, 1><<<gt, fm::EgPlan<1>::THREADS, fm::EgPlan<1>::SMEM_BYTES, st>>>(m, bt, ag);
       LAUNCH_OK(h);
@@ -245,10 +247,10 @@ int run_pass(FmHandle* h, void* ws, const Layout& L, const float* x_t, const uin
           auto uptr = [&](int id) { return h->d_w + h->off_h[fm::G_COUNT + m.L * fm::C_COUNT + upd * fm::U_COUNT + id]; };
           float* H = at<float>(ws, L.SA);
           const int gt = (int)(L.EPA / 128);
-          fm::EgArgs a1{uptr(fm::U_EUPD_TC1), nullptr, ef, nullptr, EAB, x, H, nullptr, nullptr, L.EP, h->tc_debug};
+          fm::EgArgs a1{uptr(fm::U_EUPD_TC1), nullptr, ef, nullptr, EAB, x, H, nullptr, nullptr, L.EP, h->trace_mode == 3 ? h->d_trace : nullptr, h->trace_cta, h->tc_debug};
           fm::k_egemm_tc<D, fm::EG_EU1, 1><<<gt, fm::EgPlan<1>::THREADS, fm::EgPlan<1>::SMEM_BYTES, st>>>(m, bt, a1);
           LAUNCH_OK(h);
-          fm::EgArgs a2{uptr(fm::U_EUPD_TC2), uptr(fm::U_EUPD_B2), H, ef, nullptr, nullptr, ef, uptr(fm::U_EUPD_LN_W), uptr(fm::U_EUPD_LN_B), L.EP, h->tc_debug};
+          fm::EgArgs a2{uptr(fm::U_EUPD_TC2), uptr(fm::U_EUPD_B2), H, ef, nullptr, nullptr, ef, uptr(fm::U_EUPD_LN_W), uptr(fm::U_EUPD_LN_B), L.EP, h->trace_mode == 4 ? h->d_trace : nullptr, h->trace_cta, h->tc_debug};
           fm::k_egemm_tc<D, fm::EG_EU2, 1><<<gt, fm::EgPlan<1>::THREADS, fm::EgPlan<1>::SMEM_BYTES, st>>>(m, bt, a2);
           LAUNCH_OK(h);
           done = true;
@@ -563,8 +565,21 @@ int fm_set_option(FmHandle* h, const char* name, int32_t value) {
     return 0;
   }
   if (n == "tc_debug") { h->tc_debug = value; return 0; }
+  if (n == "tc_trace_mode") { h->trace_mode = value; return 0; }
+  if (n == "tc_trace") {       // value < 0: off; otherwise the CTA index whose timeline is recorded (every egemm launch overwrites it)
+    if (value < 0) { h->trace_cta = 0; if (h->d_trace) { cudaFree(h->d_trace); h->d_trace = nullptr; } return 0; }
+    if (!h->d_trace) { CUDA_OK(cudaMalloc(&h->d_trace, 64 * sizeof(long long))); }
+    CUDA_OK(cudaMemset(h->d_trace, 0, 64 * sizeof(long long)));
+    h->trace_cta = value;
+    return 0;
+  }
   if (n == "eg_nh") { if (value != 1 && value != 2) return fail("fm_set_option: eg_nh must be 1 or 2"); h->eg_nh = value; return 0; }
   return fail("fm_set_option: unknown option");
+}
+int fm_debug_read_trace(FmHandle* h, int64_t* out64_host) {
+  if (!h || !out64_host || !h->d_trace) return fail("fm_debug_read_trace: tracing is off");
+  CUDA_OK(cudaMemcpy(out64_host, h->d_trace, 64 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return 0;
 }
 int fm_get_option(FmHandle* h, const char* name, int32_t* value) {
   if (!h || !name || !value) return fail("fm_get_option: null argument");

@@ -52,6 +52,8 @@ struct EgArgs {
   const float* ln_w;         // EU2: LayerNorm gamma / beta
   const float* ln_b;
   long long EP;              // padded edge slots (multiple of 64)
+  long long* trace;          // optional clock64 stamps of one CTA (timeline experiments)
+  int trace_cta;
   int dbg;                   // timing experiments: 1 no weight copies, 2 no MMA issue, 4 loaders skip global reads, 8 no epilogue math/stores
 };
 
@@ -118,6 +120,7 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
     r_dd[r] = (short)dd;
     my_dist = dist;
   }
+  if (a.trace && blockIdx.x == a.trace_cta && tid == 64) a.trace[0] = clock64();
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -177,85 +180,90 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
           }
         }
         tc::umma_commit(&x_empty[st]);
+        if (a.trace && blockIdx.x == a.trace_cta) a.trace[16 + j] = clock64();
       }
       tc::umma_commit(acc_full);
     }
   } else {
     // ---- activation loaders: one edge row per thread, fp32 -> (hi, lo) SW128 images ------------------------------------------------
-    const int r = tid - 64, h = r >> 7, rr = r & 127;
-    const long long slot = slot0 + r;
-    const bool valid = r_src[r] >= 0 && !(a.dbg & 4);
     const float sigma = m.rbf_dmax / (float)D::R;
     const float* mu = m.g(G_RBF_MU);
-    // fetch of one k-slab of this thread's row into registers (issued one slab ahead of its conversion: the HBM / L2 round
-    // trip overlaps the wait for the stage and the MMAs of the previous slab)
+    // One warp owns 32 consecutive edge rows.  A load instruction covers 4 rows x 128 B (lanes 8g..8g+7 read the 8 16-byte
+    // chunks of row 4i + g): full 128-byte lines per request.  The fetch of slab j+1 is issued before slab j is converted, so
+    // the HBM / L2 round trip overlaps the wait for the stage and the MMAs of the previous slab.
+    const int wrow0 = (warp - 2) * 32, lg = lane >> 3, ch = lane & 7;
     auto fetch = [&](int j, float4 (&buf)[8]) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int i = 0; i < 8; ++i) {
+        const int rw = wrow0 + 4 * i + lg;                     // row inside the tile
+        const long long sl_ = slot0 + rw;
+        const bool ok = r_src[rw] >= 0 && !(a.dbg & 4);
         float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid) {
-          if (MODE == EG_MSG0) {
-            if (j == 0) {
-              const float dd = my_dist;
-              val = make_float4(rbf_f(dd, mu[c * 4], sigma), rbf_f(dd, mu[c * 4 + 1], sigma), rbf_f(dd, mu[c * 4 + 2], sigma),
-                                rbf_f(dd, mu[c * 4 + 3], sigma));
-            } else if (j <= D::F / 32) {
-              val = __ldg(reinterpret_cast<const float4*>(a.in_s + (size_t)slot * D::F + (j - 1) * 32) + c);
-            } else {
-              const int k0 = (j - 1 - D::F / 32) * 32 + c * 4;
-              if (k0 < SH_W) val = *(reinterpret_cast<const float4*>(a.in_sh + (size_t)slot * SH_W + k0));
+        if (MODE == EG_MSG0 || MODE == EG_EU1) {
+          const float dd = __shfl_sync(0xffffffffu, my_dist, 4 * i + lg);      // the row's distance lives in lane (row % 32)
+          const bool rbf_slab = MODE == EG_MSG0 ? j == 0 : j == D::F / 32;
+          if (rbf_slab) {
+            if (ok) val = make_float4(rbf_f(dd, mu[ch * 4], sigma), rbf_f(dd, mu[ch * 4 + 1], sigma), rbf_f(dd, mu[ch * 4 + 2], sigma),
+                                      rbf_f(dd, mu[ch * 4 + 3], sigma));
+          } else if (MODE == EG_MSG0) {
+            if (ok) {
+              if (j <= D::F / 32) val = __ldg(reinterpret_cast<const float4*>(a.in_s + (size_t)sl_ * D::F + (j - 1) * 32) + ch);
+              else {
+                const int k0 = (j - 1 - D::F / 32) * 32 + ch * 4;
+                if (k0 < SH_W) val = *(reinterpret_cast<const float4*>(a.in_sh + (size_t)sl_ * SH_W + k0));
+              }
             }
-          } else if (MODE == EG_MSG) {
-            if (j < S / 32) val = *(reinterpret_cast<const float4*>(a.in_s + (size_t)slot * S + j * 32) + c);
-            else {
-              const int k0 = (j - S / 32) * 32 + c * 4;
-              if (k0 < SH_W) val = *(reinterpret_cast<const float4*>(a.in_sh + (size_t)slot * SH_W + k0));
-            }
-          } else if (MODE == EG_EU1) {
-            if (j < D::F / 32) val = *(reinterpret_cast<const float4*>(a.in_s + (size_t)slot * D::F + j * 32) + c);
-            else {
-              const float dd = my_dist;
-              val = make_float4(rbf_f(dd, mu[c * 4], sigma), rbf_f(dd, mu[c * 4 + 1], sigma), rbf_f(dd, mu[c * 4 + 2], sigma),
-                                rbf_f(dd, mu[c * 4 + 3], sigma));
-            }
-          } else if (MODE == EG_EU2) {
-            val = *(reinterpret_cast<const float4*>(a.in_s + (size_t)slot * D::F + j * 32) + c);
           } else {
-            val = *(reinterpret_cast<const float4*>(a.in_s + (size_t)slot * S + j * 32) + c);
+            if (ok) val = *(reinterpret_cast<const float4*>(a.in_s + (size_t)sl_ * D::F + j * 32) + ch);
           }
+        } else if (MODE == EG_MSG) {
+          if (ok) {
+            if (j < S / 32) val = *(reinterpret_cast<const float4*>(a.in_s + (size_t)sl_ * S + j * 32) + ch);
+            else {
+              const int k0 = (j - S / 32) * 32 + ch * 4;
+              if (k0 < SH_W) val = *(reinterpret_cast<const float4*>(a.in_sh + (size_t)sl_ * SH_W + k0));
+            }
+          }
+        } else if (MODE == EG_EU2) {
+          if (ok) val = *(reinterpret_cast<const float4*>(a.in_s + (size_t)sl_ * D::F + j * 32) + ch);
+        } else {
+          if (ok) val = *(reinterpret_cast<const float4*>(a.in_s + (size_t)sl_ * S + j * 32) + ch);
         }
-        buf[c] = val;
+        buf[i] = val;
       }
     };
     float4 cur[8], nxt[8];
     fetch(0, cur);
+    if (a.trace && blockIdx.x == a.trace_cta && tid == 64) a.trace[1] = clock64();
     for (int j = 0; j < NSLAB; ++j) {
       const int st = j & 1;
       if (j + 1 < NSLAB) fetch(j + 1, nxt);
       if (j >= 2) tc::mbar_wait(&x_empty[st], ((j >> 1) - 1) & 1);
-      uint8_t* hi = xst + st * EG_XSTAGE + h * 16384;
-      uint8_t* lo = hi + LO_OFF;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const float4 val = cur[c];
+      for (int i = 0; i < 8; ++i) {
+        const int rw = wrow0 + 4 * i + lg, hh = rw >> 7, rr_ = rw & 127;
+        uint8_t* hi = xst + st * EG_XSTAGE + hh * 16384;
+        const float4 val = cur[i];
         float4 vh, vl;
         tc::split_tf32(val.x, vh.x, vl.x); tc::split_tf32(val.y, vh.y, vl.y);
         tc::split_tf32(val.z, vh.z, vl.z); tc::split_tf32(val.w, vh.w, vl.w);
-        const uint32_t off = tc::sw128_off(rr, c * 4);
+        const uint32_t off = tc::sw128_off(rr_, ch * 4);
         *reinterpret_cast<float4*>(hi + off) = vh;
-        *reinterpret_cast<float4*>(lo + off) = vl;
+        *reinterpret_cast<float4*>(hi + LO_OFF + off) = vl;
       }
       tc::fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&x_full[st])) : "memory");
       }
+      if (a.trace && blockIdx.x == a.trace_cta && tid == 64) a.trace[2 + j] = clock64();
 #pragma unroll
-      for (int c = 0; c < 8; ++c) cur[c] = nxt[c];
+      for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
     }
     // ---- epilogue: TMEM -> registers -> bias / gathered pre-activation -> activation -> coalesced global stores ------------------------
     tc::mbar_wait(acc_full, 0);
     tc::tc_fence_after();
+    if (a.trace && blockIdx.x == a.trace_cta && tid == 64) a.trace[30] = clock64();
     const int q = warp & 3, eh = (warp - 2) >> 2;
     if ((MODE != EG_GATE || q == 0) && !(a.dbg & 8)) {
       for (int mt = 0; mt < NMT; ++mt) {
@@ -314,6 +322,7 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
       }
     }
   }
+  if (a.trace && blockIdx.x == a.trace_cta && tid == 64) a.trace[31] = clock64();
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 1) tc::tmem_dealloc(tmem, TMEM_COLS);

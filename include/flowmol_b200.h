@@ -112,6 +112,8 @@ int fm_debug_tc_gemm(const float* w_host, const float* x_host, int32_t K, float*
  *          1 tcgen05 3xTF32 message kernel (flowmol3 dimensions; fp32-faithful error-compensated tensor-core path) */
 int fm_set_option(FmHandle* h, const char* name, int32_t value);
 int fm_get_option(FmHandle* h, const char* name, int32_t* value);
+/* timeline experiments: after fm_set_option(h, "tc_trace", cta) every k_egemm_tc launch records clock64 stamps of that CTA */
+int fm_debug_read_trace(FmHandle* h, int64_t* out64_host);
 /* number of kernels launched by the last fm_forward / fm_integrate call on this handle */
 int64_t fm_last_launch_count(FmHandle* h);
 

@@ -28,8 +28,18 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 // ---- math (accurate versions: the parity bar is the reference's fp32 noise floor) ---------------------------------
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }          // torch.nn.SiLU
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }    // torch.sigmoid
+// 1 / v for v in [1, inf]: MUFU.RCP (1 ulp), branch-free.  The IEEE division / __frcp_rn compile to a call with a slow path
+// behind a reconvergence barrier, which serialises unrolled epilogues into one ~130-cycle dependent chain per element
+// (measured on k_egemm_tc: 34 k cycles for 256 elements per thread, profiles/r01c).
+__device__ __forceinline__ float rcp_fast(float v) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ float silu_f(float x) { return x * rcp_fast(1.0f + expf(-x)); }   // torch.nn.SiLU: x / (1 + exp(-x))
+__device__ __forceinline__ float sigmoid_f(float x) { return rcp_fast(1.0f + expf(-x)); }    // torch.sigmoid
+// tensor-core pipeline epilogues: ex2.approx based exponential as well (error ~1e-7 of the activation, below 3xTF32's)
+__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_fast(1.0f + __expf(-x)); }
 
 // flowmol/models/gvp.py:14-21 -- sqrt(clamp(x^2+y^2+z^2, 1e-8))
 __device__ __forceinline__ float norm_no_nan3(float x, float y, float z) {

@@ -292,7 +292,7 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {      // padding rows are computed and stored too (their slots exist)
               const float z = acc[i] + ((MODE == EG_MSG0 || MODE == EG_EU1) ? pre[i] : bias);
-              const float sg = __frcp_rn(1.0f + __expf(-z));
+              const float sg = sigmoid_fast(z);
               op[(size_t)i * OW] = MODE == EG_GATE ? sg : z * sg;
             }
           } else {
@@ -300,7 +300,7 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               const float z = acc[i] + bias;
-              acc[i] = __fadd_rn(pre[i], z * __frcp_rn(1.0f + __expf(-z)));
+              acc[i] = __fadd_rn(pre[i], z * sigmoid_fast(z));
             }
 #pragma unroll
             for (int i = 0; i < 32; ++i) { const float t = warp_sum(acc[i]); if (lane == i) red[q * 32 + i] = t; }
@@ -314,7 +314,7 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               const float var = (red[128 + i] + red[160 + i] + red[192 + i] + red[224 + i]) * (1.0f / 128.0f);
-              op[(size_t)i * OW] = (acc[i] - pre[i]) * (1.0f / sqrtf(var + 1e-5f)) * gam + bet;
+              op[(size_t)i * OW] = (acc[i] - pre[i]) * rsqrtf(var + 1e-5f) * gam + bet;
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");     // red[] is rewritten by the next chunk
           }

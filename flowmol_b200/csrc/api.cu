@@ -96,6 +96,7 @@ struct FmHandle {
   std::vector<long long> off_h;   // host copy of the weight offset table
   std::unordered_map<void*, Layout> batches;
   int64_t launches = 0;
+  int eg_nh_gate = 1;
   int eg_nh = 2;               // 128-edge halves per CTA of k_egemm_tc (2: 1 CTA/SM, 1: 2 CTAs/SM)
   long long* d_trace = nullptr;   // clock64 stamps of one egemm CTA (timeline experiments)
   int trace_cta = 0, trace_mode = 1;
@@ -189,8 +190,8 @@ int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
       }
       LAUNCH_OK(h);
       fm::EgArgs ag{wptr(tcg[g]), wptr(gb[g] + fm::GV_BG), outs[g], nullptr, nullptr, nullptr, GT, nullptr, nullptr, L.EP, h->trace_mode == 2 ? h->d_trace : nullptr, h->trace_cta, h->tc_debug};
-      if (NHsel == 2) fm::k_egemm_tc<D, fm::EG_GATE, 2><<<gt, fm::EgPlan<2>::THREADS, fm::EgPlan<2>::SMEM_BYTES, st>>>(m, bt, ag);
-      else fm::k_egemm_tc<D, fm::EG_GATE, 1><<<gt, fm::EgPlan<1>::THREADS, fm::EgPlan<1>::SMEM_BYTES, st>>>(m, bt, ag);
+      if (h->eg_nh_gate == 2) fm::k_egemm_tc<D, fm::EG_GATE, 2><<<(int)(L.EPA / 256), fm::EgPlan<2>::THREADS, fm::EgPlan<2>::SMEM_BYTES, st>>>(m, bt, ag);
+      else fm::k_egemm_tc<D, fm::EG_GATE, 1><<<(int)(L.EPA / 128), fm::EgPlan<1>::THREADS, fm::EgPlan<1>::SMEM_BYTES, st>>>(m, bt, ag);
       LAUNCH_OK(h);
       if (g < 2) { fm::k_vec_b<D><<<L.nET, fm::NT, vsm, st>>>(m, bt, l, g + 1, VH, SH, GT); LAUNCH_OK(h); }
       cur = outs[g];
@@ -573,6 +574,7 @@ int fm_set_option(FmHandle* h, const char* name, int32_t value) {
     h->trace_cta = value;
     return 0;
   }
+  if (n == "eg_nh_gate") { if (value != 1 && value != 2) return fail("fm_set_option: eg_nh_gate must be 1 or 2"); h->eg_nh_gate = value; return 0; }
   if (n == "eg_nh") { if (value != 1 && value != 2) return fail("fm_set_option: eg_nh must be 1 or 2"); h->eg_nh = value; return 0; }
   return fail("fm_set_option: unknown option");
 }

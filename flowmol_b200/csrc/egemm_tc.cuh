@@ -26,14 +26,16 @@ template <int NH>
 struct EgPlan {
   static constexpr int T = 128 * NH;
   static constexpr int THREADS = 64 + 128 * NH;
-  static constexpr int RING = NH == 2 ? 4 : 3;
+  static constexpr int RING_BYTES = (NH == 2 ? 6 : 3) * TC_UNIT;   // weight ring
+  static constexpr int MAX_SLOTS = 12;                             // barriers reserved (small gate units use more slots)
   static constexpr int XSTAGE = 32768 * NH;               // hi halves | lo halves, 16 KB each
   static constexpr int OFF_X = 0;
   static constexpr int OFF_RING = 2 * XSTAGE;
-  static constexpr int OFF_ROW = OFF_RING + RING * TC_UNIT;   // int src[T]; int16 (dst - src)[T]
+  static constexpr int OFF_ROW = OFF_RING + RING_BYTES;       // int src[T]; int16 (dst - src)[T]
   static constexpr int OFF_BAR = OFF_ROW + T * 6;
-  static_assert(NH == 2 || OFF_BAR + (2 * RING + 5) * 8 + 16 <= 115712, "2 CTAs per SM need <= 113 KB each");
-  static constexpr int BYTES = OFF_BAR + (2 * RING + 5) * 8 + 16;
+  static_assert(NH == 2 || OFF_BAR + (2 * MAX_SLOTS + 5) * 8 + 16 <= 115712, "2 CTAs per SM need <= 113 KB each");
+  static_assert(NH == 1 || OFF_BAR + (2 * MAX_SLOTS + 5) * 8 + 16 <= 232448, "1 CTA per SM: 227 KB");
+  static constexpr int BYTES = OFF_BAR + (2 * MAX_SLOTS + 5) * 8 + 16;
   static constexpr size_t SMEM_BYTES = BYTES;             // the dynamic shared-memory base is 1024-byte aligned (declared so)
 };
 
@@ -61,7 +63,7 @@ template <class D, int MODE, int NH>
 __global__ void __launch_bounds__(EgPlan<NH>::THREADS, NH == 1 ? 2 : 1)
 k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
   using PL = EgPlan<NH>;
-  constexpr int EG_T = PL::T, EG_RING = PL::RING, EG_XSTAGE = PL::XSTAGE;
+  constexpr int EG_T = PL::T, EG_XSTAGE = PL::XSTAGE;
   constexpr int LO_OFF = NH * 16384;                          // offset of the lo images inside a stage
   constexpr int S = D::S;
   constexpr bool IS_EU = MODE == EG_EU1 || MODE == EG_EU2;
@@ -72,6 +74,7 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
   constexpr int OW = MODE == EG_GATE ? 32 : (IS_EU ? D::F : S);          // output row width
   static_assert(!IS_EU || (NH == 1 && D::F == 128), "edge-update modes: one 128-edge half, F = 128");
   constexpr int UNIT_BYTES = MODE == EG_GATE ? 32 * 128 : TC_UNIT;
+  constexpr int EG_RING = (PL::RING_BYTES / UNIT_BYTES) < PL::MAX_SLOTS ? (PL::RING_BYTES / UNIT_BYTES) : PL::MAX_SLOTS;   // slots of UNIT_BYTES
   constexpr int SH_W = 40;                                     // row pitch of the norm buffer
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   uint8_t* base = smem_dyn;
@@ -80,7 +83,7 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
   int* r_src = reinterpret_cast<int*>(base + PL::OFF_ROW);
   short* r_dd = reinterpret_cast<short*>(r_src + EG_T);        // dst - src (same molecule, |.| < 2000)
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + PL::OFF_BAR);
-  uint64_t *w_full = bars, *w_empty = bars + EG_RING, *x_full = bars + 2 * EG_RING, *x_empty = x_full + 2, *acc_full = x_empty + 2;
+  uint64_t *w_full = bars, *w_empty = bars + PL::MAX_SLOTS, *x_full = bars + 2 * PL::MAX_SLOTS, *x_empty = x_full + 2, *acc_full = x_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long slot0 = (long long)blockIdx.x * EG_T;
@@ -135,7 +138,7 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
         if (use > 0) tc::mbar_wait(&w_empty[sl], (use - 1) & 1);
         if (a.dbg & 1) { tc::mbar_arrive_expect_tx(&w_full[sl], 0u); continue; }
         tc::mbar_arrive_expect_tx(&w_full[sl], UNIT_BYTES);
-        tc::bulk_g2s(ring + sl * TC_UNIT, reinterpret_cast<const uint8_t*>(a.units) + (size_t)u * UNIT_BYTES, UNIT_BYTES, &w_full[sl]);
+        tc::bulk_g2s(ring + sl * UNIT_BYTES, reinterpret_cast<const uint8_t*>(a.units) + (size_t)u * UNIT_BYTES, UNIT_BYTES, &w_full[sl]);
       }
     }
   } else if (warp == 1) {
@@ -153,7 +156,7 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
             const uint32_t sl = u % EG_RING, use = u / EG_RING;
             tc::mbar_wait(&w_full[sl], use & 1);
             tc::tc_fence_after();
-            const uint32_t wb = tc::smem_u32(ring + sl * TC_UNIT);
+            const uint32_t wb = tc::smem_u32(ring + sl * UNIT_BYTES);
             for (int h = 0; h < NH; ++h) {
               const uint32_t d = tmem + (uint32_t)((mt * NH + h) * 128);
               for (int ks = 0; ks < ksteps && !(a.dbg & 2); ++ks) {
@@ -169,7 +172,7 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
             const uint32_t sl = u % EG_RING, use = u / EG_RING;
             tc::mbar_wait(&w_full[sl], use & 1);
             tc::tc_fence_after();
-            const uint32_t wb = tc::smem_u32(ring + sl * TC_UNIT);
+            const uint32_t wb = tc::smem_u32(ring + sl * UNIT_BYTES);
             for (int h = 0; h < NH; ++h) {
               const uint32_t d = tmem + (uint32_t)((mt * NH + h) * 128);
               for (int ks = 0; ks < ksteps && !(a.dbg & 2); ++ks)
@@ -270,22 +273,28 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
         const int f = mt * 128 + q * 32 + lane;
         const float bias = (MODE == EG_MSG0 || MODE == EG_EU1) ? 0.f : a.bias[f];
         float* red = reinterpret_cast<float*>(xst);            // EU2: cross-warp LayerNorm partials (the stages are idle now)
-        for (int c = 0; c < 4; ++c) {
-          float acc[32], pre[32];
-          tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((mt * NH + eh) * 128 + c * 32), acc);
+        float pre[32], pnext[32];
+        auto gather = [&](int c, float (&dst_)[32]) {          // per-edge pre-activations / residuals of chunk c (L2 / HBM gathers)
           if (MODE == EG_MSG0) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) pre[i] = __ldg(a.P + (size_t)max(r_src[eh * 128 + c * 32 + i], 0) * S + f);
+            for (int i = 0; i < 32; ++i) dst_[i] = __ldg(a.P + (size_t)max(r_src[eh * 128 + c * 32 + i], 0) * S + f);
           } else if (MODE == EG_EU1) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               const int e = c * 32 + i, sn = max(r_src[e], 0);
-              pre[i] = __fadd_rn(__ldg(a.P + (size_t)sn * 2 * D::F + f), __ldg(a.P + (size_t)(sn + r_dd[e]) * 2 * D::F + D::F + f));
+              dst_[i] = __fadd_rn(__ldg(a.P + (size_t)sn * 2 * D::F + f), __ldg(a.P + (size_t)(sn + r_dd[e]) * 2 * D::F + D::F + f));
             }
           } else if (MODE == EG_EU2) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) pre[i] = a.in_sh[(size_t)(slot0 + c * 32 + i) * D::F + f];     // residual: current ef
+            for (int i = 0; i < 32; ++i) dst_[i] = a.in_sh[(size_t)(slot0 + c * 32 + i) * D::F + f];     // residual: current ef
           }
+        };
+        constexpr bool GATHERS = MODE == EG_MSG0 || MODE == EG_EU1 || MODE == EG_EU2;
+        if (GATHERS) gather(0, pre);
+        for (int c = 0; c < 4; ++c) {
+          float acc[32];
+          tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((mt * NH + eh) * 128 + c * 32), acc);
+          if (GATHERS && c + 1 < 4) gather(c + 1, pnext);     // in flight while this chunk is finished
           tc::tmem_ld_wait();
           float* op = a.out + (size_t)(slot0 + eh * 128 + c * 32) * OW + f;
           if (MODE != EG_EU2) {
@@ -302,13 +311,21 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
               const float z = acc[i] + bias;
               acc[i] = __fadd_rn(pre[i], z * sigmoid_fast(z));
             }
+            {
+              float t[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { const float t = warp_sum(acc[i]); if (lane == i) red[q * 32 + i] = t; }
+              for (int i = 0; i < 32; ++i) t[i] = acc[i];
+              red[q * 32 + lane] = warp_transpose_sum(t);      // lane i <- sum over the warp's 32 features of edge i
+            }
             asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll
             for (int i = 0; i < 32; ++i) pre[i] = (red[i] + red[32 + i] + red[64 + i] + red[96 + i]) * (1.0f / 128.0f);   // mean
+            {
+              float t[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { const float dlt = acc[i] - pre[i]; const float t = warp_sum(dlt * dlt); if (lane == i) red[128 + q * 32 + i] = t; }
+              for (int i = 0; i < 32; ++i) { const float dlt = acc[i] - pre[i]; t[i] = dlt * dlt; }
+              red[128 + q * 32 + lane] = warp_transpose_sum(t);
+            }
             asm volatile("bar.sync 1, 128;" ::: "memory");
             const float gam = a.ln_w[f], bet = a.ln_b[f];
 #pragma unroll
@@ -317,6 +334,10 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
               op[(size_t)i * OW] = (acc[i] - pre[i]) * rsqrtf(var + 1e-5f) * gam + bet;
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");     // red[] is rewritten by the next chunk
+          }
+          if (GATHERS) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) pre[i] = pnext[i];
           }
         }
       }

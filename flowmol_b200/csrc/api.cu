@@ -555,6 +555,40 @@ int fm_workspace_tensor(FmHandle* h, void* ws, const char* name, void** ptr, siz
 
 int64_t fm_last_launch_count(FmHandle* h) { return h ? h->launches : -1; }
 
+// Time the dominant kernel of the wide pipeline alone: the 292 -> 256 message linear (k_egemm_tc<EG_MSG>) of conv `layer`,
+// GVP 1, on the buffers left by the last fm_forward (CUDA events on the launching stream).
+int fm_time_egemm_msg(FmHandle* h, void* ws, int32_t layer, int32_t iters, float* ms_avg, void* stream) {
+  if (!h || !ws || !ms_avg || iters < 1 || layer < 0 || layer >= h->cfg.n_convs) return fail("fm_time_egemm_msg: bad argument");
+  if (h->variant != 0 || !h->has_tc) return fail("fm_time_egemm_msg: tensor-core pipeline not available for this model");
+  const Layout* Lp;
+  if (find_batch(h, ws, &Lp)) return -1;
+  const Layout& L = *Lp;
+  using D = fm::DimsFlowmol3;
+  CUDA_OK(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const fm::BatchRT bt = batch_rt(ws, L);
+  auto wptr = [&](int id) { return h->d_w + h->off_h[fm::G_COUNT + layer * fm::C_COUNT + id]; };
+  fm::EgArgs a{wptr(fm::C_MSG1_TCW), wptr(fm::C_MSG1_WHCP + fm::GV_B), at<float>(ws, L.SA), at<float>(ws, L.SH), nullptr, nullptr,
+               at<float>(ws, L.SB), nullptr, nullptr, L.EP, nullptr, 0, 0};
+  cudaEvent_t e0, e1;
+  CUDA_OK(cudaEventCreate(&e0));
+  CUDA_OK(cudaEventCreate(&e1));
+  CUDA_OK(cudaStreamSynchronize(st));
+  CUDA_OK(cudaEventRecord(e0, st));
+  for (int i = 0; i < iters; ++i) {
+    if (h->eg_nh == 2) fm::k_egemm_tc<D, fm::EG_MSG, 2><<<(int)(L.EPA / 256), fm::EgPlan<2>::THREADS, fm::EgPlan<2>::SMEM_BYTES, st>>>(h->rt, bt, a);
+    else fm::k_egemm_tc<D, fm::EG_MSG, 1><<<(int)(L.EPA / 128), fm::EgPlan<1>::THREADS, fm::EgPlan<1>::SMEM_BYTES, st>>>(h->rt, bt, a);
+  }
+  CUDA_OK(cudaEventRecord(e1, st));
+  CUDA_OK(cudaEventSynchronize(e1));
+  CUDA_OK(cudaGetLastError());
+  float ms = 0.f;
+  CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *ms_avg = ms / (float)iters;
+  return 0;
+}
+
 int fm_set_option(FmHandle* h, const char* name, int32_t value) {
   if (!h || !name) return fail("fm_set_option: null argument");
   const std::string n(name);

@@ -125,6 +125,13 @@ class CTMCVectorFieldB200:
             _lib.check(self.lib.fm_time_conv_edge(self._h, self._ws.data_ptr(), int(layer), int(iters), C.byref(ms), self._stream()))
         return float(ms.value)
 
+    def time_egemm_msg(self, layer=1, iters=5):
+        """Mean duration (ms) of the 292 -> 256 message linear on the tensor cores (bench roofline, flowmol3 dims)."""
+        ms = C.c_float()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.fm_time_egemm_msg(self._h, self._ws.data_ptr(), int(layer), int(iters), C.byref(ms), self._stream()))
+        return float(ms.value)
+
     def _pred_buffers(self, N, U):
         dev = self.device
         return {'x': torch.empty(N, 3, device=dev), 'a': torch.empty(N, self.n_atom_types, device=dev),

@@ -108,8 +108,12 @@ int fm_time_conv_edge(FmHandle* h, void* workspace, int32_t layer, int32_t iters
 /* stand-alone check of the tcgen05 building blocks (host buffers): out[128][64] = W[128][K] . X[64][K]^T, K in {32,64,96,128};
  * passes = 1 (plain TF32) or 3 (error-compensated 3xTF32) */
 int fm_debug_tc_gemm(const float* w_host, const float* x_host, int32_t K, float* out_host, int32_t passes, int device);
+/* same, for the dominant kernel of the default flowmol3 pipeline: the 292 -> 256 message linear k_egemm_tc<EG_MSG> (GVP 1) */
+int fm_time_egemm_msg(FmHandle* h, void* workspace, int32_t layer, int32_t iters, float* ms_avg, void* stream);
 /* options: "conv_impl" = 0 fp32 CUDA-core message kernel (bit-for-bit the reference's fp32 arithmetic up to summation order),
- *          1 tcgen05 3xTF32 message kernel (flowmol3 dimensions; fp32-faithful error-compensated tensor-core path) */
+ *          1 fused tcgen05 3xTF32 message kernel (experimental), 2 wide tcgen05 3xTF32 pipeline (default for the flowmol3
+ *          dimensions; message linears + EdgeUpdate on the tensor cores); "eg_nh" / "eg_nh_gate" = 128-edge halves per CTA of
+ *          k_egemm_tc (1: 2 CTAs/SM, 2: 1 CTA/SM); "tc_debug", "tc_trace", "tc_trace_mode": timing experiments */
 int fm_set_option(FmHandle* h, const char* name, int32_t value);
 int fm_get_option(FmHandle* h, const char* name, int32_t* value);
 /* timeline experiments: after fm_set_option(h, "tc_trace", cta) every k_egemm_tc launch records clock64 stamps of that CTA */

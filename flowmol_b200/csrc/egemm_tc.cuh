@@ -74,7 +74,10 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
   constexpr int OW = MODE == EG_GATE ? 32 : (IS_EU ? D::F : S);          // output row width
   static_assert(!IS_EU || (NH == 1 && D::F == 128), "edge-update modes: one 128-edge half, F = 128");
   constexpr int UNIT_BYTES = MODE == EG_GATE ? 32 * 128 : TC_UNIT;
-  constexpr int EG_RING = (PL::RING_BYTES / UNIT_BYTES) < PL::MAX_SLOTS ? (PL::RING_BYTES / UNIT_BYTES) : PL::MAX_SLOTS;   // slots of UNIT_BYTES
+  // slots of UNIT_BYTES; the MMA always reads a full 128-row (16 KB) operand tile from the slot base (rows beyond a 32-row gate
+  // unit are stale data feeding accumulator rows nobody reads), so the last slot must still have 16 KB behind it
+  constexpr int EG_RING_FIT = (PL::RING_BYTES - TC_UNIT) / UNIT_BYTES + 1;
+  constexpr int EG_RING = EG_RING_FIT < PL::MAX_SLOTS ? EG_RING_FIT : PL::MAX_SLOTS;
   constexpr int SH_W = 40;                                     // row pitch of the norm buffer
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   uint8_t* base = smem_dyn;

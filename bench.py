@@ -289,7 +289,10 @@ def main():
                     "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
                     "peak_kind": f"dense TF32 tensor = 1/2 x bf16, {peak_src}; the kernel issues 3 TF32 MMAs per fp32 product "
                                  f"(error-compensated), so frac_of_3xTF32_ceiling = {3 * achieved / tf32_peak:.3f}",
-                    "algorithmic_flops_per_launch": flops, "ms_per_launch": ms_k, "traffic": None,
+                    "algorithmic_flops_per_launch": flops, "ms_per_launch": ms_k,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this workload from the committed ncu capture
+                    # (profiles/r01c_summary.md: 1.392 + 1.169 GB); bench.py itself never runs under a profiler
+                    "traffic": 2.561e9 if (args.workload == "geom512" and world == 1) else None,
                     "hbm": {"algorithmic_bytes_per_launch": hbm_bytes, "achieved_gbs": hbm_bytes / (ms_k * 1e-3) / 1e9,
                             "peak_gbs": hbm_peak, "frac": hbm_bytes / (ms_k * 1e-3) / 1e9 / hbm_peak},
                     "message_pass": {"what": "whole message phase of one conv layer (10 launches: 3 vec + 6 egemm + segment-sum)",

@@ -171,7 +171,7 @@ def config_dict(name, wl, gpus):
     cfg_name, dataset, B, T, idx = wl
     return {"workload": f"BASELINE.json configs[{idx}]: {dataset} sized molecules, {cfg_name} dims, {B} molecules per GPU, "
                         f"{T} timesteps", "name": name, "molecules_per_gpu": B, "global_molecules": B * gpus, "timesteps": T,
-            "sizes": "n_atoms ~ train_data_n_atoms_histogram, torch.Generator().manual_seed(1234 + 7919*rank)",
+            "sizes": "n_atoms ~ train_data_n_atoms_histogram, one global draw torch.Generator().manual_seed(1234), contiguous cost-balanced ranges per rank",
             "weights": "random init (reference constructors' distributions), seed 0", "parallelism": f"molecule sharding x{gpus}",
             "l2": "inputs larger than L2 (edge hidden state alone is ~0.6 GB per evaluation at geom512); no flush needed"}
 

@@ -97,6 +97,7 @@ struct FmHandle {
   std::unordered_map<void*, Layout> batches;
   int64_t launches = 0;
   int eg_nh_gate = 1;
+  int n_sm = 148;
   int eg_nh = 2;               // 128-edge halves per CTA of k_egemm_tc (2: 1 CTA/SM, 1: 2 CTAs/SM)
   long long* d_trace = nullptr;   // clock64 stamps of one egemm CTA (timeline experiments)
   int trace_cta = 0, trace_mode = 1;
@@ -173,7 +174,8 @@ int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
     const int NHsel = h->eg_nh;
     const int gt = (int)(L.EPA / (128 * NHsel));
     const size_t vsm = fm::VecSmem<D>::BYTES;
-    fm::k_vec_a<D><<<L.nET, fm::NT, vsm, st>>>(m, bt, l, x, v, VH, SH);
+    const int vgrid = L.nET < 2 * h->n_sm ? L.nET : 2 * h->n_sm;     // persistent: 2 CTAs per SM, tiles strided
+    fm::k_vec_a<D><<<vgrid, fm::NT, vsm, st>>>(m, bt, l, x, v, VH, SH);
     LAUNCH_OK(h);
     const int tcw[3] = {fm::C_MSG0_TCW, fm::C_MSG1_TCW, fm::C_MSG2_TCW}, tcg[3] = {fm::C_MSG0_TCG, fm::C_MSG1_TCG, fm::C_MSG2_TCG};
     const int gb[3] = {fm::C_MSG0_WHCP, fm::C_MSG1_WHCP, fm::C_MSG2_WHCP};
@@ -193,10 +195,10 @@ int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
       if (h->eg_nh_gate == 2) fm::k_egemm_tc<D, fm::EG_GATE, 2><<<(int)(L.EPA / 256), fm::EgPlan<2>::THREADS, fm::EgPlan<2>::SMEM_BYTES, st>>>(m, bt, ag);
       else fm::k_egemm_tc<D, fm::EG_GATE, 1><<<(int)(L.EPA / 128), fm::EgPlan<1>::THREADS, fm::EgPlan<1>::SMEM_BYTES, st>>>(m, bt, ag);
       LAUNCH_OK(h);
-      if (g < 2) { fm::k_vec_b<D><<<L.nET, fm::NT, vsm, st>>>(m, bt, l, g + 1, VH, SH, GT); LAUNCH_OK(h); }
+      if (g < 2) { fm::k_vec_b<D><<<vgrid, fm::NT, vsm, st>>>(m, bt, l, g + 1, VH, SH, GT); LAUNCH_OK(h); }
       cur = outs[g];
     }
-    fm::k_vec_c<D><<<L.nET, fm::NT, vsm, st>>>(m, bt, l, VH, GT, SA, M, partF, partL);
+    fm::k_vec_c<D><<<vgrid, fm::NT, vsm, st>>>(m, bt, l, VH, GT, SA, M, partF, partL);
     LAUNCH_OK(h);
   }
   return 0;
@@ -350,6 +352,7 @@ int fm_create(const FmConfig* cfg, const float* w_host, size_t n_floats, const i
   h->cfg = c; h->device = device; h->variant = variant;
   h->has_tc = off_host[fm::G_COUNT + fm::C_MSG0_TCW] >= 0;
   h->off_h.assign(off_host, off_host + n_off);
+  { cudaDeviceProp pr; if (cudaGetDeviceProperties(&pr, device) == cudaSuccess) h->n_sm = pr.multiProcessorCount; }
   h->conv_impl = (variant == 0 && h->has_tc) ? 2 : 0;   // flowmol3 dims: wide tcgen05 3xTF32 pipeline by default
   h->eg_nh = 1;
   h->dyn = Dyn{c.n_hidden_scalars, c.n_vec_channels, c.n_hidden_edge_feats, c.use_dst_feats ? c.s_dst : 0,

@@ -133,6 +133,43 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ A, int lda, 
   }
 }
 
+// Same contraction with the (small) weight matrix already resident in shared memory: no staging, one barrier on entry
+// (A complete) and one on exit.  Used by the persistent vector-stage kernels, which load their two matrices once per CTA.
+template <int PLANES, int CPT, int RPW = 8>
+__device__ __forceinline__ void tile_gemm_resident(const float* __restrict__ A, int lda, int plane_stride, int K,
+                                                   const float* __restrict__ Wsm, float (&acc)[PLANES][RPW][CPT]) {
+  constexpr int NP = 32 * CPT;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int p = 0; p < PLANES; ++p)
+#pragma unroll
+    for (int r = 0; r < RPW; ++r)
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) acc[p][r][c] = 0.0f;
+  __syncthreads();
+  for (int kk = 0; kk < K; kk += 4) {
+#pragma unroll
+    for (int p = 0; p < PLANES; ++p) {
+      float4 a[RPW];
+      const float* ap = A + p * plane_stride + (warp * RPW) * lda + kk;
+#pragma unroll
+      for (int r = 0; r < RPW; ++r) a[r] = *reinterpret_cast<const float4*>(ap + r * lda);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float w[CPT];
+        load_w<CPT>(Wsm + (kk + j) * NP, lane, w);
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+          const float av = j == 0 ? a[r].x : (j == 1 ? a[r].y : (j == 2 ? a[r].z : a[r].w));
+#pragma unroll
+          for (int cc = 0; cc < CPT; ++cc) acc[p][r][cc] = fmaf(av, w[cc], acc[p][r][cc]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
 // LayerNorm (eps 1e-5, affine) of rows held as an [8][CPT] register micro-tile: the 32 lanes of a warp hold the
 // 32*CPT columns of the same 8 rows.  torch.nn.LayerNorm: biased variance.
 template <int CPT>

@@ -39,8 +39,8 @@ template <class D>
 struct EdgeTile {
   int mol, n, nb, ecount, le0;
   size_t erow0;
-  __device__ explicit EdgeTile(const BatchRT& bt) {
-    const int tile = blockIdx.x;
+  int tile;
+  __device__ EdgeTile(const BatchRT& bt, int tile_) : tile(tile_) {
     mol = bt.etile_mol[tile];
     n = bt.mol_n[mol]; nb = bt.mol_node[mol]; ecount = n * (n - 1);
     le0 = (tile - bt.mol_etile[mol]) * TM;
@@ -50,13 +50,13 @@ struct EdgeTile {
 
 // stage 1 of a GVP on the tile in shared memory: Va[.., 0:v_in) -> Vb = [Vh | cross] (cols [0, h+cp)), stores VH and SH
 template <class D, int CPT_HC>
-__device__ __forceinline__ void vec_stage1(Smem<D>& sm, const int v_in, const int h, const float* __restrict__ whcp, const size_t erow0,
+__device__ __forceinline__ void vec_stage1(Smem<D>& sm, const int v_in, const int h, const float* __restrict__ whcp_sm, const size_t erow0,
                                            float* __restrict__ VH, float* __restrict__ SH) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int hc = h + D::CP;
   {
     float acc[3][RPW][CPT_HC];
-    tile_gemm<3, CPT_HC, 8, WSTAGE_FLOATS / 2>(sm.Va, D::LDVA, TM * D::LDVA, pad4(v_in), whcp, sm.wstage, acc);
+    tile_gemm_resident<3, CPT_HC>(sm.Va, D::LDVA, TM * D::LDVA, pad4(v_in), whcp_sm, acc);
     const int ncol = h + 2 * D::CP;
 #pragma unroll
     for (int p = 0; p < 3; ++p)
@@ -104,7 +104,7 @@ __device__ __forceinline__ void vec_stage1(Smem<D>& sm, const int v_in, const in
 
 // stage 2 of a GVP: Vb (loaded from VH) x Wu, gated by GT -> Va[.., 0:V)
 template <class D>
-__device__ __forceinline__ void vec_stage2(Smem<D>& sm, const int hc, const float* __restrict__ wu, const size_t erow0,
+__device__ __forceinline__ void vec_stage2(Smem<D>& sm, const int hc, const float* __restrict__ wu_sm, const size_t erow0,
                                            const float* __restrict__ VH, const float* __restrict__ GT) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   {
@@ -134,7 +134,7 @@ __device__ __forceinline__ void vec_stage2(Smem<D>& sm, const int hc, const floa
     }
   }
   float acc[3][RPW][1];
-  tile_gemm<3, 1, 8, WSTAGE_FLOATS / 2>(sm.Vb, D::LDVB, TM * D::LDVB, pad4(hc), wu, sm.wstage, acc);
+  tile_gemm_resident<3, 1>(sm.Vb, D::LDVB, TM * D::LDVB, pad4(hc), wu_sm, acc);
 #pragma unroll
   for (int p = 0; p < 3; ++p)
 #pragma unroll
@@ -143,6 +143,11 @@ __device__ __forceinline__ void vec_stage2(Smem<D>& sm, const int hc, const floa
       if (lane < D::V) sm.Va[(p * TM + row) * D::LDVA + lane] = __fmul_rn(sm.G[row * 32 + lane], acc[p][r][0]);
     }
   __syncthreads();
+}
+
+// the CTA's weight matrices ([K][32*CPT] images of the packer) -> shared memory, once per CTA
+__device__ __forceinline__ void load_resident(float* dst, const float* __restrict__ src, int floats) {
+  for (int i = threadIdx.x; i < floats / 4; i += NT) cp_async16(dst + i * 4, src + i * 4);
 }
 
 template <class D>
@@ -167,7 +172,13 @@ k_vec_a(const ModelRT m, const BatchRT bt, int layer, const float* __restrict__ 
   extern __shared__ __align__(16) float smem_raw[];
   Smem<D> sm = VecSmem<D>::carve(smem_raw);
   const int tid = threadIdx.x;
-  const EdgeTile<D> et(bt);
+  float* w_hcp = sm.wstage;                                       // [pad4(VIN0)][64]
+  load_resident(w_hcp, m.c(layer, C_MSG0_WHCP), pad4(D::VIN0) * 32 * D::CPT_HC0);
+  cp_async_commit();
+  cp_async_wait<0>();
+  for (int tile = blockIdx.x; tile < bt.n_edge_tiles; tile += gridDim.x) {
+  const EdgeTile<D> et(bt, tile);
+  __syncthreads();                                                // previous tile's readers of src/dst/Va are done
   tile_rows<D>(sm, et);
   if (tid < TM) {
     const int s = sm.src[tid], d = sm.dst[tid];
@@ -190,7 +201,8 @@ k_vec_a(const ModelRT m, const BatchRT bt, int layer, const float* __restrict__ 
     if (s >= 0 && c < D::V) val = v[((size_t)s * 3 + p) * D::V + c];
     sm.Va[pr * D::LDVA + 1 + c] = val;
   }
-  vec_stage1<D, D::CPT_HC0>(sm, D::VIN0, D::H0, m.c(layer, C_MSG0_WHCP), et.erow0, VH, SH);
+  vec_stage1<D, D::CPT_HC0>(sm, D::VIN0, D::H0, w_hcp, et.erow0, VH, SH);
+  }
 }
 
 template <class D>
@@ -199,12 +211,20 @@ k_vec_b(const ModelRT m, const BatchRT bt, int layer, int g_next /* 1 or 2 */, f
         const float* __restrict__ GT) {
   extern __shared__ __align__(16) float smem_raw[];
   Smem<D> sm = VecSmem<D>::carve(smem_raw);
-  const EdgeTile<D> et(bt);
-  tile_rows<D>(sm, et);
   const int hc_prev = (g_next == 1 ? D::H0 : D::V) + D::CP;
-  const int wu_id = g_next == 1 ? C_MSG0_WU : C_MSG1_WU;
-  vec_stage2<D>(sm, hc_prev, m.c(layer, wu_id), et.erow0, VH, GT);
-  vec_stage1<D, D::CPT_HC>(sm, D::V, D::V, m.c(layer, g_next == 1 ? C_MSG1_WHCP : C_MSG2_WHCP), et.erow0, VH, SH);
+  float* w_u = sm.wstage;                                         // [pad4(hc_prev)][32]
+  float* w_hcp = sm.wstage + 44 * 32;                             // [V][64]
+  load_resident(w_u, m.c(layer, g_next == 1 ? C_MSG0_WU : C_MSG1_WU), pad4(hc_prev) * 32);
+  load_resident(w_hcp, m.c(layer, g_next == 1 ? C_MSG1_WHCP : C_MSG2_WHCP), D::V * 32 * D::CPT_HC);
+  cp_async_commit();
+  cp_async_wait<0>();
+  for (int tile = blockIdx.x; tile < bt.n_edge_tiles; tile += gridDim.x) {
+    const EdgeTile<D> et(bt, tile);
+    __syncthreads();
+    tile_rows<D>(sm, et);
+    vec_stage2<D>(sm, hc_prev, w_u, et.erow0, VH, GT);
+    vec_stage1<D, D::CPT_HC>(sm, D::V, D::V, w_hcp, et.erow0, VH, SH);
+  }
 }
 
 template <class D>
@@ -214,10 +234,15 @@ k_vec_c(const ModelRT m, const BatchRT bt, int layer, const float* __restrict__ 
   extern __shared__ __align__(16) float smem_raw[];
   Smem<D> sm = VecSmem<D>::carve(smem_raw);
   const int tid = threadIdx.x;
-  const EdgeTile<D> et(bt);
+  float* w_u = sm.wstage;
+  load_resident(w_u, m.c(layer, C_MSG2_WU), pad4(D::V + D::CP) * 32);
+  cp_async_commit();
+  cp_async_wait<0>();
+  for (int tile = blockIdx.x; tile < bt.n_edge_tiles; tile += gridDim.x) {
+  const EdgeTile<D> et(bt, tile);
+  __syncthreads();
   tile_rows<D>(sm, et);
-  vec_stage2<D>(sm, D::V + D::CP, m.c(layer, C_MSG2_WU), et.erow0, VH, GT);
-  const int tile = blockIdx.x;
+  vec_stage2<D>(sm, D::V + D::CP, w_u, et.erow0, VH, GT);
   for (int col = tid; col < D::MW; col += NT) {
     float acc = 0.f;
     int seg_first = et.le0;
@@ -250,6 +275,7 @@ k_vec_c(const ModelRT m, const BatchRT bt, int layer, const float* __restrict__ 
         }
       }
     }
+  }
   }
 }
 

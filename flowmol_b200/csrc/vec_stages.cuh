@@ -9,10 +9,13 @@
 // GT [32] gates, S [256] scalar activations (written by k_egemm_tc).
 #pragma once
 #include "kernels.cuh"
+#include "mma3.cuh"
 
 namespace fm {
 
 constexpr int VHW = 40;   // row pitch of VH planes and SH
+constexpr int WLD_HCP = 72;   // shared-memory row pitch of [Wh | Wcp] (64 packed columns + 8: conflict-free B fragments)
+constexpr int WLD_U = 40;     // shared-memory row pitch of Wu (32 + 8)
 
 // compact shared-memory plan for the stages that never touch the scalar tile: 2 CTAs per SM (latency hiding)
 template <class D>
@@ -55,17 +58,20 @@ __device__ __forceinline__ void vec_stage1(Smem<D>& sm, const int v_in, const in
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int hc = h + D::CP;
   {
-    float acc[3][RPW][CPT_HC];
-    tile_gemm_resident<3, CPT_HC>(sm.Va, D::LDVA, TM * D::LDVA, pad4(v_in), whcp_sm, acc);
-    const int ncol = h + 2 * D::CP;
+    // [Vh | Vcp] = V x [Wh | Wcp]: 192 (edge, plane) rows x (h + 2cp <= 48) columns.  Warp w: 3 m16 tiles x 3 n8 tiles.
+    __syncthreads();
+    const int m0 = (warp >> 1) * 48, n0 = (warp & 1) * 24;
+    float acc[3][3][4];
+    warp_gemm_3xtf32<3, 3>(sm.Va, D::LDVA, m0, whcp_sm, WLD_HCP, n0, (v_in + 7) & ~7, acc);
+    const int ncol = h + 2 * D::CP, g = lane >> 2, t = lane & 3;
 #pragma unroll
-    for (int p = 0; p < 3; ++p)
+    for (int mt = 0; mt < 3; ++mt)
 #pragma unroll
-      for (int r = 0; r < RPW; ++r)
+      for (int nt = 0; nt < 3; ++nt)
 #pragma unroll
-        for (int c = 0; c < CPT_HC; ++c) {
-          const int col = ColMap<CPT_HC>::col(lane, c);
-          if (col < ncol) sm.Vb[(p * TM + warp * RPW + r) * D::LDVB + col] = acc[p][r][c];
+        for (int i = 0; i < 4; ++i) {
+          const int row = m0 + 16 * mt + g + (i >> 1) * 8, col = n0 + 8 * nt + 2 * t + (i & 1);
+          if (col < ncol) sm.Vb[row * D::LDVB + col] = acc[mt][nt][i];
         }
   }
   __syncthreads();
@@ -133,21 +139,33 @@ __device__ __forceinline__ void vec_stage2(Smem<D>& sm, const int hc, const floa
       if (idx < NG) *reinterpret_cast<float4*>(sm.G + idx * 4) = sm.src[idx >> 3] >= 0 ? gb[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
-  float acc[3][RPW][1];
-  tile_gemm_resident<3, 1>(sm.Vb, D::LDVB, TM * D::LDVB, pad4(hc), wu_sm, acc);
+  __syncthreads();
+  {
+    // Vu = Vh_ext x Wu: 192 rows x 32 columns, K = hc padded to 8.  Warp w: 3 m16 tiles x 2 n8 tiles.
+    const int m0 = (warp >> 1) * 48, n0 = (warp & 1) * 16, g = lane >> 2, t = lane & 3;
+    float acc[3][2][4];
+    warp_gemm_3xtf32<3, 2>(sm.Vb, D::LDVB, m0, wu_sm, WLD_U, n0, (hc + 7) & ~7, acc);
 #pragma unroll
-  for (int p = 0; p < 3; ++p)
+    for (int mt = 0; mt < 3; ++mt)
 #pragma unroll
-    for (int r = 0; r < RPW; ++r) {
-      const int row = warp * RPW + r;
-      if (lane < D::V) sm.Va[(p * TM + row) * D::LDVA + lane] = __fmul_rn(sm.G[row * 32 + lane], acc[p][r][0]);
-    }
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = m0 + 16 * mt + g + (i >> 1) * 8, col = n0 + 8 * nt + 2 * t + (i & 1);
+          sm.Va[row * D::LDVA + col] = __fmul_rn(sm.G[(row & (TM - 1)) * 32 + col], acc[mt][nt][i]);
+        }
+  }
   __syncthreads();
 }
 
-// the CTA's weight matrices ([K][32*CPT] images of the packer) -> shared memory, once per CTA
-__device__ __forceinline__ void load_resident(float* dst, const float* __restrict__ src, int floats) {
-  for (int i = threadIdx.x; i < floats / 4; i += NT) cp_async16(dst + i * 4, src + i * 4);
+// the CTA's weight matrices, once per CTA: src [K][np] (packer layout) -> dst [K padded to 8][ld] (padding rows zero)
+__device__ __forceinline__ void load_resident(float* dst, const float* __restrict__ src, int K, int np, int ld) {
+  const int kp = (K + 7) & ~7;
+  for (int i = threadIdx.x; i < kp * (np / 4); i += NT) {
+    const int k = i / (np / 4), c4 = i - k * (np / 4);
+    if (k < K) cp_async16(dst + k * ld + c4 * 4, src + k * np + c4 * 4);
+    else *reinterpret_cast<float4*>(dst + k * ld + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
 }
 
 template <class D>
@@ -173,7 +191,7 @@ k_vec_a(const ModelRT m, const BatchRT bt, int layer, const float* __restrict__ 
   Smem<D> sm = VecSmem<D>::carve(smem_raw);
   const int tid = threadIdx.x;
   float* w_hcp = sm.wstage;                                       // [pad4(VIN0)][64]
-  load_resident(w_hcp, m.c(layer, C_MSG0_WHCP), pad4(D::VIN0) * 32 * D::CPT_HC0);
+  load_resident(w_hcp, m.c(layer, C_MSG0_WHCP), pad4(D::VIN0), 32 * D::CPT_HC0, WLD_HCP);
   cp_async_commit();
   cp_async_wait<0>();
   for (int tile = blockIdx.x; tile < bt.n_edge_tiles; tile += gridDim.x) {
@@ -213,9 +231,9 @@ k_vec_b(const ModelRT m, const BatchRT bt, int layer, int g_next /* 1 or 2 */, f
   Smem<D> sm = VecSmem<D>::carve(smem_raw);
   const int hc_prev = (g_next == 1 ? D::H0 : D::V) + D::CP;
   float* w_u = sm.wstage;                                         // [pad4(hc_prev)][32]
-  float* w_hcp = sm.wstage + 44 * 32;                             // [V][64]
-  load_resident(w_u, m.c(layer, g_next == 1 ? C_MSG0_WU : C_MSG1_WU), pad4(hc_prev) * 32);
-  load_resident(w_hcp, m.c(layer, g_next == 1 ? C_MSG1_WHCP : C_MSG2_WHCP), D::V * 32 * D::CPT_HC);
+  float* w_hcp = sm.wstage + 40 * WLD_U;                          // [V][64 (+8)]
+  load_resident(w_u, m.c(layer, g_next == 1 ? C_MSG0_WU : C_MSG1_WU), pad4(hc_prev), 32, WLD_U);
+  load_resident(w_hcp, m.c(layer, g_next == 1 ? C_MSG1_WHCP : C_MSG2_WHCP), D::V, 32 * D::CPT_HC, WLD_HCP);
   cp_async_commit();
   cp_async_wait<0>();
   for (int tile = blockIdx.x; tile < bt.n_edge_tiles; tile += gridDim.x) {
@@ -235,7 +253,7 @@ k_vec_c(const ModelRT m, const BatchRT bt, int layer, const float* __restrict__ 
   Smem<D> sm = VecSmem<D>::carve(smem_raw);
   const int tid = threadIdx.x;
   float* w_u = sm.wstage;
-  load_resident(w_u, m.c(layer, C_MSG2_WU), pad4(D::V + D::CP) * 32);
+  load_resident(w_u, m.c(layer, C_MSG2_WU), pad4(D::V + D::CP), 32, WLD_U);
   cp_async_commit();
   cp_async_wait<0>();
   for (int tile = blockIdx.x; tile < bt.n_edge_tiles; tile += gridDim.x) {

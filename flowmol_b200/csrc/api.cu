@@ -39,6 +39,7 @@ struct Layout {
   size_t s, v, x, P, Q, vd, EAB, M, partF, partL, ef;
   size_t SA, SB, VH, SH, GT;   // wide tensor-core pipeline intermediates (per padded edge slot, rounded up to 256 slots)
   long long EPA = 0;
+  long long NPA = 0;           // node rows rounded up to 256
   size_t pred[3][4];     // [buffer][x,a,c,e]
   size_t total = 0;
 };
@@ -66,12 +67,13 @@ Layout make_layout(const Dyn& d, const int32_t* n_atoms, int B) {
   L.mol_etile = take(4ull * B); L.mol_utile = take(4ull * B);
   L.etile_mol = take(4ull * L.nET); L.utile_mol = take(4ull * L.nUT); L.node_mol = take(4ull * N);
   L.s = take(4ull * N * d.S); L.v = take(4ull * N * 3 * d.V); L.x = take(4ull * N * 3);
-  L.P = take(4ull * N * d.S); L.Q = take(4ull * N * d.S * (d.SD > 0)); L.vd = take(4ull * N * 3 * d.VD);
-  L.EAB = take(4ull * N * 2 * d.F); L.M = take(4ull * N * d.MW);
+  L.NPA = (N + 255) / 256 * 256;                  // node rows rounded up: k_egemm_tc stores whole 128-row tiles
+  L.P = take(4ull * (size_t)L.NPA * d.S); L.Q = take(4ull * N * d.S * (d.SD > 0)); L.vd = take(4ull * N * 3 * d.VD);
+  L.EAB = take(4ull * (size_t)L.NPA * 2 * d.F); L.M = take(4ull * N * d.MW);
   L.partF = take(8ull * L.nET * d.MW); L.partL = take(8ull * L.nET * d.MW);   // x2: the tensor-core kernel uses 32-row tiles
   L.EPA = (L.EP + 255) / 256 * 256;
   L.ef = take(4ull * (size_t)L.EPA * d.F);       // rounded up: the wide kernels store whole 128-slot tiles
-  const size_t wide = d.S == 256 && d.SD == 0 ? (size_t)L.EPA : 0;
+  const size_t wide = d.S == 256 && d.SD == 0 ? (size_t)std::max<long long>(L.EPA, L.NPA) : 0;   // the node pipeline reuses these
   L.SA = take(4ull * wide * d.S); L.SB = take(4ull * wide * d.S); L.VH = take(4ull * wide * 120); L.SH = take(4ull * wide * 40);
   L.GT = take(4ull * wide * 32);
   for (int k = 0; k < 3; ++k) {
@@ -103,6 +105,8 @@ struct FmHandle {
   int trace_cta = 0, trace_mode = 1;
   int tc_debug = 0;            // timing experiments (conv_tc.cuh TcCtx::dbg)
   bool has_tc = false;         // packed weights contain the UMMA operand images
+  int fuse_agg = 1;            // scalar segment-sum in the epilogue of the last message linear (k_egemm_tc<EG_MSGA>)
+  int node_impl = 0;           // 0: fused fp32 k_node_update, 1: node pipeline around k_egemm_tc (with conv_impl 2)
   int conv_impl = 0;           // 0: fp32 CUDA-core k_conv_edge, 1: tcgen05 3xTF32 k_conv_edge_tc (flowmol3 dims only)
   cudaStream_t cap_stream = nullptr;    // private stream for CUDA-graph capture (the legacy default stream cannot capture)
 };
@@ -149,6 +153,11 @@ int set_smem_attrs() {
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_EU2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<1>::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_vec_a<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::VecSmem<D>::BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_vec_b<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::VecSmem<D>::BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_node_pre<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::VecSmem<D>::BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_node_mid<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::VecSmem<D>::BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_node_post<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::VecSmem<D>::BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_MSGA, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<1>::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_LIN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<1>::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_vec_c<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::VecSmem<D>::BYTES));
   }
   return 0;
@@ -182,7 +191,10 @@ int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
     float* cur = ef;      // input activations of the current scalar linear
     float* outs[3] = {SA, SB, SA};
     for (int g = 0; g < 3; ++g) {
-      fm::EgArgs a{wptr(tcw[g]), wptr(gb[g] + fm::GV_B), cur, SH, P, x, outs[g], nullptr, nullptr, L.EP, h->trace_mode == (g == 0 ? 0 : 1) ? h->d_trace : nullptr, h->trace_cta, h->tc_debug};
+      fm::EgArgs a{wptr(tcw[g]), wptr(gb[g] + fm::GV_B), cur, SH, P, x, outs[g], nullptr, nullptr, L.EP, h->trace_mode == (g == 0 ? 0 : 1) ? h->d_trace : nullptr, h->trace_cta, 0, h->tc_debug, M, partF, partL};
+      if (g == 2 && h->fuse_agg) {       // last scalar linear: the segment-sum over in-edges rides in the epilogue
+        fm::k_egemm_tc<D, fm::EG_MSGA, 1><<<(int)(L.EPA / 128), fm::EgPlan<1>::THREADS, fm::EgPlan<1>::SMEM_BYTES, st>>>(m, bt, a);
+      } else
       if (NHsel == 2) {
         if (g == 0) fm::k_egemm_tc<D, fm::EG_MSG0, 2><<<gt, fm::EgPlan<2>::THREADS, fm::EgPlan<2>::SMEM_BYTES, st>>>(m, bt, a);
         else fm::k_egemm_tc<D, fm::EG_MSG, 2><<<gt, fm::EgPlan<2>::THREADS, fm::EgPlan<2>::SMEM_BYTES, st>>>(m, bt, a);
@@ -191,15 +203,87 @@ int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
         else fm::k_egemm_tc<D, fm::EG_MSG, 1><<<gt, fm::EgPlan<1>::THREADS, fm::EgPlan<1>::SMEM_BYTES, st>>>(m, bt, a);
       }
       LAUNCH_OK(h);
-      fm::EgArgs ag{wptr(tcg[g]), wptr(gb[g] + fm::GV_BG), outs[g], nullptr, nullptr, nullptr, GT, nullptr, nullptr, L.EP, h->trace_mode == 2 ? h->d_trace : nullptr, h->trace_cta, h->tc_debug};
+      fm::EgArgs ag{wptr(tcg[g]), wptr(gb[g] + fm::GV_BG), outs[g], nullptr, nullptr, nullptr, GT, nullptr, nullptr, L.EP, h->trace_mode == 2 ? h->d_trace : nullptr, h->trace_cta, 0, h->tc_debug};
       if (h->eg_nh_gate == 2) fm::k_egemm_tc<D, fm::EG_GATE, 2><<<(int)(L.EPA / 256), fm::EgPlan<2>::THREADS, fm::EgPlan<2>::SMEM_BYTES, st>>>(m, bt, ag);
       else fm::k_egemm_tc<D, fm::EG_GATE, 1><<<(int)(L.EPA / 128), fm::EgPlan<1>::THREADS, fm::EgPlan<1>::SMEM_BYTES, st>>>(m, bt, ag);
       LAUNCH_OK(h);
-      if (g < 2) { fm::k_vec_b<D><<<vgrid, fm::NT, vsm, st>>>(m, bt, l, g + 1, VH, SH, GT); LAUNCH_OK(h); }
+      if (g < 2) {
+        fm::k_vec_b<D><<<vgrid, fm::NT, vsm, st>>>(bt, wptr(g == 0 ? fm::C_MSG0_WU : fm::C_MSG1_WU), (g == 0 ? D::H0 : D::V) + D::CP,
+                                                     wptr(g == 0 ? fm::C_MSG1_WHCP : fm::C_MSG2_WHCP), 0, VH, SH, GT);
+        LAUNCH_OK(h);
+      }
       cur = outs[g];
     }
-    fm::k_vec_c<D><<<vgrid, fm::NT, vsm, st>>>(m, bt, l, VH, GT, SA, M, partF, partL);
+    fm::k_vec_c<D><<<vgrid, fm::NT, vsm, st>>>(m, bt, l, h->fuse_agg ? D::S : 0, VH, GT, SA, M, partF, partL);
     LAUNCH_OK(h);
+  }
+  return 0;
+}
+
+// node update of conv `l` (+ NodePositionUpdate of `upd`) as a pipeline: the six GVPs' scalar / gate linears and the per-node
+// halves of the next edge phases run through k_egemm_tc on node rows, the vector stages in vec_stages.cuh.  The edge-sized
+// scratch buffers (SA, SB, VH, SH, GT) are idle between two message passes and are reused.
+template <class D>
+int node_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int l, int upd, int has_next, int agg_rows, cudaStream_t st) {
+  if constexpr (D::S == 256 && D::V == 32 && D::SD == 0 && D::F == 128) {
+    const fm::ModelRT& m = h->rt;
+    auto wptr = [&](int ll, int id) { return h->d_w + h->off_h[fm::G_COUNT + ll * fm::C_COUNT + id]; };
+    auto uptr = [&](int id) { return h->d_w + h->off_h[fm::G_COUNT + m.L * fm::C_COUNT + upd * fm::U_COUNT + id]; };
+    float *s = at<float>(ws, L.s), *v = at<float>(ws, L.v), *x = at<float>(ws, L.x), *P = at<float>(ws, L.P), *M = at<float>(ws, L.M);
+    float *EAB = at<float>(ws, L.EAB), *partF = at<float>(ws, L.partF), *partL = at<float>(ws, L.partL);
+    float *SA = at<float>(ws, L.SA), *SB = at<float>(ws, L.SB), *VH = at<float>(ws, L.VH), *SH = at<float>(ws, L.SH), *GT = at<float>(ws, L.GT);
+    const size_t vsm = fm::VecSmem<D>::BYTES;
+    const int gt = (int)(L.NPA / 128);
+    using PL = fm::EgPlan<1>;
+    auto scalar = [&](const float* units, const float* bias, const float* in, float* out) {
+      fm::EgArgs a{units, bias, in, SH, nullptr, nullptr, out, nullptr, nullptr, (long long)L.N, nullptr, 0, fm::EGF_NODE_ROWS, 0};
+      fm::k_egemm_tc<D, fm::EG_MSG, 1><<<gt, PL::THREADS, PL::SMEM_BYTES, st>>>(m, bt, a);
+    };
+    auto gate = [&](const float* units, const float* bias, const float* in, int identity) {
+      fm::EgArgs a{units, bias, in, nullptr, nullptr, nullptr, GT, nullptr, nullptr, (long long)L.N, nullptr, 0,
+                   fm::EGF_NODE_ROWS | (identity ? fm::EGF_IDENTITY : 0), 0};
+      fm::k_egemm_tc<D, fm::EG_GATE, 1><<<gt, PL::THREADS, PL::SMEM_BYTES, st>>>(m, bt, a);
+    };
+    auto linear = [&](const float* units, const float* bias, float* out) {
+      fm::EgArgs a{units, bias, s, nullptr, nullptr, nullptr, out, nullptr, nullptr, (long long)L.N, nullptr, 0, fm::EGF_NODE_ROWS, 0};
+      fm::k_egemm_tc<D, fm::EG_LIN, 1><<<gt, PL::THREADS, PL::SMEM_BYTES, st>>>(m, bt, a);
+    };
+    const int vgrid = L.nNT < 2 * h->n_sm ? L.nNT : 2 * h->n_sm;
+    fm::k_node_pre<D><<<L.nNT, fm::NT, vsm, st>>>(m, bt, l, agg_rows, s, v, M, partF, partL, VH, SH);
+    LAUNCH_OK(h);
+    const int utw[3] = {fm::C_UPD0_TCW, fm::C_UPD1_TCW, fm::C_UPD2_TCW}, utg[3] = {fm::C_UPD0_TCG, fm::C_UPD1_TCG, fm::C_UPD2_TCG};
+    const int ub[3] = {fm::C_UPD0_WHCP, fm::C_UPD1_WHCP, fm::C_UPD2_WHCP};
+    const float* cur = s;
+    float* outs[3] = {SA, SB, SA};
+    for (int g = 0; g < 3; ++g) {
+      scalar(wptr(l, utw[g]), wptr(l, ub[g] + fm::GV_B), cur, outs[g]); LAUNCH_OK(h);
+      gate(wptr(l, utg[g]), wptr(l, ub[g] + fm::GV_BG), outs[g], 0); LAUNCH_OK(h);
+      if (g < 2) {
+        fm::k_vec_b<D><<<vgrid, fm::NT, vsm, st>>>(bt, wptr(l, ub[g] + fm::GV_WU), D::V + D::CP, wptr(l, ub[g + 1] + fm::GV_WHCP), 1, VH, SH, GT);
+        LAUNCH_OK(h);
+      }
+      cur = outs[g];
+    }
+    fm::k_node_mid<D><<<L.nNT, fm::NT, vsm, st>>>(m, bt, l, upd, s, v, SA, VH, SH, GT);
+    LAUNCH_OK(h);
+    if (has_next) { linear(wptr(l + 1, fm::C_WSRC_TC), wptr(l + 1, fm::C_BSRC), P); LAUNCH_OK(h); }
+    if (upd >= 0) {
+      linear(uptr(fm::U_EUPD_WN_TC), uptr(fm::U_EUPD_BN), EAB); LAUNCH_OK(h);
+      const int ptw[3] = {fm::U_POS0_TCW, fm::U_POS1_TCW, fm::U_POS2_TCW}, ptg[3] = {fm::U_POS0_TCG, fm::U_POS1_TCG, fm::U_POS2_TCG};
+      const int pb[3] = {fm::U_POS0_WHCP, fm::U_POS1_WHCP, fm::U_POS2_WHCP};
+      cur = s;
+      for (int g = 0; g < 3; ++g) {
+        scalar(uptr(ptw[g]), uptr(pb[g] + fm::GV_B), cur, outs[g]); LAUNCH_OK(h);
+        gate(uptr(ptg[g]), uptr(pb[g] + fm::GV_BG), outs[g], g == 2); LAUNCH_OK(h);
+        if (g < 2) {
+          fm::k_vec_b<D><<<vgrid, fm::NT, vsm, st>>>(bt, uptr(pb[g] + fm::GV_WU), D::V + D::CP, uptr(pb[g + 1] + fm::GV_WHCP), 1, VH, SH, GT);
+          LAUNCH_OK(h);
+        }
+        cur = outs[g];
+      }
+      fm::k_node_post<D><<<L.nNT, fm::NT, vsm, st>>>(m, bt, upd, x, VH, GT);
+      LAUNCH_OK(h);
+    }
   }
   return 0;
 }
@@ -240,8 +324,13 @@ int run_pass(FmHandle* h, void* ws, const Layout& L, const float* x_t, const uin
     int upd = -1;
     if (l != 0 && (l + 1) % m.convs_per_update == 0) upd = m.separate_updaters ? l / m.convs_per_update : 0;   // vector_field.py:321-326
     const int has_next = l + 1 < m.L;
-    fm::k_node_update<D><<<L.nNT, fm::NT, smem, st>>>(m, bt, l, upd, has_next, agg_rows, s, v, x, M, partF, partL, P, EAB);
-    LAUNCH_OK(h);
+    if (h->conv_impl == 2 && h->node_impl == 1) {
+      int rc = node_wide<D>(h, ws, L, bt, l, upd, has_next, agg_rows, st);
+      if (rc) return rc;
+    } else {
+      fm::k_node_update<D><<<L.nNT, fm::NT, smem, st>>>(m, bt, l, upd, has_next, agg_rows, s, v, x, M, partF, partL, P, EAB);
+      LAUNCH_OK(h);
+    }
     if (m.use_dst && has_next) { fm::k_dst_proj<D><<<L.nNT, fm::NT, smem, st>>>(m, bt, l + 1, s, v, Q, vd); LAUNCH_OK(h); }
     if (upd >= 0) {
       bool done = false;
@@ -250,10 +339,10 @@ int run_pass(FmHandle* h, void* ws, const Layout& L, const float* x_t, const uin
           auto uptr = [&](int id) { return h->d_w + h->off_h[fm::G_COUNT + m.L * fm::C_COUNT + upd * fm::U_COUNT + id]; };
           float* H = at<float>(ws, L.SA);
           const int gt = (int)(L.EPA / 128);
-          fm::EgArgs a1{uptr(fm::U_EUPD_TC1), nullptr, ef, nullptr, EAB, x, H, nullptr, nullptr, L.EP, h->trace_mode == 3 ? h->d_trace : nullptr, h->trace_cta, h->tc_debug};
+          fm::EgArgs a1{uptr(fm::U_EUPD_TC1), nullptr, ef, nullptr, EAB, x, H, nullptr, nullptr, L.EP, h->trace_mode == 3 ? h->d_trace : nullptr, h->trace_cta, 0, h->tc_debug};
           fm::k_egemm_tc<D, fm::EG_EU1, 1><<<gt, fm::EgPlan<1>::THREADS, fm::EgPlan<1>::SMEM_BYTES, st>>>(m, bt, a1);
           LAUNCH_OK(h);
-          fm::EgArgs a2{uptr(fm::U_EUPD_TC2), uptr(fm::U_EUPD_B2), H, ef, nullptr, nullptr, ef, uptr(fm::U_EUPD_LN_W), uptr(fm::U_EUPD_LN_B), L.EP, h->trace_mode == 4 ? h->d_trace : nullptr, h->trace_cta, h->tc_debug};
+          fm::EgArgs a2{uptr(fm::U_EUPD_TC2), uptr(fm::U_EUPD_B2), H, ef, nullptr, nullptr, ef, uptr(fm::U_EUPD_LN_W), uptr(fm::U_EUPD_LN_B), L.EP, h->trace_mode == 4 ? h->d_trace : nullptr, h->trace_cta, 0, h->tc_debug};
           fm::k_egemm_tc<D, fm::EG_EU2, 1><<<gt, fm::EgPlan<1>::THREADS, fm::EgPlan<1>::SMEM_BYTES, st>>>(m, bt, a2);
           LAUNCH_OK(h);
           done = true;
@@ -354,6 +443,7 @@ int fm_create(const FmConfig* cfg, const float* w_host, size_t n_floats, const i
   h->off_h.assign(off_host, off_host + n_off);
   { cudaDeviceProp pr; if (cudaGetDeviceProperties(&pr, device) == cudaSuccess) h->n_sm = pr.multiProcessorCount; }
   h->conv_impl = (variant == 0 && h->has_tc) ? 2 : 0;   // flowmol3 dims: wide tcgen05 3xTF32 pipeline by default
+  h->node_impl = (h->conv_impl == 2 && off_host[fm::G_COUNT + fm::C_UPD0_TCW] >= 0) ? 1 : 0;
   h->eg_nh = 1;
   h->dyn = Dyn{c.n_hidden_scalars, c.n_vec_channels, c.n_hidden_edge_feats, c.use_dst_feats ? c.s_dst : 0,
                c.use_dst_feats ? c.v_dst : 0, c.n_atom_types, c.n_charges, c.n_bond_types,
@@ -602,6 +692,13 @@ int fm_set_option(FmHandle* h, const char* name, int32_t value) {
     h->conv_impl = value;
     return 0;
   }
+  if (n == "node_impl") {
+    if (value < 0 || value > 1) return fail("fm_set_option: node_impl must be 0 (fused fp32 kernel) or 1 (tensor-core node pipeline)");
+    if (value == 1 && (h->variant != 0 || h->off_h[fm::G_COUNT + fm::C_UPD0_TCW] < 0)) return fail("fm_set_option: no tensor-core images for the node pipeline");
+    h->node_impl = value;
+    return 0;
+  }
+  if (n == "fuse_agg") { h->fuse_agg = value ? 1 : 0; return 0; }
   if (n == "tc_debug") { h->tc_debug = value; return 0; }
   if (n == "tc_trace_mode") { h->trace_mode = value; return 0; }
   if (n == "tc_trace") {       // value < 0: off; otherwise the CTA index whose timeline is recorded (every egemm launch overwrites it)
@@ -623,6 +720,7 @@ int fm_debug_read_trace(FmHandle* h, int64_t* out64_host) {
 int fm_get_option(FmHandle* h, const char* name, int32_t* value) {
   if (!h || !name || !value) return fail("fm_get_option: null argument");
   if (std::string(name) == "conv_impl") { *value = h->conv_impl; return 0; }
+  if (std::string(name) == "node_impl") { *value = h->node_impl; return 0; }
   return fail("fm_get_option: unknown option");
 }
 

@@ -39,7 +39,12 @@ struct EgPlan {
   static constexpr size_t SMEM_BYTES = BYTES;             // the dynamic shared-memory base is 1024-byte aligned (declared so)
 };
 
-enum EgMode : int { EG_MSG0 = 0, EG_MSG = 1, EG_GATE = 2, EG_EU1 = 3, EG_EU2 = 4 };
+enum EgMode : int { EG_MSG0 = 0, EG_MSG = 1, EG_GATE = 2, EG_EU1 = 3, EG_EU2 = 4, EG_LIN = 5, EG_MSGA = 6 };
+// EG_MSGA: EG_MSG whose epilogue also reduces the scalar messages over the in-edges of every destination node (edges are
+// dst-major, so a thread walks its feature's 128 edge values in order): writes M / partL / partF exactly like k_vec_c.
+// EG_LIN: plain linear out = W in + b over S inputs / S outputs (per-node halves of the next edge phases, node rows).
+enum EgFlags : int { EGF_NODE_ROWS = 1,      // rows are nodes (EP = node count) instead of padded edge slots
+                     EGF_IDENTITY = 2 };     // EG_GATE without the sigmoid (vector gate of the last position GVP)
 // EG_EU1 / EG_EU2: the two linears of EdgeUpdate (flowmol/models/vector_field.py:844-880): h = SiLU(We [ef | rbf(d)] + EA[src] +
 // EB[dst]);  ef <- LayerNorm(ef + SiLU(W2 h + b2)).  NH = 1 only.
 
@@ -56,7 +61,11 @@ struct EgArgs {
   long long EP;              // padded edge slots (multiple of 64)
   long long* trace;          // optional clock64 stamps of one CTA (timeline experiments)
   int trace_cta;
+  int flags;                 // EgFlags
   int dbg;                   // timing experiments: 1 no weight copies, 2 no MMA issue, 4 loaders skip global reads, 8 no epilogue math/stores
+  float* M;                  // MSGA: aggregated messages [N][MW] and the per-64-slot-tile partial sums (see k_conv_edge)
+  float* partF;
+  float* partL;
 };
 
 template <class D, int MODE, int NH>
@@ -67,7 +76,8 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
   constexpr int LO_OFF = NH * 16384;                          // offset of the lo images inside a stage
   constexpr int S = D::S;
   constexpr bool IS_EU = MODE == EG_EU1 || MODE == EG_EU2;
-  constexpr int K = MODE == EG_MSG0 ? D::KE0 : (MODE == EG_MSG ? D::K1 : (MODE == EG_EU1 ? D::F + D::R : (MODE == EG_EU2 ? D::F : S)));
+  constexpr bool IS_MSG = MODE == EG_MSG || MODE == EG_MSGA;
+  constexpr int K = MODE == EG_MSG0 ? D::KE0 : (IS_MSG ? D::K1 : (MODE == EG_EU1 ? D::F + D::R : (MODE == EG_EU2 ? D::F : S)));
   constexpr int NSLAB = (K + 31) / 32;
   constexpr int LAST_KSTEPS = ((K - 1) % 32) / 8 + 1;
   constexpr int NMT = MODE == EG_GATE ? 1 : (IS_EU ? D::F / 128 : S / 128);
@@ -106,11 +116,21 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
     const long long slot = slot0 + r;
     int s = -1, dd = 0;
     float dist = 0.f;
-    if (slot < a.EP) {
+    if (a.flags & EGF_NODE_ROWS) {
+      if (slot < a.EP) s = 0;
+    } else if (slot < a.EP) {
       const int t64 = (int)(slot >> 6), mol = bt.etile_mol[t64];
       const int n = bt.mol_n[mol], le = (int)(slot - ((long long)bt.mol_etile[mol] << 6));
       if (le < n * (n - 1)) {
         s = 0;
+        if (MODE == EG_MSGA) {
+          const int j = le / (n - 1), rem = le - j * (n - 1);
+          s = bt.mol_node[mol] + j;                                   // destination node
+          const bool tail = rem == n - 2;                            // the node's last in-edge
+          // bit 0: the node's segment ends here inside this 64-slot tile; bit 1: ... with the node's last in-edge;
+          // bit 2: that segment began with the node's first in-edge (it lies in the same 64-slot tile)
+          dd = (((r & 63) == 63 || tail) ? 1 : 0) | (tail ? 2 : 0) | (rem <= (r & 63) ? 4 : 0);
+        }
         if (MODE == EG_MSG0 || MODE == EG_EU1) {
           int i, j;
           edge_src_dst(le, n, i, j);
@@ -123,7 +143,15 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
       }
     }
     r_src[r] = s;
-    r_dd[r] = (short)dd;
+    if (MODE == EG_MSGA) {      // one 32-bit mask per 32-row chunk (= per loader warp) instead of per-row flags
+      const unsigned em = __ballot_sync(0xffffffffu, dd & 1), tm = __ballot_sync(0xffffffffu, dd & 2), hm = __ballot_sync(0xffffffffu, dd & 4);
+      if (lane == 0) {
+        unsigned* masks = reinterpret_cast<unsigned*>(r_dd);
+        masks[(warp - 2) * 3 + 0] = em; masks[(warp - 2) * 3 + 1] = tm; masks[(warp - 2) * 3 + 2] = hm;
+      }
+    } else {
+      r_dd[r] = (short)dd;
+    }
     my_dist = dist;
   }
   if (a.trace && blockIdx.x == a.trace_cta && tid == 64) a.trace[0] = clock64();
@@ -222,7 +250,7 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
           } else {
             if (ok) val = *(reinterpret_cast<const float4*>(a.in_s + (size_t)sl_ * D::F + j * 32) + ch);
           }
-        } else if (MODE == EG_MSG) {
+        } else if (IS_MSG) {
           if (ok) {
             if (j < S / 32) val = *(reinterpret_cast<const float4*>(a.in_s + (size_t)sl_ * S + j * 32) + ch);
             else {
@@ -274,6 +302,7 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
     if ((MODE != EG_GATE || q == 0) && !(a.dbg & 8)) {
       for (int mt = 0; mt < NMT; ++mt) {
         const int f = mt * 128 + q * 32 + lane;
+        float run = 0.f;                                       // MSGA: running segment sum of feature f
         const float bias = (MODE == EG_MSG0 || MODE == EG_EU1) ? 0.f : a.bias[f];
         float* red = reinterpret_cast<float*>(xst);            // EU2: cross-warp LayerNorm partials (the stages are idle now)
         float pre[32], pnext[32];
@@ -300,12 +329,34 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
           if (GATHERS && c + 1 < 4) gather(c + 1, pnext);     // in flight while this chunk is finished
           tc::tmem_ld_wait();
           float* op = a.out + (size_t)(slot0 + eh * 128 + c * 32) * OW + f;
+          unsigned em = 0, tm = 0, hm = 0;
+          if (MODE == EG_MSGA) {
+            const unsigned* masks = reinterpret_cast<const unsigned*>(r_dd) + (eh * 4 + c) * 3;
+            em = masks[0]; tm = masks[1]; hm = masks[2];
+          }
           if (MODE != EG_EU2) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {      // padding rows are computed and stored too (their slots exist)
               const float z = acc[i] + ((MODE == EG_MSG0 || MODE == EG_EU1) ? pre[i] : bias);
+              if (MODE == EG_LIN) { op[(size_t)i * OW] = z; continue; }
               const float sg = sigmoid_fast(z);
-              op[(size_t)i * OW] = MODE == EG_GATE ? sg : z * sg;
+              const float o = MODE == EG_GATE ? ((a.flags & EGF_IDENTITY) ? z : sg) : z * sg;
+              op[(size_t)i * OW] = o;
+              if (MODE == EG_MSGA) {
+                // dst-major edges: the sum over a node's in-edges is a running sum along this thread's row of the accumulator.
+                // Slots after a molecule's last edge add garbage that is dropped at the next 64-slot boundary.
+                if (i == 0 && (c & 1) == 0) run = 0.f;
+                run = __fadd_rn(run, o);
+                if ((em >> i) & 1u) {                        // uniform over the CTA's epilogue threads
+                  const int row = eh * 128 + c * 32 + i, d = r_src[row];
+                  const size_t t64 = (size_t)((slot0 + row) >> 6);
+                  const bool head = (hm >> i) & 1u, tail = (tm >> i) & 1u;
+                  if (head && tail) a.M[(size_t)d * D::MW + f] = run;
+                  else if (head) a.partL[t64 * D::MW + f] = run;
+                  else a.partF[t64 * D::MW + f] = run;
+                  run = 0.f;
+                }
+              }
             }
           } else {
             // y = ef + SiLU(W2 h + b2);  LayerNorm over the 128 features of every edge = over the lanes of the 4 epilogue warps

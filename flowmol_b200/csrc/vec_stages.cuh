@@ -210,45 +210,235 @@ k_vec_a(const ModelRT m, const BatchRT bt, int layer, const float* __restrict__ 
     sm.Va[(1 * TM + tid) * D::LDVA] = uy;
     sm.Va[(2 * TM + tid) * D::LDVA] = uz;
   }
-  constexpr int VW = D::LDVA - 1;
-  for (int idx = tid; idx < 3 * TM * VW; idx += NT) {
-    const int pr = idx / VW, c = idx - pr * VW;
-    const int p = pr / TM, row = pr - p * TM;
-    float val = 0.f;
-    const int s = sm.src[row];
-    if (s >= 0 && c < D::V) val = v[((size_t)s * 3 + p) * D::V + c];
-    sm.Va[pr * D::LDVA + 1 + c] = val;
+  {
+    // v of the source node: 3 planes x V floats per edge, float4 gathers all in flight (v is L2 resident), then the K padding
+    constexpr int Q4 = D::V / 4, NQ = 3 * TM * Q4, PER = (NQ + NT - 1) / NT;
+    float4 buf[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int idx = tid + i * NT;
+      buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx < NQ) {
+        const int row = idx / (3 * Q4), rem = idx - row * (3 * Q4);          // rem = plane * Q4 + quad: contiguous in v[src]
+        const int s = sm.src[row];
+        if (s >= 0) buf[i] = __ldg(reinterpret_cast<const float4*>(v + (size_t)s * 3 * D::V) + rem);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int idx = tid + i * NT;
+      if (idx < NQ) {
+        const int row = idx / (3 * Q4), rem = idx - row * (3 * Q4), p = rem / Q4, q = rem - p * Q4;
+        float* d = sm.Va + (p * TM + row) * D::LDVA + 1 + q * 4;
+        d[0] = buf[i].x; d[1] = buf[i].y; d[2] = buf[i].z; d[3] = buf[i].w;
+      }
+    }
+    constexpr int PADW = D::LDVA - 1 - D::V;
+    for (int idx = tid; idx < 3 * TM * PADW; idx += NT) {
+      const int pr = idx / PADW, c = idx - pr * PADW;
+      sm.Va[pr * D::LDVA + 1 + D::V + c] = 0.f;
+    }
   }
   vec_stage1<D, D::CPT_HC0>(sm, D::VIN0, D::H0, w_hcp, et.erow0, VH, SH);
   }
 }
 
+// validity of the 64 rows of a node tile (rows = nodes; src >= 0 marks a live row for the vector stages)
+template <class D>
+__device__ __forceinline__ void node_tile_rows(Smem<D>& sm, int g0, int N) {
+  if (threadIdx.x < TM) { sm.src[threadIdx.x] = g0 + (int)threadIdx.x < N ? 0 : -1; sm.dst[threadIdx.x] = -1; }
+  __syncthreads();
+}
+
+// stage 2 of one GVP (Wu [hc_prev][32]) then stage 1 of the next (Whcp [V][64]); rows are padded edge slots, or nodes
 template <class D>
 __global__ void __launch_bounds__(NT, 2)
-k_vec_b(const ModelRT m, const BatchRT bt, int layer, int g_next /* 1 or 2 */, float* __restrict__ VH, float* __restrict__ SH,
-        const float* __restrict__ GT) {
+k_vec_b(const BatchRT bt, const float* __restrict__ wu, int hc_prev, const float* __restrict__ whcp, int node_rows,
+        float* __restrict__ VH, float* __restrict__ SH, const float* __restrict__ GT) {
   extern __shared__ __align__(16) float smem_raw[];
   Smem<D> sm = VecSmem<D>::carve(smem_raw);
-  const int hc_prev = (g_next == 1 ? D::H0 : D::V) + D::CP;
-  float* w_u = sm.wstage;                                         // [pad4(hc_prev)][32]
+  float* w_u = sm.wstage;                                         // [pad8(hc_prev)][32 (+8)]
   float* w_hcp = sm.wstage + 40 * WLD_U;                          // [V][64 (+8)]
-  load_resident(w_u, m.c(layer, g_next == 1 ? C_MSG0_WU : C_MSG1_WU), pad4(hc_prev), 32, WLD_U);
-  load_resident(w_hcp, m.c(layer, g_next == 1 ? C_MSG1_WHCP : C_MSG2_WHCP), D::V, 32 * D::CPT_HC, WLD_HCP);
+  load_resident(w_u, wu, pad4(hc_prev), 32, WLD_U);
+  load_resident(w_hcp, whcp, D::V, 32 * D::CPT_HC, WLD_HCP);
   cp_async_commit();
   cp_async_wait<0>();
-  for (int tile = blockIdx.x; tile < bt.n_edge_tiles; tile += gridDim.x) {
-    const EdgeTile<D> et(bt, tile);
+  const int n_tiles = node_rows ? bt.n_node_tiles : bt.n_edge_tiles;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     __syncthreads();
-    tile_rows<D>(sm, et);
-    vec_stage2<D>(sm, hc_prev, w_u, et.erow0, VH, GT);
-    vec_stage1<D, D::CPT_HC>(sm, D::V, D::V, w_hcp, et.erow0, VH, SH);
+    if (node_rows) node_tile_rows<D>(sm, tile * TM, bt.N);
+    else { const EdgeTile<D> et(bt, tile); tile_rows<D>(sm, et); }
+    const size_t erow0 = (size_t)tile * TM;
+    vec_stage2<D>(sm, hc_prev, w_u, erow0, VH, GT);
+    vec_stage1<D, D::CPT_HC>(sm, D::V, D::V, w_hcp, erow0, VH, SH);
+  }
+}
+
+// ---- node update as a pipeline around k_egemm_tc (node rows) ----------------------------------------------------------------------
+// GVPLayerNorm (gvp.py:169-184), scalar half: one warp per row, lanes over columns; `f(col)` is the pre-norm value
+template <class D, class F>
+__device__ __forceinline__ void row_scalar_layernorm(float* __restrict__ out_row, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, F f) {
+  const int lane = threadIdx.x & 31;
+  float val[D::CPT_S];
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < D::CPT_S; ++c) { val[c] = f(lane + 32 * c); s += val[c]; }
+  const float mean = warp_sum(s) * (1.0f / D::S);
+  float q = 0.f;
+#pragma unroll
+  for (int c = 0; c < D::CPT_S; ++c) { const float d = val[c] - mean; q = fmaf(d, d, q); }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / D::S) + 1e-5f);
+#pragma unroll
+  for (int c = 0; c < D::CPT_S; ++c) {
+    const int col = lane + 32 * c;
+    out_row[col] = (val[c] - mean) * rstd * gamma[col] + beta[col];
+  }
+}
+// vector half on the tile in Va: v / (sqrt(mean_c clamp(|v_c|^2, 1e-8) + eps) + eps); the result is also stored to v[g]
+template <class D>
+__device__ __forceinline__ void tile_vec_layernorm(float* __restrict__ Va, float* __restrict__ v, int g0, int N) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int r = 0; r < RPW; ++r) {
+    const int row = warp * RPW + r, g = g0 + row;
+    float a = 0.f, b = 0.f, c = 0.f, vq = 0.f;
+    if (lane < D::V) {
+      a = Va[(0 * TM + row) * D::LDVA + lane]; b = Va[(1 * TM + row) * D::LDVA + lane]; c = Va[(2 * TM + row) * D::LDVA + lane];
+      vq = fmaxf(__fadd_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)), __fmul_rn(c, c)), 1e-8f);
+    }
+    const float vn = __fadd_rn(sqrtf(__fadd_rn(warp_sum(vq) * (1.0f / D::V), 1e-5f)), 1e-5f);
+    if (lane < D::V) {
+      a = __fdiv_rn(a, vn); b = __fdiv_rn(b, vn); c = __fdiv_rn(c, vn);
+      Va[(0 * TM + row) * D::LDVA + lane] = a; Va[(1 * TM + row) * D::LDVA + lane] = b; Va[(2 * TM + row) * D::LDVA + lane] = c;
+      if (g < N) {
+        v[((size_t)g * 3 + 0) * D::V + lane] = a; v[((size_t)g * 3 + 1) * D::V + lane] = b; v[((size_t)g * 3 + 2) * D::V + lane] = c;
+      }
+    }
+  }
+}
+
+// k_node_pre: (s, v) <- GVPLayerNorm((s, v) + aggregated message)  (gvp.py:509-513), then stage 1 of the first update GVP
+template <class D>
+__global__ void __launch_bounds__(NT, 2)
+k_node_pre(const ModelRT m, const BatchRT bt, int layer, int agg_rows, float* __restrict__ s, float* __restrict__ v,
+           const float* __restrict__ M, const float* __restrict__ partF, const float* __restrict__ partL,
+           float* __restrict__ VH, float* __restrict__ SH) {
+  extern __shared__ __align__(16) float smem_raw[];
+  Smem<D> sm = VecSmem<D>::carve(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  float* w_hcp = sm.wstage;
+  load_resident(w_hcp, m.c(layer, C_UPD0_WHCP), D::V, 32 * D::CPT_HC, WLD_HCP);
+  cp_async_commit();
+  const int g0 = blockIdx.x * TM;
+  node_tile_rows<D>(sm, g0, bt.N);
+  // per-row aggregation plan (see gather_message): first / last piece of the node's in-edge segment, and the normaliser
+  if (tid < TM) {
+    const int g = g0 + tid;
+    int t0 = 0, t1 = 0;
+    float div = 0.f;
+    if (g < bt.N) {
+      const int mol = bt.node_mol[g], n = bt.mol_n[mol], j = g - bt.mol_node[mol];
+      const int first = j * (n - 1), last = first + n - 2, tb = bt.mol_etile[mol] * (TM / agg_rows);
+      t0 = tb + first / agg_rows; t1 = tb + last / agg_rows;
+      div = m.msg_norm > 0.f ? m.msg_norm : (m.msg_norm < 0.f ? (float)(n - 1) : 0.f);      // 'mean': over the in-edges
+    }
+    sm.dst[tid] = t0; sm.aux[tid] = t1; sm.dist[tid] = div;
+  }
+  __syncthreads();
+  auto message = [&](int row, int g, int col) {
+    const int t0 = sm.dst[row], t1 = sm.aux[row];
+    float msg;
+    if (t0 == t1) msg = M[(size_t)g * D::MW + col];
+    else {
+      msg = partL[(size_t)t0 * D::MW + col];
+      for (int t = t0 + 1; t <= t1; ++t) msg = __fadd_rn(msg, partF[(size_t)t * D::MW + col]);
+    }
+    const float div = sm.dist[row];
+    return div != 0.f ? __fdiv_rn(msg, div) : msg;
+  };
+  for (int r = 0; r < RPW; ++r) {
+    const int row = warp * RPW + r, g = g0 + row;
+    if (g >= bt.N) break;
+    float* srow = s + (size_t)g * D::S;
+    row_scalar_layernorm<D>(srow, m.c(layer, C_LN_MSG_W), m.c(layer, C_LN_MSG_B),
+                            [&](int col) { return __fadd_rn(srow[col], message(row, g, col)); });
+  }
+#pragma unroll 4
+  for (int idx = tid; idx < TM * 3 * D::V; idx += NT) {
+    const int row = idx / (3 * D::V), pc = idx - row * 3 * D::V, g = g0 + row;
+    float val = 0.f;
+    if (g < bt.N) val = __fadd_rn(v[(size_t)g * 3 * D::V + pc], message(row, g, D::S + pc));
+    sm.Va[((pc / D::V) * TM + row) * D::LDVA + (pc % D::V)] = val;
+  }
+  __syncthreads();
+  tile_vec_layernorm<D>(sm.Va, v, g0, bt.N);
+  cp_async_wait<0>();
+  vec_stage1<D, D::CPT_HC>(sm, D::V, D::V, w_hcp, (size_t)g0, VH, SH);
+}
+
+// k_node_mid: stage 2 of the last update GVP, (s, v) <- GVPLayerNorm((s, v) + update)  (gvp.py:515-519), then stage 1 of the first
+// NodePositionUpdate GVP when this conv is followed by a molecule update
+template <class D>
+__global__ void __launch_bounds__(NT, 2)
+k_node_mid(const ModelRT m, const BatchRT bt, int layer, int updater, float* __restrict__ s, float* __restrict__ v,
+           const float* __restrict__ S3, float* __restrict__ VH, float* __restrict__ SH, const float* __restrict__ GT) {
+  extern __shared__ __align__(16) float smem_raw[];
+  Smem<D> sm = VecSmem<D>::carve(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  float* w_u = sm.wstage;
+  float* w_hcp = sm.wstage + 40 * WLD_U;
+  load_resident(w_u, m.c(layer, C_UPD2_WU), pad4(D::V + D::CP), 32, WLD_U);
+  if (updater >= 0) load_resident(w_hcp, m.u(updater, U_POS0_WHCP), D::V, 32 * D::CPT_HC, WLD_HCP);
+  cp_async_commit();
+  cp_async_wait<0>();
+  const int g0 = blockIdx.x * TM;
+  __syncthreads();
+  node_tile_rows<D>(sm, g0, bt.N);
+  vec_stage2<D>(sm, D::V + D::CP, w_u, (size_t)g0, VH, GT);
+  for (int r = 0; r < RPW; ++r) {
+    const int g = g0 + warp * RPW + r;
+    if (g >= bt.N) break;
+    float* srow = s + (size_t)g * D::S;
+    const float* urow = S3 + (size_t)g * D::S;
+    row_scalar_layernorm<D>(srow, m.c(layer, C_LN_UPD_W), m.c(layer, C_LN_UPD_B),
+                            [&](int col) { return __fadd_rn(srow[col], urow[col]); });
+  }
+  for (int idx = tid; idx < TM * 3 * D::V; idx += NT) {
+    const int row = idx / (3 * D::V), pc = idx - row * 3 * D::V, g = g0 + row;
+    float* p = sm.Va + ((pc / D::V) * TM + row) * D::LDVA + (pc % D::V);
+    *p = g < bt.N ? __fadd_rn(v[(size_t)g * 3 * D::V + pc], *p) : 0.f;
+  }
+  __syncthreads();
+  tile_vec_layernorm<D>(sm.Va, v, g0, bt.N);
+  if (updater >= 0) vec_stage1<D, D::CPT_HC>(sm, D::V, D::V, w_hcp, (size_t)g0, VH, SH);
+}
+
+// k_node_post: stage 2 of the last position GVP (one output vector); x += that vector   (vector_field.py:813-842)
+template <class D>
+__global__ void __launch_bounds__(NT, 2)
+k_node_post(const ModelRT m, const BatchRT bt, int updater, float* __restrict__ x, const float* __restrict__ VH,
+            const float* __restrict__ GT) {
+  extern __shared__ __align__(16) float smem_raw[];
+  Smem<D> sm = VecSmem<D>::carve(smem_raw);
+  const int tid = threadIdx.x;
+  float* w_u = sm.wstage;
+  load_resident(w_u, m.u(updater, U_POS2_WU), pad4(D::V + D::CP), 32, WLD_U);
+  cp_async_commit();
+  cp_async_wait<0>();
+  const int g0 = blockIdx.x * TM;
+  __syncthreads();
+  node_tile_rows<D>(sm, g0, bt.N);
+  vec_stage2<D>(sm, D::V + D::CP, w_u, (size_t)g0, VH, GT);
+  if (tid < TM * 3) {
+    const int row = tid / 3, p = tid - row * 3, g = g0 + row;
+    if (g < bt.N) x[g * 3 + p] = __fadd_rn(x[g * 3 + p], sm.Va[(p * TM + row) * D::LDVA]);
   }
 }
 
 template <class D>
 __global__ void __launch_bounds__(NT, 2)
-k_vec_c(const ModelRT m, const BatchRT bt, int layer, const float* __restrict__ VH, const float* __restrict__ GT,
-        const float* __restrict__ Smsg, float* __restrict__ M, float* __restrict__ partF, float* __restrict__ partL) {
+k_vec_c(const ModelRT m, const BatchRT bt, int layer, int first_col /* S when k_egemm_tc<EG_MSGA> reduced the scalar columns */,
+        const float* __restrict__ VH, const float* __restrict__ GT, const float* __restrict__ Smsg, float* __restrict__ M, float* __restrict__ partF, float* __restrict__ partL) {
   extern __shared__ __align__(16) float smem_raw[];
   Smem<D> sm = VecSmem<D>::carve(smem_raw);
   const int tid = threadIdx.x;
@@ -261,7 +451,7 @@ k_vec_c(const ModelRT m, const BatchRT bt, int layer, const float* __restrict__ 
   __syncthreads();
   tile_rows<D>(sm, et);
   vec_stage2<D>(sm, D::V + D::CP, w_u, et.erow0, VH, GT);
-  for (int col = tid; col < D::MW; col += NT) {
+  for (int col = first_col + tid; col < D::MW; col += NT) {
     float acc = 0.f;
     int seg_first = et.le0;
     for (int r0 = 0; r0 < TM; r0 += 16) {

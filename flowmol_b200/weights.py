@@ -337,6 +337,11 @@ def pack(cfg: ModelConfig, sd):
                 P.raw(c(f"MSG{i}_TCG"), tc_units(_np(sd, f"{p}.edge_message.{i}.scalar_to_vector_gates.weight"), 32))
         for i in range(3):
             _pack_gvp(P, c(f"UPD{i}_WHCP"), sd, f"{p}.node_update.{i}")
+        if S % 128 == 0 and V <= 32 and 2 * F == S:      # node pipeline on the tensor cores (node rows through k_egemm_tc)
+            for i in range(3):
+                P.raw(c(f"UPD{i}_TCW"), tc_units(_np(sd, f"{p}.node_update.{i}.to_feats_out.0.weight"), 128))
+                P.raw(c(f"UPD{i}_TCG"), tc_units(_np(sd, f"{p}.node_update.{i}.scalar_to_vector_gates.weight"), 32))
+            P.raw(c("WSRC_TC"), tc_units(w0[:S].T, 128))
         P.vec(c("LN_MSG_W"), _np(sd, f"{p}.message_layer_norm.feat_norm.weight"))
         P.vec(c("LN_MSG_B"), _np(sd, f"{p}.message_layer_norm.feat_norm.bias"))
         P.vec(c("LN_UPD_W"), _np(sd, f"{p}.update_layer_norm.feat_norm.weight"))
@@ -355,4 +360,10 @@ def pack(cfg: ModelConfig, sd):
         if F == 128 and S % 128 == 0 and V <= 32:        # tensor-core images of the two EdgeUpdate linears (features on M)
             P.raw(c("EUPD_TC1"), tc_units(w1[2 * S:].T, 128))                                  # [F, F + R], k order ef | d
             P.raw(c("EUPD_TC2"), tc_units(_np(sd, p + ".edge_update_fn.2.weight"), 128))       # [F, F]
+        if S % 128 == 0 and V <= 32 and 2 * F == S:
+            for i in range(3):
+                q = f"node_position_updaters.{u}.gvps.{i}"
+                P.raw(c(f"POS{i}_TCW"), tc_units(_np(sd, q + ".to_feats_out.0.weight"), 128))
+                P.raw(c(f"POS{i}_TCG"), tc_units(_np(sd, q + ".scalar_to_vector_gates.weight"), 32))
+            P.raw(c("EUPD_WN_TC"), tc_units(np.concatenate([w1[:S], w1[S:2 * S]], axis=1).T, 128))   # [2F, S]: EA | EB rows
     return P.blob(), P.offsets

@@ -170,9 +170,10 @@ def test_results_do_not_depend_on_batch_composition_or_sharding():
 
 
 def test_fp32_and_tensor_core_message_kernels_agree():
-    """conv_impl 0 (fp32 CUDA cores), 1 (fused tcgen05) and 2 (wide tcgen05 pipeline, default) on the same inputs."""
+    """conv_impl 0 (fp32 CUDA cores), 1 (fused tcgen05) and 2 (wide tcgen05 pipeline, default) on the same inputs;
+    with conv_impl 2 both node-update implementations (node_impl 1: pipeline around k_egemm_tc, default; 0: fused fp32 kernel)."""
     cfg, vf = cuda_model("flowmol3", 11, 61)
-    assert vf.get_option("conv_impl") == 2
+    assert vf.get_option("conv_impl") == 2 and vf.get_option("node_impl") == 1
     n_atoms = np.array([9, 70, 3, 33])
     bt = O.make_batch(n_atoms)
     gen = torch.Generator().manual_seed(8)
@@ -180,13 +181,18 @@ def test_fp32_and_tensor_core_message_kernels_agree():
     a, c, e = torch.randint(0, 12, (bt.N,), generator=gen), torch.randint(0, 7, (bt.N,), generator=gen), torch.randint(0, 5, (bt.U,), generator=gen)
     outs = {}
     try:
-        for impl in (0, 1, 2):
-            vf.set_option("conv_impl", impl)
+        for impl in (0, 1, 2, 3, 4):
+            vf.set_option("conv_impl", min(impl, 2))
+            vf.set_option("node_impl", 0 if impl == 3 else 1)
+            vf.set_option("fuse_agg", 0 if impl == 4 else 1)      # 4: scalar segment-sum in k_vec_c instead of the egemm epilogue
             d0 = vf.forward_tokens(n_atoms, x, torch.full_like(a, 11), torch.full_like(c, 6), torch.full_like(e, 4), 0.0, None)
             outs[impl] = {k: v.cpu() for k, v in vf.forward_tokens(n_atoms, x, a, c, e, 0.4, d0).items()}
     finally:
         vf.set_option("conv_impl", 2)
-    for impl in (1, 2):
+        vf.set_option("node_impl", 1)
+        vf.set_option("fuse_agg", 1)
+    assert all(torch.equal(outs[4][k], outs[2][k]) for k in "xace")      # same sums in the same order: bit-identical
+    for impl in (1, 2, 3):
         assert (outs[impl]["x"] - outs[0]["x"]).abs().max() <= TOL_X
         for k in "ace":
             assert (outs[impl][k] - outs[0][k]).abs().max() <= TOL_P

@@ -11,13 +11,14 @@ vf = CTMCVectorFieldB200(cfg, WT.init_state_dict(cfg, 0))
 n_atoms = draw_sizes("geom", 512)
 x0, a0, c0, e0 = make_prior(n_atoms, 11, 100)
 for spec in (sys.argv[1:] or ["0"]):
-    impl, nh, gnh = (spec.split(":") + ["1", "1"])[:3]
-    impl, nh, gnh = int(impl), int(nh), int(gnh)
+    impl, nh, gnh, node = (spec.split(":") + ["1", "1", "1"])[:4]
+    impl, nh, gnh, node = int(impl), int(nh), int(gnh), int(node)
     vf.set_option("conv_impl", impl)
     vf.set_option("eg_nh", nh)
     vf.set_option("eg_nh_gate", gnh)
+    vf.set_option("node_impl", node if impl == 2 else 0)
     d = vf.forward_tokens(n_atoms, x0, a0, c0, e0, 0.0, None); torch.cuda.synchronize()
     ts = []
     for _ in range(3):
         t0 = time.time(); d = vf.forward_tokens(n_atoms, x0, a0, c0, e0, 0.3, d); torch.cuda.synchronize(); ts.append(time.time() - t0)
-    print(f"impl {impl} eg_nh {nh} gate_nh {gnh}: forward ms {min(ts)*1e3:.2f}  conv_edge ms {vf.time_conv_edge(1, 3):.3f}")
+    print(f"impl {impl} eg_nh {nh} gate_nh {gnh} node_impl {node}: forward ms {min(ts)*1e3:.2f}  conv_edge ms {vf.time_conv_edge(1, 3):.3f}")

@@ -68,6 +68,15 @@ struct EgArgs {
   float* partL;
 };
 
+// EG_MSGA: one finished segment sum of feature f.  Deliberately not inlined: the call sits behind a rarely taken branch in a
+// 32-way unrolled loop, and inlining the three-way store there tripled the kernel's code size (instruction-cache misses).
+__device__ __noinline__ void eg_store_segment(float* __restrict__ M, float* __restrict__ partF, float* __restrict__ partL, int mw,
+                                              int d, long long t64, unsigned head_tail, int f, float run) {
+  if (head_tail == 3u) M[(size_t)d * mw + f] = run;
+  else if (head_tail & 1u) partL[(size_t)t64 * mw + f] = run;
+  else partF[(size_t)t64 * mw + f] = run;
+}
+
 template <class D, int MODE, int NH>
 __global__ void __launch_bounds__(EgPlan<NH>::THREADS, NH == 1 ? 2 : 1)
 k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
@@ -266,12 +275,16 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
         buf[i] = val;
       }
     };
-    float4 cur[8], nxt[8];
+    // Prefetch distance: the narrow modes (one 128-feature tile: few MMAs per slab) are bound by the bytes in flight per SM,
+    // not by the tensor pipe -- keep two slabs of loads outstanding there; the wide message linears hide one slab behind MMAs.
+    constexpr bool DEEP = NMT == 1;
+    float4 cur[8], nxt[8], nx2[8];
     fetch(0, cur);
+    if (NSLAB > 1) fetch(1, nxt);
     if (a.trace && blockIdx.x == a.trace_cta && tid == 64) a.trace[1] = clock64();
     for (int j = 0; j < NSLAB; ++j) {
       const int st = j & 1;
-      if (j + 1 < NSLAB) fetch(j + 1, nxt);
+      if constexpr (DEEP) { if (j + 2 < NSLAB) fetch(j + 2, nx2); }
       if (j >= 2) tc::mbar_wait(&x_empty[st], ((j >> 1) - 1) & 1);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -293,13 +306,17 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
       if (a.trace && blockIdx.x == a.trace_cta && tid == 64) a.trace[2 + j] = clock64();
 #pragma unroll
       for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+      if constexpr (DEEP) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) nxt[i] = nx2[i];
+      } else {
+        if (j + 2 < NSLAB) fetch(j + 2, nxt);
+      }
     }
     // ---- epilogue: TMEM -> registers -> bias / gathered pre-activation -> activation -> coalesced global stores ------------------------
-    tc::mbar_wait(acc_full, 0);
-    tc::tc_fence_after();
-    if (a.trace && blockIdx.x == a.trace_cta && tid == 64) a.trace[30] = clock64();
     const int q = warp & 3, eh = (warp - 2) >> 2;
     if ((MODE != EG_GATE || q == 0) && !(a.dbg & 8)) {
+#pragma unroll 1
       for (int mt = 0; mt < NMT; ++mt) {
         const int f = mt * 128 + q * 32 + lane;
         float run = 0.f;                                       // MSGA: running segment sum of feature f
@@ -322,7 +339,13 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
           }
         };
         constexpr bool GATHERS = MODE == EG_MSG0 || MODE == EG_EU1 || MODE == EG_EU2;
-        if (GATHERS) gather(0, pre);
+        if (GATHERS) gather(0, pre);                          // in flight while the last MMAs drain
+        if (mt == 0) {
+          tc::mbar_wait(acc_full, 0);
+          tc::tc_fence_after();
+          if (a.trace && blockIdx.x == a.trace_cta && tid == 64) a.trace[30] = clock64();
+        }
+#pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           float acc[32];
           tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((mt * NH + eh) * 128 + c * 32), acc);
@@ -342,18 +365,20 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
               const float sg = sigmoid_fast(z);
               const float o = MODE == EG_GATE ? ((a.flags & EGF_IDENTITY) ? z : sg) : z * sg;
               op[(size_t)i * OW] = o;
-              if (MODE == EG_MSGA) {
-                // dst-major edges: the sum over a node's in-edges is a running sum along this thread's row of the accumulator.
-                // Slots after a molecule's last edge add garbage that is dropped at the next 64-slot boundary.
-                if (i == 0 && (c & 1) == 0) run = 0.f;
-                run = __fadd_rn(run, o);
+              if (MODE == EG_MSGA) acc[i] = o;
+            }
+            if (MODE == EG_MSGA) {
+              // dst-major edges: the sum over a node's in-edges is a running sum along this thread's row of the accumulator
+              // (a second pass, so the activations above keep their instruction-level parallelism).  Slots after a molecule's
+              // last edge add garbage that is dropped at the next 64-slot boundary.
+              if ((c & 1) == 0) run = 0.f;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                run = __fadd_rn(run, acc[i]);
                 if ((em >> i) & 1u) {                        // uniform over the CTA's epilogue threads
-                  const int row = eh * 128 + c * 32 + i, d = r_src[row];
-                  const size_t t64 = (size_t)((slot0 + row) >> 6);
-                  const bool head = (hm >> i) & 1u, tail = (tm >> i) & 1u;
-                  if (head && tail) a.M[(size_t)d * D::MW + f] = run;
-                  else if (head) a.partL[t64 * D::MW + f] = run;
-                  else a.partF[t64 * D::MW + f] = run;
+                  const int row = eh * 128 + c * 32 + i;
+                  eg_store_segment(a.M, a.partF, a.partL, D::MW, r_src[row], (slot0 + row) >> 6,
+                                   ((hm >> i) & 1u) | (((tm >> i) & 1u) << 1), f, run);
                   run = 0.f;
                 }
               }

@@ -187,6 +187,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cuda-graph", type=int, default=0)
     ap.add_argument("--conv-impl", type=int, default=None, help="0 fp32 CUDA-core kernels, 2 wide tcgen05 pipeline (default where built)")
+    ap.add_argument("--tc-prec", type=int, default=None, help="operand format of the tensor-core linears: 1 scaled fp16 hi/lo (default), 0 3xTF32")
     args = ap.parse_args()
     wl = list(WORKLOADS[args.workload])
     if args.timesteps:
@@ -210,6 +211,8 @@ def main():
     vf = CTMCVectorFieldB200(cfg, WT.init_state_dict(cfg, 0), device=dev)
     if args.conv_impl is not None:
         vf.set_option("conv_impl", args.conv_impl)
+    if args.tc_prec is not None:
+        vf.set_option("tc_prec", args.tc_prec)
     # one GLOBAL batch of B x world molecules, cut into contiguous cost-balanced ranges (flowmol_b200/sharding.py); global
     # molecule ids key the noise, so the molecules are the same at any world size
     from flowmol_b200 import sharding as SH
@@ -276,22 +279,26 @@ def main():
     ffma_peak = 148 * 128 * 2 * (peaks.get("sm_max_mhz", 1965.0) * 1e6) / 1e12
     impl = vf.get_option("conv_impl")
     ms_pass = vf.time_conv_edge(layer=1, iters=3)
+    prec = vf.get_option("tc_prec") if impl == 2 else 0
     if impl == 2:
-        # default flowmol3 pipeline: the dominant kernel is k_egemm_tc (5 modes, ~60 % of a step); its 292 -> 256 message
+        # default flowmol3 pipeline: the dominant kernel is k_egemm_tc (7 modes, ~60 % of a step); its 292 -> 256 message
         # linear is timed alone.  Algorithmic work = the reference's 2*292*256 FLOP per edge; executed on the tensor cores as
-        # 3xTF32 (3 MMAs per product), so the attainable ceiling of this kernel is TF32/3 -- stated, not hidden.
+        # three MMAs per fp32 product (hi*hi + lo*hi + hi*lo) on fp16 (default) or TF32 operands, so the attainable ceiling of
+        # this kernel is a third of the operand format's dense peak -- stated, not hidden.
         ms_k = vf.time_egemm_msg(layer=1, iters=5)
         flops = 2 * 292 * 256 * E
         achieved = flops / (ms_k * 1e-3) / 1e12
         hbm_bytes = E * (292 + 256) * 4
         hbm_peak = peaks.get("hbm_gbs") or 6650.0
-        roofline = {"kernel": "k_egemm_tc<EG_MSG> (292->256 message linear of one GVP, 3xTF32 tcgen05, all edges)", "bound": "tensor",
-                    "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
-                    "peak_kind": f"dense TF32 tensor = 1/2 x bf16, {peak_src}; the kernel issues 3 TF32 MMAs per fp32 product "
-                                 f"(error-compensated), so frac_of_3xTF32_ceiling = {3 * achieved / tf32_peak:.3f}",
+        op_peak, op_name = (bf16, "dense fp16/bf16 tensor") if prec == 1 else (tf32_peak, "dense TF32 tensor = 1/2 x bf16")
+        roofline = {"kernel": f"k_egemm_tc<EG_MSG> (292->256 message linear of one GVP, {'fp16x3' if prec == 1 else '3xTF32'} tcgen05, all edges)",
+                    "bound": "tensor", "achieved": achieved, "peak": op_peak, "unit": "TFLOP/s", "frac": achieved / op_peak,
+                    "peak_kind": f"{op_name}, {peak_src}; the kernel issues 3 MMAs per fp32 product (error-compensated hi/lo "
+                                 f"operands), so frac_of_x3_ceiling = {3 * achieved / op_peak:.3f}",
                     "algorithmic_flops_per_launch": flops, "ms_per_launch": ms_k,
                     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this workload from the committed ncu capture
-                    # (profiles/r01c_summary.md: 1.392 + 1.169 GB); bench.py itself never runs under a profiler
+                    # (profiles/: 1.392 + 1.169 GB, the operand format does not change the HBM traffic); bench.py itself never
+                    # runs under a profiler
                     "traffic": 2.561e9 if (args.workload == "geom512" and world == 1) else None,
                     "hbm": {"algorithmic_bytes_per_launch": hbm_bytes, "achieved_gbs": hbm_bytes / (ms_k * 1e-3) / 1e9,
                             "peak_gbs": hbm_peak, "frac": hbm_bytes / (ms_k * 1e-3) / 1e9 / hbm_peak},
@@ -310,7 +317,9 @@ def main():
     total_flops = (fe * E + fn_ * N) * T * world
     line = {"metric": f"molecules/sec @{T} steps ({dataset.upper()} batch)", "value": value, "unit": "molecules/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 (message linears as error-compensated 3xTF32 on tcgen05, fp32 accumulate)" if impl == 2 else "f32",
+            "vs_baseline": None,
+            "dtype": ("f32 (tensor-core linears as error-compensated " + ("scaled fp16 hi/lo x3" if prec == 1 else "3xTF32") +
+                      " on tcgen05, fp32 accumulate)") if impl == 2 else "f32",
             "data": "synthetic", "config": config_dict(args.workload, wl, world),
             "e2e": {"value": e2e_value, "unit": "molecules/s", "h2d_bytes_per_step": int(N * 12 + 2 * N + U + 4 * B),
                     "d2h_bytes_per_step": int(N * 12 + 2 * N + U), "ms_per_step": ms_e2e},

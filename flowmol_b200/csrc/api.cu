@@ -108,6 +108,9 @@ struct FmHandle {
   int fuse_agg = 1;            // scalar segment-sum in the epilogue of the last message linear (k_egemm_tc<EG_MSGA>)
   int node_impl = 0;           // 0: fused fp32 k_node_update, 1: node pipeline around k_egemm_tc (with conv_impl 2)
   int conv_impl = 0;           // 0: fp32 CUDA-core k_conv_edge, 1: tcgen05 3xTF32 k_conv_edge_tc (flowmol3 dims only)
+  int tc_prec = 0;             // operand format of k_egemm_tc: 0 = 3xTF32 images, 1 = scaled fp16 hi/lo images ("fp16x3")
+  bool has_h16 = false;        // packed weights carry the fp16 images
+  int* d_status = nullptr;     // device status word: bit 0 = an activation left the fp16 operand range (tc_prec 1)
   cudaStream_t cap_stream = nullptr;    // private stream for CUDA-graph capture (the legacy default stream cannot capture)
 };
 
@@ -143,25 +146,47 @@ int set_smem_attrs() {
   CUDA_OK(cudaFuncSetAttribute(fm::k_edge_head<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   if constexpr (D::S == 256 && D::V == 32 && D::SD == 0) {
     CUDA_OK(cudaFuncSetAttribute(fm::k_conv_edge_tc<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::TcPlan<D>::SMEM_BYTES));
-    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_MSG0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<2>::SMEM_BYTES));
-    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_MSG, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<2>::SMEM_BYTES));
-    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_GATE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<2>::SMEM_BYTES));
-    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_MSG0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<1>::SMEM_BYTES));
-    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_MSG, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<1>::SMEM_BYTES));
-    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_GATE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<1>::SMEM_BYTES));
-    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_EU1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<1>::SMEM_BYTES));
-    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_EU2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<1>::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_MSG0, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<2>::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_MSG0, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<2>::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_MSG, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<2>::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_MSG, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<2>::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_GATE, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<2>::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_GATE, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<2>::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_MSG0, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<1>::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_MSG0, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<1>::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_MSG, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<1>::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_MSG, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<1>::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_GATE, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<1>::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_GATE, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<1>::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_EU1, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<1>::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_EU1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<1>::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_EU2, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<1>::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_EU2, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<1>::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_vec_a<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::VecSmem<D>::BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_vec_b<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::VecSmem<D>::BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_node_pre<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::VecSmem<D>::BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_node_mid<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::VecSmem<D>::BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_node_post<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::VecSmem<D>::BYTES));
-    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_MSGA, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<1>::SMEM_BYTES));
-    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_LIN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<1>::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_MSGA, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<1>::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_MSGA, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<1>::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_LIN, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<1>::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_LIN, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<1>::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_vec_c<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::VecSmem<D>::BYTES));
   }
   return 0;
 }
+
+// k_egemm_tc in the operand precision selected on the handle
+template <class D, int MODE, int NH>
+void launch_eg(FmHandle* h, int grid, cudaStream_t st, const fm::ModelRT& m, const fm::BatchRT& bt, fm::EgArgs a) {
+  using PL = fm::EgPlan<NH>;
+  a.status = h->d_status;
+  if (h->tc_prec) fm::k_egemm_tc<D, MODE, NH, 1><<<grid, PL::THREADS, PL::SMEM_BYTES, st>>>(m, bt, a);
+  else fm::k_egemm_tc<D, MODE, NH, 0><<<grid, PL::THREADS, PL::SMEM_BYTES, st>>>(m, bt, a);
+}
+// id of a tensor-core image entry in the selected precision (the fp16 twins follow the TF32 entries, weight_layout.py)
+inline int tc_c(const FmHandle* h, int id) { return id + (h->tc_prec ? (int)fm::C_MSG0_TCW_H - (int)fm::C_MSG0_TCW : 0); }
+inline int tc_u(const FmHandle* h, int id) { return id + (h->tc_prec ? (int)fm::U_EUPD_TC1_H - (int)fm::U_EUPD_TC1 : 0); }
 
 #define LAUNCH_OK(h)                                                                                       \
   do {                                                                                                     \
@@ -191,21 +216,21 @@ int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
     float* cur = ef;      // input activations of the current scalar linear
     float* outs[3] = {SA, SB, SA};
     for (int g = 0; g < 3; ++g) {
-      fm::EgArgs a{wptr(tcw[g]), wptr(gb[g] + fm::GV_B), cur, SH, P, x, outs[g], nullptr, nullptr, L.EP, h->trace_mode == (g == 0 ? 0 : 1) ? h->d_trace : nullptr, h->trace_cta, 0, h->tc_debug, M, partF, partL};
+      fm::EgArgs a{wptr(tc_c(h, tcw[g])), wptr(gb[g] + fm::GV_B), cur, SH, P, x, outs[g], nullptr, nullptr, L.EP, h->trace_mode == (g == 0 ? 0 : 1) ? h->d_trace : nullptr, h->trace_cta, 0, h->tc_debug, M, partF, partL};
       if (g == 2 && h->fuse_agg) {       // last scalar linear: the segment-sum over in-edges rides in the epilogue
-        fm::k_egemm_tc<D, fm::EG_MSGA, 1><<<(int)(L.EPA / 128), fm::EgPlan<1>::THREADS, fm::EgPlan<1>::SMEM_BYTES, st>>>(m, bt, a);
+        launch_eg<D, fm::EG_MSGA, 1>(h, (int)(L.EPA / 128), st, m, bt, a);
       } else
       if (NHsel == 2) {
-        if (g == 0) fm::k_egemm_tc<D, fm::EG_MSG0, 2><<<gt, fm::EgPlan<2>::THREADS, fm::EgPlan<2>::SMEM_BYTES, st>>>(m, bt, a);
-        else fm::k_egemm_tc<D, fm::EG_MSG, 2><<<gt, fm::EgPlan<2>::THREADS, fm::EgPlan<2>::SMEM_BYTES, st>>>(m, bt, a);
+        if (g == 0) launch_eg<D, fm::EG_MSG0, 2>(h, gt, st, m, bt, a);
+        else launch_eg<D, fm::EG_MSG, 2>(h, gt, st, m, bt, a);
       } else {
-        if (g == 0) fm::k_egemm_tc<D, fm::EG_MSG0, 1><<<gt, fm::EgPlan<1>::THREADS, fm::EgPlan<1>::SMEM_BYTES, st>>>(m, bt, a);
-        else fm::k_egemm_tc<D, fm::EG_MSG, 1><<<gt, fm::EgPlan<1>::THREADS, fm::EgPlan<1>::SMEM_BYTES, st>>>(m, bt, a);
+        if (g == 0) launch_eg<D, fm::EG_MSG0, 1>(h, gt, st, m, bt, a);
+        else launch_eg<D, fm::EG_MSG, 1>(h, gt, st, m, bt, a);
       }
       LAUNCH_OK(h);
-      fm::EgArgs ag{wptr(tcg[g]), wptr(gb[g] + fm::GV_BG), outs[g], nullptr, nullptr, nullptr, GT, nullptr, nullptr, L.EP, h->trace_mode == 2 ? h->d_trace : nullptr, h->trace_cta, 0, h->tc_debug};
-      if (h->eg_nh_gate == 2) fm::k_egemm_tc<D, fm::EG_GATE, 2><<<(int)(L.EPA / 256), fm::EgPlan<2>::THREADS, fm::EgPlan<2>::SMEM_BYTES, st>>>(m, bt, ag);
-      else fm::k_egemm_tc<D, fm::EG_GATE, 1><<<(int)(L.EPA / 128), fm::EgPlan<1>::THREADS, fm::EgPlan<1>::SMEM_BYTES, st>>>(m, bt, ag);
+      fm::EgArgs ag{wptr(tc_c(h, tcg[g])), wptr(gb[g] + fm::GV_BG), outs[g], nullptr, nullptr, nullptr, GT, nullptr, nullptr, L.EP, h->trace_mode == 2 ? h->d_trace : nullptr, h->trace_cta, 0, h->tc_debug};
+      if (h->eg_nh_gate == 2) launch_eg<D, fm::EG_GATE, 2>(h, (int)(L.EPA / 256), st, m, bt, ag);
+      else launch_eg<D, fm::EG_GATE, 1>(h, (int)(L.EPA / 128), st, m, bt, ag);
       LAUNCH_OK(h);
       if (g < 2) {
         fm::k_vec_b<D><<<vgrid, fm::NT, vsm, st>>>(bt, wptr(g == 0 ? fm::C_MSG0_WU : fm::C_MSG1_WU), (g == 0 ? D::H0 : D::V) + D::CP,
@@ -237,16 +262,16 @@ int node_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
     using PL = fm::EgPlan<1>;
     auto scalar = [&](const float* units, const float* bias, const float* in, float* out) {
       fm::EgArgs a{units, bias, in, SH, nullptr, nullptr, out, nullptr, nullptr, (long long)L.N, nullptr, 0, fm::EGF_NODE_ROWS, 0};
-      fm::k_egemm_tc<D, fm::EG_MSG, 1><<<gt, PL::THREADS, PL::SMEM_BYTES, st>>>(m, bt, a);
+      launch_eg<D, fm::EG_MSG, 1>(h, gt, st, m, bt, a);
     };
     auto gate = [&](const float* units, const float* bias, const float* in, int identity) {
       fm::EgArgs a{units, bias, in, nullptr, nullptr, nullptr, GT, nullptr, nullptr, (long long)L.N, nullptr, 0,
                    fm::EGF_NODE_ROWS | (identity ? fm::EGF_IDENTITY : 0), 0};
-      fm::k_egemm_tc<D, fm::EG_GATE, 1><<<gt, PL::THREADS, PL::SMEM_BYTES, st>>>(m, bt, a);
+      launch_eg<D, fm::EG_GATE, 1>(h, gt, st, m, bt, a);
     };
     auto linear = [&](const float* units, const float* bias, float* out) {
       fm::EgArgs a{units, bias, s, nullptr, nullptr, nullptr, out, nullptr, nullptr, (long long)L.N, nullptr, 0, fm::EGF_NODE_ROWS, 0};
-      fm::k_egemm_tc<D, fm::EG_LIN, 1><<<gt, PL::THREADS, PL::SMEM_BYTES, st>>>(m, bt, a);
+      launch_eg<D, fm::EG_LIN, 1>(h, gt, st, m, bt, a);
     };
     const int vgrid = L.nNT < 2 * h->n_sm ? L.nNT : 2 * h->n_sm;
     fm::k_node_pre<D><<<L.nNT, fm::NT, vsm, st>>>(m, bt, l, agg_rows, s, v, M, partF, partL, VH, SH);
@@ -256,8 +281,8 @@ int node_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
     const float* cur = s;
     float* outs[3] = {SA, SB, SA};
     for (int g = 0; g < 3; ++g) {
-      scalar(wptr(l, utw[g]), wptr(l, ub[g] + fm::GV_B), cur, outs[g]); LAUNCH_OK(h);
-      gate(wptr(l, utg[g]), wptr(l, ub[g] + fm::GV_BG), outs[g], 0); LAUNCH_OK(h);
+      scalar(wptr(l, tc_c(h, utw[g])), wptr(l, ub[g] + fm::GV_B), cur, outs[g]); LAUNCH_OK(h);
+      gate(wptr(l, tc_c(h, utg[g])), wptr(l, ub[g] + fm::GV_BG), outs[g], 0); LAUNCH_OK(h);
       if (g < 2) {
         fm::k_vec_b<D><<<vgrid, fm::NT, vsm, st>>>(bt, wptr(l, ub[g] + fm::GV_WU), D::V + D::CP, wptr(l, ub[g + 1] + fm::GV_WHCP), 1, VH, SH, GT);
         LAUNCH_OK(h);
@@ -266,15 +291,15 @@ int node_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
     }
     fm::k_node_mid<D><<<L.nNT, fm::NT, vsm, st>>>(m, bt, l, upd, s, v, SA, VH, SH, GT);
     LAUNCH_OK(h);
-    if (has_next) { linear(wptr(l + 1, fm::C_WSRC_TC), wptr(l + 1, fm::C_BSRC), P); LAUNCH_OK(h); }
+    if (has_next) { linear(wptr(l + 1, tc_c(h, fm::C_WSRC_TC)), wptr(l + 1, fm::C_BSRC), P); LAUNCH_OK(h); }
     if (upd >= 0) {
-      linear(uptr(fm::U_EUPD_WN_TC), uptr(fm::U_EUPD_BN), EAB); LAUNCH_OK(h);
+      linear(uptr(tc_u(h, fm::U_EUPD_WN_TC)), uptr(fm::U_EUPD_BN), EAB); LAUNCH_OK(h);
       const int ptw[3] = {fm::U_POS0_TCW, fm::U_POS1_TCW, fm::U_POS2_TCW}, ptg[3] = {fm::U_POS0_TCG, fm::U_POS1_TCG, fm::U_POS2_TCG};
       const int pb[3] = {fm::U_POS0_WHCP, fm::U_POS1_WHCP, fm::U_POS2_WHCP};
       cur = s;
       for (int g = 0; g < 3; ++g) {
-        scalar(uptr(ptw[g]), uptr(pb[g] + fm::GV_B), cur, outs[g]); LAUNCH_OK(h);
-        gate(uptr(ptg[g]), uptr(pb[g] + fm::GV_BG), outs[g], g == 2); LAUNCH_OK(h);
+        scalar(uptr(tc_u(h, ptw[g])), uptr(pb[g] + fm::GV_B), cur, outs[g]); LAUNCH_OK(h);
+        gate(uptr(tc_u(h, ptg[g])), uptr(pb[g] + fm::GV_BG), outs[g], g == 2); LAUNCH_OK(h);
         if (g < 2) {
           fm::k_vec_b<D><<<vgrid, fm::NT, vsm, st>>>(bt, uptr(pb[g] + fm::GV_WU), D::V + D::CP, uptr(pb[g + 1] + fm::GV_WHCP), 1, VH, SH, GT);
           LAUNCH_OK(h);
@@ -339,11 +364,11 @@ int run_pass(FmHandle* h, void* ws, const Layout& L, const float* x_t, const uin
           auto uptr = [&](int id) { return h->d_w + h->off_h[fm::G_COUNT + m.L * fm::C_COUNT + upd * fm::U_COUNT + id]; };
           float* H = at<float>(ws, L.SA);
           const int gt = (int)(L.EPA / 128);
-          fm::EgArgs a1{uptr(fm::U_EUPD_TC1), nullptr, ef, nullptr, EAB, x, H, nullptr, nullptr, L.EP, h->trace_mode == 3 ? h->d_trace : nullptr, h->trace_cta, 0, h->tc_debug};
-          fm::k_egemm_tc<D, fm::EG_EU1, 1><<<gt, fm::EgPlan<1>::THREADS, fm::EgPlan<1>::SMEM_BYTES, st>>>(m, bt, a1);
+          fm::EgArgs a1{uptr(tc_u(h, fm::U_EUPD_TC1)), nullptr, ef, nullptr, EAB, x, H, nullptr, nullptr, L.EP, h->trace_mode == 3 ? h->d_trace : nullptr, h->trace_cta, 0, h->tc_debug};
+          launch_eg<D, fm::EG_EU1, 1>(h, gt, st, m, bt, a1);
           LAUNCH_OK(h);
-          fm::EgArgs a2{uptr(fm::U_EUPD_TC2), uptr(fm::U_EUPD_B2), H, ef, nullptr, nullptr, ef, uptr(fm::U_EUPD_LN_W), uptr(fm::U_EUPD_LN_B), L.EP, h->trace_mode == 4 ? h->d_trace : nullptr, h->trace_cta, 0, h->tc_debug};
-          fm::k_egemm_tc<D, fm::EG_EU2, 1><<<gt, fm::EgPlan<1>::THREADS, fm::EgPlan<1>::SMEM_BYTES, st>>>(m, bt, a2);
+          fm::EgArgs a2{uptr(tc_u(h, fm::U_EUPD_TC2)), uptr(fm::U_EUPD_B2), H, ef, nullptr, nullptr, ef, uptr(fm::U_EUPD_LN_W), uptr(fm::U_EUPD_LN_B), L.EP, h->trace_mode == 4 ? h->d_trace : nullptr, h->trace_cta, 0, h->tc_debug};
+          launch_eg<D, fm::EG_EU2, 1>(h, gt, st, m, bt, a2);
           LAUNCH_OK(h);
           done = true;
         }
@@ -444,6 +469,12 @@ int fm_create(const FmConfig* cfg, const float* w_host, size_t n_floats, const i
   { cudaDeviceProp pr; if (cudaGetDeviceProperties(&pr, device) == cudaSuccess) h->n_sm = pr.multiProcessorCount; }
   h->conv_impl = (variant == 0 && h->has_tc) ? 2 : 0;   // flowmol3 dims: wide tcgen05 3xTF32 pipeline by default
   h->node_impl = (h->conv_impl == 2 && off_host[fm::G_COUNT + fm::C_UPD0_TCW] >= 0) ? 1 : 0;
+  h->has_h16 = h->has_tc && off_host[fm::G_COUNT + fm::C_MSG0_TCW_H] >= 0 && off_host[fm::G_TC_INFO] >= 0;
+  if (h->has_h16 && w_host[off_host[fm::G_TC_INFO]] != fm::tc::ACT_SCALE_H16) {
+    delete h;
+    return fail("fm_create: packed fp16 images were built for a different activation scale (weights.py vs csrc/tc.cuh)");
+  }
+  h->tc_prec = h->has_h16 ? 1 : 0;       // default: fp16x3 (same 22 significand bits as 3xTF32 at twice the MMA rate)
   h->eg_nh = 1;
   h->dyn = Dyn{c.n_hidden_scalars, c.n_vec_channels, c.n_hidden_edge_feats, c.use_dst_feats ? c.s_dst : 0,
                c.use_dst_feats ? c.v_dst : 0, c.n_atom_types, c.n_charges, c.n_bond_types,
@@ -451,6 +482,8 @@ int fm_create(const FmConfig* cfg, const float* w_host, size_t n_floats, const i
   CUDA_OK(cudaMalloc(&h->d_w, n_floats * sizeof(float)));
   CUDA_OK(cudaMalloc(&h->d_off, n_off * sizeof(long long)));
   CUDA_OK(cudaMalloc(&h->d_table, sizeof(float) * (c.n_bond_types + 1) * c.n_hidden_edge_feats));
+  CUDA_OK(cudaMalloc(&h->d_status, sizeof(int)));
+  CUDA_OK(cudaMemset(h->d_status, 0, sizeof(int)));
   CUDA_OK(cudaMemcpy(h->d_w, w_host, n_floats * sizeof(float), cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(h->d_off, off_host, n_off * sizeof(long long), cudaMemcpyHostToDevice));
   fm::ModelRT& m = h->rt;
@@ -470,7 +503,7 @@ int fm_create(const FmConfig* cfg, const float* w_host, size_t n_floats, const i
 
 void fm_destroy(FmHandle* h) {
   if (!h) return;
-  cudaFree(h->d_w); cudaFree(h->d_off); cudaFree(h->d_table);
+  cudaFree(h->d_w); cudaFree(h->d_off); cudaFree(h->d_table); cudaFree(h->d_status);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   delete h;
 }
@@ -620,8 +653,15 @@ int fm_sample_host(FmHandle* h, const int32_t* n_atoms, int32_t B, float* x_host
     CUDA_OK(cudaMemcpyAsync(c_host, dc, L.N, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaMemcpyAsync(e_host, de, L.U, cudaMemcpyDeviceToHost, st));
   }
+  int status = 0;
+  if (rc == 0) CUDA_OK(cudaMemcpyAsync(&status, h->d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
   cudaFreeAsync(dx, st); cudaFreeAsync(da, st); cudaFreeAsync(dc, st); cudaFreeAsync(de, st);
   CUDA_OK(cudaStreamSynchronize(st));
+  if (status & 1) {
+    cudaMemsetAsync(h->d_status, 0, sizeof(int), st);
+    return fail("fm_sample_host: an activation left the fp16 operand range of the tensor-core linears; "
+                "re-run with fm_set_option(h, \"tc_prec\", 0) (3xTF32)");
+  }
   return rc;
 }
 
@@ -661,7 +701,7 @@ int fm_time_egemm_msg(FmHandle* h, void* ws, int32_t layer, int32_t iters, float
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const fm::BatchRT bt = batch_rt(ws, L);
   auto wptr = [&](int id) { return h->d_w + h->off_h[fm::G_COUNT + layer * fm::C_COUNT + id]; };
-  fm::EgArgs a{wptr(fm::C_MSG1_TCW), wptr(fm::C_MSG1_WHCP + fm::GV_B), at<float>(ws, L.SA), at<float>(ws, L.SH), nullptr, nullptr,
+  fm::EgArgs a{wptr(tc_c(h, fm::C_MSG1_TCW)), wptr(fm::C_MSG1_WHCP + fm::GV_B), at<float>(ws, L.SA), at<float>(ws, L.SH), nullptr, nullptr,
                at<float>(ws, L.SB), nullptr, nullptr, L.EP, nullptr, 0, 0};
   cudaEvent_t e0, e1;
   CUDA_OK(cudaEventCreate(&e0));
@@ -669,8 +709,8 @@ int fm_time_egemm_msg(FmHandle* h, void* ws, int32_t layer, int32_t iters, float
   CUDA_OK(cudaStreamSynchronize(st));
   CUDA_OK(cudaEventRecord(e0, st));
   for (int i = 0; i < iters; ++i) {
-    if (h->eg_nh == 2) fm::k_egemm_tc<D, fm::EG_MSG, 2><<<(int)(L.EPA / 256), fm::EgPlan<2>::THREADS, fm::EgPlan<2>::SMEM_BYTES, st>>>(h->rt, bt, a);
-    else fm::k_egemm_tc<D, fm::EG_MSG, 1><<<(int)(L.EPA / 128), fm::EgPlan<1>::THREADS, fm::EgPlan<1>::SMEM_BYTES, st>>>(h->rt, bt, a);
+    if (h->eg_nh == 2) launch_eg<D, fm::EG_MSG, 2>(h, (int)(L.EPA / 256), st, h->rt, bt, a);
+    else launch_eg<D, fm::EG_MSG, 1>(h, (int)(L.EPA / 128), st, h->rt, bt, a);
   }
   CUDA_OK(cudaEventRecord(e1, st));
   CUDA_OK(cudaEventSynchronize(e1));
@@ -699,6 +739,12 @@ int fm_set_option(FmHandle* h, const char* name, int32_t value) {
     return 0;
   }
   if (n == "fuse_agg") { h->fuse_agg = value ? 1 : 0; return 0; }
+  if (n == "tc_prec") {
+    if (value < 0 || value > 1) return fail("fm_set_option: tc_prec must be 0 (3xTF32) or 1 (fp16x3)");
+    if (value == 1 && !h->has_h16) return fail("fm_set_option: packed weights carry no fp16 operand images");
+    h->tc_prec = value;
+    return 0;
+  }
   if (n == "tc_debug") { h->tc_debug = value; return 0; }
   if (n == "tc_trace_mode") { h->trace_mode = value; return 0; }
   if (n == "tc_trace") {       // value < 0: off; otherwise the CTA index whose timeline is recorded (every egemm launch overwrites it)
@@ -721,12 +767,25 @@ int fm_get_option(FmHandle* h, const char* name, int32_t* value) {
   if (!h || !name || !value) return fail("fm_get_option: null argument");
   if (std::string(name) == "conv_impl") { *value = h->conv_impl; return 0; }
   if (std::string(name) == "node_impl") { *value = h->node_impl; return 0; }
+  if (std::string(name) == "tc_prec") { *value = h->tc_prec; return 0; }
+  if (std::string(name) == "status") {      // synchronising read-and-clear of the device status word (see fm_check_status)
+    int v = 0;
+    CUDA_OK(cudaSetDevice(h->device));
+    CUDA_OK(cudaDeviceSynchronize());
+    CUDA_OK(cudaMemcpy(&v, h->d_status, sizeof(int), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemset(h->d_status, 0, sizeof(int)));
+    *value = v;
+    return 0;
+  }
   return fail("fm_get_option: unknown option");
 }
 
 // stand-alone tcgen05 check (host buffers): out[128][64] = W[128][K] . X[64][K]^T, passes = 1 (plain TF32) or 3 (3xTF32)
 int fm_debug_tc_gemm(const float* w_host, const float* x_host, int32_t K, float* out_host, int32_t passes, int device) {
-  if (!w_host || !x_host || !out_host || K < 32 || K % 32 || K > 128 || (passes != 1 && passes != 3)) return fail("fm_debug_tc_gemm: bad argument");
+  // passes: 1 plain TF32, 3 error-compensated 3xTF32, 16 scaled fp16 hi/lo ("fp16x3", K a multiple of 64)
+  if (!w_host || !x_host || !out_host || K < 32 || K % 32 || K > 128 || (passes != 1 && passes != 3 && passes != 16) ||
+      (passes == 16 && K % 64))
+    return fail("fm_debug_tc_gemm: bad argument");
   CUDA_OK(cudaSetDevice(device));
   float *dw = nullptr, *dx = nullptr, *dout = nullptr;
   CUDA_OK(cudaMalloc(&dw, sizeof(float) * 128 * K));
@@ -736,7 +795,15 @@ int fm_debug_tc_gemm(const float* w_host, const float* x_host, int32_t K, float*
   CUDA_OK(cudaMemcpy(dx, x_host, sizeof(float) * 64 * K, cudaMemcpyHostToDevice));
   const int smem = (K / 32) * 48 * 1024 + 1024;
   CUDA_OK(cudaFuncSetAttribute(fm::k_tc_gemm_test, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  fm::k_tc_gemm_test<<<1, 128, smem>>>(dw, dx, K, dout, passes);
+  if (passes == 16) {
+    float wmax = 0.f;
+    for (int i = 0; i < 128 * K; ++i) wmax = fmaxf(wmax, fabsf(w_host[i]));
+    const float w_scale = wmax > 0.f ? exp2f(13.0f - floorf(log2f(wmax))) : 1.0f;      // weights.py:h16_weight_scale
+    CUDA_OK(cudaFuncSetAttribute(fm::k_tc_gemm_test_h16, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    fm::k_tc_gemm_test_h16<<<1, 128, smem>>>(dw, dx, K, dout, w_scale);
+  } else {
+    fm::k_tc_gemm_test<<<1, 128, smem>>>(dw, dx, K, dout, passes);
+  }
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaDeviceSynchronize());
   CUDA_OK(cudaMemcpy(out_host, dout, sizeof(float) * 128 * 64, cudaMemcpyDeviceToHost));

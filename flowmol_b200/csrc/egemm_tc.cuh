@@ -66,6 +66,7 @@ struct EgArgs {
   float* M;                  // MSGA: aggregated messages [N][MW] and the per-64-slot-tile partial sums (see k_conv_edge)
   float* partF;
   float* partL;
+  int* status;               // PREC 1: bit 0 is set when an activation leaves the fp16 operand range (|x| >= ACT_LIMIT_H16)
 };
 
 // EG_MSGA: one finished segment sum of feature f.  Deliberately not inlined: the call sits behind a rarely taken branch in a
@@ -77,7 +78,11 @@ __device__ __noinline__ void eg_store_segment(float* __restrict__ M, float* __re
   else partF[(size_t)t64 * mw + f] = run;
 }
 
-template <class D, int MODE, int NH>
+// PREC 0: error-compensated 3xTF32 (32 k values per 128-byte operand row).  PREC 1: scaled fp16 hi/lo ("fp16x3": 64 k values per
+// row, kind::f16 MMAs at twice the TF32 rate, half the weight-image bytes; same 22 significand bits, see tc.cuh).  The byte
+// geometry of the operand tiles, the weight ring, the stages and the barrier protocol are identical in both modes; the loaders
+// still fetch 32-float chunks of K (two per fp16 slab).
+template <class D, int MODE, int NH, int PREC>
 __global__ void __launch_bounds__(EgPlan<NH>::THREADS, NH == 1 ? 2 : 1)
 k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
   using PL = EgPlan<NH>;
@@ -87,8 +92,10 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
   constexpr bool IS_EU = MODE == EG_EU1 || MODE == EG_EU2;
   constexpr bool IS_MSG = MODE == EG_MSG || MODE == EG_MSGA;
   constexpr int K = MODE == EG_MSG0 ? D::KE0 : (IS_MSG ? D::K1 : (MODE == EG_EU1 ? D::F + D::R : (MODE == EG_EU2 ? D::F : S)));
-  constexpr int NSLAB = (K + 31) / 32;
-  constexpr int LAST_KSTEPS = ((K - 1) % 32) / 8 + 1;
+  constexpr int KS = PREC ? 64 : 32;                          // k values per operand row (one slab)
+  constexpr int NSLAB = (K + KS - 1) / KS;
+  constexpr int NCH = (K + 31) / 32;                          // 32-float chunks of K the loaders fetch (== NSLAB for PREC 0)
+  constexpr int LAST_KSTEPS = ((K - 1) % KS) / (KS / 4) + 1;
   constexpr int NMT = MODE == EG_GATE ? 1 : (IS_EU ? D::F / 128 : S / 128);
   constexpr int OW = MODE == EG_GATE ? 32 : (IS_EU ? D::F : S);          // output row width
   static_assert(!IS_EU || (NH == 1 && D::F == 128), "edge-update modes: one 128-edge half, F = 128");
@@ -184,7 +191,10 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
   } else if (warp == 1) {
     // ---- MMA issuer ----------------------------------------------------------------------------------------------------------
     if (lane == 0) {
-      const uint32_t idesc = tc::idesc_tf32(128, 128);
+      const uint32_t idesc = PREC ? tc::idesc_f16(128, 128) : tc::idesc_tf32(128, 128);
+      auto umma = [](uint32_t d, uint64_t da, uint64_t db, uint32_t id, uint32_t acc) {
+        if (PREC) tc::umma_f16(d, da, db, id, acc); else tc::umma_tf32(d, da, db, id, acc);
+      };
       uint32_t u = 0;
       for (int j = 0; j < NSLAB; ++j) {
         const int st = j & 1, ksteps = (j == NSLAB - 1) ? LAST_KSTEPS : 4;
@@ -201,8 +211,8 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
               const uint32_t d = tmem + (uint32_t)((mt * NH + h) * 128);
               for (int ks = 0; ks < ksteps && !(a.dbg & 2); ++ks) {
                 const uint64_t dw = tc::desc_sw128(wb + 32 * ks);
-                tc::umma_tf32(d, dw, tc::desc_sw128(xb + LO_OFF + h * 16384 + 32 * ks), idesc, (j > 0 || ks > 0) ? 1u : 0u);
-                tc::umma_tf32(d, dw, tc::desc_sw128(xb + h * 16384 + 32 * ks), idesc, 1u);
+                umma(d, dw, tc::desc_sw128(xb + LO_OFF + h * 16384 + 32 * ks), idesc, (j > 0 || ks > 0) ? 1u : 0u);
+                umma(d, dw, tc::desc_sw128(xb + h * 16384 + 32 * ks), idesc, 1u);
               }
             }
             tc::umma_commit(&w_empty[sl]);
@@ -216,7 +226,7 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
             for (int h = 0; h < NH; ++h) {
               const uint32_t d = tmem + (uint32_t)((mt * NH + h) * 128);
               for (int ks = 0; ks < ksteps && !(a.dbg & 2); ++ks)
-                tc::umma_tf32(d, tc::desc_sw128(wb + 32 * ks), tc::desc_sw128(xb + h * 16384 + 32 * ks), idesc, 1u);
+                umma(d, tc::desc_sw128(wb + 32 * ks), tc::desc_sw128(xb + h * 16384 + 32 * ks), idesc, 1u);
             }
             tc::umma_commit(&w_empty[sl]);
             ++u;
@@ -279,39 +289,56 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
     // not by the tensor pipe -- keep two slabs of loads outstanding there; the wide message linears hide one slab behind MMAs.
     constexpr bool DEEP = NMT == 1;
     float4 cur[8], nxt[8], nx2[8];
+    float amax = 0.f;                                      // PREC 1: largest |activation| this thread converted
     fetch(0, cur);
-    if (NSLAB > 1) fetch(1, nxt);
+    if (NCH > 1) fetch(1, nxt);
     if (a.trace && blockIdx.x == a.trace_cta && tid == 64) a.trace[1] = clock64();
-    for (int j = 0; j < NSLAB; ++j) {
-      const int st = j & 1;
-      if constexpr (DEEP) { if (j + 2 < NSLAB) fetch(j + 2, nx2); }
-      if (j >= 2) tc::mbar_wait(&x_empty[st], ((j >> 1) - 1) & 1);
+    for (int j = 0; j < NCH; ++j) {
+      // chunk j fills the whole operand row of slab j (PREC 0) or half `hf` of the row of slab j / 2 (PREC 1)
+      const int sb = PREC ? (j >> 1) : j, hf = PREC ? (j & 1) : 0, st = sb & 1;
+      if constexpr (DEEP) { if (j + 2 < NCH) fetch(j + 2, nx2); }
+      if (sb >= 2 && hf == 0) tc::mbar_wait(&x_empty[st], ((sb >> 1) - 1) & 1);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int rw = wrow0 + 4 * i + lg, hh = rw >> 7, rr_ = rw & 127;
         uint8_t* hi = xst + st * EG_XSTAGE + hh * 16384;
         const float4 val = cur[i];
-        float4 vh, vl;
-        tc::split_tf32(val.x, vh.x, vl.x); tc::split_tf32(val.y, vh.y, vl.y);
-        tc::split_tf32(val.z, vh.z, vl.z); tc::split_tf32(val.w, vh.w, vl.w);
-        const uint32_t off = tc::sw128_off(rr_, ch * 4);
-        *reinterpret_cast<float4*>(hi + off) = vh;
-        *reinterpret_cast<float4*>(hi + LO_OFF + off) = vl;
+        if constexpr (PREC) {
+          amax = fmaxf(amax, fmaxf(fmaxf(fabsf(val.x), fabsf(val.y)), fmaxf(fabsf(val.z), fabsf(val.w))));
+          uint2 vh, vl;
+          tc::split_h16x2(val.x * tc::ACT_SCALE_H16, val.y * tc::ACT_SCALE_H16, vh.x, vl.x);
+          tc::split_h16x2(val.z * tc::ACT_SCALE_H16, val.w * tc::ACT_SCALE_H16, vh.y, vl.y);
+          const uint32_t off = tc::sw128_off_h(rr_, hf * 32 + ch * 4);
+          *reinterpret_cast<uint2*>(hi + off) = vh;
+          *reinterpret_cast<uint2*>(hi + LO_OFF + off) = vl;
+        } else {
+          float4 vh, vl;
+          tc::split_tf32(val.x, vh.x, vl.x); tc::split_tf32(val.y, vh.y, vl.y);
+          tc::split_tf32(val.z, vh.z, vl.z); tc::split_tf32(val.w, vh.w, vl.w);
+          const uint32_t off = tc::sw128_off(rr_, ch * 4);
+          *reinterpret_cast<float4*>(hi + off) = vh;
+          *reinterpret_cast<float4*>(hi + LO_OFF + off) = vl;
+        }
       }
-      tc::fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) {
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&x_full[st])) : "memory");
+      if (!PREC || hf == 1 || j == NCH - 1) {              // the slab's operand rows are complete
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&x_full[st])) : "memory");
+        }
       }
-      if (a.trace && blockIdx.x == a.trace_cta && tid == 64) a.trace[2 + j] = clock64();
+      if (a.trace && blockIdx.x == a.trace_cta && tid == 64) a.trace[2 + (j < 14 ? j : 13)] = clock64();
 #pragma unroll
       for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
       if constexpr (DEEP) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) nxt[i] = nx2[i];
       } else {
-        if (j + 2 < NSLAB) fetch(j + 2, nxt);
+        if (j + 2 < NCH) fetch(j + 2, nxt);
       }
+    }
+    if constexpr (PREC) {
+      if (!(amax < tc::ACT_LIMIT_H16) && a.status) atomicOr(a.status, 1);     // also catches NaN
     }
     // ---- epilogue: TMEM -> registers -> bias / gathered pre-activation -> activation -> coalesced global stores ------------------------
     const int q = warp & 3, eh = (warp - 2) >> 2;
@@ -321,6 +348,8 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
         const int f = mt * 128 + q * 32 + lane;
         float run = 0.f;                                       // MSGA: running segment sum of feature f
         const float bias = (MODE == EG_MSG0 || MODE == EG_EU1) ? 0.f : a.bias[f];
+        // PREC 1: undo the power-of-two operand scales (exact); the factor sits right behind the weight units (weights.py:tc_units_h16)
+        const float unscale = PREC ? a.units[(size_t)NSLAB * NMT * 2 * (UNIT_BYTES / 4)] : 1.0f;
         float* red = reinterpret_cast<float*>(xst);            // EU2: cross-warp LayerNorm partials (the stages are idle now)
         float pre[32], pnext[32];
         auto gather = [&](int c, float (&dst_)[32]) {          // per-edge pre-activations / residuals of chunk c (L2 / HBM gathers)
@@ -360,7 +389,7 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
           if (MODE != EG_EU2) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {      // padding rows are computed and stored too (their slots exist)
-              const float z = acc[i] + ((MODE == EG_MSG0 || MODE == EG_EU1) ? pre[i] : bias);
+              const float z = (PREC ? acc[i] * unscale : acc[i]) + ((MODE == EG_MSG0 || MODE == EG_EU1) ? pre[i] : bias);
               if (MODE == EG_LIN) { op[(size_t)i * OW] = z; continue; }
               const float sg = sigmoid_fast(z);
               const float o = MODE == EG_GATE ? ((a.flags & EGF_IDENTITY) ? z : sg) : z * sg;
@@ -387,7 +416,7 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
             // y = ef + SiLU(W2 h + b2);  LayerNorm over the 128 features of every edge = over the lanes of the 4 epilogue warps
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              const float z = acc[i] + bias;
+              const float z = (PREC ? acc[i] * unscale : acc[i]) + bias;
               acc[i] = __fadd_rn(pre[i], z * sigmoid_fast(z));
             }
             {

@@ -4,6 +4,7 @@
 //   x*w ~= hi_x*hi_w + lo_x*hi_w + hi_x*lo_w   (dropped lo*lo term ~2^-24 relative) accumulated in fp32 in TMEM,
 // which keeps the fused edge kernels inside the fp32 parity budget while running on the 5th-gen tensor cores.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -101,6 +102,19 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// instruction descriptor, kind::f16 with fp16 operands, fp32 accumulate, both operands K-major (a_format = b_format = 0: F16)
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // completion of all previously issued MMAs of this thread -> one arrival on the mbarrier
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -119,6 +133,28 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 // byte offset of element (row, k) inside a [rows][32] fp32 SW128 K-major slab
 __device__ __forceinline__ uint32_t sw128_off(int row, int k) {
   return (uint32_t)(row * 128 + ((((k >> 2) ^ (row & 7)) << 4) | ((k & 3) << 2)));
+}
+
+
+// ---- fp16x3 split ("scaled fp16 hi/lo") ----------------------------------------------------------------------------------------
+// x * 2^s = hi + lo with hi = fp16_rn(x 2^s), lo = fp16_rn(x 2^s - hi): the same 22 significand bits as the TF32 split, in
+// operands half as wide that the tensor cores consume at twice the rate.  The power-of-two scales (activations: ACT_SCALE_H16,
+// weights: per matrix, chosen on the host so that max |w| 2^s lies in [2^13, 2^14)) keep `lo` out of fp16's subnormal range
+// for every value that matters and are undone exactly in the epilogue.  |x| 2^s must stay below 65504 (checked by the loaders).
+constexpr float ACT_SCALE_H16 = 8.0f;
+constexpr float ACT_LIMIT_H16 = 65504.0f / ACT_SCALE_H16;
+// two consecutive k values -> packed (hi, hi) and (lo, lo) half2 words; element k sits in the low half (lower address)
+__device__ __forceinline__ void split_h16x2(float a, float b, uint32_t& hi2, uint32_t& lo2) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi2 = *reinterpret_cast<const uint32_t*>(&h);
+  lo2 = *reinterpret_cast<const uint32_t*>(&l);
+}
+// byte offset of fp16 element (row, k), k in [0, 64), inside a [rows][64] fp16 SW128 K-major slab (same byte geometry as the
+// [rows][32] fp32 slab: 128-byte rows, 16-byte chunks XOR-swizzled by row % 8)
+__device__ __forceinline__ uint32_t sw128_off_h(int row, int k) {
+  return (uint32_t)(row * 128 + ((((k >> 3) ^ (row & 7)) << 4) | ((k & 7) << 1)));
 }
 
 }  // namespace tc

@@ -73,4 +73,70 @@ __global__ void __launch_bounds__(128, 1) k_tc_gemm_test(const float* __restrict
   if (warp == 0) tc::tmem_dealloc(tm, 64);
 }
 
+// Same check for the scaled fp16 hi/lo operands ("fp16x3", kind::f16): K a multiple of 64, slabs of 64 k values with the byte
+// geometry of the TF32 slabs.  `w_scale` is the power-of-two weight scale the host packer would choose.
+__global__ void __launch_bounds__(128, 1) k_tc_gemm_test_h16(const float* __restrict__ W, const float* __restrict__ X, int K,
+                                                             float* __restrict__ out /*[128][64]*/, float w_scale) {
+  extern __shared__ __align__(1024) uint8_t tsm[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int nslab = K / 64;
+  const uint32_t SLAB = 48 * 1024;
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tsm) + 1023) & ~uintptr_t(1023));
+  for (int s = 0; s < nslab; ++s) {
+    uint8_t* sb = base + (size_t)s * SLAB;
+    for (int idx = tid; idx < TCT_M * 32; idx += 128) {          // two k values per step
+      const int r = idx >> 5, k = (idx & 31) * 2;
+      uint32_t hi, lo;
+      tc::split_h16x2(W[(size_t)r * K + s * 64 + k] * w_scale, W[(size_t)r * K + s * 64 + k + 1] * w_scale, hi, lo);
+      *reinterpret_cast<uint32_t*>(sb + tc::sw128_off_h(r, k)) = hi;
+      *reinterpret_cast<uint32_t*>(sb + 16384 + tc::sw128_off_h(r, k)) = lo;
+    }
+    for (int idx = tid; idx < TCT_N * 32; idx += 128) {
+      const int r = idx >> 5, k = (idx & 31) * 2;
+      uint32_t hi, lo;
+      tc::split_h16x2(X[(size_t)r * K + s * 64 + k] * tc::ACT_SCALE_H16, X[(size_t)r * K + s * 64 + k + 1] * tc::ACT_SCALE_H16, hi, lo);
+      *reinterpret_cast<uint32_t*>(sb + 32768 + tc::sw128_off_h(r, k)) = hi;
+      *reinterpret_cast<uint32_t*>(sb + 40960 + tc::sw128_off_h(r, k)) = lo;
+    }
+  }
+  if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
+  if (warp == 0) tc::tmem_alloc(&tmem_base, 64);
+  tc::fence_proxy_async();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tm = tmem_base;
+  if (tid == 0) {
+    const uint32_t idesc = tc::idesc_f16(TCT_M, TCT_N);
+    uint32_t accum = 0;
+    for (int s = 0; s < nslab; ++s) {
+      const uint32_t sb = tc::smem_u32(base + (size_t)s * SLAB);
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t ko = j * 32;            // 16 fp16 = 32 bytes per k-step inside the swizzle atom
+        const uint64_t whi = tc::desc_sw128(sb + ko), wlo = tc::desc_sw128(sb + 16384 + ko);
+        const uint64_t xhi = tc::desc_sw128(sb + 32768 + ko), xlo = tc::desc_sw128(sb + 40960 + ko);
+        tc::umma_f16(tm, wlo, xhi, idesc, accum); accum = 1;
+        tc::umma_f16(tm, whi, xlo, idesc, accum);
+        tc::umma_f16(tm, whi, xhi, idesc, accum);
+      }
+    }
+    tc::umma_commit(&bar);
+  }
+  tc::mbar_wait(&bar, 0);
+  tc::tc_fence_after();
+  const float unscale = 1.0f / (w_scale * tc::ACT_SCALE_H16);
+  float v[32];
+  for (int c = 0; c < TCT_N; c += 32) {
+    tc::tmem_ld32(tm + ((uint32_t)(warp * 32) << 16) + c, v);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) out[(size_t)tid * TCT_N + c + i] = v[i] * unscale;
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tm, 64);
+}
+
 }  // namespace fm

@@ -109,7 +109,9 @@ class CTMCVectorFieldB200:
         return self._ws[off:off + 4 * cnt.value].view(torch.float32)
 
     def set_option(self, name, value):
-        """'conv_impl': 0 = fp32 CUDA-core message kernel, 1 = tcgen05 3xTF32 message kernel (flowmol3 dims)."""
+        """'conv_impl': 0 = fp32 CUDA-core message kernel, 1 = fused tcgen05 3xTF32 message kernel, 2 = wide tcgen05 pipeline
+        (default for the flowmol3 dims); 'tc_prec': operand format of the wide pipeline, 1 = scaled fp16 hi/lo images
+        ("fp16x3", default) or 0 = 3xTF32; 'node_impl', 'fuse_agg', 'eg_nh': see include/flowmol_b200.h."""
         _lib.check(self.lib.fm_set_option(self._h, name.encode(), int(value)))
         return self
 
@@ -117,6 +119,15 @@ class CTMCVectorFieldB200:
         v = C.c_int32()
         _lib.check(self.lib.fm_get_option(self._h, name.encode(), C.byref(v)))
         return int(v.value)
+
+    def check_status(self):
+        """Synchronising read-and-clear of the device status word; raises if an activation left the fp16 operand range of the
+        tensor-core linears (|x| >= 8188 with tc_prec 1) -- the results of that call are invalid, re-run with tc_prec 0."""
+        with torch.cuda.device(self.device):
+            st = self.get_option("status")
+        if st & 1:
+            raise RuntimeError("flowmol_b200: an activation left the fp16 operand range of the tensor-core linears; "
+                               "call set_option('tc_prec', 0) (3xTF32 operands) and re-run")
 
     def time_conv_edge(self, layer=1, iters=5):
         """Mean duration (ms) of the hot kernel re-launched on the state left by the last forward (bench roofline)."""
@@ -163,6 +174,7 @@ class CTMCVectorFieldB200:
                                            e.data_ptr(), float(t), C.byref(pv) if pv is not None else None, C.byref(po),
                                            int(stop_after_conv), self._stream()))
         self.last_launches = int(self.lib.fm_last_launch_count(self._h))
+        self.check_status()
         return out
 
     def _opts(self, n_timesteps, stochasticity, high_confidence_threshold, seed, mol_id_offset, tspan, cuda_graph):
@@ -190,6 +202,7 @@ class CTMCVectorFieldB200:
             _lib.check(self.lib.fm_integrate(self._h, self._ws.data_ptr(), x.data_ptr(), a.data_ptr(), c.data_ptr(),
                                              e.data_ptr(), C.byref(o), self._stream()))
         self.last_launches = int(self.lib.fm_last_launch_count(self._h))
+        self.check_status()
         return {'x': x, 'a': a, 'c': c, 'e': e}
 
     def sample_host(self, n_atoms, x0, a0, c0, e0_upper, n_timesteps, seed, stochasticity=None,

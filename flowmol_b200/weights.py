@@ -173,6 +173,12 @@ def _pad32(n):
 
 
 class Packer:
+    """Collects entries of the packed blob.  `tc(idx, idx_h, w_fk, rows)` stores both operand-image formats of one matrix."""
+
+    def tc(self, idx, idx_h, w_fk, rows_per_unit):
+        self.raw(idx, tc_units(w_fk, rows_per_unit))
+        self.raw(idx_h, tc_units_h16(w_fk, rows_per_unit))
+
     def __init__(self, n_entries):
         self.chunks = []
         self.size = 0
@@ -257,6 +263,55 @@ def tc_units(w_fk, rows_per_unit):
     return np.concatenate(chunks)
 
 
+ACT_SCALE_H16 = 8.0      # == fm::tc::ACT_SCALE_H16 (csrc/tc.cuh); fm_create refuses a blob built for another value
+
+
+def sw128_image_h16(tile):
+    """[rows, 64] fp16 -> byte image of a K-major SWIZZLE_128B UMMA operand tile (same 128-byte rows / 16-byte chunk
+    swizzle as `sw128_image`; a chunk holds 8 halves), returned as float32 words for the blob (csrc/tc.cuh:sw128_off_h)."""
+    rows = tile.shape[0]
+    t = np.asarray(tile, dtype=np.float16).reshape(rows, 8, 8)
+    out = np.empty_like(t)
+    r = np.arange(rows)
+    for c in range(8):
+        out[r, c ^ (r & 7)] = t[r, c]
+    return np.ascontiguousarray(out).reshape(-1).view(np.float32)
+
+
+def h16_weight_scale(w):
+    """Power of two s with max|w| * s in [2^13, 2^14): keeps the fp16 `lo` parts of all significant weights normal."""
+    m = float(np.abs(w).max())
+    return 1.0 if m == 0.0 or not np.isfinite(m) else float(2.0 ** (13 - math.floor(math.log2(m))))
+
+
+def split_h16(x):
+    x = np.asarray(x, dtype=np.float32)
+    hi = x.astype(np.float16)
+    return hi, (x - hi.astype(np.float32)).astype(np.float16)
+
+
+def tc_units_h16(w_fk, rows_per_unit):
+    """fp16x3 twin of `tc_units`: w_fk [features, K] fp32 -> for k-slab s (64 columns), for m-tile m: [hi unit | lo unit] of
+    w * scale in fp16, each rows_per_unit*128 B, followed by 4 floats [1 / (ACT_SCALE_H16 * scale), scale, 0, 0] -- the exact
+    power-of-two factor the kernel's epilogue multiplies the accumulator with."""
+    w = np.asarray(w_fk, dtype=np.float32)
+    Fdim, K = w.shape
+    ns, nm = (K + 63) // 64, (Fdim + rows_per_unit - 1) // rows_per_unit
+    scale = h16_weight_scale(w)
+    wp = np.zeros((nm * rows_per_unit, ns * 64), np.float32)
+    wp[:Fdim, :K] = w * np.float32(scale)
+    hi, lo = split_h16(wp)
+    assert np.isfinite(hi.astype(np.float32)).all()
+    chunks = []
+    for s_ in range(ns):
+        for m in range(nm):
+            sl = (slice(m * rows_per_unit, (m + 1) * rows_per_unit), slice(s_ * 64, s_ * 64 + 64))
+            chunks.append(sw128_image_h16(hi[sl]))
+            chunks.append(sw128_image_h16(lo[sl]))
+    chunks.append(np.array([1.0 / (ACT_SCALE_H16 * scale), scale, 0.0, 0.0], np.float32))
+    return np.concatenate(chunks)
+
+
 def _pack_gvp(P, base, sd, p, w_rows=None):
     """GVP under state_dict prefix `p` -> 6 consecutive entries starting at id `base`.
     [Wh | Wcp] are fused into one operand (they multiply the same input); `w_rows` selects/reorders the rows of the
@@ -313,6 +368,8 @@ def pack(cfg: ModelConfig, sd):
     _pack_linear(P, g("NHEAD2_W"), g("NHEAD2_B"), sd, "node_output_head.2")
     _pack_linear(P, g("EHEAD0_W"), g("EHEAD0_B"), sd, "to_edge_logits.0")
     _pack_linear(P, g("EHEAD2_W"), g("EHEAD2_B"), sd, "to_edge_logits.2")
+    if S % 128 == 0 and V <= 32:
+        P.raw(g("TC_INFO"), np.array([ACT_SCALE_H16, 0.0, 0.0, 0.0], np.float32))
     sdst, vdst = cfg.s_dst, cfg.v_dst
     for l in range(L):
         p = f"conv_layers.{l}"
@@ -333,15 +390,15 @@ def pack(cfg: ModelConfig, sd):
         if S % 128 == 0 and V <= 32:     # tensor-core images: features on the UMMA M axis (128-row tiles), gates 32-row units
             for i in range(3):
                 wt = _np(sd, f"{p}.edge_message.{i}.to_feats_out.0.weight")            # [S, in]
-                P.raw(c(f"MSG{i}_TCW"), tc_units(wt[:, rows_edge] if i == 0 else wt, 128))
-                P.raw(c(f"MSG{i}_TCG"), tc_units(_np(sd, f"{p}.edge_message.{i}.scalar_to_vector_gates.weight"), 32))
+                P.tc(c(f"MSG{i}_TCW"), c(f"MSG{i}_TCW_H"), wt[:, rows_edge] if i == 0 else wt, 128)
+                P.tc(c(f"MSG{i}_TCG"), c(f"MSG{i}_TCG_H"), _np(sd, f"{p}.edge_message.{i}.scalar_to_vector_gates.weight"), 32)
         for i in range(3):
             _pack_gvp(P, c(f"UPD{i}_WHCP"), sd, f"{p}.node_update.{i}")
         if S % 128 == 0 and V <= 32 and 2 * F == S:      # node pipeline on the tensor cores (node rows through k_egemm_tc)
             for i in range(3):
-                P.raw(c(f"UPD{i}_TCW"), tc_units(_np(sd, f"{p}.node_update.{i}.to_feats_out.0.weight"), 128))
-                P.raw(c(f"UPD{i}_TCG"), tc_units(_np(sd, f"{p}.node_update.{i}.scalar_to_vector_gates.weight"), 32))
-            P.raw(c("WSRC_TC"), tc_units(w0[:S].T, 128))
+                P.tc(c(f"UPD{i}_TCW"), c(f"UPD{i}_TCW_H"), _np(sd, f"{p}.node_update.{i}.to_feats_out.0.weight"), 128)
+                P.tc(c(f"UPD{i}_TCG"), c(f"UPD{i}_TCG_H"), _np(sd, f"{p}.node_update.{i}.scalar_to_vector_gates.weight"), 32)
+            P.tc(c("WSRC_TC"), c("WSRC_TC_H"), w0[:S].T, 128)
         P.vec(c("LN_MSG_W"), _np(sd, f"{p}.message_layer_norm.feat_norm.weight"))
         P.vec(c("LN_MSG_B"), _np(sd, f"{p}.message_layer_norm.feat_norm.bias"))
         P.vec(c("LN_UPD_W"), _np(sd, f"{p}.update_layer_norm.feat_norm.weight"))
@@ -358,12 +415,12 @@ def pack(cfg: ModelConfig, sd):
         _pack_linear(P, c("EUPD_W2"), c("EUPD_B2"), sd, p + ".edge_update_fn.2")
         P.vec(c("EUPD_LN_W"), _np(sd, p + ".edge_norm.weight")); P.vec(c("EUPD_LN_B"), _np(sd, p + ".edge_norm.bias"))
         if F == 128 and S % 128 == 0 and V <= 32:        # tensor-core images of the two EdgeUpdate linears (features on M)
-            P.raw(c("EUPD_TC1"), tc_units(w1[2 * S:].T, 128))                                  # [F, F + R], k order ef | d
-            P.raw(c("EUPD_TC2"), tc_units(_np(sd, p + ".edge_update_fn.2.weight"), 128))       # [F, F]
+            P.tc(c("EUPD_TC1"), c("EUPD_TC1_H"), w1[2 * S:].T, 128)                                  # [F, F + R], k order ef | d
+            P.tc(c("EUPD_TC2"), c("EUPD_TC2_H"), _np(sd, p + ".edge_update_fn.2.weight"), 128)       # [F, F]
         if S % 128 == 0 and V <= 32 and 2 * F == S:
             for i in range(3):
                 q = f"node_position_updaters.{u}.gvps.{i}"
-                P.raw(c(f"POS{i}_TCW"), tc_units(_np(sd, q + ".to_feats_out.0.weight"), 128))
-                P.raw(c(f"POS{i}_TCG"), tc_units(_np(sd, q + ".scalar_to_vector_gates.weight"), 32))
-            P.raw(c("EUPD_WN_TC"), tc_units(np.concatenate([w1[:S], w1[S:2 * S]], axis=1).T, 128))   # [2F, S]: EA | EB rows
+                P.tc(c(f"POS{i}_TCW"), c(f"POS{i}_TCW_H"), _np(sd, q + ".to_feats_out.0.weight"), 128)
+                P.tc(c(f"POS{i}_TCG"), c(f"POS{i}_TCG_H"), _np(sd, q + ".scalar_to_vector_gates.weight"), 32)
+            P.tc(c("EUPD_WN_TC"), c("EUPD_WN_TC_H"), np.concatenate([w1[:S], w1[S:2 * S]], axis=1).T, 128)   # [2F, S]: EA | EB rows
     return P.blob(), P.offsets

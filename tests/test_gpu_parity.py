@@ -171,9 +171,10 @@ def test_results_do_not_depend_on_batch_composition_or_sharding():
 
 def test_fp32_and_tensor_core_message_kernels_agree():
     """conv_impl 0 (fp32 CUDA cores), 1 (fused tcgen05) and 2 (wide tcgen05 pipeline, default) on the same inputs;
-    with conv_impl 2 both node-update implementations (node_impl 1: pipeline around k_egemm_tc, default; 0: fused fp32 kernel)."""
+    with conv_impl 2 both node-update implementations (node_impl 1: pipeline around k_egemm_tc, default; 0: fused fp32 kernel)
+    and both operand formats (tc_prec 1: scaled fp16 hi/lo, default; 0: 3xTF32 -- variant 5)."""
     cfg, vf = cuda_model("flowmol3", 11, 61)
-    assert vf.get_option("conv_impl") == 2 and vf.get_option("node_impl") == 1
+    assert vf.get_option("conv_impl") == 2 and vf.get_option("node_impl") == 1 and vf.get_option("tc_prec") == 1
     n_atoms = np.array([9, 70, 3, 33])
     bt = O.make_batch(n_atoms)
     gen = torch.Generator().manual_seed(8)
@@ -181,18 +182,20 @@ def test_fp32_and_tensor_core_message_kernels_agree():
     a, c, e = torch.randint(0, 12, (bt.N,), generator=gen), torch.randint(0, 7, (bt.N,), generator=gen), torch.randint(0, 5, (bt.U,), generator=gen)
     outs = {}
     try:
-        for impl in (0, 1, 2, 3, 4):
+        for impl in (0, 1, 2, 3, 4, 5):
             vf.set_option("conv_impl", min(impl, 2))
+            vf.set_option("tc_prec", 0 if impl == 5 else 1)
             vf.set_option("node_impl", 0 if impl == 3 else 1)
             vf.set_option("fuse_agg", 0 if impl == 4 else 1)      # 4: scalar segment-sum in k_vec_c instead of the egemm epilogue
             d0 = vf.forward_tokens(n_atoms, x, torch.full_like(a, 11), torch.full_like(c, 6), torch.full_like(e, 4), 0.0, None)
             outs[impl] = {k: v.cpu() for k, v in vf.forward_tokens(n_atoms, x, a, c, e, 0.4, d0).items()}
     finally:
         vf.set_option("conv_impl", 2)
+        vf.set_option("tc_prec", 1)
         vf.set_option("node_impl", 1)
         vf.set_option("fuse_agg", 1)
     assert all(torch.equal(outs[4][k], outs[2][k]) for k in "xace")      # same sums in the same order: bit-identical
-    for impl in (1, 2, 3):
+    for impl in (1, 2, 3, 5):
         assert (outs[impl]["x"] - outs[0]["x"]).abs().max() <= TOL_X
         for k in "ace":
             assert (outs[impl][k] - outs[0][k]).abs().max() <= TOL_P
@@ -275,3 +278,44 @@ def test_tcgen05_3xtf32_gemm_building_block():
         print(f"K={K} rel err 1xTF32 {errs[1]:.2e} 3xTF32 {errs[3]:.2e} fp32 {fp32:.2e}")
         assert errs[1] < 5e-3, errs
         assert errs[3] < 2e-6, errs
+
+
+def test_tcgen05_fp16x3_gemm_building_block():
+    """tcgen05.mma kind::f16 on scaled fp16 hi/lo operands (64 k values per SW128 row): fp32-level accuracy, also for inputs
+    with a wide dynamic range (small values keep their low part thanks to the power-of-two operand scales)."""
+    from flowmol_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(1)
+    for K in (64, 128):
+        for kind in ("normal", "wide"):
+            W = (rng.uniform(-1, 1, (128, K)) / np.sqrt(K)).astype(np.float32)
+            X = rng.standard_normal((64, K)).astype(np.float32)
+            if kind == "wide":
+                X *= np.where(rng.random((64, K)) < 0.5, 1e-3, 30.0).astype(np.float32)
+                W *= np.where(rng.random((128, K)) < 0.5, 1e-2, 1.0).astype(np.float32)
+            want = W.astype(np.float64) @ X.astype(np.float64).T
+            out = np.zeros((128, 64), np.float32)
+            _lib.check(lib.fm_debug_tc_gemm(W.ctypes.data, X.ctypes.data, K, out.ctypes.data, 16, 0))
+            out3 = np.zeros((128, 64), np.float32)
+            _lib.check(lib.fm_debug_tc_gemm(W.ctypes.data, X.ctypes.data, K, out3.ctypes.data, 3, 0))
+            err, err3 = (float(np.abs(o - want).max() / np.abs(want).max()) for o in (out, out3))
+            print(f"K={K} {kind}: rel err fp16x3 {err:.2e} 3xTF32 {err3:.2e}")
+            assert err < 2e-6, (K, kind, err)
+
+
+def test_fp16_operand_overflow_is_reported_not_silent():
+    """Activations beyond the fp16 operand range (|x| >= 8188) must raise, and the 3xTF32 operands must still work."""
+    from flowmol_b200.vector_field import CTMCVectorFieldB200
+    cfg = ModelConfig.named("flowmol3", 11)
+    sd = WT.init_state_dict(cfg, 71)
+    sd["scalar_embedding.4.weight"] = sd["scalar_embedding.4.weight"] * 1e5        # LayerNorm gain: node scalars ~1e5
+    vf = CTMCVectorFieldB200(cfg, sd, device="cuda:0")
+    n_atoms = np.array([5, 8])
+    bt = O.make_batch(n_atoms)
+    x = torch.randn(bt.N, 3, generator=torch.Generator().manual_seed(0))
+    args = (n_atoms, x, torch.full((bt.N,), 11), torch.full((bt.N,), 6), torch.full((bt.U,), 4), 0.0, None)
+    with pytest.raises(RuntimeError, match="fp16 operand range"):
+        vf.forward_tokens(*args)
+    vf.set_option("tc_prec", 0)
+    d = vf.forward_tokens(*args)
+    assert torch.isfinite(d["a"]).all()

@@ -13,6 +13,7 @@
 #include "kernels.cuh"
 #include "conv_tc.cuh"
 #include "egemm_tc.cuh"
+#include "egemm_p.cuh"
 #include "vec_stages.cuh"
 #include "tc_test.cuh"
 
@@ -108,6 +109,7 @@ struct FmHandle {
   int fuse_agg = 1;            // scalar segment-sum in the epilogue of the last message linear (k_egemm_tc<EG_MSGA>)
   int node_impl = 0;           // 0: fused fp32 k_node_update, 1: node pipeline around k_egemm_tc (with conv_impl 2)
   int conv_impl = 0;           // 0: fp32 CUDA-core k_conv_edge, 1: tcgen05 3xTF32 k_conv_edge_tc (flowmol3 dims only)
+  int eg_persist = 1;          // tc_prec 1: persistent role-specialised k_egemm_p (1 CTA / SM, double-buffered accumulators)
   int tc_prec = 0;             // operand format of k_egemm_tc: 0 = 3xTF32 images, 1 = scaled fp16 hi/lo images ("fp16x3")
   bool has_h16 = false;        // packed weights carry the fp16 images
   int* d_status = nullptr;     // device status word: bit 0 = an activation left the fp16 operand range (tc_prec 1)
@@ -172,6 +174,13 @@ int set_smem_attrs() {
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_LIN, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<1>::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_LIN, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<1>::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_vec_c<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::VecSmem<D>::BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_MSG0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_MSG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_EU1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_EU2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_LIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_MSGA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
   }
   return 0;
 }
@@ -181,6 +190,10 @@ template <class D, int MODE, int NH>
 void launch_eg(FmHandle* h, int grid, cudaStream_t st, const fm::ModelRT& m, const fm::BatchRT& bt, fm::EgArgs a) {
   using PL = fm::EgPlan<NH>;
   a.status = h->d_status;
+  if (NH == 1 && h->tc_prec == 1 && h->eg_persist) {      // `grid` = number of 128-row tiles
+    fm::k_egemm_p<D, MODE><<<grid < h->n_sm ? grid : h->n_sm, fm::EgpPlan::THREADS, fm::EgpPlan::SMEM_BYTES, st>>>(m, bt, a, grid);
+    return;
+  }
   if (h->tc_prec) fm::k_egemm_tc<D, MODE, NH, 1><<<grid, PL::THREADS, PL::SMEM_BYTES, st>>>(m, bt, a);
   else fm::k_egemm_tc<D, MODE, NH, 0><<<grid, PL::THREADS, PL::SMEM_BYTES, st>>>(m, bt, a);
 }
@@ -739,6 +752,7 @@ int fm_set_option(FmHandle* h, const char* name, int32_t value) {
     return 0;
   }
   if (n == "fuse_agg") { h->fuse_agg = value ? 1 : 0; return 0; }
+  if (n == "eg_persist") { h->eg_persist = value ? 1 : 0; return 0; }
   if (n == "tc_prec") {
     if (value < 0 || value > 1) return fail("fm_set_option: tc_prec must be 0 (3xTF32) or 1 (fp16x3)");
     if (value == 1 && !h->has_h16) return fail("fm_set_option: packed weights carry no fp16 operand images");
@@ -768,6 +782,7 @@ int fm_get_option(FmHandle* h, const char* name, int32_t* value) {
   if (std::string(name) == "conv_impl") { *value = h->conv_impl; return 0; }
   if (std::string(name) == "node_impl") { *value = h->node_impl; return 0; }
   if (std::string(name) == "tc_prec") { *value = h->tc_prec; return 0; }
+  if (std::string(name) == "eg_persist") { *value = h->eg_persist; return 0; }
   if (std::string(name) == "status") {      // synchronising read-and-clear of the device status word (see fm_check_status)
     int v = 0;
     CUDA_OK(cudaSetDevice(h->device));

@@ -1,0 +1,426 @@
+// k_egemm_p -- persistent, role-specialised version of k_egemm_tc (same modes, same arguments, same results bit for bit).
+//
+// What the profile of k_egemm_tc said (profiles/r01e_summary.md): tensor pipe 31 % active, DRAM 36 % of peak, the sampled
+// stalls spread over "loader waits for its global loads", "epilogue waits for the accumulator" and "warps parked at the final
+// barrier".  A CTA there is one 128-edge tile whose phases run one after the other (bookkeeping -> k-loop -> epilogue) with the
+// same four warps loading and draining; only the co-resident CTA overlaps them.  Here ONE CTA per SM walks over tiles
+// (tile = blockIdx.x + i * gridDim.x) with three independent pipelines that never wait for each other's phases:
+//
+//   warp 0      weight producer   bulk-TMA ring of operand images, runs ahead across tile boundaries
+//   warps 1-2   MMA issuers       tcgen05.mma into one of TWO TMEM accumulator buffers (2 x 256 columns); issuer w owns the 128-feature
+//                                 tile w (its own accumulator columns and its own weight units), so two threads share the issue work
+//   warps 3-10  activation loaders fp32 -> scaled fp16 (hi, lo) SW128 images into a 4-stage ring; group 0 (warps 2-5) writes the
+//                                 first 32 k values of every 64-wide slab, group 1 the second 32; global loads are
+//                                 prefetched one chunk ahead, across tile boundaries
+//   warps 11-14 epilogue          TMEM -> registers -> activation -> global; drains buffer b while the MMAs fill buffer b ^ 1
+//
+// All ring positions / mbarrier phases are running counters that every role advances identically per tile, so nothing is
+// re-initialised between tiles.  PREC 1 (fp16x3 operands) only: the 32-float loader chunks pair up into 64-wide slabs.
+#pragma once
+#include "egemm_tc.cuh"
+
+namespace fm {
+
+struct EgpPlan {
+  static constexpr int T = 128;                             // rows (edges / nodes) per tile
+  static constexpr int NST = 4;                             // activation stages
+  static constexpr int XSTAGE = 32768;                      // hi image 16 KB | lo image 16 KB
+  static constexpr int RING_BYTES = 4 * TC_UNIT;            // weight ring
+  static constexpr int MAX_SLOTS = 12;
+  static constexpr int THREADS = 15 * 32;
+  static constexpr int W_LOAD0 = 3, W_EPI0 = 11;              // first loader / epilogue warp
+  static constexpr int OFF_X = 0;
+  static constexpr int OFF_RING = NST * XSTAGE;
+  static constexpr int OFF_ROW = OFF_RING + RING_BYTES;     // 2 x { int src[T]; short dd[T] } (epilogue bookkeeping, double buffered)
+  static constexpr int OFF_RED = OFF_ROW + 2 * T * 6;       // EU2 LayerNorm partials (256 floats)
+  static constexpr int OFF_BAR = OFF_RED + 1024;
+  static constexpr int NBAR = 2 * MAX_SLOTS + 2 * NST + 4;
+  static constexpr int BYTES = OFF_BAR + NBAR * 8 + 16;
+  static constexpr size_t SMEM_BYTES = BYTES;
+  static_assert(BYTES <= 232448, "227 KB of shared memory per CTA");
+};
+
+template <class D, int MODE>
+__global__ void __launch_bounds__(EgpPlan::THREADS, 1)
+k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) {
+  using PL = EgpPlan;
+  constexpr int S = D::S;
+  constexpr bool IS_EU = MODE == EG_EU1 || MODE == EG_EU2;
+  constexpr bool IS_MSG = MODE == EG_MSG || MODE == EG_MSGA;
+  constexpr int K = MODE == EG_MSG0 ? D::KE0 : (IS_MSG ? D::K1 : (MODE == EG_EU1 ? D::F + D::R : (MODE == EG_EU2 ? D::F : S)));
+  constexpr int NSLAB = (K + 63) / 64;
+  constexpr int NCH = (K + 31) / 32;
+  constexpr int LAST_KSTEPS = ((K - 1) % 64) / 16 + 1;
+  constexpr int NMT = MODE == EG_GATE ? 1 : (IS_EU ? D::F / 128 : S / 128);
+  constexpr int OW = MODE == EG_GATE ? 32 : (IS_EU ? D::F : S);
+  static_assert(!IS_EU || D::F == 128, "edge-update modes: F = 128");
+  constexpr int UNIT_BYTES = MODE == EG_GATE ? 32 * 128 : TC_UNIT;
+  constexpr int RING_FIT = (PL::RING_BYTES - TC_UNIT) / UNIT_BYTES + 1;      // the MMA reads 16 KB from every slot base
+  constexpr int RING = RING_FIT < PL::MAX_SLOTS ? RING_FIT : PL::MAX_SLOTS;
+  constexpr uint32_t NU = NSLAB * NMT * 2;                                     // weight units per tile
+  constexpr int NST = PL::NST;
+  constexpr int SH_W = 40;
+  constexpr int LO_OFF = 16384;
+  extern __shared__ __align__(1024) uint8_t smem_dyn[];
+  uint8_t* xst = smem_dyn + PL::OFF_X;
+  uint8_t* ring = smem_dyn + PL::OFF_RING;
+  float* red = reinterpret_cast<float*>(smem_dyn + PL::OFF_RED);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_dyn + PL::OFF_BAR);
+  uint64_t *w_full = bars, *w_empty = bars + PL::MAX_SLOTS, *x_full = bars + 2 * PL::MAX_SLOTS, *x_empty = x_full + NST;
+  uint64_t *acc_full = x_empty + NST, *acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_my = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  if (tid == 0) {
+    for (int i = 0; i < RING; ++i) { tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < NST; ++i) { tc::mbar_init(&x_full[i], 8); tc::mbar_init(&x_empty[i], NMT); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], NMT); tc::mbar_init(&acc_empty[i], 4); }
+    tc::fence_mbar_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ---- weight producer ---------------------------------------------------------------------------------------------------------
+    if (lane == 0) {
+      uint32_t u = 0;
+      for (int it = 0; it < n_my; ++it) {
+        for (uint32_t k = 0; k < NU; ++k, ++u) {
+          const uint32_t sl = u % RING, use = u / RING;
+          if (use > 0) tc::mbar_wait(&w_empty[sl], (use - 1) & 1);
+          tc::mbar_arrive_expect_tx(&w_full[sl], UNIT_BYTES);
+          tc::bulk_g2s(ring + sl * UNIT_BYTES, reinterpret_cast<const uint8_t*>(a.units) + (size_t)k * UNIT_BYTES, UNIT_BYTES, &w_full[sl]);
+        }
+      }
+    }
+  } else if (warp <= 2) {
+    // ---- MMA issuers: warp 1 + mt issues the MMAs of feature tile mt (the whole warp stays converged, one elected lane issues) -----
+    const int mt = warp - 1;
+    if (mt < NMT) {
+      const bool leader = tc::elect_one();
+      const uint32_t idesc = tc::idesc_f16(128, 128);
+      // this issuer's weight units are every NMT-th pair of the stream: ring slot / phase advance by 2 * NMT units per slab
+      uint32_t sl = 2 * mt, ph = 0, g = 0;
+      const uint32_t ring_lo = tc::smem_u32(ring) >> 4, x_lo = tc::smem_u32(xst) >> 4;
+      for (int it = 0; it < n_my; ++it) {
+        const int b = it & 1;
+        if (it >= 2) { tc::mbar_wait(&acc_empty[b], ((it >> 1) - 1) & 1); tc::tc_fence_after(); }
+        const uint32_t d = tmem + (uint32_t)(b * 256 + mt * 128);
+        for (int j = 0; j < NSLAB; ++j, ++g) {
+          const uint32_t st = g % NST, ksteps = (j == NSLAB - 1) ? LAST_KSTEPS : 4;
+          tc::mbar_wait(&x_full[st], (g / NST) & 1);
+          const uint32_t xh = x_lo + st * (PL::XSTAGE >> 4), xl = xh + (LO_OFF >> 4);
+          tc::mbar_wait(&w_full[sl], ph);
+          tc::tc_fence_after();
+          const uint32_t wh = ring_lo + sl * (UNIT_BYTES >> 4);
+          if (leader) {
+#pragma unroll
+            for (uint32_t ks = 0; ks < 4; ++ks) {
+              if (ks < ksteps) {
+                const uint64_t dw = tc::desc_sw128_lo(wh + 2 * ks);
+                tc::umma_f16(d, dw, tc::desc_sw128_lo(xl + 2 * ks), idesc, (j > 0 || ks > 0) ? 1u : 0u);
+                tc::umma_f16(d, dw, tc::desc_sw128_lo(xh + 2 * ks), idesc, 1u);
+              }
+            }
+            tc::umma_commit(&w_empty[sl]);
+          }
+          tc::mbar_wait(&w_full[sl + 1], ph);
+          tc::tc_fence_after();
+          const uint32_t wl = wh + (UNIT_BYTES >> 4);
+          if (leader) {
+#pragma unroll
+            for (uint32_t ks = 0; ks < 4; ++ks)
+              if (ks < ksteps) tc::umma_f16(d, tc::desc_sw128_lo(wl + 2 * ks), tc::desc_sw128_lo(xh + 2 * ks), idesc, 1u);
+            tc::umma_commit(&w_empty[sl + 1]);
+            tc::umma_commit(&x_empty[st]);
+          }
+          sl += 2 * NMT;
+          if (sl >= RING) { sl -= RING; ph ^= 1; }
+        }
+        if (leader) tc::umma_commit(&acc_full[b]);
+      }
+    }
+  } else if (warp < PL::W_EPI0) {
+    // ---- activation loaders ------------------------------------------------------------------------------------------------------------------
+    // Warps w and w + 4 own the same 32 rows; group `grp` converts chunk 2 * slab + grp of every slab.  Row bookkeeping (validity,
+    // src node, distance) lives in registers: lane l holds row wrow0 + l, the fetch reads it with a shuffle.
+    const int grp = (warp - PL::W_LOAD0) >> 2, wrow0 = ((warp - PL::W_LOAD0) & 3) * 32, lg = lane >> 3, ch = lane & 7;
+    const float sigma = m.rbf_dmax / (float)D::R;
+    const float* mu = m.g(G_RBF_MU);
+    int r_ok = 0;              // row valid (of the tile the NEXT fetch belongs to)
+    float r_dist = 0.f;
+    long long f_slot0 = 0;
+    auto rowinfo = [&](int it) {
+      f_slot0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * PL::T;
+      const long long slot = f_slot0 + wrow0 + lane;
+      int ok = 0;
+      float dist = 0.f;
+      if (a.flags & EGF_NODE_ROWS) {
+        ok = slot < a.EP;
+      } else if (slot < a.EP) {
+        const int t64 = (int)(slot >> 6), mol = bt.etile_mol[t64];
+        const int n = bt.mol_n[mol], le = (int)(slot - ((long long)bt.mol_etile[mol] << 6));
+        if (le < n * (n - 1)) {
+          ok = 1;
+          if (MODE == EG_MSG0 || MODE == EG_EU1) {
+            int i, j;
+            edge_src_dst(le, n, i, j);
+            const int nb = bt.mol_node[mol];
+            float dx, dy, dz;
+            dist = pair_dist(a.x, nb + i, nb + j, dx, dy, dz);
+          }
+        }
+      }
+      r_ok = ok;
+      r_dist = dist;
+    };
+    // chunk of slab `sb` this group converts: k values [64 sb + 32 grp, +32).  `sb` is a compile-time constant at every call site
+    // (the slab loops are fully unrolled), so the source selection below folds to one path per call.
+    auto fetch = [&](const int sb, float4 (&buf)[8]) {
+      const int j = 2 * sb + grp;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rl = 4 * i + lg;                              // row inside the warp's 32
+        const long long sl_ = f_slot0 + wrow0 + rl;
+        const bool ok = __shfl_sync(0xffffffffu, r_ok, rl) != 0;
+        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (MODE == EG_MSG0 || MODE == EG_EU1) {
+          const float dd = __shfl_sync(0xffffffffu, r_dist, rl);
+          // MSG0: k order rbf(32) | ef(F) | norms;  EU1: ef(F) | rbf(32)
+          const bool maybe_rbf = MODE == EG_MSG0 ? sb == 0 : sb == D::F / 64;
+          if (maybe_rbf && grp == 0) {
+            if (ok) val = make_float4(rbf_f(dd, mu[ch * 4], sigma), rbf_f(dd, mu[ch * 4 + 1], sigma), rbf_f(dd, mu[ch * 4 + 2], sigma),
+                                      rbf_f(dd, mu[ch * 4 + 3], sigma));
+          } else if (MODE == EG_MSG0) {
+            if (ok) {
+              if (j <= D::F / 32) val = __ldg(reinterpret_cast<const float4*>(a.in_s + (size_t)sl_ * D::F + (j - 1) * 32) + ch);
+              else {
+                const int k0 = (j - 1 - D::F / 32) * 32 + ch * 4;
+                if (k0 < SH_W) val = *(reinterpret_cast<const float4*>(a.in_sh + (size_t)sl_ * SH_W + k0));
+              }
+            }
+          } else {
+            if (ok) val = *(reinterpret_cast<const float4*>(a.in_s + (size_t)sl_ * D::F + j * 32) + ch);
+          }
+        } else if (IS_MSG) {
+          if (ok) {
+            if (sb < S / 64) val = *(reinterpret_cast<const float4*>(a.in_s + (size_t)sl_ * S + j * 32) + ch);
+            else {
+              const int k0 = (j - S / 32) * 32 + ch * 4;
+              if (k0 < SH_W) val = *(reinterpret_cast<const float4*>(a.in_sh + (size_t)sl_ * SH_W + k0));
+            }
+          }
+        } else if (MODE == EG_EU2) {
+          if (ok) val = *(reinterpret_cast<const float4*>(a.in_s + (size_t)sl_ * D::F + j * 32) + ch);
+        } else {
+          if (ok) val = *(reinterpret_cast<const float4*>(a.in_s + (size_t)sl_ * S + j * 32) + ch);
+        }
+        buf[i] = val;
+      }
+    };
+    // group 1 has no chunk in the last slab when K spans an odd number of 32-wide chunks
+    constexpr int NMY1 = NCH / 2;
+    float4 cur[8], nxt[8];
+    float amax = 0.f;
+    if (n_my > 0) { rowinfo(0); fetch(0, cur); }
+    uint32_t g = 0;                                            // running slab counter (stage / phase bookkeeping)
+    for (int it = 0; it < n_my; ++it) {
+#pragma unroll
+      for (int s = 0; s < NSLAB; ++s, ++g) {
+        const uint32_t st = g % NST, use = g / NST;
+        const bool mine = s < NMY1 || grp == 0;                // this group has a chunk in slab s
+        if (mine) {                                            // prefetch this group's next chunk: same tile, or slab 0 of the next tile
+          const bool last_mine = (s + 1 == NSLAB) || (s + 1 == NMY1 && grp == 1);
+          if (!last_mine) {
+            fetch(s + 1 < NSLAB ? s + 1 : 0, nxt);
+          } else if (it + 1 < n_my) {
+            rowinfo(it + 1);
+            fetch(0, nxt);
+          }
+        }
+        if (use > 0) tc::mbar_wait(&x_empty[st], (use - 1) & 1);
+        if (mine) {
+          uint8_t* hi = xst + st * PL::XSTAGE;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr_ = wrow0 + 4 * i + lg;
+            const float4 val = cur[i];
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(val.x), fabsf(val.y)), fmaxf(fabsf(val.z), fabsf(val.w))));
+            uint2 vh, vl;
+            tc::split_h16x2(val.x * tc::ACT_SCALE_H16, val.y * tc::ACT_SCALE_H16, vh.x, vl.x);
+            tc::split_h16x2(val.z * tc::ACT_SCALE_H16, val.w * tc::ACT_SCALE_H16, vh.y, vl.y);
+            const uint32_t off = tc::sw128_off_h(rr_, grp * 32 + ch * 4);
+            *reinterpret_cast<uint2*>(hi + off) = vh;
+            *reinterpret_cast<uint2*>(hi + LO_OFF + off) = vl;
+          }
+          tc::fence_proxy_async();
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&x_full[st])) : "memory");
+        if (mine) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+        }
+      }
+    }
+    if (!(amax < tc::ACT_LIMIT_H16) && a.status) atomicOr(a.status, 1);
+  } else {
+    // ---- epilogue: TMEM -> registers -> bias / gathered pre-activation -> activation -> coalesced global stores ---------------------------
+    const int q = warp & 3, et = tid - PL::W_EPI0 * 32;                 // TMEM lane quarter; index among the 128 epilogue threads
+    const float unscale = a.units[(size_t)NU * (UNIT_BYTES / 4)];
+    constexpr bool GATHERS = MODE == EG_MSG0 || MODE == EG_EU1 || MODE == EG_EU2;
+    constexpr bool NEED_ROWS = MODE == EG_MSG0 || MODE == EG_EU1 || MODE == EG_MSGA;
+    for (int it = 0; it < n_my; ++it) {
+      const int b = it & 1;
+      const long long slot0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * PL::T;
+      int* r_src = reinterpret_cast<int*>(smem_dyn + PL::OFF_ROW + b * (PL::T * 6));
+      short* r_dd = reinterpret_cast<short*>(r_src + PL::T);
+      if (NEED_ROWS) {
+        const int r = et;
+        const long long slot = slot0 + r;
+        int s = -1, dd = 0;
+        if (slot < a.EP) {
+          const int t64 = (int)(slot >> 6), mol = bt.etile_mol[t64];
+          const int n = bt.mol_n[mol], le = (int)(slot - ((long long)bt.mol_etile[mol] << 6));
+          if (le < n * (n - 1)) {
+            s = 0;
+            if (MODE == EG_MSGA) {
+              const int j = le / (n - 1), rem = le - j * (n - 1);
+              s = bt.mol_node[mol] + j;
+              const bool tail = rem == n - 2;
+              dd = (((r & 63) == 63 || tail) ? 1 : 0) | (tail ? 2 : 0) | (rem <= (r & 63) ? 4 : 0);
+            } else {
+              int i, j;
+              edge_src_dst(le, n, i, j);
+              s = bt.mol_node[mol] + i;
+              dd = j - i;
+            }
+          }
+        }
+        r_src[r] = s;
+        if (MODE == EG_MSGA) {
+          const unsigned em = __ballot_sync(0xffffffffu, dd & 1), tm = __ballot_sync(0xffffffffu, dd & 2), hm = __ballot_sync(0xffffffffu, dd & 4);
+          if (lane == 0) {
+            unsigned* masks = reinterpret_cast<unsigned*>(r_dd);
+            masks[(et >> 5) * 3 + 0] = em; masks[(et >> 5) * 3 + 1] = tm; masks[(et >> 5) * 3 + 2] = hm;
+          }
+        } else {
+          r_dd[r] = (short)dd;
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");           // the four epilogue warps (buffers alternate: one barrier per tile)
+      }
+      const bool active = MODE != EG_GATE || q == 0;
+#pragma unroll 1
+      for (int mt = 0; mt < NMT; ++mt) {
+        const int f = mt * 128 + q * 32 + lane;
+        float run = 0.f;
+        const float bias = (MODE == EG_MSG0 || MODE == EG_EU1 || !active) ? 0.f : a.bias[f];
+        float pre[32], pnext[32];
+        auto gather = [&](int c, float (&dst_)[32]) {
+          if (MODE == EG_MSG0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dst_[i] = __ldg(a.P + (size_t)max(r_src[c * 32 + i], 0) * S + f);
+          } else if (MODE == EG_EU1) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int e = c * 32 + i, sn = max(r_src[e], 0);
+              dst_[i] = __fadd_rn(__ldg(a.P + (size_t)sn * 2 * D::F + f), __ldg(a.P + (size_t)(sn + r_dd[e]) * 2 * D::F + D::F + f));
+            }
+          } else if (MODE == EG_EU2) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dst_[i] = a.in_sh[(size_t)(slot0 + c * 32 + i) * D::F + f];
+          }
+        };
+        if (GATHERS) gather(0, pre);
+        if (mt == 0) {
+          tc::mbar_wait(&acc_full[b], (it >> 1) & 1);
+          tc::tc_fence_after();
+        }
+        if (active) {
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            float acc[32];
+            tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 256 + mt * 128 + c * 32), acc);
+            if (GATHERS && c + 1 < 4) gather(c + 1, pnext);
+            tc::tmem_ld_wait();
+            float* op = a.out + (size_t)(slot0 + c * 32) * OW + f;
+            unsigned em = 0, tm = 0, hm = 0;
+            if (MODE == EG_MSGA) {
+              const unsigned* masks = reinterpret_cast<const unsigned*>(r_dd) + c * 3;
+              em = masks[0]; tm = masks[1]; hm = masks[2];
+            }
+            if (MODE != EG_EU2) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float z = acc[i] * unscale + ((MODE == EG_MSG0 || MODE == EG_EU1) ? pre[i] : bias);
+                if (MODE == EG_LIN) { op[(size_t)i * OW] = z; continue; }
+                const float sg = sigmoid_fast(z);
+                const float o = MODE == EG_GATE ? ((a.flags & EGF_IDENTITY) ? z : sg) : z * sg;
+                op[(size_t)i * OW] = o;
+                if (MODE == EG_MSGA) acc[i] = o;
+              }
+              if (MODE == EG_MSGA) {
+                if ((c & 1) == 0) run = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  run = __fadd_rn(run, acc[i]);
+                  if ((em >> i) & 1u) {
+                    const int row = c * 32 + i;
+                    eg_store_segment(a.M, a.partF, a.partL, D::MW, r_src[row], (slot0 + row) >> 6,
+                                     ((hm >> i) & 1u) | (((tm >> i) & 1u) << 1), f, run);
+                    run = 0.f;
+                  }
+                }
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float z = acc[i] * unscale + bias;
+                acc[i] = __fadd_rn(pre[i], z * sigmoid_fast(z));
+              }
+              {
+                float t[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) t[i] = acc[i];
+                red[q * 32 + lane] = warp_transpose_sum(t);
+              }
+              asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+              for (int i = 0; i < 32; ++i) pre[i] = (red[i] + red[32 + i] + red[64 + i] + red[96 + i]) * (1.0f / 128.0f);
+              {
+                float t[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { const float dlt = acc[i] - pre[i]; t[i] = dlt * dlt; }
+                red[128 + q * 32 + lane] = warp_transpose_sum(t);
+              }
+              asm volatile("bar.sync 1, 128;" ::: "memory");
+              const float gam = a.ln_w[f], bet = a.ln_b[f];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float var = (red[128 + i] + red[160 + i] + red[192 + i] + red[224 + i]) * (1.0f / 128.0f);
+                op[(size_t)i * OW] = (acc[i] - pre[i]) * rsqrtf(var + 1e-5f) * gam + bet;
+              }
+              asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            if (GATHERS) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) pre[i] = pnext[i];
+            }
+          }
+        }
+      }
+      // this warp has read everything it needs from accumulator buffer b
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&acc_empty[b])) : "memory");
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace fm

@@ -31,11 +31,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint (ns): the hardware parks the thread until the phase completes or the time limit expires, so a
+// waiting warp does not burn issue slots of the scheduler it shares with the warps it is waiting for (profiles/r01g: spin loops
+// were ~40 % of all warp instructions of the persistent kernel)
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 // bounded wait: a protocol bug must trap (and surface as a CUDA error), never hang the GPU
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) __trap();
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+    if (++spins > 400000u) __trap();          // >= seconds
   }
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -115,6 +132,22 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// one lane of the (converged) warp: the MMA-issuing warps stay converged so that descriptors / addresses live in uniform
+// registers and the issue loop is a handful of instructions per MMA (an `if (lane == 0)` region forces per-MMA R2UR moves and a
+// compiler-generated ELECT loop around every tcgen05 instruction)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// SW128 K-major descriptor from its low word ((smem address >> 4) & 0x3FFF): the high word is the same for every operand tile
+__device__ __forceinline__ uint64_t desc_sw128_lo(uint32_t lo) { return ((uint64_t)0x40004040u << 32) | lo; }
 // completion of all previously issued MMAs of this thread -> one arrival on the mbarrier
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -138,10 +171,12 @@ __device__ __forceinline__ uint32_t sw128_off(int row, int k) {
 
 // ---- fp16x3 split ("scaled fp16 hi/lo") ----------------------------------------------------------------------------------------
 // x * 2^s = hi + lo with hi = fp16_rn(x 2^s), lo = fp16_rn(x 2^s - hi): the same 22 significand bits as the TF32 split, in
-// operands half as wide that the tensor cores consume at twice the rate.  The power-of-two scales (activations: ACT_SCALE_H16,
-// weights: per matrix, chosen on the host so that max |w| 2^s lies in [2^13, 2^14)) keep `lo` out of fp16's subnormal range
-// for every value that matters and are undone exactly in the epilogue.  |x| 2^s must stay below 65504 (checked by the loaders).
-constexpr float ACT_SCALE_H16 = 8.0f;
+// operands half as wide that the tensor cores consume at twice the rate.  Weights carry a per-matrix power-of-two scale chosen on
+// the host so that max |w| 2^s lies in [2^13, 2^14): `lo` stays out of fp16's subnormal range for every weight that matters; the
+// scale is undone exactly in the epilogue.  Activations are not scaled: their `lo` parts go subnormal only for |x| < 2^-3, an
+// absolute error <= 2^-25 per element, below the fp32 accumulation noise of the products (simulated in tests/test_host_logic.py).
+// |x| must stay below 65504 (checked by the loaders; reported through the status word).
+constexpr float ACT_SCALE_H16 = 1.0f;      // activations: no scale needed (|x| < 2^-3 loses low bits at an absolute 2^-25, below fp32 noise)
 constexpr float ACT_LIMIT_H16 = 65504.0f / ACT_SCALE_H16;
 // two consecutive k values -> packed (hi, hi) and (lo, lo) half2 words; element k sits in the low half (lower address)
 __device__ __forceinline__ void split_h16x2(float a, float b, uint32_t& hi2, uint32_t& lo2) {

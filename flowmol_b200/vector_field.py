@@ -122,7 +122,7 @@ class CTMCVectorFieldB200:
 
     def check_status(self):
         """Synchronising read-and-clear of the device status word; raises if an activation left the fp16 operand range of the
-        tensor-core linears (|x| >= 8188 with tc_prec 1) -- the results of that call are invalid, re-run with tc_prec 0."""
+        tensor-core linears (|x| >= 65504 with tc_prec 1) -- the results of that call are invalid, re-run with tc_prec 0."""
         with torch.cuda.device(self.device):
             st = self.get_option("status")
         if st & 1:

@@ -263,7 +263,7 @@ def tc_units(w_fk, rows_per_unit):
     return np.concatenate(chunks)
 
 
-ACT_SCALE_H16 = 8.0      # == fm::tc::ACT_SCALE_H16 (csrc/tc.cuh); fm_create refuses a blob built for another value
+ACT_SCALE_H16 = 1.0      # == fm::tc::ACT_SCALE_H16 (csrc/tc.cuh); fm_create refuses a blob built for another value
 
 
 def sw128_image_h16(tile):

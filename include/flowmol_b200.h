@@ -115,7 +115,7 @@ int fm_time_egemm_msg(FmHandle* h, void* workspace, int32_t layer, int32_t iters
  *          dimensions; message linears + EdgeUpdate on the tensor cores); "eg_nh" / "eg_nh_gate" = 128-edge halves per CTA of
  *          k_egemm_tc (1: 2 CTAs/SM, 2: 1 CTA/SM); "tc_prec" = operand format of the wide pipeline's tensor-core linears:
  *          1 (default) scaled fp16 hi/lo images, three kind::f16 MMAs per product ("fp16x3": the 22 significand bits of 3xTF32 at
- *          twice the MMA rate and half the weight-image bytes; activations must stay below 8188 in magnitude), 0 3xTF32;
+ *          twice the MMA rate and half the weight-image bytes; activations must stay below 65504 in magnitude), 0 3xTF32;
  *          "tc_debug", "tc_trace", "tc_trace_mode": timing experiments.
  *          fm_get_option(h, "status", &v) synchronises the device and reads-and-clears the status word: bit 0 = an activation
  *          left the fp16 operand range since the last read (results invalid; switch to tc_prec 0).  fm_sample_host checks it. */

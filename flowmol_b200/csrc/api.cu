@@ -110,6 +110,7 @@ struct FmHandle {
   int node_impl = 0;           // 0: fused fp32 k_node_update, 1: node pipeline around k_egemm_tc (with conv_impl 2)
   int conv_impl = 0;           // 0: fp32 CUDA-core k_conv_edge, 1: tcgen05 3xTF32 k_conv_edge_tc (flowmol3 dims only)
   int eg_persist = 1;          // tc_prec 1: persistent role-specialised k_egemm_p (1 CTA / SM, double-buffered accumulators)
+  int eg_img = 1;              // k_egemm_p: consecutive tensor-core linears hand their activations over as fp16 (hi, lo) operand images
   int tc_prec = 0;             // operand format of k_egemm_tc: 0 = 3xTF32 images, 1 = scaled fp16 hi/lo images ("fp16x3")
   bool has_h16 = false;        // packed weights carry the fp16 images
   int* d_status = nullptr;     // device status word: bit 0 = an activation left the fp16 operand range (tc_prec 1)
@@ -181,17 +182,25 @@ int set_smem_attrs() {
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_EU2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_LIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_MSGA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_MSG0, fm::EGI_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_MSG, fm::EGI_IN | fm::EGI_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_MSGA, fm::EGI_IN | fm::EGI_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_GATE, fm::EGI_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_EU1, fm::EGI_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_EU2, fm::EGI_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
   }
   return 0;
 }
 
 // k_egemm_tc in the operand precision selected on the handle
-template <class D, int MODE, int NH>
+// operand-image hand-over between consecutive linears: only k_egemm_p knows it (callers pass IMG != 0 only when img_on(h))
+inline bool img_on(const FmHandle* h) { return h->eg_img && h->tc_prec == 1 && h->eg_persist && h->eg_nh == 1 && h->eg_nh_gate == 1 && h->fuse_agg; }
+template <class D, int MODE, int NH, int IMG = 0>
 void launch_eg(FmHandle* h, int grid, cudaStream_t st, const fm::ModelRT& m, const fm::BatchRT& bt, fm::EgArgs a) {
   using PL = fm::EgPlan<NH>;
   a.status = h->d_status;
   if (NH == 1 && h->tc_prec == 1 && h->eg_persist) {      // `grid` = number of 128-row tiles
-    fm::k_egemm_p<D, MODE><<<grid < h->n_sm ? grid : h->n_sm, fm::EgpPlan::THREADS, fm::EgpPlan::SMEM_BYTES, st>>>(m, bt, a, grid);
+    fm::k_egemm_p<D, MODE, IMG><<<grid < h->n_sm ? grid : h->n_sm, fm::EgpPlan::THREADS, fm::EgpPlan::SMEM_BYTES, st>>>(m, bt, a, grid);
     return;
   }
   if (h->tc_prec) fm::k_egemm_tc<D, MODE, NH, 1><<<grid, PL::THREADS, PL::SMEM_BYTES, st>>>(m, bt, a);
@@ -220,6 +229,7 @@ int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
     const size_t smem = D::SMEM_BYTES;
     const int NHsel = h->eg_nh;
     const int gt = (int)(L.EPA / (128 * NHsel));
+    const bool img = img_on(h);
     const size_t vsm = fm::VecSmem<D>::BYTES;
     const int vgrid = L.nET < 2 * h->n_sm ? L.nET : 2 * h->n_sm;     // persistent: 2 CTAs per SM, tiles strided
     fm::k_vec_a<D><<<vgrid, fm::NT, vsm, st>>>(m, bt, l, x, v, VH, SH);
@@ -230,6 +240,11 @@ int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
     float* outs[3] = {SA, SB, SA};
     for (int g = 0; g < 3; ++g) {
       fm::EgArgs a{wptr(tc_c(h, tcw[g])), wptr(gb[g] + fm::GV_B), cur, SH, P, x, outs[g], nullptr, nullptr, L.EP, h->trace_mode == (g == 0 ? 0 : 1) ? h->d_trace : nullptr, h->trace_cta, 0, h->tc_debug, M, partF, partL};
+      if (img) {                         // fp16 (hi, lo) operand images between the linears (k_egemm_p only; implies fuse_agg)
+        if (g == 0) launch_eg<D, fm::EG_MSG0, 1, fm::EGI_OUT>(h, gt, st, m, bt, a);
+        else if (g == 1) launch_eg<D, fm::EG_MSG, 1, fm::EGI_IN | fm::EGI_OUT>(h, gt, st, m, bt, a);
+        else launch_eg<D, fm::EG_MSGA, 1, fm::EGI_IN | fm::EGI_OUT>(h, gt, st, m, bt, a);
+      } else
       if (g == 2 && h->fuse_agg) {       // last scalar linear: the segment-sum over in-edges rides in the epilogue
         launch_eg<D, fm::EG_MSGA, 1>(h, (int)(L.EPA / 128), st, m, bt, a);
       } else
@@ -242,7 +257,8 @@ int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
       }
       LAUNCH_OK(h);
       fm::EgArgs ag{wptr(tc_c(h, tcg[g])), wptr(gb[g] + fm::GV_BG), outs[g], nullptr, nullptr, nullptr, GT, nullptr, nullptr, L.EP, h->trace_mode == 2 ? h->d_trace : nullptr, h->trace_cta, 0, h->tc_debug};
-      if (h->eg_nh_gate == 2) launch_eg<D, fm::EG_GATE, 2>(h, (int)(L.EPA / 256), st, m, bt, ag);
+      if (img) launch_eg<D, fm::EG_GATE, 1, fm::EGI_IN>(h, (int)(L.EPA / 128), st, m, bt, ag);
+      else if (h->eg_nh_gate == 2) launch_eg<D, fm::EG_GATE, 2>(h, (int)(L.EPA / 256), st, m, bt, ag);
       else launch_eg<D, fm::EG_GATE, 1>(h, (int)(L.EPA / 128), st, m, bt, ag);
       LAUNCH_OK(h);
       if (g < 2) {
@@ -378,10 +394,12 @@ int run_pass(FmHandle* h, void* ws, const Layout& L, const float* x_t, const uin
           float* H = at<float>(ws, L.SA);
           const int gt = (int)(L.EPA / 128);
           fm::EgArgs a1{uptr(tc_u(h, fm::U_EUPD_TC1)), nullptr, ef, nullptr, EAB, x, H, nullptr, nullptr, L.EP, h->trace_mode == 3 ? h->d_trace : nullptr, h->trace_cta, 0, h->tc_debug};
-          launch_eg<D, fm::EG_EU1, 1>(h, gt, st, m, bt, a1);
+          if (img_on(h)) launch_eg<D, fm::EG_EU1, 1, fm::EGI_OUT>(h, gt, st, m, bt, a1);
+          else launch_eg<D, fm::EG_EU1, 1>(h, gt, st, m, bt, a1);
           LAUNCH_OK(h);
           fm::EgArgs a2{uptr(tc_u(h, fm::U_EUPD_TC2)), uptr(fm::U_EUPD_B2), H, ef, nullptr, nullptr, ef, uptr(fm::U_EUPD_LN_W), uptr(fm::U_EUPD_LN_B), L.EP, h->trace_mode == 4 ? h->d_trace : nullptr, h->trace_cta, 0, h->tc_debug};
-          launch_eg<D, fm::EG_EU2, 1>(h, gt, st, m, bt, a2);
+          if (img_on(h)) launch_eg<D, fm::EG_EU2, 1, fm::EGI_IN>(h, gt, st, m, bt, a2);
+          else launch_eg<D, fm::EG_EU2, 1>(h, gt, st, m, bt, a2);
           LAUNCH_OK(h);
           done = true;
         }
@@ -720,14 +738,21 @@ int fm_time_egemm_msg(FmHandle* h, void* ws, int32_t layer, int32_t iters, float
   CUDA_OK(cudaEventCreate(&e0));
   CUDA_OK(cudaEventCreate(&e1));
   CUDA_OK(cudaStreamSynchronize(st));
+  int status_before = 0;
+  CUDA_OK(cudaMemcpy(&status_before, h->d_status, sizeof(int), cudaMemcpyDeviceToHost));
   CUDA_OK(cudaEventRecord(e0, st));
   for (int i = 0; i < iters; ++i) {
-    if (h->eg_nh == 2) launch_eg<D, fm::EG_MSG, 2>(h, (int)(L.EPA / 256), st, h->rt, bt, a);
+    if (img_on(h)) launch_eg<D, fm::EG_MSG, 1, fm::EGI_IN | fm::EGI_OUT>(h, (int)(L.EPA / 128), st, h->rt, bt, a);
+    else if (h->eg_nh == 2) launch_eg<D, fm::EG_MSG, 2>(h, (int)(L.EPA / 256), st, h->rt, bt, a);
     else launch_eg<D, fm::EG_MSG, 1>(h, (int)(L.EPA / 128), st, h->rt, bt, a);
   }
   CUDA_OK(cudaEventRecord(e1, st));
   CUDA_OK(cudaEventSynchronize(e1));
   CUDA_OK(cudaGetLastError());
+  // the scratch buffers hold whatever the last phase left there (not this linear's real input): a range flag raised by this
+  // timing run says nothing about the model
+  CUDA_OK(cudaMemcpyAsync(h->d_status, &status_before, sizeof(int), cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaStreamSynchronize(st));
   float ms = 0.f;
   CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
   cudaEventDestroy(e0); cudaEventDestroy(e1);
@@ -753,6 +778,7 @@ int fm_set_option(FmHandle* h, const char* name, int32_t value) {
   }
   if (n == "fuse_agg") { h->fuse_agg = value ? 1 : 0; return 0; }
   if (n == "eg_persist") { h->eg_persist = value ? 1 : 0; return 0; }
+  if (n == "eg_img") { h->eg_img = value ? 1 : 0; return 0; }
   if (n == "tc_prec") {
     if (value < 0 || value > 1) return fail("fm_set_option: tc_prec must be 0 (3xTF32) or 1 (fp16x3)");
     if (value == 1 && !h->has_h16) return fail("fm_set_option: packed weights carry no fp16 operand images");
@@ -783,6 +809,7 @@ int fm_get_option(FmHandle* h, const char* name, int32_t* value) {
   if (std::string(name) == "node_impl") { *value = h->node_impl; return 0; }
   if (std::string(name) == "tc_prec") { *value = h->tc_prec; return 0; }
   if (std::string(name) == "eg_persist") { *value = h->eg_persist; return 0; }
+  if (std::string(name) == "eg_img") { *value = h->eg_img; return 0; }
   if (std::string(name) == "status") {      // synchronising read-and-clear of the device status word (see fm_check_status)
     int v = 0;
     CUDA_OK(cudaSetDevice(h->device));

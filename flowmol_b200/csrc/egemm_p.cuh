@@ -40,11 +40,23 @@ struct EgpPlan {
   static_assert(BYTES <= 232448, "227 KB of shared memory per CTA");
 };
 
-template <class D, int MODE>
+// IMG: "operand images" between consecutive tensor-core linears.  Bit 1 (EGI_OUT): the epilogue stores its output rows not as fp32
+// but already split into the (hi, lo) fp16 SW128 operand images the next linear's MMAs read -- per 128-row tile and 64-wide k-slab
+// one 32 KB block [hi image 16 KB | lo image 16 KB], the same 4 bytes per element.  Bit 0 (EGI_IN): `in_s` holds such images and
+// every k-slab of it is ONE 32 KB bulk-TMA copy into the activation stage (up to NST stages = 128 KB in flight per SM, no
+// registers, no conversion instructions) instead of 8 loader warps' LDG -> split -> STS round trip (profiles/r01g: that path was
+// ~40 % of the kernel's instructions and left the GATE linear at 2.4 TB/s).  The split is the same function of the same fp32
+// value on either side, so the results are bit-identical to the fp32 hand-over.
+enum EgImg : int { EGI_IN = 1, EGI_OUT = 2 };
+
+template <class D, int MODE, int IMG = 0>
 __global__ void __launch_bounds__(EgpPlan::THREADS, 1)
 k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) {
   using PL = EgpPlan;
   constexpr int S = D::S;
+  constexpr bool IMG_IN = (IMG & EGI_IN) != 0, IMG_OUT = (IMG & EGI_OUT) != 0;
+  static_assert(!IMG_IN || MODE == EG_MSG || MODE == EG_MSGA || MODE == EG_GATE || MODE == EG_EU2, "image input: in_s feeds whole k-slabs");
+  static_assert(!IMG_OUT || MODE == EG_MSG0 || MODE == EG_MSG || MODE == EG_MSGA || MODE == EG_EU1, "image output: activations of a next linear");
   constexpr bool IS_EU = MODE == EG_EU1 || MODE == EG_EU2;
   constexpr bool IS_MSG = MODE == EG_MSG || MODE == EG_MSGA;
   constexpr int K = MODE == EG_MSG0 ? D::KE0 : (IS_MSG ? D::K1 : (MODE == EG_EU1 ? D::F + D::R : (MODE == EG_EU2 ? D::F : S)));
@@ -59,6 +71,8 @@ k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
   constexpr int RING = RING_FIT < PL::MAX_SLOTS ? RING_FIT : PL::MAX_SLOTS;
   constexpr uint32_t NU = NSLAB * NMT * 2;                                     // weight units per tile
   constexpr int NST = PL::NST;
+  constexpr int NIMG = IMG_IN ? (MODE == EG_EU2 ? D::F / 64 : S / 64) : 0;     // leading k-slabs that arrive as operand images
+  static_assert(NIMG <= NSLAB, "image slabs are a prefix of K");
   constexpr int SH_W = 40;
   constexpr int LO_OFF = 16384;
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
@@ -225,20 +239,39 @@ k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
     constexpr int NMY1 = NCH / 2;
     float4 cur[8], nxt[8];
     float amax = 0.f;
-    if (n_my > 0) { rowinfo(0); fetch(0, cur); }
+    static_assert(NIMG == NSLAB || NIMG < NMY1, "both loader groups own a chunk in the first converted slab");
+    if (n_my > 0 && NIMG < NSLAB) { rowinfo(0); fetch(NIMG, cur); }
     uint32_t g = 0;                                            // running slab counter (stage / phase bookkeeping)
     for (int it = 0; it < n_my; ++it) {
 #pragma unroll
       for (int s = 0; s < NSLAB; ++s, ++g) {
         const uint32_t st = g % NST, use = g / NST;
+        if (s < NIMG) {
+          // operand-image slab: one 32 KB bulk copy (hi | lo) straight into the stage, issued by the first loader warp.  Every
+          // loader warp still waits for the stage and arrives, so the barrier's arrival count is the same for both kinds of slab
+          // and no warp can run a whole phase ahead of the others.
+          if (use > 0) tc::mbar_wait(&x_empty[st], (use - 1) & 1);
+          if (lane == 0) {
+            if (warp == PL::W_LOAD0) {
+              const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
+              tc::mbar_arrive_expect_tx(&x_full[st], PL::XSTAGE);
+              tc::bulk_g2s(xst + st * PL::XSTAGE, reinterpret_cast<const uint8_t*>(a.in_s) + ((size_t)tile * NIMG + s) * PL::XSTAGE,
+                           PL::XSTAGE, &x_full[st]);
+            } else {
+              asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&x_full[st])) : "memory");
+            }
+          }
+          __syncwarp();
+          continue;
+        }
         const bool mine = s < NMY1 || grp == 0;                // this group has a chunk in slab s
-        if (mine) {                                            // prefetch this group's next chunk: same tile, or slab 0 of the next tile
+        if (mine) {                                            // prefetch this group's next chunk: same tile, or the first converted slab of the next tile
           const bool last_mine = (s + 1 == NSLAB) || (s + 1 == NMY1 && grp == 1);
           if (!last_mine) {
-            fetch(s + 1 < NSLAB ? s + 1 : 0, nxt);
+            fetch(s + 1 < NSLAB ? s + 1 : NIMG, nxt);
           } else if (it + 1 < n_my) {
             rowinfo(it + 1);
-            fetch(0, nxt);
+            fetch(NIMG, nxt);
           }
         }
         if (use > 0) tc::mbar_wait(&x_empty[st], (use - 1) & 1);
@@ -271,6 +304,7 @@ k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
     // ---- epilogue: TMEM -> registers -> bias / gathered pre-activation -> activation -> coalesced global stores ---------------------------
     const int q = warp & 3, et = tid - PL::W_EPI0 * 32;                 // TMEM lane quarter; index among the 128 epilogue threads
     const float unscale = a.units[(size_t)NU * (UNIT_BYTES / 4)];
+    float omax = 0.f;                                                  // IMG_OUT: largest |activation| this thread split into fp16 (hi, lo)
     constexpr bool GATHERS = MODE == EG_MSG0 || MODE == EG_EU1 || MODE == EG_EU2;
     constexpr bool NEED_ROWS = MODE == EG_MSG0 || MODE == EG_EU1 || MODE == EG_MSGA;
     for (int it = 0; it < n_my; ++it) {
@@ -359,8 +393,32 @@ k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
                 if (MODE == EG_LIN) { op[(size_t)i * OW] = z; continue; }
                 const float sg = sigmoid_fast(z);
                 const float o = MODE == EG_GATE ? ((a.flags & EGF_IDENTITY) ? z : sg) : z * sg;
-                op[(size_t)i * OW] = o;
-                if (MODE == EG_MSGA) acc[i] = o;
+                if (!IMG_OUT) op[(size_t)i * OW] = o;
+                if (MODE == EG_MSGA || IMG_OUT) acc[i] = o;
+              }
+              if constexpr (IMG_OUT) {
+                // Operand images of the next linear.  Feature f is k = f % 64 of slab f / 64; row r of a slab image is 128 bytes of
+                // 64 fp16 whose 16-byte chunks are XOR-swizzled by r % 8.  Lanes 2m / 2m+1 hold neighbouring k: they swap one
+                // packed (hi, lo) word per row pair so that the even lane stores the 32-bit (k, k+1) words of row 2t and the odd
+                // lane those of row 2t + 1 -- a warp store covers two rows x 64 contiguous bytes (four full sectors).
+                const int odd = lane & 1, kk = (q & 1) * 32 + (lane & ~1);
+                uint8_t* ob = reinterpret_cast<uint8_t*>(a.out) + ((size_t)(slot0 >> 7) * (OW / 64) + (size_t)(mt * 2 + (q >> 1))) * PL::XSTAGE +
+                              (size_t)((c * 32 + odd) * 128 + (kk & 7) * 2);
+                const uint32_t c0x = (uint32_t)((kk >> 3) ^ odd);
+                const uint32_t sel_keep = odd ? 0x7632u : 0x5410u, sel_send = odd ? 0x5410u : 0x7632u;
+                const uint32_t sel_hi = odd ? 0x1054u : 0x5410u, sel_lo = odd ? 0x3276u : 0x7632u;
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                  const float v0 = acc[2 * t], v1 = acc[2 * t + 1];
+                  omax = fmaxf(omax, fmaxf(fabsf(v0), fabsf(v1)));
+                  uint32_t h2, l2;                              // (hi(v0), hi(v1)), (lo(v0), lo(v1))
+                  tc::split_h16x2(v0, v1, h2, l2);
+                  const uint32_t keep = __byte_perm(h2, l2, sel_keep);      // (hi, lo) of the row this lane stores
+                  const uint32_t recv = __shfl_xor_sync(0xffffffffu, __byte_perm(h2, l2, sel_send), 1);
+                  uint8_t* dst_ = ob + (2 * t) * 128 + ((c0x ^ (uint32_t)((2 * t) & 7)) << 4);
+                  *reinterpret_cast<uint32_t*>(dst_) = __byte_perm(keep, recv, sel_hi);
+                  *reinterpret_cast<uint32_t*>(dst_ + LO_OFF) = __byte_perm(keep, recv, sel_lo);
+                }
               }
               if (MODE == EG_MSGA) {
                 if ((c & 1) == 0) run = 0.f;
@@ -417,6 +475,7 @@ k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&acc_empty[b])) : "memory");
     }
+    if (IMG_OUT && !(omax < tc::ACT_LIMIT_H16) && a.status) atomicOr(a.status, 1);      // also catches NaN
   }
   tc::tc_fence_before();
   __syncthreads();

@@ -116,6 +116,9 @@ int fm_time_egemm_msg(FmHandle* h, void* workspace, int32_t layer, int32_t iters
  *          k_egemm_tc (1: 2 CTAs/SM, 2: 1 CTA/SM); "tc_prec" = operand format of the wide pipeline's tensor-core linears:
  *          1 (default) scaled fp16 hi/lo images, three kind::f16 MMAs per product ("fp16x3": the 22 significand bits of 3xTF32 at
  *          twice the MMA rate and half the weight-image bytes; activations must stay below 65504 in magnitude), 0 3xTF32;
+ *          "eg_persist" = 1 (default) persistent k_egemm_p / 0 one-tile-per-CTA k_egemm_tc; "eg_img" = 1 (default) consecutive
+ *          tensor-core linears hand their activations over as fp16 (hi, lo) operand images fetched by bulk TMA / 0 as fp32 rows
+ *          converted by the consumer's loader warps (bit-identical results);
  *          "tc_debug", "tc_trace", "tc_trace_mode": timing experiments.
  *          fm_get_option(h, "status", &v) synchronises the device and reads-and-clears the status word: bit 0 = an activation
  *          left the fp16 operand range since the last read (results invalid; switch to tc_prec 0).  fm_sample_host checks it. */

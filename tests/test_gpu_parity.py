@@ -173,7 +173,9 @@ def test_fp32_and_tensor_core_message_kernels_agree():
     """conv_impl 0 (fp32 CUDA cores), 1 (fused tcgen05) and 2 (wide tcgen05 pipeline, default) on the same inputs;
     with conv_impl 2 both node-update implementations (node_impl 1: pipeline around k_egemm_tc, default; 0: fused fp32 kernel)
     and both operand formats (tc_prec 1: scaled fp16 hi/lo, default; 0: 3xTF32 -- variant 5); variant 6 runs the fp16 operands
-    through the one-tile-per-CTA kernel k_egemm_tc instead of the persistent k_egemm_p (same MMA order: bit-identical)."""
+    through the one-tile-per-CTA kernel k_egemm_tc instead of the persistent k_egemm_p (same MMA order: bit-identical); variant 7
+    is k_egemm_p with fp32 hand-over between the linears instead of the default fp16 (hi, lo) operand images (same split of the
+    same values on the other side of HBM: bit-identical)."""
     cfg, vf = cuda_model("flowmol3", 11, 61)
     assert vf.get_option("conv_impl") == 2 and vf.get_option("node_impl") == 1 and vf.get_option("tc_prec") == 1
     n_atoms = np.array([9, 70, 3, 33])
@@ -183,10 +185,12 @@ def test_fp32_and_tensor_core_message_kernels_agree():
     a, c, e = torch.randint(0, 12, (bt.N,), generator=gen), torch.randint(0, 7, (bt.N,), generator=gen), torch.randint(0, 5, (bt.U,), generator=gen)
     outs = {}
     try:
-        for impl in (0, 1, 2, 3, 4, 5, 6):
+        assert vf.get_option("eg_img") == 1
+        for impl in (0, 1, 2, 3, 4, 5, 6, 7):
             vf.set_option("conv_impl", min(impl, 2))
             vf.set_option("tc_prec", 0 if impl == 5 else 1)
             vf.set_option("eg_persist", 0 if impl == 6 else 1)
+            vf.set_option("eg_img", 0 if impl == 7 else 1)
             vf.set_option("node_impl", 0 if impl == 3 else 1)
             vf.set_option("fuse_agg", 0 if impl == 4 else 1)      # 4: scalar segment-sum in k_vec_c instead of the egemm epilogue
             d0 = vf.forward_tokens(n_atoms, x, torch.full_like(a, 11), torch.full_like(c, 6), torch.full_like(e, 4), 0.0, None)
@@ -195,10 +199,12 @@ def test_fp32_and_tensor_core_message_kernels_agree():
         vf.set_option("conv_impl", 2)
         vf.set_option("tc_prec", 1)
         vf.set_option("eg_persist", 1)
+        vf.set_option("eg_img", 1)
         vf.set_option("node_impl", 1)
         vf.set_option("fuse_agg", 1)
     assert all(torch.equal(outs[4][k], outs[2][k]) for k in "xace")      # same sums in the same order: bit-identical
     assert all(torch.equal(outs[6][k], outs[2][k]) for k in "xace")
+    assert all(torch.equal(outs[7][k], outs[2][k]) for k in "xace")
     for impl in (1, 2, 3, 5):
         assert (outs[impl]["x"] - outs[0]["x"]).abs().max() <= TOL_X
         for k in "ace":

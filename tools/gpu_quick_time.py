@@ -11,11 +11,12 @@ vf = CTMCVectorFieldB200(cfg, WT.init_state_dict(cfg, 0))
 n_atoms = draw_sizes("geom", 512)
 x0, a0, c0, e0 = make_prior(n_atoms, 11, 100)
 for spec in (sys.argv[1:] or ["0"]):
-    impl, nh, gnh, node, prec, pers = (spec.split(":") + ["1", "1", "1", "1", "1"])[:6]
-    impl, nh, gnh, node, prec, pers = int(impl), int(nh), int(gnh), int(node), int(prec), int(pers)
+    impl, nh, gnh, node, prec, pers, img = (spec.split(":") + ["1", "1", "1", "1", "1", "1"])[:7]
+    impl, nh, gnh, node, prec, pers, img = int(impl), int(nh), int(gnh), int(node), int(prec), int(pers), int(img)
     if impl == 2:
         vf.set_option("tc_prec", prec)
         vf.set_option("eg_persist", pers)
+        vf.set_option("eg_img", img)
     vf.set_option("conv_impl", impl)
     vf.set_option("eg_nh", nh)
     vf.set_option("eg_nh_gate", gnh)
@@ -24,4 +25,4 @@ for spec in (sys.argv[1:] or ["0"]):
     ts = []
     for _ in range(3):
         t0 = time.time(); d = vf.forward_tokens(n_atoms, x0, a0, c0, e0, 0.3, d); torch.cuda.synchronize(); ts.append(time.time() - t0)
-    print(f"impl {impl} eg_nh {nh} gate_nh {gnh} node_impl {node} tc_prec {prec} persist {pers}: egemm_msg ms {vf.time_egemm_msg(1, 5) if impl == 2 else 0:.3f} forward ms {min(ts)*1e3:.2f}  conv_edge ms {vf.time_conv_edge(1, 3):.3f}")
+    print(f"impl {impl} eg_nh {nh} gate_nh {gnh} node_impl {node} tc_prec {prec} persist {pers} img {img}: egemm_msg ms {vf.time_egemm_msg(1, 5) if impl == 2 else 0:.3f} forward ms {min(ts)*1e3:.2f}  conv_edge ms {vf.time_conv_edge(1, 3):.3f}")

@@ -71,19 +71,45 @@ struct EdgeTile {
   }
 };
 
-// the CTA's weight matrices, once per CTA: src [K][np] (packer layout) -> dst [K padded to 8][ld] (padding rows zero)
-__device__ __forceinline__ void load_resident(float* dst, const float* __restrict__ src, int K, int np, int ld) {
-  const int kp = (K + 7) & ~7;
-  for (int i = threadIdx.x; i < kp * (np / 4); i += NT) {
-    const int k = i / (np / 4), c4 = i - k * (np / 4);
-    if (k < K) cp_async16(dst + k * ld + c4 * 4, src + k * np + c4 * 4);
-    else *reinterpret_cast<float4*>(dst + k * ld + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+// The CTA's weight matrices, once per CTA, as fp16 (hi, lo) operand words for warp_gemm_h16x3 (mma3.cuh):
+// src [K][np] fp32 (packer layout) -> hi / lo [pad8(K) / 2][ld] packed (k, k + 1) half2 words of w * 2^s, padding rows zero.  The
+// power-of-two scale puts max |w| 2^s into [2^13, 2^14) (the `lo` parts of every weight that matters stay normal fp16 numbers) and
+// is undone exactly on the accumulators (`inv`).  Whole CTA; contains barriers.  `red`: >= 8 floats of idle shared memory.
+struct WH16 {
+  const uint32_t* hi;
+  const uint32_t* lo;
+  float inv;
+};
+__device__ __forceinline__ WH16 load_resident_h16(float* dst, const float* __restrict__ src, int K, int np, int ld, float* red) {
+  const int tid = threadIdx.x;
+  float mx = 0.f;
+  for (int i = tid; i < K * np; i += NT) mx = fmaxf(mx, fabsf(__ldg(src + i)));
+  mx = warp_max(mx);
+  if ((tid & 31) == 0) red[tid >> 5] = mx;
+  __syncthreads();
+  mx = 0.f;
+#pragma unroll
+  for (int w = 0; w < NWARP; ++w) mx = fmaxf(mx, red[w]);
+  __syncthreads();                                                   // `red` may be reused by the caller
+  const int e = mx >= 1e-30f ? (int)((__float_as_uint(mx) >> 23) & 0xffu) - 127 : 13;   // floor(log2(max |w|)); all-zero matrix: scale 1
+  const float scale = __uint_as_float((uint32_t)(127 + 13 - e) << 23), inv = __uint_as_float((uint32_t)(127 - 13 + e) << 23);
+  const int kp2 = ((K + 7) & ~7) >> 1;
+  uint32_t* hi = reinterpret_cast<uint32_t*>(dst);
+  uint32_t* lo = hi + kp2 * ld;
+  for (int i = tid; i < kp2 * np; i += NT) {
+    const int r = i / np, n = i - r * np, k = 2 * r;
+    const float w0 = k < K ? __ldg(src + k * np + n) * scale : 0.f, w1 = k + 1 < K ? __ldg(src + (k + 1) * np + n) * scale : 0.f;
+    uint32_t h2, l2;
+    tc::split_h16x2(w0, w1, h2, l2);
+    hi[r * ld + n] = h2;
+    lo[r * ld + n] = l2;
   }
+  return WH16{hi, lo, inv};
 }
 
 // stage 1 of a GVP for the pair's 16 rows: Va[.., 0:v_in) -> Vb = [Vh | cross] (cols [0, h+cp)), stores VH and SH
 template <class D>
-__device__ __forceinline__ void vec_stage1(Smem<D>& sm, const int v_in, const int h, const float* __restrict__ whcp_sm, const size_t erow0,
+__device__ __forceinline__ void vec_stage1(Smem<D>& sm, const int v_in, const int h, const WH16& whcp_sm, const size_t erow0,
                                            const int nvalid, float* __restrict__ VH, float* __restrict__ SH) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, pair = warp >> 1, pt = tid & (PT - 1);
   const int e0 = pair * PE, r0 = e0 * 3, hc = h + D::CP;
@@ -92,7 +118,8 @@ __device__ __forceinline__ void vec_stage1(Smem<D>& sm, const int v_in, const in
     // [Vh | Vcp] = V x [Wh | Wcp]: 48 flat rows x (h + 2cp <= 48) columns.  Each warp: 3 m16 tiles x 3 n8 tiles.
     const int n0 = (warp & 1) * 24;
     float acc[3][3][4];
-    warp_gemm_3xtf32<3, 3>(sm.Va, D::LDVA, r0, whcp_sm, WLD_HCP, n0, (v_in + 7) & ~7, acc);
+    warp_gemm_h16x3<3, 3>(sm.Va, D::LDVA, r0, whcp_sm.hi, whcp_sm.lo, WLD_HCP, n0, (v_in + 7) & ~7, acc);
+    const float inv = whcp_sm.inv;
     const int ncol = h + 2 * D::CP, g = lane >> 2, t = lane & 3;
 #pragma unroll
     for (int mt = 0; mt < 3; ++mt)
@@ -101,7 +128,7 @@ __device__ __forceinline__ void vec_stage1(Smem<D>& sm, const int v_in, const in
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int row = r0 + 16 * mt + g + (i >> 1) * 8, col = n0 + 8 * nt + 2 * t + (i & 1);
-          if (col < ncol) sm.Vb[row * D::LDVB + col] = acc[mt][nt][i];
+          if (col < ncol) sm.Vb[row * D::LDVB + col] = acc[mt][nt][i] * inv;
         }
   }
   pair_sync(pair);
@@ -141,7 +168,7 @@ __device__ __forceinline__ void vec_stage1(Smem<D>& sm, const int v_in, const in
 // stage 2 of a GVP for the pair's 16 rows: Vb (loaded from VH) x Wu, gated by GT -> Va[.., 0:V).  No trailing barrier:
 // vec_stage1 opens with the pair barrier, other consumers synchronise themselves.
 template <class D>
-__device__ __forceinline__ void vec_stage2(Smem<D>& sm, const int hc, const float* __restrict__ wu_sm, const size_t erow0,
+__device__ __forceinline__ void vec_stage2(Smem<D>& sm, const int hc, const WH16& wu_sm, const size_t erow0,
                                            const int nvalid, const float* __restrict__ VH, const float* __restrict__ GT) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, pair = warp >> 1, pt = tid & (PT - 1);
   const int e0 = pair * PE, r0 = e0 * 3;
@@ -177,7 +204,8 @@ __device__ __forceinline__ void vec_stage2(Smem<D>& sm, const int hc, const floa
     // Vu = Vh_ext x Wu: 48 flat rows x 32 columns, K = hc padded to 8.  Each warp: 3 m16 tiles x 2 n8 tiles.
     const int n0 = (warp & 1) * 16, g = lane >> 2, t = lane & 3;
     float acc[3][2][4];
-    warp_gemm_3xtf32<3, 2>(sm.Vb, D::LDVB, r0, wu_sm, WLD_U, n0, (hc + 7) & ~7, acc);
+    warp_gemm_h16x3<3, 2>(sm.Vb, D::LDVB, r0, wu_sm.hi, wu_sm.lo, WLD_U, n0, (hc + 7) & ~7, acc);
+    const float inv = wu_sm.inv;
 #pragma unroll
     for (int mt = 0; mt < 3; ++mt)
 #pragma unroll
@@ -185,7 +213,7 @@ __device__ __forceinline__ void vec_stage2(Smem<D>& sm, const int hc, const floa
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int row = r0 + 16 * mt + g + (i >> 1) * 8, col = n0 + 8 * nt + 2 * t + (i & 1);
-          sm.Va[row * D::LDVA + col] = __fmul_rn(sm.G[(row / 3) * 32 + col], acc[mt][nt][i]);
+          sm.Va[row * D::LDVA + col] = __fmul_rn(sm.G[(row / 3) * 32 + col], acc[mt][nt][i] * inv);
         }
   }
 }
@@ -197,10 +225,8 @@ k_vec_a(const ModelRT m, const BatchRT bt, int layer, const float* __restrict__ 
   extern __shared__ __align__(16) float smem_raw[];
   Smem<D> sm = VecSmem<D>::carve(smem_raw);
   const int tid = threadIdx.x, pair = tid >> 6, pt = tid & (PT - 1), e0 = pair * PE;
-  float* w_hcp = sm.wstage;                                       // [pad8(VIN0)][64 (+8)]
-  load_resident(w_hcp, m.c(layer, C_MSG0_WHCP), pad4(D::VIN0), 32 * D::CPT_HC0, WLD_HCP);
-  cp_async_commit();
-  cp_async_wait<0>();
+  // [pad8(VIN0)][64 (+8)] words
+  const WH16 w_hcp = load_resident_h16(sm.wstage, m.c(layer, C_MSG0_WHCP), pad4(D::VIN0), 32 * D::CPT_HC0, WLD_HCP, sm.dist);
   __syncthreads();
   for (int tile = blockIdx.x; tile < bt.n_edge_tiles; tile += gridDim.x) {
     const EdgeTile<D> et(bt, tile);
@@ -262,12 +288,9 @@ k_vec_b(const BatchRT bt, const float* __restrict__ wu, int hc_prev, const float
         float* __restrict__ VH, float* __restrict__ SH, const float* __restrict__ GT) {
   extern __shared__ __align__(16) float smem_raw[];
   Smem<D> sm = VecSmem<D>::carve(smem_raw);
-  float* w_u = sm.wstage;                                         // [pad8(hc_prev)][32 (+8)]
-  float* w_hcp = sm.wstage + 40 * WLD_U;                          // [V][64 (+8)]
-  load_resident(w_u, wu, pad4(hc_prev), 32, WLD_U);
-  load_resident(w_hcp, whcp, D::V, 32 * D::CPT_HC, WLD_HCP);
-  cp_async_commit();
-  cp_async_wait<0>();
+  // [pad8(hc_prev)][32 (+8)] words, then [V][64 (+8)] words
+  const WH16 w_u = load_resident_h16(sm.wstage, wu, pad4(hc_prev), 32, WLD_U, sm.dist);
+  const WH16 w_hcp = load_resident_h16(sm.wstage + 40 * WLD_U, whcp, D::V, 32 * D::CPT_HC, WLD_HCP, sm.dist);
   __syncthreads();
   const int n_tiles = node_rows ? bt.n_node_tiles : bt.n_edge_tiles;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -286,10 +309,7 @@ k_vec_c(const ModelRT m, const BatchRT bt, int layer, int first_col /* S when k_
   extern __shared__ __align__(16) float smem_raw[];
   Smem<D> sm = VecSmem<D>::carve(smem_raw);
   const int tid = threadIdx.x;
-  float* w_u = sm.wstage;
-  load_resident(w_u, m.c(layer, C_MSG2_WU), pad4(D::V + D::CP), 32, WLD_U);
-  cp_async_commit();
-  cp_async_wait<0>();
+  const WH16 w_u = load_resident_h16(sm.wstage, m.c(layer, C_MSG2_WU), pad4(D::V + D::CP), 32, WLD_U, sm.dist);
   for (int tile = blockIdx.x; tile < bt.n_edge_tiles; tile += gridDim.x) {
     const EdgeTile<D> et(bt, tile);
     __syncthreads();                                              // previous tile's segment-sum readers of Va / dst are done
@@ -389,9 +409,7 @@ k_node_pre(const ModelRT m, const BatchRT bt, int layer, int agg_rows, float* __
   extern __shared__ __align__(16) float smem_raw[];
   Smem<D> sm = VecSmem<D>::carve(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5;
-  float* w_hcp = sm.wstage;
-  load_resident(w_hcp, m.c(layer, C_UPD0_WHCP), D::V, 32 * D::CPT_HC, WLD_HCP);
-  cp_async_commit();
+  const WH16 w_hcp = load_resident_h16(sm.wstage, m.c(layer, C_UPD0_WHCP), D::V, 32 * D::CPT_HC, WLD_HCP, sm.dist);
   const int g0 = blockIdx.x * TM;
   // per-row aggregation plan (see gather_message): first / last piece of the node's in-edge segment, and the normaliser
   if (tid < TM) {
@@ -434,7 +452,6 @@ k_node_pre(const ModelRT m, const BatchRT bt, int layer, int agg_rows, float* __
   }
   __syncthreads();
   tile_vec_layernorm<D>(sm.Va, v, g0, bt.N);
-  cp_async_wait<0>();
   __syncthreads();
   vec_stage1<D>(sm, D::V, D::V, w_hcp, (size_t)g0, min(TM, bt.N - g0), VH, SH);
 }
@@ -448,12 +465,9 @@ k_node_mid(const ModelRT m, const BatchRT bt, int layer, int updater, float* __r
   extern __shared__ __align__(16) float smem_raw[];
   Smem<D> sm = VecSmem<D>::carve(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5;
-  float* w_u = sm.wstage;
-  float* w_hcp = sm.wstage + 40 * WLD_U;
-  load_resident(w_u, m.c(layer, C_UPD2_WU), pad4(D::V + D::CP), 32, WLD_U);
-  if (updater >= 0) load_resident(w_hcp, m.u(updater, U_POS0_WHCP), D::V, 32 * D::CPT_HC, WLD_HCP);
-  cp_async_commit();
-  cp_async_wait<0>();
+  const WH16 w_u = load_resident_h16(sm.wstage, m.c(layer, C_UPD2_WU), pad4(D::V + D::CP), 32, WLD_U, sm.dist);
+  WH16 w_hcp{nullptr, nullptr, 1.f};
+  if (updater >= 0) w_hcp = load_resident_h16(sm.wstage + 40 * WLD_U, m.u(updater, U_POS0_WHCP), D::V, 32 * D::CPT_HC, WLD_HCP, sm.dist);
   const int g0 = blockIdx.x * TM, nvalid = min(TM, bt.N - g0);
   __syncthreads();
   vec_stage2<D>(sm, D::V + D::CP, w_u, (size_t)g0, nvalid, VH, GT);
@@ -485,10 +499,7 @@ k_node_post(const ModelRT m, const BatchRT bt, int updater, float* __restrict__ 
   extern __shared__ __align__(16) float smem_raw[];
   Smem<D> sm = VecSmem<D>::carve(smem_raw);
   const int tid = threadIdx.x;
-  float* w_u = sm.wstage;
-  load_resident(w_u, m.u(updater, U_POS2_WU), pad4(D::V + D::CP), 32, WLD_U);
-  cp_async_commit();
-  cp_async_wait<0>();
+  const WH16 w_u = load_resident_h16(sm.wstage, m.u(updater, U_POS2_WU), pad4(D::V + D::CP), 32, WLD_U, sm.dist);
   const int g0 = blockIdx.x * TM;
   __syncthreads();
   vec_stage2<D>(sm, D::V + D::CP, w_u, (size_t)g0, min(TM, bt.N - g0), VH, GT);

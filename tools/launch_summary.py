@@ -7,9 +7,9 @@ MODES = {0: "MSG0", 1: "MSG", 2: "GATE", 3: "EU1", 4: "EU2", 5: "LIN", 6: "MSGA"
 for row in rows:
     k = row['Kernel Name']
     name = k.split('<')[0].replace('void ', '').split('(')[0].replace('fm::', '')
-    m = re.search(r'>, \(?(?:fm::EgMode|int)?\)?(\d+)(?:, \(int\)(\d+))?(?:, \(int\)(\d+))?>\(', k)
+    m = re.search(r'>, \(?(?:fm::EgMode|int)?\)?(\d+)(?:, (?:\(int\))?(\d+))?(?:, (?:\(int\))?(\d+))?>\(', k)
     if 'egemm' in name and m:
-        name += f"<{MODES.get(int(m.group(1)), m.group(1))}>"
+        name += f"<{MODES.get(int(m.group(1)), m.group(1))}" + (f",img{m.group(2)}" if 'egemm_p' in name and m.group(2) not in (None, '0') else "") + ">"
     name += " g=" + row.get('Grid Size', '?').strip('()').split(',')[0]
     v = float(row['Metric Value'])
     a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += v

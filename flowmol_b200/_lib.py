@@ -45,6 +45,7 @@ SYMBOLS = {
     "fm_set_option": (c_i32, [c_vp, C.c_char_p, c_i32]),
     "fm_get_option": (c_i32, [c_vp, C.c_char_p, C.POINTER(c_i32)]),
     "fm_debug_read_trace": (c_i32, [c_vp, c_vp]),
+    "fm_debug_kprof": (c_i32, [c_vp, c_vp, c_vp, c_i32, C.POINTER(c_i32)]),
     "fm_debug_tc_gemm": (c_i32, [c_vp, c_vp, c_i32, c_vp, c_i32, c_i32]),
     "fm_time_egemm_msg": (c_i32, [c_vp, c_vp, c_i32, c_i32, C.POINTER(c_f32), c_vp]),
     "fm_time_conv_edge": (c_i32, [c_vp, c_vp, c_i32, c_i32, C.POINTER(c_f32), c_vp]),

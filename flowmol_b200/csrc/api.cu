@@ -39,6 +39,7 @@ struct Layout {
   size_t mol_n, mol_node, mol_u, mol_etile, mol_utile, etile_mol, utile_mol, node_mol;
   size_t s, v, x, P, Q, vd, EAB, M, partF, partL, ef;
   size_t SA, SB, VH, SH, GT;   // wide tensor-core pipeline intermediates (per padded edge slot, rounded up to 256 slots)
+  size_t EFI;                  // fp16 (hi, lo) operand images of the edge features (egemm_p.cuh), same bytes as ef
   long long EPA = 0;
   long long NPA = 0;           // node rows rounded up to 256
   size_t pred[3][4];     // [buffer][x,a,c,e]
@@ -75,6 +76,7 @@ Layout make_layout(const Dyn& d, const int32_t* n_atoms, int B) {
   L.EPA = (L.EP + 255) / 256 * 256;
   L.ef = take(4ull * (size_t)L.EPA * d.F);       // rounded up: the wide kernels store whole 128-slot tiles
   const size_t wide = d.S == 256 && d.SD == 0 ? (size_t)std::max<long long>(L.EPA, L.NPA) : 0;   // the node pipeline reuses these
+  L.EFI = take(wide ? 4ull * (size_t)L.EPA * d.F : 0);
   L.SA = take(4ull * wide * d.S); L.SB = take(4ull * wide * d.S); L.VH = take(4ull * wide * 120); L.SH = take(4ull * wide * 40);
   L.GT = take(4ull * wide * 32);
   for (int k = 0; k < 3; ++k) {
@@ -115,6 +117,8 @@ struct FmHandle {
   bool has_h16 = false;        // packed weights carry the fp16 images
   int* d_status = nullptr;     // device status word: bit 0 = an activation left the fp16 operand range (tc_prec 1)
   cudaStream_t cap_stream = nullptr;    // private stream for CUDA-graph capture (the legacy default stream cannot capture)
+  int kprof = 0;                        // "kprof" option: a CUDA event after every launch of fm_forward (fm_debug_kprof reads them)
+  std::vector<std::pair<int, cudaEvent_t>> prof;      // (api.cu line of the launch, event recorded right after it)
 };
 
 namespace {
@@ -182,17 +186,27 @@ int set_smem_attrs() {
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_EU2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_LIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_MSGA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
-    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_MSG0, fm::EGI_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
-    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_MSG, fm::EGI_IN | fm::EGI_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
-    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_MSGA, fm::EGI_IN | fm::EGI_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
+    constexpr int IO = fm::EGI_IN | fm::EGI_OUT;
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_MSG0, IO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_MSG, IO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_MSGA, IO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_GATE, fm::EGI_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
-    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_EU1, fm::EGI_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
-    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_EU2, fm::EGI_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_EU1, IO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_EU2, IO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
   }
   return 0;
 }
 
 // k_egemm_tc in the operand precision selected on the handle
+// in-situ per-launch timing (option "kprof"): an event after every launch; consecutive differences are the launches' durations in
+// the warm pipeline (what ncu's serialised cold-cache replays cannot show).  Line 0 = start marker.
+inline void prof_mark(FmHandle* h, int line, cudaStream_t st) {
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, st);
+  h->prof.emplace_back(line, e);
+}
+
 // operand-image hand-over between consecutive linears: only k_egemm_p knows it (callers pass IMG != 0 only when img_on(h))
 inline bool img_on(const FmHandle* h) { return h->eg_img && h->tc_prec == 1 && h->eg_persist && h->eg_nh == 1 && h->eg_nh_gate == 1 && h->fuse_agg; }
 template <class D, int MODE, int NH, int IMG = 0>
@@ -210,11 +224,13 @@ void launch_eg(FmHandle* h, int grid, cudaStream_t st, const fm::ModelRT& m, con
 inline int tc_c(const FmHandle* h, int id) { return id + (h->tc_prec ? (int)fm::C_MSG0_TCW_H - (int)fm::C_MSG0_TCW : 0); }
 inline int tc_u(const FmHandle* h, int id) { return id + (h->tc_prec ? (int)fm::U_EUPD_TC1_H - (int)fm::U_EUPD_TC1 : 0); }
 
+// every call site has the launching stream in a local named `st`
 #define LAUNCH_OK(h)                                                                                       \
   do {                                                                                                     \
     ++(h)->launches;                                                                                       \
     cudaError_t e__ = cudaGetLastError();                                                                  \
     if (e__ != cudaSuccess) return fail(std::string("kernel launch failed: ") + cudaGetErrorString(e__)); \
+    if ((h)->kprof) prof_mark((h), __LINE__, st);                                                          \
   } while (0)
 
 // message pass of conv `l` as the wide tensor-core pipeline (egemm_tc.cuh + vec_stages.cuh): 10 launches
@@ -241,9 +257,16 @@ int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
     for (int g = 0; g < 3; ++g) {
       fm::EgArgs a{wptr(tc_c(h, tcw[g])), wptr(gb[g] + fm::GV_B), cur, SH, P, x, outs[g], nullptr, nullptr, L.EP, h->trace_mode == (g == 0 ? 0 : 1) ? h->d_trace : nullptr, h->trace_cta, 0, h->tc_debug, M, partF, partL};
       if (img) {                         // fp16 (hi, lo) operand images between the linears (k_egemm_p only; implies fuse_agg)
-        if (g == 0) launch_eg<D, fm::EG_MSG0, 1, fm::EGI_OUT>(h, gt, st, m, bt, a);
-        else if (g == 1) launch_eg<D, fm::EG_MSG, 1, fm::EGI_IN | fm::EGI_OUT>(h, gt, st, m, bt, a);
-        else launch_eg<D, fm::EG_MSGA, 1, fm::EGI_IN | fm::EGI_OUT>(h, gt, st, m, bt, a);
+        constexpr int IO = fm::EGI_IN | fm::EGI_OUT;
+        a.in_img = g == 0 ? at<float>(ws, L.EFI) : cur;
+        a.out_img = outs[g];
+        if (g == 0) {
+          launch_eg<D, fm::EG_MSG0, 1, IO>(h, gt, st, m, bt, a);
+        } else if (g == 1) {
+          launch_eg<D, fm::EG_MSG, 1, IO>(h, gt, st, m, bt, a);
+        } else {
+          launch_eg<D, fm::EG_MSGA, 1, IO>(h, gt, st, m, bt, a);
+        }
       } else
       if (g == 2 && h->fuse_agg) {       // last scalar linear: the segment-sum over in-edges rides in the epilogue
         launch_eg<D, fm::EG_MSGA, 1>(h, (int)(L.EPA / 128), st, m, bt, a);
@@ -257,6 +280,7 @@ int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
       }
       LAUNCH_OK(h);
       fm::EgArgs ag{wptr(tc_c(h, tcg[g])), wptr(gb[g] + fm::GV_BG), outs[g], nullptr, nullptr, nullptr, GT, nullptr, nullptr, L.EP, h->trace_mode == 2 ? h->d_trace : nullptr, h->trace_cta, 0, h->tc_debug};
+      ag.in_img = outs[g];
       if (img) launch_eg<D, fm::EG_GATE, 1, fm::EGI_IN>(h, (int)(L.EPA / 128), st, m, bt, ag);
       else if (h->eg_nh_gate == 2) launch_eg<D, fm::EG_GATE, 2>(h, (int)(L.EPA / 256), st, m, bt, ag);
       else launch_eg<D, fm::EG_GATE, 1>(h, (int)(L.EPA / 128), st, m, bt, ag);
@@ -358,6 +382,13 @@ int run_pass(FmHandle* h, void* ws, const Layout& L, const float* x_t, const uin
   if (m.use_dst) { fm::k_dst_proj<D><<<L.nNT, fm::NT, smem, st>>>(m, bt, 0, s, v, Q, vd); LAUNCH_OK(h); }
   fm::k_edge_init<D><<<L.nUT, fm::NT, smem, st>>>(m, bt, x_t, e_t, prev, has_prev, ef);
   LAUNCH_OK(h);
+  if constexpr (D::S == 256 && D::V == 32 && D::SD == 0 && D::F == 128) {
+    if (h->conv_impl == 2 && img_on(h)) {        // entry of the operand-image chain (egemm_p.cuh)
+      const int nt = (int)(L.EPA / 128);
+      fm::k_ef_image<D><<<nt < 4 * h->n_sm ? nt : 4 * h->n_sm, 256, 0, st>>>(bt, ef, at<float>(ws, L.EFI), L.EP, nt);
+      LAUNCH_OK(h);
+    }
+  }
   CUDA_OK(cudaMemcpyAsync(x, x_t, sizeof(float) * 3 * L.N, cudaMemcpyDeviceToDevice, st));
   for (int l = 0; l < m.L; ++l) {
     int agg_rows = fm::TM;
@@ -394,11 +425,13 @@ int run_pass(FmHandle* h, void* ws, const Layout& L, const float* x_t, const uin
           float* H = at<float>(ws, L.SA);
           const int gt = (int)(L.EPA / 128);
           fm::EgArgs a1{uptr(tc_u(h, fm::U_EUPD_TC1)), nullptr, ef, nullptr, EAB, x, H, nullptr, nullptr, L.EP, h->trace_mode == 3 ? h->d_trace : nullptr, h->trace_cta, 0, h->tc_debug};
-          if (img_on(h)) launch_eg<D, fm::EG_EU1, 1, fm::EGI_OUT>(h, gt, st, m, bt, a1);
+          a1.in_img = at<float>(ws, L.EFI); a1.out_img = H;
+          if (img_on(h)) launch_eg<D, fm::EG_EU1, 1, fm::EGI_IN | fm::EGI_OUT>(h, gt, st, m, bt, a1);
           else launch_eg<D, fm::EG_EU1, 1>(h, gt, st, m, bt, a1);
           LAUNCH_OK(h);
           fm::EgArgs a2{uptr(tc_u(h, fm::U_EUPD_TC2)), uptr(fm::U_EUPD_B2), H, ef, nullptr, nullptr, ef, uptr(fm::U_EUPD_LN_W), uptr(fm::U_EUPD_LN_B), L.EP, h->trace_mode == 4 ? h->d_trace : nullptr, h->trace_cta, 0, h->tc_debug};
-          if (img_on(h)) launch_eg<D, fm::EG_EU2, 1, fm::EGI_IN>(h, gt, st, m, bt, a2);
+          a2.in_img = H; a2.out_img = at<float>(ws, L.EFI);
+          if (img_on(h)) launch_eg<D, fm::EG_EU2, 1, fm::EGI_IN | fm::EGI_OUT>(h, gt, st, m, bt, a2);
           else launch_eg<D, fm::EG_EU2, 1>(h, gt, st, m, bt, a2);
           LAUNCH_OK(h);
           done = true;
@@ -535,6 +568,7 @@ int fm_create(const FmConfig* cfg, const float* w_host, size_t n_floats, const i
 void fm_destroy(FmHandle* h) {
   if (!h) return;
   cudaFree(h->d_w); cudaFree(h->d_off); cudaFree(h->d_table); cudaFree(h->d_status);
+  for (auto& pe : h->prof) cudaEventDestroy(pe.second);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   delete h;
 }
@@ -587,6 +621,7 @@ int fm_forward(FmHandle* h, void* ws, const float* x_t, const uint8_t* a_t, cons
   if (find_batch(h, ws, &L)) return -1;
   CUDA_OK(cudaSetDevice(h->device));
   h->launches = 0;
+  if (h->kprof) prof_mark(h, 0, static_cast<cudaStream_t>(stream));
   fm::PredPtr pv, po{nullptr, nullptr, nullptr, nullptr};
   if (prev) pv = fm::PredPtr{prev->x, prev->a, prev->c, prev->e};
   if (out) po = fm::PredPtr{out->x, out->a, out->c, out->e};
@@ -742,6 +777,7 @@ int fm_time_egemm_msg(FmHandle* h, void* ws, int32_t layer, int32_t iters, float
   CUDA_OK(cudaMemcpy(&status_before, h->d_status, sizeof(int), cudaMemcpyDeviceToHost));
   CUDA_OK(cudaEventRecord(e0, st));
   for (int i = 0; i < iters; ++i) {
+    a.in_img = a.in_s; a.out_img = a.out;
     if (img_on(h)) launch_eg<D, fm::EG_MSG, 1, fm::EGI_IN | fm::EGI_OUT>(h, (int)(L.EPA / 128), st, h->rt, bt, a);
     else if (h->eg_nh == 2) launch_eg<D, fm::EG_MSG, 2>(h, (int)(L.EPA / 256), st, h->rt, bt, a);
     else launch_eg<D, fm::EG_MSG, 1>(h, (int)(L.EPA / 128), st, h->rt, bt, a);
@@ -785,6 +821,12 @@ int fm_set_option(FmHandle* h, const char* name, int32_t value) {
     h->tc_prec = value;
     return 0;
   }
+  if (n == "kprof") {
+    for (auto& pe : h->prof) cudaEventDestroy(pe.second);
+    h->prof.clear();
+    h->kprof = value ? 1 : 0;
+    return 0;
+  }
   if (n == "tc_debug") { h->tc_debug = value; return 0; }
   if (n == "tc_trace_mode") { h->trace_mode = value; return 0; }
   if (n == "tc_trace") {       // value < 0: off; otherwise the CTA index whose timeline is recorded (every egemm launch overwrites it)
@@ -801,6 +843,23 @@ int fm_set_option(FmHandle* h, const char* name, int32_t value) {
 int fm_debug_read_trace(FmHandle* h, int64_t* out64_host) {
   if (!h || !out64_host || !h->d_trace) return fail("fm_debug_read_trace: tracing is off");
   CUDA_OK(cudaMemcpy(out64_host, h->d_trace, 64 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return 0;
+}
+// launches recorded since fm_set_option(h, "kprof", 1): api.cu line of each launch and its duration (ms, event to event)
+int fm_debug_kprof(FmHandle* h, int32_t* lines_host, float* ms_host, int32_t cap, int32_t* n_out) {
+  if (!h || !lines_host || !ms_host || !n_out) return fail("fm_debug_kprof: null argument");
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaDeviceSynchronize());
+  int n = 0;
+  for (size_t i = 1; i < h->prof.size() && n < cap; ++i) {
+    if (h->prof[i].first == 0) continue;                 // start marker of the next forward
+    float ms = 0.f;
+    CUDA_OK(cudaEventElapsedTime(&ms, h->prof[i - 1].second, h->prof[i].second));
+    lines_host[n] = h->prof[i].first;
+    ms_host[n] = ms;
+    ++n;
+  }
+  *n_out = n;
   return 0;
 }
 int fm_get_option(FmHandle* h, const char* name, int32_t* value) {

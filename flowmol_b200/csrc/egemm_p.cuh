@@ -1,21 +1,22 @@
 // k_egemm_p -- persistent, role-specialised version of k_egemm_tc (same modes, same arguments, same results bit for bit).
 //
-// What the profile of k_egemm_tc said (profiles/r01e_summary.md): tensor pipe 31 % active, DRAM 36 % of peak, the sampled
-// stalls spread over "loader waits for its global loads", "epilogue waits for the accumulator" and "warps parked at the final
-// barrier".  A CTA there is one 128-edge tile whose phases run one after the other (bookkeeping -> k-loop -> epilogue) with the
-// same four warps loading and draining; only the co-resident CTA overlaps them.  Here ONE CTA per SM walks over tiles
-// (tile = blockIdx.x + i * gridDim.x) with three independent pipelines that never wait for each other's phases:
+// What the profiles said.  k_egemm_tc (profiles/r01e): tensor pipe 31 % active, DRAM 36 % of peak; a CTA there is one 128-edge
+// tile whose phases run one after the other with the same four warps loading and draining.  First persistent version (r01g-r01k):
+// once consecutive linears hand their activations over as ready-made operand images (below), every mode of the kernel is bound by
+// its EPILOGUE -- four warps, one per scheduler, ~20 instructions per output element -- while eight loader warps mostly spin.
+// Hence this split: ONE CTA per SM walks over tiles (tile = blockIdx.x + i * gridDim.x) with
 //
 //   warp 0      weight producer   bulk-TMA ring of operand images, runs ahead across tile boundaries
 //   warps 1-2   MMA issuers       tcgen05.mma into one of TWO TMEM accumulator buffers (2 x 256 columns); issuer w owns the 128-feature
-//                                 tile w (its own accumulator columns and its own weight units), so two threads share the issue work
-//   warps 3-10  activation loaders fp32 -> scaled fp16 (hi, lo) SW128 images into a 4-stage ring; group 0 (warps 2-5) writes the
-//                                 first 32 k values of every 64-wide slab, group 1 the second 32; global loads are
-//                                 prefetched one chunk ahead, across tile boundaries
-//   warps 11-14 epilogue          TMEM -> registers -> activation -> global; drains buffer b while the MMAs fill buffer b ^ 1
+//                                 tile w (its own accumulator columns and its own weight units)
+//   warps 3-6   activation loaders k-slabs that exist as operand images: one 32 KB bulk-TMA copy per slab (issued by warp 3);
+//                                 everything else (rbf of the edge length, vector norms, fp32 node rows): fp32 -> fp16 (hi, lo)
+//                                 SW128 images, 32 rows per warp, 32-wide chunks, loads prefetched one chunk ahead across tiles
+//   warps 7-14  epilogue          TMEM -> registers -> activation -> global; two warps per TMEM lane quarter (each takes 64 of
+//                                 the tile's 128 rows), draining buffer b while the MMAs fill buffer b ^ 1
 //
 // All ring positions / mbarrier phases are running counters that every role advances identically per tile, so nothing is
-// re-initialised between tiles.  PREC 1 (fp16x3 operands) only: the 32-float loader chunks pair up into 64-wide slabs.
+// re-initialised between tiles.  PREC 1 (fp16x3 operands) only.
 #pragma once
 #include "egemm_tc.cuh"
 
@@ -27,26 +28,28 @@ struct EgpPlan {
   static constexpr int XSTAGE = 32768;                      // hi image 16 KB | lo image 16 KB
   static constexpr int RING_BYTES = 4 * TC_UNIT;            // weight ring
   static constexpr int MAX_SLOTS = 12;
-  static constexpr int THREADS = 15 * 32;
-  static constexpr int W_LOAD0 = 3, W_EPI0 = 11;              // first loader / epilogue warp
+  static constexpr int NLW = 4, NEW = 8;                    // loader / epilogue warps
+  static constexpr int THREADS = (3 + NLW + NEW) * 32;
+  static constexpr int W_LOAD0 = 3, W_EPI0 = 3 + NLW;       // first loader / epilogue warp
+  static_assert(W_EPI0 + NEW == THREADS / 32 && NLW * 32 == T, "one loader warp per 32 rows");
   static constexpr int OFF_X = 0;
   static constexpr int OFF_RING = NST * XSTAGE;
   static constexpr int OFF_ROW = OFF_RING + RING_BYTES;     // 2 x { int src[T]; short dd[T] } (epilogue bookkeeping, double buffered)
-  static constexpr int OFF_RED = OFF_ROW + 2 * T * 6;       // EU2 LayerNorm partials (256 floats)
-  static constexpr int OFF_BAR = OFF_RED + 1024;
+  static constexpr int OFF_RED = OFF_ROW + 2 * T * 6;       // EU2 LayerNorm partials (2 row halves x 256 floats)
+  static constexpr int OFF_BAR = OFF_RED + 2048;
   static constexpr int NBAR = 2 * MAX_SLOTS + 2 * NST + 4;
   static constexpr int BYTES = OFF_BAR + NBAR * 8 + 16;
   static constexpr size_t SMEM_BYTES = BYTES;
   static_assert(BYTES <= 232448, "227 KB of shared memory per CTA");
 };
 
-// IMG: "operand images" between consecutive tensor-core linears.  Bit 1 (EGI_OUT): the epilogue stores its output rows not as fp32
-// but already split into the (hi, lo) fp16 SW128 operand images the next linear's MMAs read -- per 128-row tile and 64-wide k-slab
-// one 32 KB block [hi image 16 KB | lo image 16 KB], the same 4 bytes per element.  Bit 0 (EGI_IN): `in_s` holds such images and
-// every k-slab of it is ONE 32 KB bulk-TMA copy into the activation stage (up to NST stages = 128 KB in flight per SM, no
-// registers, no conversion instructions) instead of 8 loader warps' LDG -> split -> STS round trip (profiles/r01g: that path was
-// ~40 % of the kernel's instructions and left the GATE linear at 2.4 TB/s).  The split is the same function of the same fp32
-// value on either side, so the results are bit-identical to the fp32 hand-over.
+// IMG: "operand images" between consecutive tensor-core linears.  Bit 1 (EGI_OUT): the epilogue stores its output rows (also)
+// already split into the (hi, lo) fp16 SW128 operand images the next linear's MMAs read -- per 128-row tile and 64-wide k-slab
+// one 32 KB block [hi image 16 KB | lo image 16 KB], the same 4 bytes per element -- at `out_img`.  Bit 0 (EGI_IN): `in_img`
+// holds such images for the leading k-slabs of this linear and each of them is ONE 32 KB bulk-TMA copy into the activation stage
+// (up to NST stages = 128 KB in flight per SM, no registers, no conversion instructions) instead of a loader round trip
+// LDG -> split -> STS (profiles/r01g: ~40 % of the kernel's instructions, the GATE linear stuck at 2.4 TB/s).  The split is the
+// same function of the same fp32 value on either side of HBM, so the results are bit-identical to the fp32 hand-over.
 enum EgImg : int { EGI_IN = 1, EGI_OUT = 2 };
 
 template <class D, int MODE, int IMG = 0>
@@ -55,30 +58,33 @@ k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
   using PL = EgpPlan;
   constexpr int S = D::S;
   constexpr bool IMG_IN = (IMG & EGI_IN) != 0, IMG_OUT = (IMG & EGI_OUT) != 0;
-  static_assert(!IMG_IN || MODE == EG_MSG || MODE == EG_MSGA || MODE == EG_GATE || MODE == EG_EU2, "image input: in_s feeds whole k-slabs");
-  static_assert(!IMG_OUT || MODE == EG_MSG0 || MODE == EG_MSG || MODE == EG_MSGA || MODE == EG_EU1, "image output: activations of a next linear");
+  static_assert(!IMG_IN || (MODE != EG_LIN), "image input: MSG0 / EU1 (edge features), MSG / MSGA / GATE / EU2 (previous linear)");
+  static_assert(!IMG_OUT || MODE == EG_MSG0 || MODE == EG_MSG || MODE == EG_MSGA || MODE == EG_EU1 || MODE == EG_EU2,
+                "image output: activations of a next linear (EU2: the new edge features, next to their fp32 rows)");
   constexpr bool IS_EU = MODE == EG_EU1 || MODE == EG_EU2;
   constexpr bool IS_MSG = MODE == EG_MSG || MODE == EG_MSGA;
   constexpr int K = MODE == EG_MSG0 ? D::KE0 : (IS_MSG ? D::K1 : (MODE == EG_EU1 ? D::F + D::R : (MODE == EG_EU2 ? D::F : S)));
   constexpr int NSLAB = (K + 63) / 64;
-  constexpr int NCH = (K + 31) / 32;
+  constexpr int NCH = (K + 31) / 32;                        // 32-float chunks of K
   constexpr int LAST_KSTEPS = ((K - 1) % 64) / 16 + 1;
   constexpr int NMT = MODE == EG_GATE ? 1 : (IS_EU ? D::F / 128 : S / 128);
   constexpr int OW = MODE == EG_GATE ? 32 : (IS_EU ? D::F : S);
   static_assert(!IS_EU || D::F == 128, "edge-update modes: F = 128");
+  static_assert(D::F % 64 == 0 && S % 64 == 0, "image slabs are 64 k values");
   constexpr int UNIT_BYTES = MODE == EG_GATE ? 32 * 128 : TC_UNIT;
   constexpr int RING_FIT = (PL::RING_BYTES - TC_UNIT) / UNIT_BYTES + 1;      // the MMA reads 16 KB from every slot base
   constexpr int RING = RING_FIT < PL::MAX_SLOTS ? RING_FIT : PL::MAX_SLOTS;
   constexpr uint32_t NU = NSLAB * NMT * 2;                                     // weight units per tile
   constexpr int NST = PL::NST;
-  constexpr int NIMG = IMG_IN ? (MODE == EG_EU2 ? D::F / 64 : S / 64) : 0;     // leading k-slabs that arrive as operand images
+  // leading k-slabs that arrive as operand images: the edge features (MSG0, EU1: k order ef | rbf | ...) or the whole previous linear
+  constexpr int NIMG = IMG_IN ? ((MODE == EG_MSG0 || IS_EU) ? D::F / 64 : S / 64) : 0;
   static_assert(NIMG <= NSLAB, "image slabs are a prefix of K");
+  constexpr int FIRST_CH = 2 * NIMG;                        // first chunk the loader warps convert
   constexpr int SH_W = 40;
   constexpr int LO_OFF = 16384;
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   uint8_t* xst = smem_dyn + PL::OFF_X;
   uint8_t* ring = smem_dyn + PL::OFF_RING;
-  float* red = reinterpret_cast<float*>(smem_dyn + PL::OFF_RED);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_dyn + PL::OFF_BAR);
   uint64_t *w_full = bars, *w_empty = bars + PL::MAX_SLOTS, *x_full = bars + 2 * PL::MAX_SLOTS, *x_empty = x_full + NST;
   uint64_t *acc_full = x_empty + NST, *acc_empty = acc_full + 2;
@@ -87,8 +93,8 @@ k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
   const int n_my = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   if (tid == 0) {
     for (int i = 0; i < RING; ++i) { tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < NST; ++i) { tc::mbar_init(&x_full[i], 8); tc::mbar_init(&x_empty[i], NMT); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], NMT); tc::mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < NST; ++i) { tc::mbar_init(&x_full[i], PL::NLW); tc::mbar_init(&x_empty[i], NMT); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], NMT); tc::mbar_init(&acc_empty[i], PL::NEW); }
     tc::fence_mbar_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
@@ -159,9 +165,10 @@ k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
     }
   } else if (warp < PL::W_EPI0) {
     // ---- activation loaders ------------------------------------------------------------------------------------------------------------------
-    // Warps w and w + 4 own the same 32 rows; group `grp` converts chunk 2 * slab + grp of every slab.  Row bookkeeping (validity,
-    // src node, distance) lives in registers: lane l holds row wrow0 + l, the fetch reads it with a shuffle.
-    const int grp = (warp - PL::W_LOAD0) >> 2, wrow0 = ((warp - PL::W_LOAD0) & 3) * 32, lg = lane >> 3, ch = lane & 7;
+    // Warp w owns rows [32 w, 32 w + 32) of the tile.  Row bookkeeping (validity, edge length) lives in registers: lane l holds row
+    // wrow0 + l, the fetch reads it with a shuffle.  A load instruction covers 4 rows x 128 B (lanes 8g..8g+7 read the 8 16-byte
+    // pieces of row 4i + g of a 32-float chunk).
+    const int wrow0 = (warp - PL::W_LOAD0) * 32, lg = lane >> 3, ch = lane & 7;
     const float sigma = m.rbf_dmax / (float)D::R;
     const float* mu = m.g(G_RBF_MU);
     int r_ok = 0;              // row valid (of the tile the NEXT fetch belongs to)
@@ -191,10 +198,10 @@ k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
       r_ok = ok;
       r_dist = dist;
     };
-    // chunk of slab `sb` this group converts: k values [64 sb + 32 grp, +32).  `sb` is a compile-time constant at every call site
-    // (the slab loops are fully unrolled), so the source selection below folds to one path per call.
-    auto fetch = [&](const int sb, float4 (&buf)[8]) {
-      const int j = 2 * sb + grp;
+    // chunk j = k values [32 j, 32 j + 32) of this linear's input row; j is a compile-time constant at every call site (the slab /
+    // chunk loops are fully unrolled), so the source selection below folds to one path per call.
+    // k order: MSG0  ef(F) | rbf(32) | norms;  EU1  ef(F) | rbf(32);  MSG / MSGA  s'(S) | norms;  EU2  h(F);  GATE / LIN  s(S)
+    auto fetch = [&](const int j, float4 (&buf)[8]) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int rl = 4 * i + lg;                              // row inside the warp's 32
@@ -203,25 +210,18 @@ k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
         float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
         if (MODE == EG_MSG0 || MODE == EG_EU1) {
           const float dd = __shfl_sync(0xffffffffu, r_dist, rl);
-          // MSG0: k order rbf(32) | ef(F) | norms;  EU1: ef(F) | rbf(32)
-          const bool maybe_rbf = MODE == EG_MSG0 ? sb == 0 : sb == D::F / 64;
-          if (maybe_rbf && grp == 0) {
+          if (j == D::F / 32) {
             if (ok) val = make_float4(rbf_f(dd, mu[ch * 4], sigma), rbf_f(dd, mu[ch * 4 + 1], sigma), rbf_f(dd, mu[ch * 4 + 2], sigma),
                                       rbf_f(dd, mu[ch * 4 + 3], sigma));
-          } else if (MODE == EG_MSG0) {
-            if (ok) {
-              if (j <= D::F / 32) val = __ldg(reinterpret_cast<const float4*>(a.in_s + (size_t)sl_ * D::F + (j - 1) * 32) + ch);
-              else {
-                const int k0 = (j - 1 - D::F / 32) * 32 + ch * 4;
-                if (k0 < SH_W) val = *(reinterpret_cast<const float4*>(a.in_sh + (size_t)sl_ * SH_W + k0));
-              }
-            }
-          } else {
-            if (ok) val = *(reinterpret_cast<const float4*>(a.in_s + (size_t)sl_ * D::F + j * 32) + ch);
+          } else if (j < D::F / 32) {
+            if (ok) val = __ldg(reinterpret_cast<const float4*>(a.in_s + (size_t)sl_ * D::F + j * 32) + ch);
+          } else {                                               // MSG0 only
+            const int k0 = (j - 1 - D::F / 32) * 32 + ch * 4;
+            if (ok && k0 < SH_W) val = *(reinterpret_cast<const float4*>(a.in_sh + (size_t)sl_ * SH_W + k0));
           }
         } else if (IS_MSG) {
           if (ok) {
-            if (sb < S / 64) val = *(reinterpret_cast<const float4*>(a.in_s + (size_t)sl_ * S + j * 32) + ch);
+            if (j < S / 32) val = *(reinterpret_cast<const float4*>(a.in_s + (size_t)sl_ * S + j * 32) + ch);
             else {
               const int k0 = (j - S / 32) * 32 + ch * 4;
               if (k0 < SH_W) val = *(reinterpret_cast<const float4*>(a.in_sh + (size_t)sl_ * SH_W + k0));
@@ -235,12 +235,9 @@ k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
         buf[i] = val;
       }
     };
-    // group 1 has no chunk in the last slab when K spans an odd number of 32-wide chunks
-    constexpr int NMY1 = NCH / 2;
     float4 cur[8], nxt[8];
     float amax = 0.f;
-    static_assert(NIMG == NSLAB || NIMG < NMY1, "both loader groups own a chunk in the first converted slab");
-    if (n_my > 0 && NIMG < NSLAB) { rowinfo(0); fetch(NIMG, cur); }
+    if (n_my > 0 && FIRST_CH < NCH) { rowinfo(0); fetch(FIRST_CH, cur); }
     uint32_t g = 0;                                            // running slab counter (stage / phase bookkeeping)
     for (int it = 0; it < n_my; ++it) {
 #pragma unroll
@@ -255,7 +252,7 @@ k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
             if (warp == PL::W_LOAD0) {
               const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
               tc::mbar_arrive_expect_tx(&x_full[st], PL::XSTAGE);
-              tc::bulk_g2s(xst + st * PL::XSTAGE, reinterpret_cast<const uint8_t*>(a.in_s) + ((size_t)tile * NIMG + s) * PL::XSTAGE,
+              tc::bulk_g2s(xst + st * PL::XSTAGE, reinterpret_cast<const uint8_t*>(a.in_img) + ((size_t)tile * NIMG + s) * PL::XSTAGE,
                            PL::XSTAGE, &x_full[st]);
             } else {
               asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&x_full[st])) : "memory");
@@ -264,19 +261,19 @@ k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
           __syncwarp();
           continue;
         }
-        const bool mine = s < NMY1 || grp == 0;                // this group has a chunk in slab s
-        if (mine) {                                            // prefetch this group's next chunk: same tile, or the first converted slab of the next tile
-          const bool last_mine = (s + 1 == NSLAB) || (s + 1 == NMY1 && grp == 1);
-          if (!last_mine) {
-            fetch(s + 1 < NSLAB ? s + 1 : NIMG, nxt);
+        uint8_t* hi = xst + st * PL::XSTAGE;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int j = 2 * s + h;
+          if (j >= NCH) break;                                 // K spans an odd number of chunks: the MMAs stop before this half
+          // prefetch the next chunk: same tile, or the first converted chunk of the next tile
+          if (j + 1 < NCH) {
+            fetch(j + 1, nxt);
           } else if (it + 1 < n_my) {
             rowinfo(it + 1);
-            fetch(NIMG, nxt);
+            fetch(FIRST_CH, nxt);
           }
-        }
-        if (use > 0) tc::mbar_wait(&x_empty[st], (use - 1) & 1);
-        if (mine) {
-          uint8_t* hi = xst + st * PL::XSTAGE;
+          if (h == 0 && use > 0) tc::mbar_wait(&x_empty[st], (use - 1) & 1);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rr_ = wrow0 + 4 * i + lg;
@@ -285,24 +282,24 @@ k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
             uint2 vh, vl;
             tc::split_h16x2(val.x * tc::ACT_SCALE_H16, val.y * tc::ACT_SCALE_H16, vh.x, vl.x);
             tc::split_h16x2(val.z * tc::ACT_SCALE_H16, val.w * tc::ACT_SCALE_H16, vh.y, vl.y);
-            const uint32_t off = tc::sw128_off_h(rr_, grp * 32 + ch * 4);
+            const uint32_t off = tc::sw128_off_h(rr_, h * 32 + ch * 4);
             *reinterpret_cast<uint2*>(hi + off) = vh;
             *reinterpret_cast<uint2*>(hi + LO_OFF + off) = vl;
           }
-          tc::fence_proxy_async();
-        }
-        __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&x_full[st])) : "memory");
-        if (mine) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
         }
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&x_full[st])) : "memory");
       }
     }
     if (!(amax < tc::ACT_LIMIT_H16) && a.status) atomicOr(a.status, 1);
   } else {
     // ---- epilogue: TMEM -> registers -> bias / gathered pre-activation -> activation -> coalesced global stores ---------------------------
-    const int q = warp & 3, et = tid - PL::W_EPI0 * 32;                 // TMEM lane quarter; index among the 128 epilogue threads
+    // warp -> TMEM lane quarter q (a warp may only touch lanes 32 (warp % 4) ...) and row half hf: rows [64 hf, 64 hf + 64) = chunks 2 hf, 2 hf + 1
+    const int q = warp & 3, hf = (warp - PL::W_EPI0) >> 2, et = tid - PL::W_EPI0 * 32;     // et: index among the 256 epilogue threads
+    float* red = reinterpret_cast<float*>(smem_dyn + PL::OFF_RED) + hf * 256;
     const float unscale = a.units[(size_t)NU * (UNIT_BYTES / 4)];
     float omax = 0.f;                                                  // IMG_OUT: largest |activation| this thread split into fp16 (hi, lo)
     constexpr bool GATHERS = MODE == EG_MSG0 || MODE == EG_EU1 || MODE == EG_EU2;
@@ -313,38 +310,40 @@ k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
       int* r_src = reinterpret_cast<int*>(smem_dyn + PL::OFF_ROW + b * (PL::T * 6));
       short* r_dd = reinterpret_cast<short*>(r_src + PL::T);
       if (NEED_ROWS) {
-        const int r = et;
-        const long long slot = slot0 + r;
-        int s = -1, dd = 0;
-        if (slot < a.EP) {
-          const int t64 = (int)(slot >> 6), mol = bt.etile_mol[t64];
-          const int n = bt.mol_n[mol], le = (int)(slot - ((long long)bt.mol_etile[mol] << 6));
-          if (le < n * (n - 1)) {
-            s = 0;
-            if (MODE == EG_MSGA) {
-              const int j = le / (n - 1), rem = le - j * (n - 1);
-              s = bt.mol_node[mol] + j;
-              const bool tail = rem == n - 2;
-              dd = (((r & 63) == 63 || tail) ? 1 : 0) | (tail ? 2 : 0) | (rem <= (r & 63) ? 4 : 0);
-            } else {
-              int i, j;
-              edge_src_dst(le, n, i, j);
-              s = bt.mol_node[mol] + i;
-              dd = j - i;
+        if (et < PL::T) {                                       // the first four epilogue warps: one row each
+          const int r = et;
+          const long long slot = slot0 + r;
+          int s = -1, dd = 0;
+          if (slot < a.EP) {
+            const int t64 = (int)(slot >> 6), mol = bt.etile_mol[t64];
+            const int n = bt.mol_n[mol], le = (int)(slot - ((long long)bt.mol_etile[mol] << 6));
+            if (le < n * (n - 1)) {
+              s = 0;
+              if (MODE == EG_MSGA) {
+                const int j = le / (n - 1), rem = le - j * (n - 1);
+                s = bt.mol_node[mol] + j;
+                const bool tail = rem == n - 2;
+                dd = (((r & 63) == 63 || tail) ? 1 : 0) | (tail ? 2 : 0) | (rem <= (r & 63) ? 4 : 0);
+              } else {
+                int i, j;
+                edge_src_dst(le, n, i, j);
+                s = bt.mol_node[mol] + i;
+                dd = j - i;
+              }
             }
           }
-        }
-        r_src[r] = s;
-        if (MODE == EG_MSGA) {
-          const unsigned em = __ballot_sync(0xffffffffu, dd & 1), tm = __ballot_sync(0xffffffffu, dd & 2), hm = __ballot_sync(0xffffffffu, dd & 4);
-          if (lane == 0) {
-            unsigned* masks = reinterpret_cast<unsigned*>(r_dd);
-            masks[(et >> 5) * 3 + 0] = em; masks[(et >> 5) * 3 + 1] = tm; masks[(et >> 5) * 3 + 2] = hm;
+          r_src[r] = s;
+          if (MODE == EG_MSGA) {
+            const unsigned em = __ballot_sync(0xffffffffu, dd & 1), tm = __ballot_sync(0xffffffffu, dd & 2), hm = __ballot_sync(0xffffffffu, dd & 4);
+            if (lane == 0) {
+              unsigned* masks = reinterpret_cast<unsigned*>(r_dd);
+              masks[(et >> 5) * 3 + 0] = em; masks[(et >> 5) * 3 + 1] = tm; masks[(et >> 5) * 3 + 2] = hm;
+            }
+          } else {
+            r_dd[r] = (short)dd;
           }
-        } else {
-          r_dd[r] = (short)dd;
         }
-        asm volatile("bar.sync 2, 128;" ::: "memory");           // the four epilogue warps (buffers alternate: one barrier per tile)
+        asm volatile("bar.sync 2, 256;" ::: "memory");           // the eight epilogue warps (buffers alternate: one barrier per tile)
       }
       const bool active = MODE != EG_GATE || q == 0;
 #pragma unroll 1
@@ -368,17 +367,18 @@ k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
             for (int i = 0; i < 32; ++i) dst_[i] = a.in_sh[(size_t)(slot0 + c * 32 + i) * D::F + f];
           }
         };
-        if (GATHERS) gather(0, pre);
+        if (GATHERS) gather(2 * hf, pre);
         if (mt == 0) {
           tc::mbar_wait(&acc_full[b], (it >> 1) & 1);
           tc::tc_fence_after();
         }
         if (active) {
 #pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
+          for (int ci = 0; ci < 2; ++ci) {
+            const int c = 2 * hf + ci;
             float acc[32];
             tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 256 + mt * 128 + c * 32), acc);
-            if (GATHERS && c + 1 < 4) gather(c + 1, pnext);
+            if (GATHERS && ci == 0) gather(c + 1, pnext);
             tc::tmem_ld_wait();
             float* op = a.out + (size_t)(slot0 + c * 32) * OW + f;
             unsigned em = 0, tm = 0, hm = 0;
@@ -396,32 +396,8 @@ k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
                 if (!IMG_OUT) op[(size_t)i * OW] = o;
                 if (MODE == EG_MSGA || IMG_OUT) acc[i] = o;
               }
-              if constexpr (IMG_OUT) {
-                // Operand images of the next linear.  Feature f is k = f % 64 of slab f / 64; row r of a slab image is 128 bytes of
-                // 64 fp16 whose 16-byte chunks are XOR-swizzled by r % 8.  Lanes 2m / 2m+1 hold neighbouring k: they swap one
-                // packed (hi, lo) word per row pair so that the even lane stores the 32-bit (k, k+1) words of row 2t and the odd
-                // lane those of row 2t + 1 -- a warp store covers two rows x 64 contiguous bytes (four full sectors).
-                const int odd = lane & 1, kk = (q & 1) * 32 + (lane & ~1);
-                uint8_t* ob = reinterpret_cast<uint8_t*>(a.out) + ((size_t)(slot0 >> 7) * (OW / 64) + (size_t)(mt * 2 + (q >> 1))) * PL::XSTAGE +
-                              (size_t)((c * 32 + odd) * 128 + (kk & 7) * 2);
-                const uint32_t c0x = (uint32_t)((kk >> 3) ^ odd);
-                const uint32_t sel_keep = odd ? 0x7632u : 0x5410u, sel_send = odd ? 0x5410u : 0x7632u;
-                const uint32_t sel_hi = odd ? 0x1054u : 0x5410u, sel_lo = odd ? 0x3276u : 0x7632u;
-#pragma unroll
-                for (int t = 0; t < 16; ++t) {
-                  const float v0 = acc[2 * t], v1 = acc[2 * t + 1];
-                  omax = fmaxf(omax, fmaxf(fabsf(v0), fabsf(v1)));
-                  uint32_t h2, l2;                              // (hi(v0), hi(v1)), (lo(v0), lo(v1))
-                  tc::split_h16x2(v0, v1, h2, l2);
-                  const uint32_t keep = __byte_perm(h2, l2, sel_keep);      // (hi, lo) of the row this lane stores
-                  const uint32_t recv = __shfl_xor_sync(0xffffffffu, __byte_perm(h2, l2, sel_send), 1);
-                  uint8_t* dst_ = ob + (2 * t) * 128 + ((c0x ^ (uint32_t)((2 * t) & 7)) << 4);
-                  *reinterpret_cast<uint32_t*>(dst_) = __byte_perm(keep, recv, sel_hi);
-                  *reinterpret_cast<uint32_t*>(dst_ + LO_OFF) = __byte_perm(keep, recv, sel_lo);
-                }
-              }
               if (MODE == EG_MSGA) {
-                if ((c & 1) == 0) run = 0.f;
+                if (ci == 0) run = 0.f;
                 const unsigned em_lo = em & 0x7fffffffu;
                 if (__popc(em_lo) <= 1) {
                   // Common case (in-edge segments of n - 1 >= 32 rows): at most one segment ends before the chunk's last row.
@@ -460,6 +436,7 @@ k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
                 }
               }
             } else {
+              // y = ef + SiLU(W2 h + b2);  LayerNorm over the 128 features of every edge = over the lanes of the 4 warps of this row half
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
                 const float z = acc[i] * unscale + bias;
@@ -471,7 +448,7 @@ k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
                 for (int i = 0; i < 32; ++i) t[i] = acc[i];
                 red[q * 32 + lane] = warp_transpose_sum(t);
               }
-              asm volatile("bar.sync 1, 128;" ::: "memory");
+              if (hf == 0) asm volatile("bar.sync 3, 128;" ::: "memory"); else asm volatile("bar.sync 4, 128;" ::: "memory");
 #pragma unroll
               for (int i = 0; i < 32; ++i) pre[i] = (red[i] + red[32 + i] + red[64 + i] + red[96 + i]) * (1.0f / 128.0f);
               {
@@ -480,14 +457,40 @@ k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
                 for (int i = 0; i < 32; ++i) { const float dlt = acc[i] - pre[i]; t[i] = dlt * dlt; }
                 red[128 + q * 32 + lane] = warp_transpose_sum(t);
               }
-              asm volatile("bar.sync 1, 128;" ::: "memory");
+              if (hf == 0) asm volatile("bar.sync 3, 128;" ::: "memory"); else asm volatile("bar.sync 4, 128;" ::: "memory");
               const float gam = a.ln_w[f], bet = a.ln_b[f];
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
                 const float var = (red[128 + i] + red[160 + i] + red[192 + i] + red[224 + i]) * (1.0f / 128.0f);
-                op[(size_t)i * OW] = (acc[i] - pre[i]) * rsqrtf(var + 1e-5f) * gam + bet;
+                const float y = (acc[i] - pre[i]) * rsqrtf(var + 1e-5f) * gam + bet;
+                op[(size_t)i * OW] = y;
+                if (IMG_OUT) acc[i] = y;
               }
-              asm volatile("bar.sync 1, 128;" ::: "memory");
+              if (hf == 0) asm volatile("bar.sync 3, 128;" ::: "memory"); else asm volatile("bar.sync 4, 128;" ::: "memory");
+            }
+            if constexpr (IMG_OUT) {
+              // Operand images of the next linear.  Feature f is k = f % 64 of slab f / 64; row r of a slab image is 128 bytes of
+              // 64 fp16 whose 16-byte pieces are XOR-swizzled by r % 8.  Lanes 2m / 2m+1 hold neighbouring k: they swap one
+              // packed (hi, lo) word per row pair so that the even lane stores the 32-bit (k, k+1) words of row 2t and the odd
+              // lane those of row 2t + 1 -- a warp store covers two rows x 64 contiguous bytes (four full sectors).
+              const int odd = lane & 1, kk = (q & 1) * 32 + (lane & ~1);
+              uint8_t* ob = reinterpret_cast<uint8_t*>(a.out_img) + ((size_t)(slot0 >> 7) * (OW / 64) + (size_t)(mt * 2 + (q >> 1))) * PL::XSTAGE +
+                            (size_t)((c * 32 + odd) * 128 + (kk & 7) * 2);
+              const uint32_t c0x = (uint32_t)((kk >> 3) ^ odd);
+              const uint32_t sel_keep = odd ? 0x7632u : 0x5410u, sel_send = odd ? 0x5410u : 0x7632u;
+              const uint32_t sel_hi = odd ? 0x1054u : 0x5410u, sel_lo = odd ? 0x3276u : 0x7632u;
+#pragma unroll
+              for (int t = 0; t < 16; ++t) {
+                const float v0 = acc[2 * t], v1 = acc[2 * t + 1];
+                omax = fmaxf(omax, fmaxf(fabsf(v0), fabsf(v1)));
+                uint32_t h2, l2;                              // (hi(v0), hi(v1)), (lo(v0), lo(v1))
+                tc::split_h16x2(v0, v1, h2, l2);
+                const uint32_t keep = __byte_perm(h2, l2, sel_keep);      // (hi, lo) of the row this lane stores
+                const uint32_t recv = __shfl_xor_sync(0xffffffffu, __byte_perm(h2, l2, sel_send), 1);
+                uint8_t* dst_ = ob + (2 * t) * 128 + ((c0x ^ (uint32_t)((2 * t) & 7)) << 4);
+                *reinterpret_cast<uint32_t*>(dst_) = __byte_perm(keep, recv, sel_hi);
+                *reinterpret_cast<uint32_t*>(dst_ + LO_OFF) = __byte_perm(keep, recv, sel_lo);
+              }
             }
             if (GATHERS) {
 #pragma unroll
@@ -506,6 +509,43 @@ k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 1) tc::tmem_dealloc(tmem, 512);
+}
+
+// fp32 edge features -> their operand images (the entry of the image chain: k_edge_init writes fp32 rows only).  Dead rows (the
+// padding slots of a molecule's block and everything beyond EP) become zeros in BOTH buffers, so that the linears -- which compute
+// every row of a tile -- never see uninitialised data there.
+template <class D>
+__global__ void __launch_bounds__(256) k_ef_image(const BatchRT bt, float* __restrict__ ef, float* __restrict__ img, long long EP, int n_tiles) {
+  static_assert(D::F % 64 == 0, "image slabs are 64 k values");
+  constexpr int F4 = D::F / 4;
+  __shared__ int ok_row[128];
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    __syncthreads();
+    if (threadIdx.x < 128) {
+      const long long slot = (long long)tile * 128 + threadIdx.x;
+      int ok = 0;
+      if (slot < EP) {
+        const int t64 = (int)(slot >> 6), mol = bt.etile_mol[t64];
+        const int n = bt.mol_n[mol], le = (int)(slot - ((long long)bt.mol_etile[mol] << 6));
+        ok = le < n * (n - 1);
+      }
+      ok_row[threadIdx.x] = ok;
+    }
+    __syncthreads();
+    uint8_t* ib = reinterpret_cast<uint8_t*>(img) + (size_t)tile * (D::F / 64) * EgpPlan::XSTAGE;
+    for (int idx = threadIdx.x; idx < 128 * F4; idx += 256) {
+      const int row = idx / F4, k = (idx - row * F4) * 4;
+      float4* src = reinterpret_cast<float4*>(ef + ((size_t)tile * 128 + row) * D::F + k);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok_row[row]) v = *src; else *src = v;
+      uint2 vh, vl;
+      tc::split_h16x2(v.x, v.y, vh.x, vl.x);
+      tc::split_h16x2(v.z, v.w, vh.y, vl.y);
+      uint8_t* d = ib + (size_t)(k >> 6) * EgpPlan::XSTAGE + tc::sw128_off_h(row, k & 63);
+      *reinterpret_cast<uint2*>(d) = vh;
+      *reinterpret_cast<uint2*>(d + 16384) = vl;
+    }
+  }
 }
 
 }  // namespace fm

@@ -67,6 +67,8 @@ struct EgArgs {
   float* partF;
   float* partL;
   int* status;               // PREC 1: bit 0 is set when an activation leaves the fp16 operand range (|x| >= ACT_LIMIT_H16)
+  const float* in_img;       // k_egemm_p<.., EGI_IN>: fp16 (hi, lo) operand images of the leading k-slabs (egemm_p.cuh)
+  float* out_img;            // k_egemm_p<.., EGI_OUT>: where the output's operand images go
 };
 
 // EG_MSGA: one finished segment sum of feature f.  Deliberately not inlined: the call sits behind a rarely taken branch in a
@@ -254,13 +256,16 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
         float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
         if (MODE == EG_MSG0 || MODE == EG_EU1) {
           const float dd = __shfl_sync(0xffffffffu, my_dist, 4 * i + lg);      // the row's distance lives in lane (row % 32)
-          const bool rbf_slab = MODE == EG_MSG0 ? j == 0 : j == D::F / 32;
+          // k order of the first message linear: rbf | ef | norms in the 3xTF32 images, ef | rbf | norms in the fp16 images
+          // (weights.py: the edge features are whole k-slabs there, k_egemm_p fetches them as operand images)
+          const bool rbf_slab = (MODE == EG_MSG0 && !PREC) ? j == 0 : j == D::F / 32;
+          const int jf = PREC ? j : j - 1;                       // MSG0: ef chunk index
           if (rbf_slab) {
             if (ok) val = make_float4(rbf_f(dd, mu[ch * 4], sigma), rbf_f(dd, mu[ch * 4 + 1], sigma), rbf_f(dd, mu[ch * 4 + 2], sigma),
                                       rbf_f(dd, mu[ch * 4 + 3], sigma));
           } else if (MODE == EG_MSG0) {
             if (ok) {
-              if (j <= D::F / 32) val = __ldg(reinterpret_cast<const float4*>(a.in_s + (size_t)sl_ * D::F + (j - 1) * 32) + ch);
+              if (j <= D::F / 32) val = __ldg(reinterpret_cast<const float4*>(a.in_s + (size_t)sl_ * D::F + jf * 32) + ch);
               else {
                 const int k0 = (j - 1 - D::F / 32) * 32 + ch * 4;
                 if (k0 < SH_W) val = *(reinterpret_cast<const float4*>(a.in_sh + (size_t)sl_ * SH_W + k0));

@@ -390,7 +390,14 @@ def pack(cfg: ModelConfig, sd):
         if S % 128 == 0 and V <= 32:     # tensor-core images: features on the UMMA M axis (128-row tiles), gates 32-row units
             for i in range(3):
                 wt = _np(sd, f"{p}.edge_message.{i}.to_feats_out.0.weight")            # [S, in]
-                P.tc(c(f"MSG{i}_TCW"), c(f"MSG{i}_TCW_H"), wt[:, rows_edge] if i == 0 else wt, 128)
+                if i == 0:
+                    # fp16 images: k order ef(F) | d(R) | sh, so that the edge features are whole 64-wide k-slabs (they arrive
+                    # as ready-made operand images by bulk TMA, csrc/egemm_p.cuh); the 3xTF32 images keep d | ef | sh
+                    rows_edge_h = rows_edge[R:R + F] + rows_edge[:R] + rows_edge[R + F:]
+                    P.raw(c("MSG0_TCW"), tc_units(wt[:, rows_edge], 128))
+                    P.raw(c("MSG0_TCW_H"), tc_units_h16(wt[:, rows_edge_h], 128))
+                else:
+                    P.tc(c(f"MSG{i}_TCW"), c(f"MSG{i}_TCW_H"), wt, 128)
                 P.tc(c(f"MSG{i}_TCG"), c(f"MSG{i}_TCG_H"), _np(sd, f"{p}.edge_message.{i}.scalar_to_vector_gates.weight"), 32)
         for i in range(3):
             _pack_gvp(P, c(f"UPD{i}_WHCP"), sd, f"{p}.node_update.{i}")

@@ -126,6 +126,10 @@ int fm_set_option(FmHandle* h, const char* name, int32_t value);
 int fm_get_option(FmHandle* h, const char* name, int32_t* value);
 /* timeline experiments: after fm_set_option(h, "tc_trace", cta) every k_egemm_tc launch records clock64 stamps of that CTA */
 int fm_debug_read_trace(FmHandle* h, int64_t* out64_host);
+/* in-situ per-launch timing: after fm_set_option(h, "kprof", 1) every kernel launch of fm_forward is followed by a CUDA event;
+ * returns, for up to `cap` launches, the csrc/api.cu line of the launch and its duration in ms (event to event, warm pipeline).
+ * fm_set_option(h, "kprof", 0 or 1) clears the record. */
+int fm_debug_kprof(FmHandle* h, int32_t* lines_host, float* ms_host, int32_t cap, int32_t* n_out);
 /* number of kernels launched by the last fm_forward / fm_integrate call on this handle */
 int64_t fm_last_launch_count(FmHandle* h);
 

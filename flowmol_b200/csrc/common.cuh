@@ -53,6 +53,15 @@ __device__ __forceinline__ float norm_no_nan3(float x, float y, float z) {
   return sqrtf(fmaxf(q, 1e-8f));
 }
 
+// branch-free square root for q >= 1e-8 (MUFU.RSQ + one Newton step in fma arithmetic: within 1 ulp of sqrtf, whose IEEE routine
+// carries a slow-path branch that breaks up unrolled loops)
+__device__ __forceinline__ float sqrt_pos(float q) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(q));
+  const float s = q * r;
+  return fmaf(0.5f * r, fmaf(-s, s, q), s);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -23,8 +23,11 @@ struct Dims {
   static constexpr int XW = cmax(cmax(cmax(K1, KE0), cmax(2 * F + R, F + 4 + R + F + 4)),
                                  cmax(2 * TOK + TD, S + AMAX + 8 + R));
   static constexpr int XLD = ((XW + 3) / 4) * 4 + 4;
-  static constexpr int LDVA = ((cmax(VIN0, V) + 7) / 8) * 8 + 4;   // K padded to 8 for the warp-MMA path; +4: conflict-free fragment loads
-  static constexpr int LDVB = ((H0 + 2 * CP + 7) / 8) * 8 + 4;
+  // vector-plane row pitches: K padded to 8 for the warp-MMA path, and pitch % 16 == 8 so that the 64-bit A-fragment loads /
+  // accumulator stores of mma.m16n8k16 (rows g = 0..3 of a half warp, 2 words each) fall into four disjoint bank octets
+  static constexpr int vpitch(int k) { return ((k + 7) / 8) * 8 + ((((k + 7) / 8) * 8) % 16 == 0 ? 8 : 0); }
+  static constexpr int LDVA = vpitch(cmax(VIN0, V));
+  static constexpr int LDVB = vpitch(H0 + 2 * CP);
   static_assert(S % 32 == 0 && F % 32 == 0, "S and F must be multiples of 32");
   static_assert(V % 4 == 0 && R % 4 == 0 && TOK % 4 == 0 && TD % 4 == 0, "V, R, token dims must be multiples of 4");
   // shared-memory plan of the tile kernels (floats)

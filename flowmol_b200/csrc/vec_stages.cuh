@@ -107,6 +107,20 @@ __device__ __forceinline__ WH16 load_resident_h16(float* dst, const float* __res
   return WH16{hi, lo, inv};
 }
 
+// HBM -> L2 prefetch of the 16-row VH / GT blocks a warp pair will read for its NEXT tile (one bulk-prefetch instruction each, no
+// registers held): the loads at the top of the next tile then see L2 latency instead of HBM latency (ncu r01o: ~20 % of the
+// vector-stage kernels' samples sat on those loads and the barrier behind them).
+__device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void prefetch_pair_inputs(const float* __restrict__ VH, const float* __restrict__ GT, size_t erow0_next) {
+  if ((threadIdx.x & (PT - 1)) == 0) {
+    const size_t r = erow0_next + (size_t)(threadIdx.x >> 6) * PE;
+    prefetch_l2(VH + r * 3 * VHW, PE * 3 * VHW * 4);
+    prefetch_l2(GT + r * 32, PE * 32 * 4);
+  }
+}
+
 // stage 1 of a GVP for the pair's 16 rows: Va[.., 0:v_in) -> Vb = [Vh | cross] (cols [0, h+cp)), stores VH and SH
 template <class D>
 __device__ __forceinline__ void vec_stage1(Smem<D>& sm, const int v_in, const int h, const WH16& whcp_sm, const size_t erow0,
@@ -126,9 +140,10 @@ __device__ __forceinline__ void vec_stage1(Smem<D>& sm, const int v_in, const in
 #pragma unroll
       for (int nt = 0; nt < 3; ++nt)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int row = r0 + 16 * mt + g + (i >> 1) * 8, col = n0 + 8 * nt + 2 * t + (i & 1);
-          if (col < ncol) sm.Vb[row * D::LDVB + col] = acc[mt][nt][i] * inv;
+        for (int hh = 0; hh < 2; ++hh) {                   // accumulator pairs (c0, c1) / (c2, c3): two adjacent columns
+          const int row = r0 + 16 * mt + g + hh * 8, col = n0 + 8 * nt + 2 * t;
+          if (col < ncol)                                    // col + 1 == ncol: a padding column of the weights, its accumulator is 0
+            *reinterpret_cast<float2*>(sm.Vb + row * D::LDVB + col) = make_float2(acc[mt][nt][2 * hh] * inv, acc[mt][nt][2 * hh + 1] * inv);
         }
   }
   pair_sync(pair);
@@ -148,14 +163,19 @@ __device__ __forceinline__ void vec_stage1(Smem<D>& sm, const int v_in, const in
     const int e = e0 + idx / (VHW / 4), c4 = idx % (VHW / 4);
     const bool okr = e < nvalid;
     const float* b0 = sm.Vb + (e * 3) * D::LDVB + c4 * 4;
+    const float4 pa = *reinterpret_cast<const float4*>(b0), pb = *reinterpret_cast<const float4*>(b0 + D::LDVB),
+                 pc = *reinterpret_cast<const float4*>(b0 + 2 * D::LDVB);
+    const float ra[4] = {pa.x, pa.y, pa.z, pa.w}, rb[4] = {pb.x, pb.y, pb.z, pb.w}, rc[4] = {pc.x, pc.y, pc.z, pc.w};
     float va[4], vb_[4], vc[4], nn[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const bool ok = okr && c4 * 4 + k < hc;
-      va[k] = ok ? b0[k] : 0.f;
-      vb_[k] = ok ? b0[D::LDVB + k] : 0.f;
-      vc[k] = ok ? b0[2 * D::LDVB + k] : 0.f;
-      nn[k] = ok ? norm_no_nan3(va[k], vb_[k], vc[k]) : 0.f;
+      va[k] = ok ? ra[k] : 0.f;
+      vb_[k] = ok ? rb[k] : 0.f;
+      vc[k] = ok ? rc[k] : 0.f;
+      // gvp.py:14-21 sqrt(clamp(x^2 + y^2 + z^2, 1e-8)), square root within 1 ulp (sqrt_pos)
+      const float q = __fadd_rn(__fadd_rn(__fmul_rn(va[k], va[k]), __fmul_rn(vb_[k], vb_[k])), __fmul_rn(vc[k], vc[k]));
+      nn[k] = ok ? sqrt_pos(fmaxf(q, 1e-8f)) : 0.f;
     }
     float4* vh = reinterpret_cast<float4*>(VH + (erow0 + e) * 3 * VHW);
     vh[c4] = make_float4(va[0], va[1], va[2], va[3]);
@@ -206,14 +226,25 @@ __device__ __forceinline__ void vec_stage2(Smem<D>& sm, const int hc, const WH16
     float acc[3][2][4];
     warp_gemm_h16x3<3, 2>(sm.Vb, D::LDVB, r0, wu_sm.hi, wu_sm.lo, WLD_U, n0, (hc + 7) & ~7, acc);
     const float inv = wu_sm.inv;
+    float2 gg[3][2][2];                                      // gates first: all 12 shared-memory loads in flight together
 #pragma unroll
     for (int mt = 0; mt < 3; ++mt)
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int row = r0 + 16 * mt + g + (i >> 1) * 8, col = n0 + 8 * nt + 2 * t + (i & 1);
-          sm.Va[row * D::LDVA + col] = __fmul_rn(sm.G[(row / 3) * 32 + col], acc[mt][nt][i] * inv);
+        for (int hh = 0; hh < 2; ++hh) {
+          const int row = r0 + 16 * mt + g + hh * 8, col = n0 + 8 * nt + 2 * t;
+          gg[mt][nt][hh] = *reinterpret_cast<const float2*>(sm.G + (row / 3) * 32 + col);
+        }
+#pragma unroll
+    for (int mt = 0; mt < 3; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int row = r0 + 16 * mt + g + hh * 8, col = n0 + 8 * nt + 2 * t;
+          *reinterpret_cast<float2*>(sm.Va + row * D::LDVA + col) =
+              make_float2(__fmul_rn(gg[mt][nt][hh].x, acc[mt][nt][2 * hh] * inv), __fmul_rn(gg[mt][nt][hh].y, acc[mt][nt][2 * hh + 1] * inv));
         }
   }
 }
@@ -296,6 +327,7 @@ k_vec_b(const BatchRT bt, const float* __restrict__ wu, int hc_prev, const float
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const size_t erow0 = (size_t)tile * TM;
     const int nvalid = node_rows ? min(TM, bt.N - tile * TM) : EdgeTile<D>(bt, tile).nvalid;
+    if (tile + (int)gridDim.x < n_tiles) prefetch_pair_inputs(VH, GT, (size_t)(tile + gridDim.x) * TM);
     vec_stage2<D>(sm, hc_prev, w_u, erow0, nvalid, VH, GT);
     vec_stage1<D>(sm, D::V, D::V, w_hcp, erow0, nvalid, VH, SH);
   }
@@ -317,6 +349,7 @@ k_vec_c(const ModelRT m, const BatchRT bt, int layer, int first_col /* S when k_
       const int le = et.le0 + tid;
       sm.dst[tid] = le < et.ecount ? et.nb + le / (et.n - 1) : -1;
     }
+    if (tile + (int)gridDim.x < bt.n_edge_tiles) prefetch_pair_inputs(VH, GT, (size_t)(tile + gridDim.x) * TM);
     vec_stage2<D>(sm, D::V + D::CP, w_u, et.erow0, et.nvalid, VH, GT);
     __syncthreads();
     for (int col = first_col + tid; col < D::MW; col += NT) {

@@ -144,13 +144,13 @@ template <class D>
 int set_smem_attrs() {
   const int bytes = (int)D::SMEM_BYTES;
   CUDA_OK(cudaFuncSetAttribute(fm::k_node_embed<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  CUDA_OK(cudaFuncSetAttribute(fm::k_edge_init<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_OK(cudaFuncSetAttribute(fm::k_edge_init<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EdgeSmem<D>::BYTES));
   CUDA_OK(cudaFuncSetAttribute(fm::k_conv_edge<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CUDA_OK(cudaFuncSetAttribute(fm::k_node_update<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CUDA_OK(cudaFuncSetAttribute(fm::k_dst_proj<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CUDA_OK(cudaFuncSetAttribute(fm::k_edge_update<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CUDA_OK(cudaFuncSetAttribute(fm::k_node_head<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  CUDA_OK(cudaFuncSetAttribute(fm::k_edge_head<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  CUDA_OK(cudaFuncSetAttribute(fm::k_edge_head<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EdgeSmem<D>::BYTES));
   if constexpr (D::S == 256 && D::V == 32 && D::SD == 0) {
     CUDA_OK(cudaFuncSetAttribute(fm::k_conv_edge_tc<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::TcPlan<D>::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_tc<D, fm::EG_MSG0, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgPlan<2>::SMEM_BYTES));
@@ -380,7 +380,7 @@ int run_pass(FmHandle* h, void* ws, const Layout& L, const float* x_t, const uin
   fm::k_node_embed<D><<<L.nNT, fm::NT, smem, st>>>(m, bt, x_t, a_t, c_t, t, prev, has_prev, s, v, P);
   LAUNCH_OK(h);
   if (m.use_dst) { fm::k_dst_proj<D><<<L.nNT, fm::NT, smem, st>>>(m, bt, 0, s, v, Q, vd); LAUNCH_OK(h); }
-  fm::k_edge_init<D><<<L.nUT, fm::NT, smem, st>>>(m, bt, x_t, e_t, prev, has_prev, ef);
+  fm::k_edge_init<D><<<L.nUT, fm::NT, fm::EdgeSmem<D>::BYTES, st>>>(m, bt, x_t, e_t, prev, has_prev, ef);
   LAUNCH_OK(h);
   if constexpr (D::S == 256 && D::V == 32 && D::SD == 0 && D::F == 128) {
     if (h->conv_impl == 2 && img_on(h)) {        // entry of the operand-image chain (egemm_p.cuh)
@@ -443,7 +443,7 @@ int run_pass(FmHandle* h, void* ws, const Layout& L, const float* x_t, const uin
   }
   fm::k_node_head<D><<<L.nNT, fm::NT, smem, st>>>(m, bt, s, out.a, out.c);
   LAUNCH_OK(h);
-  fm::k_edge_head<D><<<L.nUT, fm::NT, smem, st>>>(m, bt, ef, out.e);
+  fm::k_edge_head<D><<<L.nUT, fm::NT, fm::EdgeSmem<D>::BYTES, st>>>(m, bt, ef, out.e);
   LAUNCH_OK(h);
   fm::k_com<<<(L.B + 7) / 8, 256, 0, st>>>(bt, x, out.x, remove_com);
   LAUNCH_OK(h);

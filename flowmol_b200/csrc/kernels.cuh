@@ -41,6 +41,30 @@ struct Smem {
   }
 };
 
+// compact plan of the two upper-edge kernels (k_edge_init, k_edge_head): one activation tile [64][2F + R + 12] and a weight stage
+// for F-wide matrices -- 94 KB at flowmol3 instead of the generic 183 KB, i.e. 2 CTAs per SM (these kernels are chains of
+// gather -> GEMM -> GEMM -> store with nothing to overlap inside one CTA)
+template <class D>
+struct EdgeSmem {
+  static constexpr int XE = 2 * D::F + D::R + 12;
+  static constexpr int WST = 2 * KC * D::F;
+  static constexpr int FLOATS = TM * XE + TM + WST + D::SM_MISC;
+  static constexpr size_t BYTES = (size_t)FLOATS * 4;
+  __device__ static Smem<D> carve(float* base) {
+    Smem<D> sm(base);
+    sm.Xs = base;
+    sm.Va = nullptr; sm.Vb = nullptr;
+    sm.G = base + TM * XE;             // [64] scratch
+    sm.wstage = sm.G + TM;
+    float* misc = sm.wstage + WST;
+    sm.src = reinterpret_cast<int*>(misc);
+    sm.dst = sm.src + TM;
+    sm.dist = misc + 2 * TM;
+    sm.aux = reinterpret_cast<int*>(misc + 3 * TM);
+    return sm;
+  }
+};
+
 // rbf(d)_k = exp(-((d - mu_k)/sigma)^2), sigma = dmax / R        (flowmol/utils/embedding.py:19-34)
 __device__ __forceinline__ float rbf_f(float d, float mu, float sigma) {
   const float z = __fdiv_rn(__fsub_rn(d, mu), sigma);
@@ -228,11 +252,12 @@ __global__ void k_edge_table(const ModelRT m, float* __restrict__ table) {
 // k_edge_init: one tile = 64 upper edges (i<j) of one molecule
 // ------------------------------------------------------------------------------------------------------------------
 template <class D>
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(NT, 2)
 k_edge_init(const ModelRT m, const BatchRT bt, const float* __restrict__ x_t, const uint8_t* __restrict__ e_t,
             const PredPtr prev, int has_prev, float* __restrict__ ef) {
   extern __shared__ __align__(16) float smem_raw[];
-  Smem<D> sm(smem_raw);
+  Smem<D> sm = EdgeSmem<D>::carve(smem_raw);
+  constexpr int XE = EdgeSmem<D>::XE, WST = EdgeSmem<D>::WST;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x, mol = bt.utile_mol[tile];
   const int n = bt.mol_n[mol], nb = bt.mol_node[mol], ucount = n * (n - 1) / 2;
@@ -274,12 +299,12 @@ k_edge_init(const ModelRT m, const BatchRT bt, const float* __restrict__ x_t, co
         }
       }
     }
-    sm.Xs[row * D::XLD + c] = v;
+    sm.Xs[row * XE + c] = v;
   }
   float out[1][RPW][D::CPT_F];
   if (has_prev) {
     float acc[1][RPW][D::CPT_F];
-    tile_gemm<1, D::CPT_F>(sm.Xs, D::XLD, 0, KP, m.g(G_SCE0_W), sm.wstage, acc);
+    tile_gemm<1, D::CPT_F, RPW, WST>(sm.Xs, XE, 0, KP, m.g(G_SCE0_W), sm.wstage, acc);
     {
       const float* b = m.g(G_SCE0_B);
 #pragma unroll
@@ -287,24 +312,24 @@ k_edge_init(const ModelRT m, const BatchRT bt, const float* __restrict__ x_t, co
 #pragma unroll
         for (int c = 0; c < D::CPT_F; ++c) {
           const int col = ColMap<D::CPT_F>::col(lane, c);
-          sm.Xs[(warp * RPW + r) * D::XLD + KP + col] = silu_f(acc[0][r][c] + b[col]);
+          sm.Xs[(warp * RPW + r) * XE + KP + col] = silu_f(acc[0][r][c] + b[col]);
         }
     }
-    tile_gemm<1, D::CPT_F>(sm.Xs + KP, D::XLD, 0, D::F, m.g(G_SCE2_W), sm.wstage, acc);
+    tile_gemm<1, D::CPT_F, RPW, WST>(sm.Xs + KP, XE, 0, D::F, m.g(G_SCE2_W), sm.wstage, acc);
     const float* b = m.g(G_SCE2_B);
 #pragma unroll
     for (int r = 0; r < RPW; ++r)
 #pragma unroll
       for (int c = 0; c < D::CPT_F; ++c) {
         const int col = ColMap<D::CPT_F>::col(lane, c);
-        out[0][r][c] = __fadd_rn(sm.Xs[(warp * RPW + r) * D::XLD + col], silu_f(acc[0][r][c] + b[col]));
+        out[0][r][c] = __fadd_rn(sm.Xs[(warp * RPW + r) * XE + col], silu_f(acc[0][r][c] + b[col]));
       }
   } else {
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < RPW; ++r)
 #pragma unroll
-      for (int c = 0; c < D::CPT_F; ++c) out[0][r][c] = sm.Xs[(warp * RPW + r) * D::XLD + ColMap<D::CPT_F>::col(lane, c)];
+      for (int c = 0; c < D::CPT_F; ++c) out[0][r][c] = sm.Xs[(warp * RPW + r) * XE + ColMap<D::CPT_F>::col(lane, c)];
   }
   // mirrored store (self_conditioning.py:79-82)
 #pragma unroll
@@ -785,10 +810,11 @@ k_node_head(const ModelRT m, const BatchRT bt, const float* __restrict__ s, floa
 }
 
 template <class D>
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(NT, 2)
 k_edge_head(const ModelRT m, const BatchRT bt, const float* __restrict__ ef, float* __restrict__ pe) {
   extern __shared__ __align__(16) float smem_raw[];
-  Smem<D> sm(smem_raw);
+  Smem<D> sm = EdgeSmem<D>::carve(smem_raw);
+  constexpr int XE = EdgeSmem<D>::XE, WST = EdgeSmem<D>::WST;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x, mol = bt.utile_mol[tile];
   const int n = bt.mol_n[mol], ucount = n * (n - 1) / 2;
@@ -815,10 +841,10 @@ k_edge_head(const ModelRT m, const BatchRT bt, const float* __restrict__ ef, flo
       const float4 b = *(reinterpret_cast<const float4*>(ef + (ebase + sm.dst[row]) * D::F) + c4);
       val = make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
     }
-    *reinterpret_cast<float4*>(sm.Xs + row * D::XLD + c4 * 4) = val;
+    *reinterpret_cast<float4*>(sm.Xs + row * XE + c4 * 4) = val;
   }
   float acc[1][RPW][D::CPT_F];
-  tile_gemm<1, D::CPT_F>(sm.Xs, D::XLD, 0, D::F, m.g(G_EHEAD0_W), sm.wstage, acc);
+  tile_gemm<1, D::CPT_F, RPW, WST>(sm.Xs, XE, 0, D::F, m.g(G_EHEAD0_W), sm.wstage, acc);
   {
     const float* b = m.g(G_EHEAD0_B);
 #pragma unroll
@@ -826,11 +852,11 @@ k_edge_head(const ModelRT m, const BatchRT bt, const float* __restrict__ ef, flo
 #pragma unroll
       for (int c = 0; c < D::CPT_F; ++c) {
         const int col = ColMap<D::CPT_F>::col(lane, c);
-        sm.Xs[(warp * RPW + r) * D::XLD + col] = silu_f(acc[0][r][c] + b[col]);
+        sm.Xs[(warp * RPW + r) * XE + col] = silu_f(acc[0][r][c] + b[col]);
       }
   }
   float lg[1][RPW][1];
-  tile_gemm<1, 1>(sm.Xs, D::XLD, 0, D::F, m.g(G_EHEAD2_W), sm.wstage, lg);
+  tile_gemm<1, 1, RPW, WST>(sm.Xs, XE, 0, D::F, m.g(G_EHEAD2_W), sm.wstage, lg);
   const int EB = m.EB;
   const float bias = m.g(G_EHEAD2_B)[lane];
 #pragma unroll

@@ -22,6 +22,10 @@ class FmPred(C.Structure):
     _fields_ = [("x", c_vp), ("a", c_vp), ("c", c_vp), ("e", c_vp)]
 
 
+class FmTraj(C.Structure):
+    _fields_ = [("x", c_vp), ("a", c_vp), ("c", c_vp), ("e", c_vp), ("x1", c_vp), ("a1", c_vp), ("c1", c_vp), ("e1", c_vp)]
+
+
 class FmSampleOpts(C.Structure):
     _fields_ = [("n_timesteps", c_i32), ("stochasticity", c_f32), ("high_confidence_threshold", c_f32),
                 ("cat_temperature", c_f32), ("seed", c_u64), ("mol_id_offset", c_i32),
@@ -38,6 +42,7 @@ SYMBOLS = {
     "fm_batch_init": (c_i32, [c_vp, c_vp, c_i32, c_vp, C.c_size_t, c_vp]),
     "fm_forward": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, C.POINTER(FmPred), C.POINTER(FmPred), c_i32, c_vp]),
     "fm_integrate": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.POINTER(FmSampleOpts), c_vp]),
+    "fm_integrate_traj": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.POINTER(FmSampleOpts), C.POINTER(FmTraj), c_vp]),
     "fm_sample_host": (c_i32, [c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, C.POINTER(FmSampleOpts), c_vp, C.c_size_t, c_vp]),
     "fm_workspace_tensor": (c_i32, [c_vp, c_vp, C.c_char_p, C.POINTER(c_vp), C.POINTER(C.c_size_t)]),
     "fm_debug_time_grid": (None, [c_i32, c_vp]),

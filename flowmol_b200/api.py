@@ -43,11 +43,12 @@ class SampledMolecule:
     Decode rules (molecule_builder.py:217-265): atom type = argmax a_1 with fake atoms dropped, charge = argmax c_1 - 2,
     bond order = argmax e_1 on upper-triangle edges with the mask token mapped to 0, zero-order bonds dropped."""
 
-    def __init__(self, x, a_idx, c_idx, e_idx_upper, atom_type_map, fake_atoms=True, explicit_aromaticity=False):
+    def __init__(self, x, a_idx, c_idx, e_idx_upper, atom_type_map, fake_atoms=True, explicit_aromaticity=False,
+                 traj_frames=None, build_xt_traj=True, build_ep_traj=True, align_traj=True, show_fake_atoms=False):
         atom_type_map = list(atom_type_map)
         n = int(x.shape[0])
         keep = np.ones(n, dtype=bool)
-        if fake_atoms:
+        if fake_atoms and not show_fake_atoms:
             keep = a_idx != len(atom_type_map)              # the fake-atom token sits right after the real types
         symbols_all = atom_type_map + (['Sn'] if fake_atoms else []) + ['Se']     # 'Se' marks a still-masked atom
         new_index = np.cumsum(keep) - 1
@@ -63,7 +64,36 @@ class SampledMolecule:
         self.bond_dst_idxs = torch.from_numpy(new_index[iu[1][sel]].astype(np.int64))
         self.num_atoms = int(keep.sum())
         self.atom_type_map = atom_type_map
+        self.fake_atoms, self.explicit_aromaticity, self.align_traj = fake_atoms, explicit_aromaticity, align_traj
         self.rdkit_mol = self.build_molecule()
+        # trajectories (molecule_builder.py:75-84): one decoded frame molecule per step, aligned to the last frame
+        self.traj_frames = traj_frames
+        self.traj_mols, self.ep_traj_mols = None, None
+        if traj_frames is not None:
+            if build_xt_traj:
+                self.traj_mols = self.process_traj_frames(traj_frames)
+            if build_ep_traj and 'x_1_pred' in traj_frames:
+                self.ep_traj_mols = self.process_traj_frames(traj_frames, ep_traj=True)
+
+    def process_traj_frames(self, traj_frames, ep_traj=False):
+        """molecule_builder.py:156-214: every frame decoded like a final molecule, fake atoms shown (as 'Sn'), positions
+        rigidly aligned to the last frame.  Returns SampledMolecule objects (their `.rdkit_mol` is set when rdkit is present)."""
+        sfx = '_1_pred' if ep_traj else ''
+        xs = traj_frames['x' + sfx]
+        x_final = xs[-1].numpy()
+        n = x_final.shape[0]
+        n_up = n * (n - 1) // 2
+        mols = []
+        for k in range(xs.shape[0]):
+            pos = xs[k].numpy()
+            if self.align_traj:
+                pos = rigid_alignment(pos, x_final)
+            a = traj_frames['a' + sfx][k].argmax(-1).numpy()
+            c = traj_frames['c' + sfx][k].argmax(-1).numpy()
+            e = traj_frames['e' + sfx][k][:n_up].argmax(-1).numpy()
+            mols.append(SampledMolecule(pos.astype(np.float32), a, c, e, self.atom_type_map, fake_atoms=self.fake_atoms,
+                                        explicit_aromaticity=self.explicit_aromaticity, show_fake_atoms=True))
+        return mols
 
     def build_molecule(self):
         try:
@@ -90,6 +120,18 @@ class SampledMolecule:
             conf.SetAtomPosition(i, Point3D(*map(float, p)))
         mol.AddConformer(conf)
         return mol
+
+
+def rigid_alignment(x_0, x_1):
+    """Kabsch alignment of x_0 onto x_1 (flowmol/data_processing/priors.py:128-169: R = V U^T from the SVD of x_0c^T x_1c, no
+    reflection correction), numpy [n,3] -> [n,3].  The reference adds `x_0_mean - R x_0_mean` on top, which vanishes for the
+    COM-free frames it is applied to; here the aligned cloud is simply centred on x_1's centroid."""
+    x_0, x_1 = np.asarray(x_0, dtype=np.float64), np.asarray(x_1, dtype=np.float64)
+    m0, m1 = x_0.mean(0, keepdims=True), x_1.mean(0, keepdims=True)
+    a, b = x_0 - m0, x_1 - m1
+    u, _, vt = np.linalg.svd(a.T @ b)
+    rot = vt.T @ u.T
+    return (a @ rot.T + m1).astype(np.float32)
 
 
 class FlowMolB200:
@@ -172,6 +214,25 @@ class FlowMolB200:
         g.edata['e_0'] = one_hot(torch.full((E,), self.n_bond_types), self.n_bond_types + 1).float().to(g.device)
         return g
 
+    def prior_from_x0(self, n_atoms, x_0):
+        """The `prior=` dict of `sample` (flowmol.py:532-545) for given COM-free positions and the all-mask CTMC state --
+        lets a caller that shards one batch over several GPUs draw the positions ONCE for the whole batch and hand every rank
+        its slice (flowmol_b200/cli.py)."""
+        n = torch.as_tensor(n_atoms).long()
+        N, E = int(n.sum()), int((n * (n - 1)).sum())
+        return {'x_0': x_0.float(), 'fake_atoms': self.fake_atoms,
+                'a_0': one_hot(torch.full((N,), self.n_atom_types), self.n_atom_types + 1).float(),
+                'c_0': one_hot(torch.full((N,), 6), 7).float(),
+                'e_0': one_hot(torch.full((E,), self.n_bond_types), self.n_bond_types + 1).float()}
+
+    @staticmethod
+    def centered_normal(n_atoms, generator=None):
+        """COM-free N(0,1) positions for molecules of the given sizes (priors.py:27-35), [sum n, 3] on the CPU."""
+        n = torch.as_tensor(n_atoms).long()
+        x = torch.randn(int(n.sum()), 3, generator=generator)
+        nbi = torch.arange(len(n)).repeat_interleave(n)
+        return x - (torch.zeros(len(n), 3).index_add_(0, nbi, x) / n[:, None].float())[nbi]
+
     @torch.no_grad()
     def sample(self, n_atoms, n_timesteps=None, device="cuda:0", stochasticity=None, high_confidence_threshold=None,
                xt_traj=False, ep_traj=False, prior=None, **kwargs):
@@ -179,8 +240,7 @@ class FlowMolB200:
             self._materialise(device)
         if n_timesteps is None:
             n_timesteps = self.default_n_timesteps
-        if xt_traj or ep_traj:
-            raise NotImplementedError("trajectory capture (xt_traj / ep_traj) is not implemented yet")
+        visualize = bool(xt_traj or ep_traj)                                                   # flowmol.py:497
         dev = self.vector_field.device
         g = MolGraphBatch(torch.as_tensor(n_atoms).cpu(), device=dev)
         if prior is None:
@@ -194,9 +254,10 @@ class FlowMolB200:
             elif not prior['fake_atoms'] and self.fake_atoms:
                 a0 = torch.cat([torch.zeros(a0.shape[0], 1, device=dev), a0], dim=-1)
             g.ndata['a_0'] = a0
-        g = self.vector_field.integrate(g, g.node_batch_idx(), upper_edge_mask=g.upper_edge_mask(), n_timesteps=n_timesteps,
-                                        visualize=False, stochasticity=stochasticity,
-                                        high_confidence_threshold=high_confidence_threshold, **kwargs)
+        itg = self.vector_field.integrate(g, g.node_batch_idx(), upper_edge_mask=g.upper_edge_mask(), n_timesteps=n_timesteps,
+                                          visualize=visualize, stochasticity=stochasticity,
+                                          high_confidence_threshold=high_confidence_threshold, **kwargs)
+        g, traj_frames = itg if visualize else (itg, None)                                     # flowmol.py:559-562
         g.edata['ue_mask'] = g.upper_edge_mask()
         g = g.to('cpu')                                                                        # flowmol.py:564 (device -> host)
         uem = g.edata['ue_mask']
@@ -206,11 +267,13 @@ class FlowMolB200:
         e_idx = g.edata['e_1'].argmax(-1).numpy()
         x = g.ndata['x_1'].numpy()
         uem = uem.numpy()
-        for n in g.n_atoms.tolist():
+        for mi, n in enumerate(g.n_atoms.tolist()):
             e = n * (n - 1)
             mols.append(SampledMolecule(x[no:no + n], a_idx[no:no + n], c_idx[no:no + n], e_idx[eo:eo + e][uem[eo:eo + e]],
                                         self.atom_type_map, fake_atoms=self.fake_atoms,
-                                        explicit_aromaticity=self.explicit_aromaticity))
+                                        explicit_aromaticity=self.explicit_aromaticity,
+                                        traj_frames=traj_frames[mi] if visualize else None,
+                                        build_xt_traj=xt_traj, build_ep_traj=ep_traj))
             no += n
             eo += e
         return mols

@@ -630,6 +630,11 @@ int fm_forward(FmHandle* h, void* ws, const float* x_t, const uint8_t* a_t, cons
 }
 
 int fm_integrate(FmHandle* h, void* ws, float* x, uint8_t* a, uint8_t* c, uint8_t* e, const FmSampleOpts* o, void* stream) {
+  return fm_integrate_traj(h, ws, x, a, c, e, o, nullptr, stream);
+}
+
+int fm_integrate_traj(FmHandle* h, void* ws, float* x, uint8_t* a, uint8_t* c, uint8_t* e, const FmSampleOpts* o,
+                      const FmTraj* traj, void* stream) {
   if (!h || !ws || !x || !a || !c || !e || !o) return fail("fm_integrate: null argument");
   if (o->n_timesteps < 2) return fail("fm_integrate: n_timesteps must be >= 2");
   const Layout* Lp;
@@ -649,6 +654,12 @@ int fm_integrate(FmHandle* h, void* ws, float* x, uint8_t* a, uint8_t* c, uint8_
     if (!h->cap_stream) CUDA_OK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
     st = h->cap_stream;
     CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  }
+  if (traj) {                                                     // frame 0 = the prior (ctmc_vector_field.py:187-202)
+    if (traj->x) CUDA_OK(cudaMemcpyAsync(traj->x, x, sizeof(float) * 3 * L.N, cudaMemcpyDeviceToDevice, st));
+    if (traj->a) CUDA_OK(cudaMemcpyAsync(traj->a, a, L.N, cudaMemcpyDeviceToDevice, st));
+    if (traj->c) CUDA_OK(cudaMemcpyAsync(traj->c, c, L.N, cudaMemcpyDeviceToDevice, st));
+    if (traj->e && L.U > 0) CUDA_OK(cudaMemcpyAsync(traj->e, e, L.U, cudaMemcpyDeviceToDevice, st));
   }
   int rc = 0;
   for (int k = 1; k < T && rc == 0; ++k) {                        // ctmc_vector_field.py:205-232
@@ -675,7 +686,19 @@ int fm_integrate(FmHandle* h, void* ws, float* x, uint8_t* a, uint8_t* c, uint8_
     sc.seed_lo = (uint32_t)(o->seed & 0xffffffffull);
     sc.seed_hi = (uint32_t)(o->seed >> 32);
     sc.mol_id_offset = o->mol_id_offset;
-    fm::k_ctmc_step<<<L.B, 256, 0, st>>>(bt, h->rt.A, h->rt.C, h->rt.EB, cur.x, cur.a, cur.c, cur.e, x, a, c, e, sc);
+    fm::TrajFrame tf{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (traj) {                                                   // frame k of the state, frame k - 1 of the endpoint predictions
+      const size_t N = (size_t)L.N, U = (size_t)L.U;
+      if (traj->x) tf.x = traj->x + (size_t)k * N * 3;
+      if (traj->a) tf.a = traj->a + (size_t)k * N;
+      if (traj->c) tf.c = traj->c + (size_t)k * N;
+      if (traj->e) tf.e = traj->e + (size_t)k * U;
+      if (traj->x1) tf.x1 = traj->x1 + (size_t)(k - 1) * N * 3;
+      if (traj->a1) tf.a1 = traj->a1 + (size_t)(k - 1) * N;
+      if (traj->c1) tf.c1 = traj->c1 + (size_t)(k - 1) * N;
+      if (traj->e1) tf.e1 = traj->e1 + (size_t)(k - 1) * U;
+    }
+    fm::k_ctmc_step<<<L.B, 256, 0, st>>>(bt, h->rt.A, h->rt.C, h->rt.EB, cur.x, cur.a, cur.c, cur.e, x, a, c, e, sc, tf);
     ++h->launches;
     if (cudaGetLastError() != cudaSuccess) rc = fail("k_ctmc_step launch failed");
   }

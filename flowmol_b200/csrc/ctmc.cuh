@@ -46,9 +46,11 @@ __device__ __forceinline__ int block_sum_int(int v, int* scratch /*NWARP ints*/)
 }
 
 // one modality of one molecule: `cnt` items, categories K (mask index == K)
+// `frame` / `x1_frame` (optional): this step's trajectory frames of the new state and of the sampled endpoint x1
+// (the reference's `<feat>_t` and `<feat>_1_pred` after the step, ctmc_vector_field.py:408-409 / 235-255)
 __device__ __forceinline__ void campbell_modality(const float* __restrict__ phat /*[cnt][K]*/, uint8_t* __restrict__ state,
                                                   int cnt, int K, int modality, uint32_t mol_gid, const StepScalars& sc,
-                                                  int* scratch) {
+                                                  int* scratch, uint8_t* __restrict__ frame, uint8_t* __restrict__ x1_frame) {
   const float q_u = sc.unmask_prob[modality], q_m = sc.mask_prob[modality];
   float p[KMAXC];
   // pass 1: per-molecule counts of masked / high-confidence masked items      (ctmc_utils.py:6-18)
@@ -91,13 +93,24 @@ __device__ __forceinline__ void campbell_modality(const float* __restrict__ phat
     if (!sc.last_step && (u24(rnd.z) < q_m) && !masked) zn = K;
     if (will_unmask) zn = x1;
     state[it] = (uint8_t)zn;
+    if (frame) frame[it] = (uint8_t)zn;
+    if (x1_frame) x1_frame[it] = (uint8_t)x1;
   }
 }
+
+// per-step trajectory frames (device pointers of THIS step's frame, any may be null)
+struct TrajFrame {
+  float* x;                 // [N,3] positions after the step
+  uint8_t *a, *c, *e;       // token state after the step ([N], [N], [U])
+  float* x1;                // [N,3] predicted endpoint positions (x_1_pred)
+  uint8_t *a1, *c1, *e1;    // sampled endpoint tokens (a/c/e_1_pred)
+};
 
 __global__ void __launch_bounds__(256)
 k_ctmc_step(const BatchRT bt, int A, int C, int EB, const float* __restrict__ px, const float* __restrict__ pa,
             const float* __restrict__ pc, const float* __restrict__ pe, float* __restrict__ x_t,
-            uint8_t* __restrict__ a_t, uint8_t* __restrict__ c_t, uint8_t* __restrict__ e_t, const StepScalars sc) {
+            uint8_t* __restrict__ a_t, uint8_t* __restrict__ c_t, uint8_t* __restrict__ e_t, const StepScalars sc,
+            const TrajFrame tf) {
   __shared__ int scratch[32];
   const int mol = blockIdx.x;
   const int n = bt.mol_n[mol], nb = bt.mol_node[mol], ub = bt.mol_u[mol], ucount = n * (n - 1) / 2;
@@ -106,12 +119,15 @@ k_ctmc_step(const BatchRT bt, int A, int C, int EB, const float* __restrict__ px
   for (int i = threadIdx.x; i < n * 3; i += blockDim.x) {
     const int g = nb * 3 + i;
     const float vf = __fmul_rn(coef, __fsub_rn(px[g], x_t[g]));
-    x_t[g] = __fadd_rn(x_t[g], __fmul_rn(sc.dt, vf));
+    const float xn = __fadd_rn(x_t[g], __fmul_rn(sc.dt, vf));
+    x_t[g] = xn;
+    if (tf.x) tf.x[g] = xn;
+    if (tf.x1) tf.x1[g] = px[g];
   }
   const uint32_t gid = (uint32_t)(mol + sc.mol_id_offset);
-  campbell_modality(pa + (size_t)nb * A, a_t + nb, n, A, 0, gid, sc, scratch);
-  campbell_modality(pc + (size_t)nb * C, c_t + nb, n, C, 1, gid, sc, scratch);
-  campbell_modality(pe + (size_t)ub * EB, e_t + ub, ucount, EB, 2, gid, sc, scratch);
+  campbell_modality(pa + (size_t)nb * A, a_t + nb, n, A, 0, gid, sc, scratch, tf.a ? tf.a + nb : nullptr, tf.a1 ? tf.a1 + nb : nullptr);
+  campbell_modality(pc + (size_t)nb * C, c_t + nb, n, C, 1, gid, sc, scratch, tf.c ? tf.c + nb : nullptr, tf.c1 ? tf.c1 + nb : nullptr);
+  campbell_modality(pe + (size_t)ub * EB, e_t + ub, ucount, EB, 2, gid, sc, scratch, tf.e ? tf.e + ub : nullptr, tf.e1 ? tf.e1 + ub : nullptr);
 }
 
 }  // namespace fm

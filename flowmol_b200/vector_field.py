@@ -189,8 +189,12 @@ class CTMCVectorFieldB200:
         return o, ts
 
     def integrate_tokens(self, n_atoms, x0, a0, c0, e0_upper, n_timesteps, seed, stochasticity=None,
-                         high_confidence_threshold=None, mol_id_offset=0, tspan=None, cuda_graph=False):
-        """Full trajectory on device-resident token state; returns final {'x','a','c','e'} (new tensors)."""
+                         high_confidence_threshold=None, mol_id_offset=0, tspan=None, cuda_graph=False, traj=False):
+        """Full trajectory on device-resident token state; returns final {'x','a','c','e'} (new tensors).
+        traj=True also returns, under 'traj', the per-step frames the reference collects with visualize=True
+        (ctmc_vector_field.py:187-202,235-255) as device tensors: 'x' f32 [T,N,3], 'a','c' u8 [T,N], 'e' u8 [T,U] (frame 0 = the
+        prior) and the endpoint frames 'x_1_pred' f32 [T-1,N,3], 'a_1_pred','c_1_pred' u8 [T-1,N], 'e_1_pred' u8 [T-1,U]
+        (tokens sampled by campbell_step) -- written by the step kernel itself, no host round trips."""
         n = self._prepare(n_atoms)
         dev = self.device
         x = x0.to(dev, torch.float32).contiguous().clone()
@@ -198,12 +202,49 @@ class CTMCVectorFieldB200:
         c = c0.to(dev, torch.uint8).contiguous().clone()
         e = e0_upper.to(dev, torch.uint8).contiguous().clone()
         o, ts = self._opts(n_timesteps, stochasticity, high_confidence_threshold, seed, mol_id_offset, tspan, cuda_graph)
+        frames, tr = None, None
+        if traj:
+            T, N, U = len(ts), x.shape[0], e.shape[0]
+            u8 = dict(dtype=torch.uint8, device=dev)
+            frames = {'x': torch.empty(T, N, 3, device=dev), 'a': torch.empty(T, N, **u8), 'c': torch.empty(T, N, **u8),
+                      'e': torch.empty(T, U, **u8), 'x_1_pred': torch.empty(T - 1, N, 3, device=dev),
+                      'a_1_pred': torch.empty(T - 1, N, **u8), 'c_1_pred': torch.empty(T - 1, N, **u8),
+                      'e_1_pred': torch.empty(T - 1, U, **u8)}
+            tr = _lib.FmTraj(x=frames['x'].data_ptr(), a=frames['a'].data_ptr(), c=frames['c'].data_ptr(), e=frames['e'].data_ptr(),
+                             x1=frames['x_1_pred'].data_ptr(), a1=frames['a_1_pred'].data_ptr(),
+                             c1=frames['c_1_pred'].data_ptr(), e1=frames['e_1_pred'].data_ptr())
         with torch.cuda.device(dev):
-            _lib.check(self.lib.fm_integrate(self._h, self._ws.data_ptr(), x.data_ptr(), a.data_ptr(), c.data_ptr(),
-                                             e.data_ptr(), C.byref(o), self._stream()))
+            _lib.check(self.lib.fm_integrate_traj(self._h, self._ws.data_ptr(), x.data_ptr(), a.data_ptr(), c.data_ptr(),
+                                                  e.data_ptr(), C.byref(o), C.byref(tr) if tr is not None else None,
+                                                  self._stream()))
         self.last_launches = int(self.lib.fm_last_launch_count(self._h))
         self.check_status()
-        return {'x': x, 'a': a, 'c': c, 'e': e}
+        out = {'x': x, 'a': a, 'c': c, 'e': e}
+        if traj:
+            out['traj'] = frames
+        return out
+
+    def _traj_frames_per_molecule(self, n_atoms, frames):
+        """Device frames -> the reference's `reshaped_traj_frames` (ctmc_vector_field.py:268-283): one dict per molecule,
+        '<feat>' [T, n, K+1] / '<feat>_1_pred' [T-1, ...] one-hot floats on the CPU, 'x' / 'x_1_pred' [.., n, 3]; edge frames carry
+        both directions in the reference's edge order (upper triangle, then its mirror: data_processing/utils.py:4-17)."""
+        n = np.asarray(n_atoms, dtype=np.int64)
+        noff = np.concatenate([[0], np.cumsum(n)])
+        uoff = np.concatenate([[0], np.cumsum(n * (n - 1) // 2)])
+        host = {k: v.cpu() for k, v in frames.items()}
+        kdim = {'a': self.n_atom_types + 1, 'c': self.n_charges + 1, 'e': self.n_bond_types + 1}
+        out = []
+        for i in range(len(n)):
+            d = {}
+            for key in ('x', 'x_1_pred'):
+                d[key] = host[key][:, noff[i]:noff[i + 1]].clone()
+            for f in 'ace':
+                lo, hi = (uoff[i], uoff[i + 1]) if f == 'e' else (noff[i], noff[i + 1])
+                for key in (f, f + '_1_pred'):
+                    oh = one_hot(host[key][:, lo:hi].long(), kdim[f]).float()
+                    d[key] = torch.cat([oh, oh], dim=1) if f == 'e' else oh
+            out.append(d)
+        return out
 
     def sample_host(self, n_atoms, x0, a0, c0, e0_upper, n_timesteps, seed, stochasticity=None,
                     high_confidence_threshold=None, mol_id_offset=0, tspan=None, cuda_graph=False):
@@ -251,14 +292,12 @@ class CTMCVectorFieldB200:
                   dfm_type='campbell', stochasticity=None, high_confidence_threshold=None, cat_temp_func=None,
                   forward_weight_func=None, tspan=None, seed=None, mol_id_offset=0, cuda_graph=False, **kwargs):
         """CTMCVectorField.integrate (ctmc_vector_field.py:145-285): reads x_0/a_0/c_0/e_0 from the graph, writes
-        x_1/a_1/c_1/e_1 (and *_t).  `seed` selects the Philox noise stream (default: drawn from torch's global RNG so
+        x_1/a_1/c_1/e_1 (and *_t); with visualize=True returns (g, per-molecule trajectory frames) like the reference.  `seed` selects the Philox noise stream (default: drawn from torch's global RNG so
         `torch.manual_seed` / seed_everything still controls reproducibility, cf. test.py:70-71)."""
         if dfm_type not in (None, 'campbell'):
             raise NotImplementedError("only dfm_type='campbell' (the reference default) is implemented")
         if cat_temp_func is not None or forward_weight_func is not None or kwargs.get('inv_temp_func') is not None:
             raise NotImplementedError("custom temperature / forward-weight schedules are not implemented")
-        if visualize:
-            raise NotImplementedError("trajectory capture (xt_traj / ep_traj) is not implemented yet")
         if n_timesteps is None and tspan is None:
             raise ValueError("n_timesteps is required")
         n_atoms = n_atoms_of(g)
@@ -269,7 +308,7 @@ class CTMCVectorFieldB200:
         uem_d = uem.to(e0.device)
         out = self.integrate_tokens(n_atoms, g.ndata['x_0'], g.ndata['a_0'].argmax(-1), g.ndata['c_0'].argmax(-1),
                                     e0[uem_d].argmax(-1), n_timesteps, seed, stochasticity, high_confidence_threshold,
-                                    mol_id_offset, tspan, cuda_graph)
+                                    mol_id_offset, tspan, cuda_graph, traj=bool(visualize))
         a1 = one_hot(out['a'].long(), self.n_atom_types + 1).float()
         c1 = one_hot(out['c'].long(), self.n_charges + 1).float()
         eu = one_hot(out['e'].long(), self.n_bond_types + 1).float()
@@ -282,6 +321,8 @@ class CTMCVectorFieldB200:
             g.ndata[f'{k}_1'] = val
         g.edata['e_t'] = e1
         g.edata['e_1'] = e1
+        if visualize:                                                 # ctmc_vector_field.py:265-283
+            return g, self._traj_frames_per_molecule(n_atoms, out['traj'])
         return g
 
 

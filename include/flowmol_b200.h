@@ -68,6 +68,19 @@ typedef struct FmSampleOpts {
   int32_t use_cuda_graph;    /* capture the per-step launch sequence once and replay it */
 } FmSampleOpts;
 
+typedef struct FmTraj {      /* optional per-step frames, device memory owned by the caller; any pointer may be NULL.
+                              * The reference collects these on the host every step (ctmc_vector_field.py:187-202,235-255); here
+                              * the step kernel writes them as it goes, no extra launches or host round trips. */
+  float* x;                  /* [T,N,3]  positions: frame 0 = x_0, frame k = x_t after step k */
+  uint8_t* a;                /* [T,N]    atom-type tokens */
+  uint8_t* c;                /* [T,N]    charge tokens */
+  uint8_t* e;                /* [T,U]    bond tokens (upper edges) */
+  float* x1;                 /* [T-1,N,3] predicted endpoint positions of every step (x_1_pred) */
+  uint8_t* a1;               /* [T-1,N]   endpoint tokens sampled in campbell_step (a_1_pred) */
+  uint8_t* c1;               /* [T-1,N] */
+  uint8_t* e1;               /* [T-1,U] */
+} FmTraj;
+
 int fm_abi_version(void);
 const char* fm_last_error(void);
 
@@ -91,6 +104,10 @@ int fm_forward(FmHandle* h, void* workspace, const float* x_t, const uint8_t* a_
 /* full trajectory: state arrays are updated in place from (x_0, a_0, c_0, e_0) to (x_1, a_1, c_1, e_1) */
 int fm_integrate(FmHandle* h, void* workspace, float* x, uint8_t* a, uint8_t* c, uint8_t* e_upper,
                  const FmSampleOpts* opts, void* stream);
+
+/* same with trajectory capture (`traj` may be NULL): replaces integrate(..., visualize=True), ctmc_vector_field.py:145-285 */
+int fm_integrate_traj(FmHandle* h, void* workspace, float* x, uint8_t* a, uint8_t* c, uint8_t* e_upper,
+                      const FmSampleOpts* opts, const FmTraj* traj, void* stream);
 
 /* host-to-host convenience: H2D of the prior, fm_batch_init, fm_integrate, D2H of the result (synchronous) */
 int fm_sample_host(FmHandle* h, const int32_t* n_atoms_host, int32_t n_molecules, float* x_host, uint8_t* a_host,

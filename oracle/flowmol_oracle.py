@@ -369,7 +369,7 @@ def integrate(model, bt, x0, a0, c0, e0_upper, n_timesteps, seed, eta=None, hc_t
         alpha_t, alpha_tp = t_i, torch.ones(())
         vf = alpha_tp / (1 - alpha_t) * (dst['x'] - x_t)              # vector_field.py:567-569
         x_t = x_t + dt * vf * 1.0
-        new = {}
+        new, sampled = {}, {}
         for m, (name, cur, items, mols, item_mol, counts, mask_index) in enumerate((
                 ('a', a_t, node_item, node_mol, bt.node_mol, bt.n_atoms, model.A),
                 ('c', c_t, node_item, node_mol, bt.node_mol, bt.n_atoms, model.C),
@@ -378,9 +378,11 @@ def integrate(model, bt, x0, a0, c0, e0_upper, n_timesteps, seed, eta=None, hc_t
             u3 = tuple(torch.from_numpy(u) for u in philox.uniforms(items, mols, s_idx, m, seed))
             new[name], x1s = campbell_step(p, cur, eta, hc_thresh, alpha_t, alpha_tp, dt, counts, item_mol,
                                            mask_index, last, u3)
+            sampled[name] = x1s                                          # the reference's `<feat>_1_pred` (:408-409)
         a_t, c_t, e_t = new['a'], new['c'], new['e']
         prev = dst
         if record is not None:
             record.append({'x': x_t.clone(), 'a': a_t.clone(), 'c': c_t.clone(), 'e': e_t.clone(),
-                           'x1': dst['x'].clone(), 'pa': dst['a'].clone(), 'pc': dst['c'].clone(), 'pe': dst['e'].clone()})
+                           'x1': dst['x'].clone(), 'pa': dst['a'].clone(), 'pc': dst['c'].clone(), 'pe': dst['e'].clone(),
+                           'a1': sampled['a'].clone(), 'c1': sampled['c'].clone(), 'e1': sampled['e'].clone()})
     return {'x': x_t, 'a': a_t, 'c': c_t, 'e': e_t}

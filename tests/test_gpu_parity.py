@@ -147,6 +147,56 @@ def test_trajectory_vs_oracle_fresh_inputs():
         assert (got["a"] != A).all() and (got["c"] != 6).all() and (got["e"] != 4).all()
 
 
+def test_trajectory_frames_vs_oracle_every_step():
+    """fm_integrate_traj: the frames the step kernel writes (state after every step, predicted endpoint positions, endpoint
+    tokens sampled by campbell_step) against the oracle's per-step record; the capture must not change the result."""
+    cfg_name, A, n_atoms, T = "dev", 6, [6, 2, 17, 3], 16
+    cfg, vf = cuda_model(cfg_name, A, 33)
+    om = O.OracleModel(cfg, WT.init_state_dict(cfg, 33))
+    bt = O.make_batch(n_atoms)
+    x0 = torch.randn(bt.N, 3, generator=torch.Generator().manual_seed(11))
+    a0, c0, e0 = torch.full((bt.N,), A), torch.full((bt.N,), 6), torch.full((bt.U,), 4)
+    rec = []
+    with torch.no_grad():
+        want = O.integrate(om, bt, x0, a0, c0, e0, T, seed=77, record=rec)
+    got = vf.integrate_tokens(n_atoms, x0, a0, c0, e0, T, seed=77, traj=True)
+    plain = vf.integrate_tokens(n_atoms, x0, a0, c0, e0, T, seed=77)
+    assert all(torch.equal(got[k], plain[k]) for k in "xace")
+    fr = {k: v.cpu() for k, v in got["traj"].items()}
+    assert fr["x"].shape == (T, bt.N, 3) and fr["e"].shape == (T, bt.U) and fr["x_1_pred"].shape == (T - 1, bt.N, 3)
+    assert torch.equal(fr["x"][0], x0) and (fr["a"][0] == A).all() and (fr["e"][0] == 4).all()
+    for k, r in enumerate(rec):
+        for f in "ace":
+            assert torch.equal(fr[f][k + 1].long(), r[f]), (k, f)
+            assert torch.equal(fr[f + "_1_pred"][k].long(), r[f + "1"]), (k, f, "endpoint")
+        assert (fr["x"][k + 1] - r["x"]).abs().max() <= 1e-4 and (fr["x_1_pred"][k] - r["x1"]).abs().max() <= 1e-4
+    assert torch.equal(fr["x"][-1], got["x"].cpu()) and torch.equal(fr["a"][-1], got["a"].cpu())
+
+
+def test_reference_api_trajectories_xt_ep():
+    """model.sample(..., xt_traj=True, ep_traj=True): per-molecule frames in the reference's layout (ctmc_vector_field.py:268-283)
+    and decoded frame molecules (molecule_builder.py:75-84,156-214)."""
+    import flowmol_b200 as flowmol
+    model = flowmol.FlowMolB200.from_config("dev", dataset="qm9", seed=3).cuda().eval()
+    torch.manual_seed(1)
+    n_atoms, T = torch.tensor([5, 9, 3]), 12
+    mols = model.sample(n_atoms, n_timesteps=T, xt_traj=True, ep_traj=True)
+    torch.manual_seed(1)
+    plain = model.sample(n_atoms, n_timesteps=T)
+    for m, q, n in zip(mols, plain, n_atoms.tolist()):
+        assert torch.equal(m.positions, q.positions) and m.atom_types == q.atom_types       # capture changes nothing
+        tf = m.traj_frames
+        assert tf["x"].shape == (T, n, 3) and tf["a"].shape == (T, n, model.n_atom_types + 1) and tf["c"].shape == (T, n, 7)
+        assert tf["e"].shape == (T, n * (n - 1), 5) and tf["x_1_pred"].shape == (T - 1, n, 3)
+        assert tf["e_1_pred"].shape == (T - 1, n * (n - 1), 5)
+        assert torch.equal(tf["e"][:, :n * (n - 1) // 2], tf["e"][:, n * (n - 1) // 2:])       # both triangles agree
+        assert (tf["a"][0].argmax(-1) == model.n_atom_types).all()                             # frame 0 = the all-mask prior
+        assert len(m.traj_mols) == T and len(m.ep_traj_mols) == T - 1
+        assert m.traj_mols[-1].num_atoms == n                                                    # fake atoms are shown in frames
+    only_xt = model.sample(n_atoms, n_timesteps=T, xt_traj=True)
+    assert only_xt[0].traj_mols is not None and only_xt[0].ep_traj_mols is None
+
+
 def test_results_do_not_depend_on_batch_composition_or_sharding():
     """Per-molecule Philox noise + molecule-aligned tiles => bit-identical molecules however the batch is cut."""
     cfg, vf = cuda_model("flowmol3", 11, 41)

@@ -178,3 +178,57 @@ def test_lightning_checkpoint_ingestion_and_molecule_decode(tmp_path):
     assert m.atom_types == ['C', 'O', 'H'] and m.atom_charges.tolist() == [0, 1, -1] and m.num_atoms == 3
     assert m.bond_types.tolist() == [1] and m.bond_src_idxs.tolist() == [0] and m.bond_dst_idxs.tolist() == [1]
     assert torch.equal(m.positions, torch.from_numpy(x[[0, 1, 3]]))
+
+
+def test_cli_batch_planner_is_cost_aware_and_complete():
+    """flowmol_b200/cli.py:plan_batches (the batch loop of the reference's test.py:99-133, made size-aware)."""
+    from flowmol_b200.cli import plan_batches
+    rng = np.random.default_rng(0)
+    n = rng.integers(3, 182, size=500)
+    for mbs, mbe in ((128, 4_000_000), (32, 60_000), (500, 10 ** 9), (7, 100)):
+        batches = plan_batches(n, mbs, mbe)
+        flat = np.concatenate(batches)
+        assert sorted(flat.tolist()) == list(range(len(n)))                      # every molecule exactly once
+        for b in batches:
+            edges = int((n[b] * (n[b] - 1)).sum())
+            assert len(b) <= mbs and (edges <= mbe or len(b) == 1)                 # an oversized molecule gets its own batch
+        sizes = [int(n[b].max()) for b in batches]
+        assert sizes == sorted(sizes, reverse=True)                                # large molecules first, similar sizes together
+    assert len(plan_batches(n, 500, 10 ** 9)) == 1
+
+
+def test_cli_sdf_writer_and_trajectory_frame_decode(tmp_path):
+    """V2000 mol blocks from the decoded arrays (no rdkit needed), the reference's trajectory-frame layout decoded per frame
+    (molecule_builder.py:156-214) and its Kabsch alignment (priors.py:128-169)."""
+    from flowmol_b200.api import SampledMolecule, rigid_alignment
+    from flowmol_b200.cli import mol_block, write_sdf
+    amap = ['C', 'H', 'N', 'O', 'F']
+    x = np.array([[0.0, 0.0, 0.0], [1.1, 0.0, 0.0], [0.0, 1.2, 0.0], [5.0, 5.0, 5.0]], np.float32)
+    a = np.array([0, 3, 2, 5])                 # last atom: the fake-atom token -> dropped
+    c = np.array([2, 1, 3, 2])                 # charges 0, -1, +1
+    e = np.array([2, 1, 0, 0, 4, 0])           # upper edges (0,1) double, (0,2) single, (1,2) still masked -> no bond
+    m = SampledMolecule(x, a, c, e, amap, fake_atoms=True)
+    assert m.atom_types == ['C', 'O', 'N'] and m.atom_charges.tolist() == [0, -1, 1]
+    assert m.bond_types.tolist() == [2, 1] and m.bond_src_idxs.tolist() == [0, 0] and m.bond_dst_idxs.tolist() == [1, 2]
+    blk = mol_block(m, "t").split("\n")
+    assert blk[3].startswith("  3  2") and blk[3].endswith("V2000")
+    assert blk[4].split()[3] == 'C' and blk[7].split() == ['1', '2', '2', '0'] and blk[8].split() == ['1', '3', '1', '0']
+    assert blk[9].split() == ['M', 'CHG', '2', '2', '-1', '3', '1'] and blk[-1] == "M  END"
+    write_sdf(tmp_path / "o.sdf", [m, m])
+    assert (tmp_path / "o.sdf").read_text().count("$$$$") == 2
+    # alignment: a rotated + shifted copy comes back onto the target
+    th = 0.7
+    R = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]])
+    y = x @ R.T + np.array([1.0, -2.0, 0.5])
+    assert np.abs(rigid_alignment(y, x) - x).max() < 1e-5
+    # trajectory frames in the reference layout: one-hot floats, edges in both directions
+    T, n = 3, 4
+    oh = lambda idx, k: torch.nn.functional.one_hot(torch.as_tensor(idx), k).float()
+    frames = {'x': torch.from_numpy(np.stack([x + k for k in range(T)])), 'a': torch.stack([oh(a, 7)] * T),
+              'c': torch.stack([oh(c, 7)] * T), 'e': torch.stack([torch.cat([oh(e, 5), oh(e, 5)])] * T),
+              'x_1_pred': torch.from_numpy(np.stack([x] * (T - 1))), 'a_1_pred': torch.stack([oh(a, 7)] * (T - 1)),
+              'c_1_pred': torch.stack([oh(c, 7)] * (T - 1)), 'e_1_pred': torch.stack([torch.cat([oh(e, 5), oh(e, 5)])] * (T - 1))}
+    mt = SampledMolecule(x, a, c, e, amap, fake_atoms=True, traj_frames=frames)
+    assert len(mt.traj_mols) == T and len(mt.ep_traj_mols) == T - 1
+    assert mt.traj_mols[0].atom_types == ['C', 'O', 'N', 'Sn']                    # fake atoms are shown in trajectory frames
+    assert np.abs(mt.traj_mols[0].positions.numpy() - (x + T - 1)).max() < 1e-4   # every frame is aligned onto the last one

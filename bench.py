@@ -12,7 +12,8 @@ NCCL gather of the results to rank 0, inside the timed region.
 
 Printed JSON line (rank 0): metric/value/unit/..., `e2e` (same metric through fm_sample_host with pinned HOST buffers:
 H2D of the prior + batch descriptor + trajectory + D2H of the result inside the timed region), `roofline` for the dominant
-kernel (k_conv_edge, timed live with CUDA events on its stream), `cpu_baseline` (the CPU oracle port on a bounded sample),
+kernel (k_egemm_p: HBM-bound, timed live with CUDA events on its stream, per-mode numbers from in-pipeline events),
+`cpu_baseline` (the CPU oracle port on a bounded sample),
 `clocks`, `gpu_launches`.
 """
 import argparse
@@ -281,27 +282,47 @@ def main():
     ms_pass = vf.time_conv_edge(layer=1, iters=3)
     prec = vf.get_option("tc_prec") if impl == 2 else 0
     if impl == 2:
-        # default flowmol3 pipeline: the dominant kernel is k_egemm_tc (7 modes, ~60 % of a step); its 292 -> 256 message
-        # linear is timed alone.  Algorithmic work = the reference's 2*292*256 FLOP per edge; executed on the tensor cores as
-        # three MMAs per fp32 product (hi*hi + lo*hi + hi*lo) on fp16 (default) or TF32 operands, so the attainable ceiling of
-        # this kernel is a third of the operand format's dense peak -- stated, not hidden.
+        # Default flowmol3 pipeline.  The dominant kernel is k_egemm_p (persistent tcgen05 linear, 7 modes, ~53 % of a step); with
+        # the fp16 (hi, lo) operand-image hand-over its modes are HBM-bound: roofline = algorithmic bytes of the mode (the fp32
+        # rows the linear must read and write per edge) / live CUDA-event time /
+        # measured HBM peak.  Headline entry: the 292 -> 256 message linear (EG_MSG; EG_MSGA is the same linear + segment-sum),
+        # timed alone on its own stream; every mode's in-pipeline time comes from fm_debug_kprof events of one warm evaluation.
         ms_k = vf.time_egemm_msg(layer=1, iters=5)
-        flops = 2 * 292 * 256 * E
-        achieved = flops / (ms_k * 1e-3) / 1e12
-        hbm_bytes = E * (292 + 256) * 4
         hbm_peak = peaks.get("hbm_gbs") or 6650.0
-        op_peak, op_name = (bf16, "dense fp16/bf16 tensor") if prec == 1 else (tf32_peak, "dense TF32 tensor = 1/2 x bf16")
-        roofline = {"kernel": f"k_egemm_tc<EG_MSG> (292->256 message linear of one GVP, {'fp16x3' if prec == 1 else '3xTF32'} tcgen05, all edges)",
-                    "bound": "tensor", "achieved": achieved, "peak": op_peak, "unit": "TFLOP/s", "frac": achieved / op_peak,
-                    "peak_kind": f"{op_name}, {peak_src}; the kernel issues 3 MMAs per fp32 product (error-compensated hi/lo "
-                                 f"operands), so frac_of_x3_ceiling = {3 * achieved / op_peak:.3f}",
-                    "algorithmic_flops_per_launch": flops, "ms_per_launch": ms_k,
+        hbm_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks.get("hbm_gbs") else "fallback (B200_PROFILING.md 6.65 TB/s)"
+        prof = vf.kernel_profile(n_atoms, dx, da, dc, de)
+        fwd_ms = sum(t_ for _, t_ in prof.values())
+        # algorithmic HBM bytes per edge (fp32 rows read + written; per-node operands gathered from L2 are not counted) and matmul
+        # FLOP per edge of every mode
+        F_, S_ = 128, 256
+        modes = {"EG_MSG0": (4 * (F_ + 37) + 4 * S_, 2 * 197 * S_), "EG_MSG": (4 * 292 + 4 * S_, 2 * 292 * S_),
+                 "EG_MSGA": (4 * 292 + 4 * S_, 2 * 292 * S_), "EG_GATE": (4 * S_ + 4 * 32, 2 * S_ * 32),
+                 "EG_EU1": (4 * F_ + 4 * F_, 2 * 160 * F_), "EG_EU2": (4 * F_ + 4 * F_ + 4 * F_, 2 * F_ * F_)}
+        family = {}
+        for name_, (bpe, fpe) in modes.items():
+            if name_ in prof:
+                cnt, ms_f = prof[name_]
+                us = 1e3 * ms_f / cnt
+                family[name_] = {"launches_per_eval": cnt, "us_per_launch": us, "algorithmic_bytes_per_edge": bpe,
+                                 "achieved_gbs": bpe * E / (us * 1e-6) / 1e9, "frac_of_hbm_peak": bpe * E / (us * 1e-6) / 1e9 / hbm_peak,
+                                 "algorithmic_tflops": fpe * E / (us * 1e-6) / 1e12}
+        hbm_bytes = E * (292 + 256) * 4
+        achieved = hbm_bytes / (ms_k * 1e-3) / 1e9
+        flops = 2 * 292 * 256 * E
+        op_peak = bf16 if prec == 1 else tf32_peak
+        roofline = {"kernel": f"k_egemm_p<EG_MSG> (292->256 message linear of one GVP, {'fp16x3' if prec == 1 else '3xTF32'} tcgen05, "
+                              "operand images in and out, all edges)",
+                    "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                    "peak_kind": hbm_src, "algorithmic_bytes_per_launch": hbm_bytes, "ms_per_launch": ms_k,
                     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this workload from the committed ncu capture
-                    # (profiles/: 1.392 + 1.169 GB, the operand format does not change the HBM traffic); bench.py itself never
-                    # runs under a profiler
-                    "traffic": 2.561e9 if (args.workload == "geom512" and world == 1) else None,
-                    "hbm": {"algorithmic_bytes_per_launch": hbm_bytes, "achieved_gbs": hbm_bytes / (ms_k * 1e-3) / 1e9,
-                            "peak_gbs": hbm_peak, "frac": hbm_bytes / (ms_k * 1e-3) / 1e9 / hbm_peak},
+                    # (profiles/r01s_ncu_full_egemm_p.csv: 1.405 + 1.170 GB; bench.py itself never runs under a profiler)
+                    "traffic": 2.575e9 if (args.workload == "geom512" and world == 1) else None,
+                    "tensor": {"algorithmic_flops_per_launch": flops, "achieved_tflops": flops / (ms_k * 1e-3) / 1e12,
+                               "peak_tflops": op_peak, "frac": flops / (ms_k * 1e-3) / 1e12 / op_peak,
+                               "note": "3 MMAs per fp32 product (error-compensated hi/lo operands): attainable ceiling = peak / 3"},
+                    "family": family,
+                    "kernel_ms_per_eval": {k: round(t_, 4) for k, (c_, t_) in sorted(prof.items(), key=lambda kv: -kv[1][1])},
+                    "eval_ms_event_to_event": fwd_ms,
                     "message_pass": {"what": "whole message phase of one conv layer (10 launches: 3 vec + 6 egemm + segment-sum)",
                                      "ms": ms_pass, "algorithmic_tflops": CONV_EDGE_FLOP_PER_EDGE[cfg_name] * E / (ms_pass * 1e-3) / 1e12}}
     else:

@@ -129,6 +129,48 @@ class CTMCVectorFieldB200:
             raise RuntimeError("flowmol_b200: an activation left the fp16 operand range of the tensor-core linears; "
                                "call set_option('tc_prec', 0) (3xTF32 operands) and re-run")
 
+    def kernel_profile(self, n_atoms, x_t, a_idx, c_idx, e_idx_upper, t=0.3, prev=None, n_forwards=1):
+        """In-situ per-kernel timing of `n_forwards` network evaluations: fm_debug_kprof records a CUDA event after every launch
+        on the launching stream; the differences are the launches' durations in the warm pipeline.  Returns
+        {label: (launches per forward, ms per forward)} with labels read from csrc/api.cu by launch-site line."""
+        import collections
+        import os
+        import re
+        if prev is None:
+            prev = self.forward_tokens(n_atoms, x_t, a_idx, c_idx, e_idx_upper, 0.0, None)
+        prev = self.forward_tokens(n_atoms, x_t, a_idx, c_idx, e_idx_upper, t, prev)          # warm
+        torch.cuda.synchronize(self.device)
+        self.set_option("kprof", 1)
+        for _ in range(n_forwards):
+            prev = self.forward_tokens(n_atoms, x_t, a_idx, c_idx, e_idx_upper, t, prev)
+        torch.cuda.synchronize(self.device)
+        cap = 2048 * n_forwards
+        lines, ms, n = (C.c_int32 * cap)(), (C.c_float * cap)(), C.c_int32()
+        _lib.check(self.lib.fm_debug_kprof(self._h, lines, ms, cap, C.byref(n)))
+        self.set_option("kprof", 0)
+        src = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "api.cu")).read().split("\n")
+
+        def label(line):
+            for back in range(0, 4):                       # the launch is on the LAUNCH_OK line or just above it
+                tx = src[line - 1 - back]
+                m = (re.search(r"launch_eg<D, fm::(EG_\w+), \d", tx) or re.search(r"fm::(k_\w+)<", tx)
+                     or re.search(r"\b(scalar|gate|linear)\(", tx))
+                if m:
+                    return m.group(1) if m.group(1).startswith(("EG_", "k_")) else "node_" + m.group(1)
+            return f"line{line}"
+        agg, seen = collections.OrderedDict(), collections.Counter()
+        for i in range(n.value):
+            lab = label(lines[i])
+            if lab.startswith("EG_MSG"):                   # one launch site, the three linears of a message pass in turn
+                lab = ("EG_MSG0", "EG_MSG", "EG_MSGA")[seen[lines[i]] % 3]
+                seen[lines[i]] += 1
+            elif lab == "k_vec_b" and ms[i] < 0.1:
+                lab = "k_vec_b(node rows)"
+            a = agg.setdefault(lab, [0, 0.0])
+            a[0] += 1
+            a[1] += ms[i]
+        return {k: (c / n_forwards, t_ / n_forwards) for k, (c, t_) in agg.items()}
+
     def time_conv_edge(self, layer=1, iters=5):
         """Mean duration (ms) of the hot kernel re-launched on the state left by the last forward (bench roofline)."""
         ms = C.c_float()

@@ -29,7 +29,9 @@ class FmTraj(C.Structure):
 class FmSampleOpts(C.Structure):
     _fields_ = [("n_timesteps", c_i32), ("stochasticity", c_f32), ("high_confidence_threshold", c_f32),
                 ("cat_temperature", c_f32), ("seed", c_u64), ("mol_id_offset", c_i32),
-                ("tspan_host", C.POINTER(c_f32)), ("use_cuda_graph", c_i32)]
+                ("tspan_host", C.POINTER(c_f32)), ("use_cuda_graph", c_i32), ("dfm_type", c_i32),
+                ("tau_host", C.POINTER(c_f32)), ("fw_host", C.POINTER(c_f32)), ("bw_host", C.POINTER(c_f32)),
+                ("inv_temp_host", C.POINTER(c_f32))]
 
 
 # every symbol include/flowmol_b200.h declares: (restype, argtypes)
@@ -77,7 +79,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError here == header / library drift
         fn.restype = res
         fn.argtypes = args
-    if lib.fm_abi_version() != 1:
+    if lib.fm_abi_version() != 2:
         raise RuntimeError("libflowmol_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

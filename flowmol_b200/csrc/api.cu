@@ -637,6 +637,8 @@ int fm_integrate_traj(FmHandle* h, void* ws, float* x, uint8_t* a, uint8_t* c, u
                       const FmTraj* traj, void* stream) {
   if (!h || !ws || !x || !a || !c || !e || !o) return fail("fm_integrate: null argument");
   if (o->n_timesteps < 2) return fail("fm_integrate: n_timesteps must be >= 2");
+  if (o->dfm_type != 0 && o->dfm_type != 1) return fail("fm_integrate: dfm_type must be 0 (campbell) or 1 (gat)");
+  if (o->dfm_type == 1 && (!o->fw_host || !o->bw_host)) return fail("fm_integrate: dfm_type 1 (gat) needs fw_host and bw_host");
   const Layout* Lp;
   if (find_batch(h, ws, &Lp)) return -1;
   const Layout& L = *Lp;
@@ -680,7 +682,11 @@ int fm_integrate_traj(FmHandle* h, void* ws, float* x, uint8_t* a, uint8_t* c, u
       sc.mask_prob[m] = clamp01(qm);
     }
     sc.hc_thresh = o->high_confidence_threshold;
-    sc.tau = o->cat_temperature;
+    sc.tau = o->tau_host ? o->tau_host[k - 1] : o->cat_temperature;
+    sc.dfm_type = o->dfm_type;
+    sc.fw = o->fw_host ? o->fw_host[k - 1] : 1.0f;
+    sc.bw = o->bw_host ? o->bw_host[k - 1] : 0.0f;
+    sc.inv_temp = o->inv_temp_host ? o->inv_temp_host[k - 1] : 1.0f;
     sc.last_step = k == T - 1;
     sc.step_index = k;
     sc.seed_lo = (uint32_t)(o->seed & 0xffffffffull);

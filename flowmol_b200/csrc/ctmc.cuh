@@ -10,7 +10,7 @@
 
 namespace fm {
 
-constexpr int KMAXC = 16;   // max categories of one modality
+constexpr int KMAXC = 16;   // max categories of one modality (the gat sampler adds the mask class: K + 1 <= KMAXC + 1)
 
 struct StepScalars {
   float t_i, dt;
@@ -19,6 +19,9 @@ struct StepScalars {
   int last_step, step_index;
   uint32_t seed_lo, seed_hi;
   int mol_id_offset;
+  int dfm_type;                          // 0 campbell, 1 gat (ctmc_vector_field.py:377-394,463-510)
+  float fw, bw;                          // gat: forward weight of this step and the reference's `forward_weight - 1`
+  float inv_temp;                        // factor of the position update (inv_temp_func(t_i), :334); 1 by default
 };
 
 // p = softmax(log(p_hat) / tau); returns max_k p_k ("purity")          (ctmc_vector_field.py:354-356)
@@ -53,6 +56,35 @@ __device__ __forceinline__ void campbell_modality(const float* __restrict__ phat
                                                   int* scratch, uint8_t* __restrict__ frame, uint8_t* __restrict__ x1_frame) {
   const float q_u = sc.unmask_prob[modality], q_m = sc.mask_prob[modality];
   float p[KMAXC];
+  if (sc.dfm_type == 1) {
+    // gat_step (ctmc_vector_field.py:463-510), linear schedule alpha = t, alpha' = 1: Euler step of the probability velocity
+    // fw * u_forward - (fw - 1) * u_backward over K + 1 classes (mask = K), clamp, inverse-CDF draw with the item's first uniform
+    const float cf = __fdiv_rn(1.0f, __fsub_rn(1.0f, sc.t_i)), cb = __fdiv_rn(1.0f, __fadd_rn(sc.t_i, 1e-8f));
+    for (int it = threadIdx.x; it < cnt; it += blockDim.x) {
+      const int z = state[it];
+      sharpen(phat + (size_t)it * K, K, sc.tau, p);
+      const Philox4 rnd = philox4x32_10((uint32_t)it, mol_gid, (uint32_t)sc.step_index, (uint32_t)modality, sc.seed_lo, sc.seed_hi);
+      float c = 0.f, cum[KMAXC + 1], best = -1.f;
+      int amax = 0;
+      for (int k = 0; k <= K; ++k) {
+        const float p1 = k < K ? p[k] : 0.f, d = k == z ? 1.f : 0.f, dm = k == K ? 1.f : 0.f;
+        if (k < K && p1 > best) { best = p1; amax = k; }
+        const float uf = __fmul_rn(cf, __fsub_rn(p1, d)), ub = __fmul_rn(cb, __fsub_rn(d, dm));
+        const float pvel = __fsub_rn(__fmul_rn(sc.fw, uf), __fmul_rn(sc.bw, ub));
+        const float ps = fminf(fmaxf(__fadd_rn(d, __fmul_rn(sc.dt, pvel)), 1.0e-9f), 1.0f);
+        c = __fadd_rn(c, ps);
+        cum[k] = c;
+      }
+      const float thr = __fmul_rn(u24(rnd.x), c);
+      int zn = 0;
+      for (int k = 0; k <= K; ++k) zn += (cum[k] <= thr) ? 1 : 0;
+      zn = min(zn, K);
+      state[it] = (uint8_t)zn;
+      if (frame) frame[it] = (uint8_t)zn;
+      if (x1_frame) x1_frame[it] = (uint8_t)amax;         // the reference records p itself as the endpoint frame: its argmax
+    }
+    return;
+  }
   // pass 1: per-molecule counts of masked / high-confidence masked items      (ctmc_utils.py:6-18)
   int m_loc = 0, h_loc = 0;
   if (sc.hc_thresh > 0.f) {
@@ -119,7 +151,7 @@ k_ctmc_step(const BatchRT bt, int A, int C, int EB, const float* __restrict__ px
   for (int i = threadIdx.x; i < n * 3; i += blockDim.x) {
     const int g = nb * 3 + i;
     const float vf = __fmul_rn(coef, __fsub_rn(px[g], x_t[g]));
-    const float xn = __fadd_rn(x_t[g], __fmul_rn(sc.dt, vf));
+    const float xn = __fadd_rn(x_t[g], __fmul_rn(__fmul_rn(sc.dt, vf), sc.inv_temp));
     x_t[g] = xn;
     if (tf.x) tf.x[g] = xn;
     if (tf.x1) tf.x1[g] = px[g];

@@ -28,6 +28,34 @@ def _require_cuda(device):
     return torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
 
 
+def build_cat_temp_schedule(schedule, decay_max=0.8, decay_a=2):
+    """ctmc_vector_field.py:71-81: 'decay' -> max * (1 - t)^a, a number -> constant, or a callable of the fp32 time tensor."""
+    if schedule == 'decay':
+        return lambda t: decay_max * torch.pow(1 - t, decay_a)
+    if isinstance(schedule, (float, int)):
+        return lambda t: schedule
+    if callable(schedule):
+        return schedule
+    raise ValueError(f"Invalid cat_temperature_schedule: {schedule}")
+
+
+def build_fw_schedule(schedule, beta_a=0.25, beta_b=0.25, beta_max=10.0):
+    """ctmc_vector_field.py:83-95: 'beta' -> 1 + max * t^a * (1 - t)^b, a number -> constant, or a callable."""
+    if schedule == 'beta':
+        return lambda t: 1 + beta_max * torch.pow(t, beta_a) * torch.pow(1 - t, beta_b)
+    if isinstance(schedule, (float, int)):
+        return lambda t: schedule
+    if callable(schedule):
+        return schedule
+    raise ValueError(f"Invalid forward_weight_schedule: {schedule}")
+
+
+def _f32(v):
+    """A schedule value as the fp32 number the reference's tensor arithmetic would use (python floats are cast to fp32 when they
+    meet an fp32 tensor; 0-d tensors already are fp32)."""
+    return float(torch.as_tensor(v, dtype=torch.float32))
+
+
 class CTMCVectorFieldB200:
     canonical_feat_order = ['x', 'a', 'c', 'e']
 
@@ -40,6 +68,13 @@ class CTMCVectorFieldB200:
         self.eta = cfg.stochasticity
         self.hc_thresh = cfg.high_confidence_threshold
         self.cat_temperature = cfg.cat_temperature
+        # schedules of the reference's constructor (ctmc_vector_field.py:23-57,71-95): evaluated on the host once per step
+        ex = cfg.extra
+        self.dfm_type = ex.get('dfm_type', 'campbell')
+        self.cat_temp_func = build_cat_temp_schedule(ex.get('cat_temperature_schedule', cfg.cat_temperature),
+                                                     ex.get('cat_temp_decay_max', 0.8), ex.get('cat_temp_decay_a', 2))
+        self.forward_weight_func = build_fw_schedule(ex.get('forward_weight_schedule', 'beta'), ex.get('fw_beta_a', 0.25),
+                                                     ex.get('fw_beta_b', 0.25), ex.get('fw_beta_max', 10.0))
         blob, offsets = WT.pack(cfg, state_dict)
         self._blob, self._offsets = np.ascontiguousarray(blob), np.ascontiguousarray(offsets)
         if not (cfg.a_token_dim == cfg.c_token_dim == cfg.e_token_dim):
@@ -219,19 +254,47 @@ class CTMCVectorFieldB200:
         self.check_status()
         return out
 
-    def _opts(self, n_timesteps, stochasticity, high_confidence_threshold, seed, mol_id_offset, tspan, cuda_graph):
+    def _opts(self, n_timesteps, stochasticity, high_confidence_threshold, seed, mol_id_offset, tspan, cuda_graph,
+              dfm_type=None, cat_temp_func=None, forward_weight_func=None, inv_temp_func=None):
+        """FmSampleOpts + the host arrays it points to (keep the second return value alive for the duration of the call).
+        Schedules are Python callables of the fp32 time tensor t_i, as in the reference (ctmc_vector_field.py:159-162,310-311);
+        they are evaluated here once per step and handed over as per-step scalars."""
         if tspan is None:
             tspan = torch.linspace(0, 1, n_timesteps)                # ctmc_vector_field.py:170 (fp32, evaluated by torch)
-        ts = np.ascontiguousarray(tspan.detach().cpu().float().numpy())
+        tt = tspan.detach().cpu().float()
+        ts = np.ascontiguousarray(tt.numpy())
+        dfm_type = dfm_type or self.dfm_type
+        if dfm_type not in ('campbell', 'gat'):
+            raise ValueError(f"Invalid dfm_type: {dfm_type}")                                 # ctmc_vector_field.py:61-62
+        ctf = cat_temp_func if cat_temp_func is not None else self.cat_temp_func
+        keep = [ts]
+        ptr = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+        null = C.POINTER(C.c_float)()
+        tau = np.array([_f32(ctf(tt[k])) for k in range(len(ts) - 1)], dtype=np.float32)
+        fw_p, bw_p, it_p = null, null, null
+        if dfm_type == 'gat':
+            fwf = forward_weight_func if forward_weight_func is not None else self.forward_weight_func
+            fws = [fwf(tt[k]) for k in range(len(ts) - 1)]
+            fw = np.array([_f32(v) for v in fws], dtype=np.float32)
+            bw = np.array([_f32(v - 1) for v in fws], dtype=np.float32)                        # `backward_weight = forward_weight - 1` (:491)
+            keep += [fw, bw]
+            fw_p, bw_p = ptr(fw), ptr(bw)
+        if inv_temp_func is not None:
+            it = np.array([_f32(inv_temp_func(tt[k])) for k in range(len(ts) - 1)], dtype=np.float32)
+            keep.append(it)
+            it_p = ptr(it)
+        keep.append(tau)
         o = _lib.FmSampleOpts(
             n_timesteps=len(ts), stochasticity=float(self.eta if stochasticity is None else stochasticity),
             high_confidence_threshold=float(self.hc_thresh if high_confidence_threshold is None else high_confidence_threshold),
             cat_temperature=float(self.cat_temperature), seed=int(seed) & (2 ** 64 - 1), mol_id_offset=int(mol_id_offset),
-            tspan_host=ts.ctypes.data_as(C.POINTER(C.c_float)), use_cuda_graph=int(bool(cuda_graph)))
-        return o, ts
+            tspan_host=ptr(ts), use_cuda_graph=int(bool(cuda_graph)), dfm_type=1 if dfm_type == 'gat' else 0,
+            tau_host=ptr(tau), fw_host=fw_p, bw_host=bw_p, inv_temp_host=it_p)
+        return o, keep
 
     def integrate_tokens(self, n_atoms, x0, a0, c0, e0_upper, n_timesteps, seed, stochasticity=None,
-                         high_confidence_threshold=None, mol_id_offset=0, tspan=None, cuda_graph=False, traj=False):
+                         high_confidence_threshold=None, mol_id_offset=0, tspan=None, cuda_graph=False, traj=False,
+                         dfm_type=None, cat_temp_func=None, forward_weight_func=None, inv_temp_func=None):
         """Full trajectory on device-resident token state; returns final {'x','a','c','e'} (new tensors).
         traj=True also returns, under 'traj', the per-step frames the reference collects with visualize=True
         (ctmc_vector_field.py:187-202,235-255) as device tensors: 'x' f32 [T,N,3], 'a','c' u8 [T,N], 'e' u8 [T,U] (frame 0 = the
@@ -243,10 +306,11 @@ class CTMCVectorFieldB200:
         a = a0.to(dev, torch.uint8).contiguous().clone()
         c = c0.to(dev, torch.uint8).contiguous().clone()
         e = e0_upper.to(dev, torch.uint8).contiguous().clone()
-        o, ts = self._opts(n_timesteps, stochasticity, high_confidence_threshold, seed, mol_id_offset, tspan, cuda_graph)
+        o, keep = self._opts(n_timesteps, stochasticity, high_confidence_threshold, seed, mol_id_offset, tspan, cuda_graph,
+                             dfm_type, cat_temp_func, forward_weight_func, inv_temp_func)
         frames, tr = None, None
         if traj:
-            T, N, U = len(ts), x.shape[0], e.shape[0]
+            T, N, U = int(o.n_timesteps), x.shape[0], e.shape[0]
             u8 = dict(dtype=torch.uint8, device=dev)
             frames = {'x': torch.empty(T, N, 3, device=dev), 'a': torch.empty(T, N, **u8), 'c': torch.empty(T, N, **u8),
                       'e': torch.empty(T, U, **u8), 'x_1_pred': torch.empty(T - 1, N, 3, device=dev),
@@ -336,10 +400,7 @@ class CTMCVectorFieldB200:
         """CTMCVectorField.integrate (ctmc_vector_field.py:145-285): reads x_0/a_0/c_0/e_0 from the graph, writes
         x_1/a_1/c_1/e_1 (and *_t); with visualize=True returns (g, per-molecule trajectory frames) like the reference.  `seed` selects the Philox noise stream (default: drawn from torch's global RNG so
         `torch.manual_seed` / seed_everything still controls reproducibility, cf. test.py:70-71)."""
-        if dfm_type not in (None, 'campbell'):
-            raise NotImplementedError("only dfm_type='campbell' (the reference default) is implemented")
-        if cat_temp_func is not None or forward_weight_func is not None or kwargs.get('inv_temp_func') is not None:
-            raise NotImplementedError("custom temperature / forward-weight schedules are not implemented")
+        inv_temp_func = kwargs.pop('inv_temp_func', None)               # reaches step() through **kwargs in the reference (:222)
         if n_timesteps is None and tspan is None:
             raise ValueError("n_timesteps is required")
         n_atoms = n_atoms_of(g)
@@ -350,7 +411,9 @@ class CTMCVectorFieldB200:
         uem_d = uem.to(e0.device)
         out = self.integrate_tokens(n_atoms, g.ndata['x_0'], g.ndata['a_0'].argmax(-1), g.ndata['c_0'].argmax(-1),
                                     e0[uem_d].argmax(-1), n_timesteps, seed, stochasticity, high_confidence_threshold,
-                                    mol_id_offset, tspan, cuda_graph, traj=bool(visualize))
+                                    mol_id_offset, tspan, cuda_graph, traj=bool(visualize), dfm_type=dfm_type,
+                                    cat_temp_func=cat_temp_func, forward_weight_func=forward_weight_func,
+                                    inv_temp_func=inv_temp_func)
         a1 = one_hot(out['a'].long(), self.n_atom_types + 1).float()
         c1 = one_hot(out['c'].long(), self.n_charges + 1).float()
         eu = one_hot(out['e'].long(), self.n_bond_types + 1).float()

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define FM_ABI_VERSION 1
+#define FM_ABI_VERSION 2
 
 typedef struct FmHandle FmHandle;
 
@@ -66,6 +66,11 @@ typedef struct FmSampleOpts {
   int32_t mol_id_offset;     /* global id of molecule 0 of this batch (sharding-invariant noise) */
   const float* tspan_host;   /* optional [n_timesteps] fp32 time grid; NULL => fp32 linspace(0,1,n), within 1 ulp of torch.linspace (pass torch's values for bit parity) */
   int32_t use_cuda_graph;    /* capture the per-step launch sequence once and replay it */
+  int32_t dfm_type;          /* 0 = 'campbell' (mask / unmask jumps, ctmc_vector_field.py:414-461), 1 = 'gat' (:463-510) */
+  const float* tau_host;     /* optional [n_timesteps-1]: categorical temperature of every step = cat_temp_func(t_i) (:71-81,353); NULL => cat_temperature */
+  const float* fw_host;      /* dfm_type 1: [n_timesteps-1] forward weights forward_weight_func(t_i) (:83-95,385) */
+  const float* bw_host;      /* dfm_type 1: [n_timesteps-1] backward weights fw - 1, evaluated by the caller in the reference's arithmetic (:491) */
+  const float* inv_temp_host;/* optional [n_timesteps-1]: inv_temp_func(t_i) factor of the position update (:334); NULL => 1 */
 } FmSampleOpts;
 
 typedef struct FmTraj {      /* optional per-step frames, device memory owned by the caller; any pointer may be NULL.

@@ -343,8 +343,25 @@ def campbell_step(p, xt, eta, hc_thresh, alpha_t, alpha_t_prime, dt, counts, ite
     return xt, x1
 
 
+def gat_step(p, xt, alpha_t, alpha_t_prime, forward_weight, dt, mask_index, u_cat):
+    """flowmol/models/ctmc_vector_field.py:463-510 on token indices (dfm_type='gat'): one Euler step of the probability
+    velocity fw * u_forward - (fw - 1) * u_backward, then a categorical draw from the clamped transition distribution."""
+    n_classes = mask_index + 1
+    p1 = torch.cat([p, torch.zeros_like(p[:, :1])], dim=-1)
+    delta_xt = F.one_hot(xt, num_classes=n_classes).float()
+    u_forward = alpha_t_prime / (1 - alpha_t) * (p1 - delta_xt)
+    delta_mask = torch.zeros_like(delta_xt)
+    delta_mask[:, mask_index] = 1
+    u_backward = alpha_t_prime / (alpha_t + 1e-8) * (delta_xt - delta_mask)
+    backward_weight = forward_weight - 1
+    pvel = forward_weight * u_forward - backward_weight * u_backward
+    p_step = torch.clamp(delta_xt + dt * pvel, min=1.0e-9, max=1)
+    return sample_categorical(p_step, u_cat)
+
+
 def integrate(model, bt, x0, a0, c0, e0_upper, n_timesteps, seed, eta=None, hc_thresh=None, tau=0.05,
-              mol_id_offset=0, record=None):
+              mol_id_offset=0, record=None, dfm_type='campbell', cat_temp_func=None, forward_weight_func=None,
+              inv_temp_func=None):
     """flowmol/models/ctmc_vector_field.py:145-411 (integrate + step), dfm_type='campbell', linear schedule
     (alpha_t = t, alpha_t' = 1: flowmol/models/interpolant_scheduler.py:148-154), inv_temp = 1.
 
@@ -368,16 +385,21 @@ def integrate(model, bt, x0, a0, c0, e0_upper, n_timesteps, seed, eta=None, hc_t
         dt = s_i - t_i
         alpha_t, alpha_tp = t_i, torch.ones(())
         vf = alpha_tp / (1 - alpha_t) * (dst['x'] - x_t)              # vector_field.py:567-569
-        x_t = x_t + dt * vf * 1.0
+        x_t = x_t + dt * vf * (1.0 if inv_temp_func is None else inv_temp_func(t_i))      # ctmc_vector_field.py:334
+        tau_i = tau if cat_temp_func is None else cat_temp_func(t_i)                         # :353
         new, sampled = {}, {}
         for m, (name, cur, items, mols, item_mol, counts, mask_index) in enumerate((
                 ('a', a_t, node_item, node_mol, bt.node_mol, bt.n_atoms, model.A),
                 ('c', c_t, node_item, node_mol, bt.node_mol, bt.n_atoms, model.C),
                 ('e', e_t, up_item, up_mol, bt.upper_mol, n_up, model.Eb))):
-            p = F.softmax(torch.log(dst[name]) / tau, dim=-1)          # ctmc_vector_field.py:354-356
+            p = F.softmax(torch.log(dst[name]) / tau_i, dim=-1)        # ctmc_vector_field.py:354-356
             u3 = tuple(torch.from_numpy(u) for u in philox.uniforms(items, mols, s_idx, m, seed))
-            new[name], x1s = campbell_step(p, cur, eta, hc_thresh, alpha_t, alpha_tp, dt, counts, item_mol,
-                                           mask_index, last, u3)
+            if dfm_type == 'gat':                                        # :377-394 (the recorded endpoint is p itself: its argmax)
+                new[name] = gat_step(p, cur, alpha_t, alpha_tp, forward_weight_func(t_i), dt, mask_index, u3[0])
+                x1s = p.argmax(-1)
+            else:
+                new[name], x1s = campbell_step(p, cur, eta, hc_thresh, alpha_t, alpha_tp, dt, counts, item_mol,
+                                               mask_index, last, u3)
             sampled[name] = x1s                                          # the reference's `<feat>_1_pred` (:408-409)
         a_t, c_t, e_t = new['a'], new['c'], new['e']
         prev = dst

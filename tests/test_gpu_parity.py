@@ -173,6 +173,41 @@ def test_trajectory_frames_vs_oracle_every_step():
     assert torch.equal(fr["x"][-1], got["x"].cpu()) and torch.equal(fr["a"][-1], got["a"].cpu())
 
 
+def test_gat_sampler_and_schedules_vs_oracle():
+    """dfm_type='gat' (ctmc_vector_field.py:463-510) with the reference's 'beta' forward-weight schedule, a decaying categorical
+    temperature (:71-95) and an inverse-temperature factor on the positions (:334) -- the oracle side of this case is pinned
+    bit-exactly to the verbatim reference in tests/test_oracle_vs_reference.py."""
+    from flowmol_b200.vector_field import build_cat_temp_schedule, build_fw_schedule
+    ctf, fwf, itf = build_cat_temp_schedule('decay', 0.8, 2), build_fw_schedule('beta', 0.25, 0.25, 10.0), (lambda t: 1.0 + 0.5 * t)
+    for cfg_name, A, n_atoms, T in (("dev", 6, [6, 2, 17, 3], 14), ("flowmol3", 11, [5, 12], 8)):
+        cfg, vf = cuda_model(cfg_name, A, 35)
+        om = O.OracleModel(cfg, WT.init_state_dict(cfg, 35))
+        bt = O.make_batch(n_atoms)
+        x0 = torch.randn(bt.N, 3, generator=torch.Generator().manual_seed(12))
+        a0, c0, e0 = torch.full((bt.N,), A), torch.full((bt.N,), 6), torch.full((bt.U,), 4)
+        rec = []
+        with torch.no_grad():
+            want = O.integrate(om, bt, x0, a0, c0, e0, T, seed=99, record=rec, dfm_type='gat', cat_temp_func=ctf,
+                               forward_weight_func=fwf, inv_temp_func=itf)
+        got = vf.integrate_tokens(n_atoms, x0, a0, c0, e0, T, seed=99, traj=True, dfm_type='gat', cat_temp_func=ctf,
+                                  forward_weight_func=fwf, inv_temp_func=itf)
+        fr = {k: v.cpu() for k, v in got["traj"].items()}
+        for k, r in enumerate(rec):
+            for f in "ace":
+                assert torch.equal(fr[f][k + 1].long(), r[f]), (cfg_name, k, f)
+                assert torch.equal(fr[f + "_1_pred"][k].long(), r[f + "1"]), (cfg_name, k, f, "endpoint")
+            assert (fr["x"][k + 1] - r["x"]).abs().max() <= 1e-4
+        for k in "ace":
+            assert torch.equal(got[k].cpu().long(), want[k]), (cfg_name, k)
+        assert (got["x"].cpu() - want["x"]).abs().max() <= 1e-4
+        # the campbell sampler with a custom temperature schedule only
+        with torch.no_grad():
+            want = O.integrate(om, bt, x0, a0, c0, e0, T, seed=5, cat_temp_func=ctf)
+        got = vf.integrate_tokens(n_atoms, x0, a0, c0, e0, T, seed=5, cat_temp_func=ctf)
+        for k in "ace":
+            assert torch.equal(got[k].cpu().long(), want[k]), (cfg_name, k, "campbell + decay temperature")
+
+
 def test_reference_api_trajectories_xt_ep():
     """model.sample(..., xt_traj=True, ep_traj=True): per-molecule frames in the reference's layout (ctmc_vector_field.py:268-283)
     and decoded frame molecules (molecule_builder.py:75-84,156-214)."""

@@ -29,7 +29,14 @@ def test_c_abi_library_loads_and_exports_every_declared_symbol():
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.fm_abi_version() == 1
+    assert lib.fm_abi_version() == 2
+    # the ctypes mirrors list the header's struct fields in the header's order
+    hdr = open(os.path.join(ROOT, "include", "flowmol_b200.h")).read()
+    for cname, cls in (("FmSampleOpts", _lib.FmSampleOpts), ("FmTraj", _lib.FmTraj), ("FmPred", _lib.FmPred)):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), hdr, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = [re.split(r"[\s\*]+", d.strip())[-1] for d in body.split(";") if d.strip()]
+        assert names == [f[0] for f in cls._fields_], (cname, names)
     # host-only helper (no GPU needed): fallback time grid is within 1 ulp of torch.linspace
     for n in (2, 50, 250):
         out = np.zeros(n, np.float32)

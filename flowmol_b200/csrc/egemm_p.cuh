@@ -169,8 +169,8 @@ k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
     // wrow0 + l, the fetch reads it with a shuffle.  A load instruction covers 4 rows x 128 B (lanes 8g..8g+7 read the 8 16-byte
     // pieces of row 4i + g of a 32-float chunk).
     const int wrow0 = (warp - PL::W_LOAD0) * 32, lg = lane >> 3, ch = lane & 7;
-    const float sigma = m.rbf_dmax / (float)D::R;
-    const float* mu = m.g(G_RBF_MU);
+    const float inv_sigma = (float)D::R / m.rbf_dmax;
+    const float4 mu4 = *reinterpret_cast<const float4*>(m.g(G_RBF_MU) + ch * 4);      // this lane's four rbf centres
     int r_ok = 0;              // row valid (of the tile the NEXT fetch belongs to)
     float r_dist = 0.f;
     long long f_slot0 = 0;
@@ -211,8 +211,8 @@ k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
         if (MODE == EG_MSG0 || MODE == EG_EU1) {
           const float dd = __shfl_sync(0xffffffffu, r_dist, rl);
           if (j == D::F / 32) {
-            if (ok) val = make_float4(rbf_f(dd, mu[ch * 4], sigma), rbf_f(dd, mu[ch * 4 + 1], sigma), rbf_f(dd, mu[ch * 4 + 2], sigma),
-                                      rbf_f(dd, mu[ch * 4 + 3], sigma));
+            if (ok) val = make_float4(rbf_fast(dd, mu4.x, inv_sigma), rbf_fast(dd, mu4.y, inv_sigma), rbf_fast(dd, mu4.z, inv_sigma),
+                                      rbf_fast(dd, mu4.w, inv_sigma));
           } else if (j < D::F / 32) {
             if (ok) val = __ldg(reinterpret_cast<const float4*>(a.in_s + (size_t)sl_ * D::F + j * 32) + ch);
           } else {                                               // MSG0 only

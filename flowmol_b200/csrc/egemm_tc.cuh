@@ -241,12 +241,12 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
     }
   } else {
     // ---- activation loaders: one edge row per thread, fp32 -> (hi, lo) SW128 images ------------------------------------------------
-    const float sigma = m.rbf_dmax / (float)D::R;
-    const float* mu = m.g(G_RBF_MU);
+    const float inv_sigma = (float)D::R / m.rbf_dmax;
     // One warp owns 32 consecutive edge rows.  A load instruction covers 4 rows x 128 B (lanes 8g..8g+7 read the 8 16-byte
     // chunks of row 4i + g): full 128-byte lines per request.  The fetch of slab j+1 is issued before slab j is converted, so
     // the HBM / L2 round trip overlaps the wait for the stage and the MMAs of the previous slab.
     const int wrow0 = (warp - 2) * 32, lg = lane >> 3, ch = lane & 7;
+    const float4 mu4 = *reinterpret_cast<const float4*>(m.g(G_RBF_MU) + ch * 4);      // this lane's four rbf centres
     auto fetch = [&](int j, float4 (&buf)[8]) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -261,8 +261,8 @@ k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
           const bool rbf_slab = (MODE == EG_MSG0 && !PREC) ? j == 0 : j == D::F / 32;
           const int jf = PREC ? j : j - 1;                       // MSG0: ef chunk index
           if (rbf_slab) {
-            if (ok) val = make_float4(rbf_f(dd, mu[ch * 4], sigma), rbf_f(dd, mu[ch * 4 + 1], sigma), rbf_f(dd, mu[ch * 4 + 2], sigma),
-                                      rbf_f(dd, mu[ch * 4 + 3], sigma));
+            if (ok) val = make_float4(rbf_fast(dd, mu4.x, inv_sigma), rbf_fast(dd, mu4.y, inv_sigma), rbf_fast(dd, mu4.z, inv_sigma),
+                                      rbf_fast(dd, mu4.w, inv_sigma));
           } else if (MODE == EG_MSG0) {
             if (ok) {
               if (j <= D::F / 32) val = __ldg(reinterpret_cast<const float4*>(a.in_s + (size_t)sl_ * D::F + jf * 32) + ch);

@@ -71,6 +71,16 @@ __device__ __forceinline__ float rbf_f(float d, float mu, float sigma) {
   return expf(-__fmul_rn(z, z));
 }
 
+// rbf for the operand loaders of the tensor-core linears: the value is split into fp16 (hi, lo) / TF32 operands (22 significand
+// bits) right after, so the IEEE division and the accurate expf of rbf_f (~35 instructions with slow-path branches, 32 of them
+// per edge: ~17 % of k_egemm_p<MSG0>'s samples, profiles/r01s) buy nothing there.  Relative error ~1e-7.
+__device__ __forceinline__ float rbf_fast(float d, float mu, float inv_sigma) {
+  const float z = (d - mu) * inv_sigma;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+  return e;
+}
+
 // distance of an ordered node pair: ||x_a - x_b|| clamped + 1e-8   (vector_field.py:381-382)
 __device__ __forceinline__ float pair_dist(const float* __restrict__ x, int a, int b, float& dx, float& dy, float& dz) {
   dx = __fsub_rn(x[a * 3 + 0], x[b * 3 + 0]);

@@ -242,7 +242,6 @@ int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
     float *v = at<float>(ws, L.v), *x = at<float>(ws, L.x), *P = at<float>(ws, L.P), *M = at<float>(ws, L.M);
     float *partF = at<float>(ws, L.partF), *partL = at<float>(ws, L.partL), *ef = at<float>(ws, L.ef);
     float *SA = at<float>(ws, L.SA), *SB = at<float>(ws, L.SB), *VH = at<float>(ws, L.VH), *SH = at<float>(ws, L.SH), *GT = at<float>(ws, L.GT);
-    const size_t smem = D::SMEM_BYTES;
     const int NHsel = h->eg_nh;
     const int gt = (int)(L.EPA / (128 * NHsel));
     const bool img = img_on(h);

@@ -14,6 +14,8 @@
  *   fm_integrate             CTMCVectorField.integrate(g, node_batch_idx, upper_edge_mask, n_timesteps, stochasticity,
  *                            high_confidence_threshold, ...)  (ctmc_vector_field.py:145-285), the coarse seam at
  *                            flowmol/models/flowmol.py:557
+ *   fm_integrate_traj        the same with visualize=True: per-step frames of the state and of the predicted / sampled endpoint
+ *                            (ctmc_vector_field.py:187-202,235-283), written on the device by the step kernel
  *   fm_sample_host           FlowMol.sample(n_atoms, n_timesteps, prior=...) from host buffers to host buffers
  *                            (flowmol.py:489-589 minus rdkit), i.e. integrate + the H2D / D2H around it
  *

@@ -239,3 +239,38 @@ def test_cli_sdf_writer_and_trajectory_frame_decode(tmp_path):
     assert len(mt.traj_mols) == T and len(mt.ep_traj_mols) == T - 1
     assert mt.traj_mols[0].atom_types == ['C', 'O', 'N', 'Sn']                    # fake atoms are shown in trajectory frames
     assert np.abs(mt.traj_mols[0].positions.numpy() - (x + T - 1)).max() < 1e-4   # every frame is aligned onto the last one
+
+
+def test_operand_image_layout_contract_between_producer_and_consumer():
+    """The fp16 (hi, lo) operand images handed from one tensor-core linear to the next (csrc/egemm_p.cuh): the producer epilogue's
+    address arithmetic (thread = feature, lane pairs swap packed words, rows of a 128-row tile) must write exactly the SW128
+    K-major tile image the consumer's UMMA descriptor reads -- the same image format weights.py builds for the weight operands."""
+    from flowmol_b200 import weights as W
+    rng = np.random.default_rng(0)
+    T, OW = 128, 256
+    tile = rng.standard_normal((T, OW)).astype(np.float32)
+    hi, lo = W.split_h16(tile)
+    XSTAGE = 32768
+    img = np.zeros(OW // 64 * XSTAGE, np.uint8)
+    hb, lb = hi.view(np.uint16), lo.view(np.uint16)
+    # producer (egemm_p.cuh, IMG_OUT block): warp (q, hf) handles features f = mt*128 + q*32 + lane and chunks c = 2*hf + ci
+    for mt in range(OW // 128):
+        for q in range(4):
+            for c in range(4):
+                for lane in range(32):
+                    odd, kk = lane & 1, (q & 1) * 32 + (lane & ~1)
+                    ob = (mt * 2 + (q >> 1)) * XSTAGE + (c * 32 + odd) * 128 + (kk & 7) * 2
+                    c0x = (kk >> 3) ^ odd
+                    f_even = mt * 128 + q * 32 + (lane & ~1)
+                    for t in range(16):
+                        row = c * 32 + 2 * t + odd                       # even lane stores row 2t, odd lane row 2t + 1
+                        dst = ob + (2 * t) * 128 + ((c0x ^ ((2 * t) & 7)) << 4)
+                        for half, src in ((0, hb), (16384, lb)):
+                            word = np.array([src[row, f_even], src[row, f_even + 1]], np.uint16).view(np.uint8)   # (k, k + 1), k low
+                            img[dst + half:dst + half + 4] = word
+    # consumer: slab j = k values [64 j, 64 j + 64) as [hi image | lo image], each a K-major SW128 tile (weights.sw128_image_h16)
+    for j in range(OW // 64):
+        want_hi = W.sw128_image_h16(hi[:, 64 * j:64 * j + 64]).view(np.uint8)
+        want_lo = W.sw128_image_h16(lo[:, 64 * j:64 * j + 64]).view(np.uint8)
+        assert np.array_equal(img[j * XSTAGE:j * XSTAGE + 16384], want_hi), j
+        assert np.array_equal(img[j * XSTAGE + 16384:(j + 1) * XSTAGE], want_lo), j

@@ -14,6 +14,9 @@
 //                                 SW128 images, 32 rows per warp, 32-wide chunks, loads prefetched one chunk ahead across tiles
 //   warps 7-14  epilogue          TMEM -> registers -> activation -> global; two warps per TMEM lane quarter (each takes 64 of
 //                                 the tile's 128 rows), draining buffer b while the MMAs fill buffer b ^ 1
+// The per-row bookkeeping of a tile (source / destination node of every edge row, segment flags) is computed by the loaders,
+// which are one to three tiles ahead of the epilogue, and handed over through a 4-deep ring with its own mbarriers -- computed in
+// the epilogue it was a chain of dependent global loads at the top of every tile with all eight epilogue warps parked behind it.
 //
 // All ring positions / mbarrier phases are running counters that every role advances identically per tile, so nothing is
 // re-initialised between tiles.  PREC 1 (fp16x3 operands) only.
@@ -34,10 +37,11 @@ struct EgpPlan {
   static_assert(W_EPI0 + NEW == THREADS / 32 && NLW * 32 == T, "one loader warp per 32 rows");
   static constexpr int OFF_X = 0;
   static constexpr int OFF_RING = NST * XSTAGE;
-  static constexpr int OFF_ROW = OFF_RING + RING_BYTES;     // 2 x { int src[T]; short dd[T] } (epilogue bookkeeping, double buffered)
-  static constexpr int OFF_RED = OFF_ROW + 2 * T * 6;       // EU2 LayerNorm partials (2 row halves x 256 floats)
+  static constexpr int NROWBUF = 4;                          // ring of per-tile row bookkeeping (loaders run up to 3 tiles ahead of the epilogue)
+  static constexpr int OFF_ROW = OFF_RING + RING_BYTES;     // NROWBUF x { int src[T]; short dd[T] }: written by the loaders, read by the epilogue
+  static constexpr int OFF_RED = OFF_ROW + NROWBUF * T * 6; // EU2 LayerNorm partials (2 row halves x 256 floats)
   static constexpr int OFF_BAR = OFF_RED + 2048;
-  static constexpr int NBAR = 2 * MAX_SLOTS + 2 * NST + 4;
+  static constexpr int NBAR = 2 * MAX_SLOTS + 2 * NST + 4 + NROWBUF;
   static constexpr int BYTES = OFF_BAR + NBAR * 8 + 16;
   static constexpr size_t SMEM_BYTES = BYTES;
   static_assert(BYTES <= 232448, "227 KB of shared memory per CTA");
@@ -87,14 +91,16 @@ k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
   uint8_t* ring = smem_dyn + PL::OFF_RING;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_dyn + PL::OFF_BAR);
   uint64_t *w_full = bars, *w_empty = bars + PL::MAX_SLOTS, *x_full = bars + 2 * PL::MAX_SLOTS, *x_empty = x_full + NST;
-  uint64_t *acc_full = x_empty + NST, *acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t *acc_full = x_empty + NST, *acc_empty = acc_full + 2, *rows_full = acc_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rows_full + PL::NROWBUF);
+  constexpr bool NEED_ROWS = MODE == EG_MSG0 || MODE == EG_EU1 || MODE == EG_MSGA;      // the epilogue needs per-row node indices
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_my = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   if (tid == 0) {
     for (int i = 0; i < RING; ++i) { tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < NST; ++i) { tc::mbar_init(&x_full[i], PL::NLW); tc::mbar_init(&x_empty[i], NMT); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], NMT); tc::mbar_init(&acc_empty[i], PL::NEW); }
+    for (int i = 0; i < PL::NROWBUF; ++i) tc::mbar_init(&rows_full[i], PL::NLW);
     tc::fence_mbar_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
@@ -176,8 +182,9 @@ k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
     long long f_slot0 = 0;
     auto rowinfo = [&](int it) {
       f_slot0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * PL::T;
-      const long long slot = f_slot0 + wrow0 + lane;
-      int ok = 0;
+      const int r = wrow0 + lane;                               // this lane's row of the tile
+      const long long slot = f_slot0 + r;
+      int ok = 0, s = -1, dd = 0;                               // s / dd: the epilogue's bookkeeping (NEED_ROWS modes)
       float dist = 0.f;
       if (a.flags & EGF_NODE_ROWS) {
         ok = slot < a.EP;
@@ -192,11 +199,36 @@ k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
             const int nb = bt.mol_node[mol];
             float dx, dy, dz;
             dist = pair_dist(a.x, nb + i, nb + j, dx, dy, dz);
+            s = nb + i;                                           // source node; dd = dst - src (same molecule, |.| < 2000)
+            dd = j - i;
+          } else if (MODE == EG_MSGA) {
+            const int j = le / (n - 1), rem = le - j * (n - 1);
+            s = bt.mol_node[mol] + j;                             // destination node
+            const bool tail = rem == n - 2;                       // the node's last in-edge
+            // bit 0: the node's segment ends here inside this 64-slot tile; bit 1: ... with the node's last in-edge;
+            // bit 2: that segment began with the node's first in-edge (it lies in the same 64-slot tile)
+            dd = (((r & 63) == 63 || tail) ? 1 : 0) | (tail ? 2 : 0) | (rem <= (r & 63) ? 4 : 0);
           }
         }
       }
       r_ok = ok;
       r_dist = dist;
+      if (NEED_ROWS) {                                            // publish the tile's bookkeeping to the epilogue warps
+        int* r_src = reinterpret_cast<int*>(smem_dyn + PL::OFF_ROW + (it % PL::NROWBUF) * (PL::T * 6));
+        short* r_dd = reinterpret_cast<short*>(r_src + PL::T);
+        r_src[r] = s;
+        if (MODE == EG_MSGA) {      // one 32-bit mask per 32-row chunk (= per loader warp) instead of per-row flags
+          const unsigned em = __ballot_sync(0xffffffffu, dd & 1), tm = __ballot_sync(0xffffffffu, dd & 2), hm = __ballot_sync(0xffffffffu, dd & 4);
+          if (lane == 0) {
+            unsigned* masks = reinterpret_cast<unsigned*>(r_dd);
+            masks[(r >> 5) * 3 + 0] = em; masks[(r >> 5) * 3 + 1] = tm; masks[(r >> 5) * 3 + 2] = hm;
+          }
+        } else {
+          r_dd[r] = (short)dd;
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&rows_full[it % PL::NROWBUF])) : "memory");
+      }
     };
     // chunk j = k values [32 j, 32 j + 32) of this linear's input row; j is a compile-time constant at every call site (the slab /
     // chunk loops are fully unrolled), so the source selection below folds to one path per call.
@@ -298,53 +330,19 @@ k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
   } else {
     // ---- epilogue: TMEM -> registers -> bias / gathered pre-activation -> activation -> coalesced global stores ---------------------------
     // warp -> TMEM lane quarter q (a warp may only touch lanes 32 (warp % 4) ...) and row half hf: rows [64 hf, 64 hf + 64) = chunks 2 hf, 2 hf + 1
-    const int q = warp & 3, hf = (warp - PL::W_EPI0) >> 2, et = tid - PL::W_EPI0 * 32;     // et: index among the 256 epilogue threads
+    const int q = warp & 3, hf = (warp - PL::W_EPI0) >> 2;
     float* red = reinterpret_cast<float*>(smem_dyn + PL::OFF_RED) + hf * 256;
     const float unscale = a.units[(size_t)NU * (UNIT_BYTES / 4)];
     float omax = 0.f;                                                  // IMG_OUT: largest |activation| this thread split into fp16 (hi, lo)
     constexpr bool GATHERS = MODE == EG_MSG0 || MODE == EG_EU1 || MODE == EG_EU2;
-    constexpr bool NEED_ROWS = MODE == EG_MSG0 || MODE == EG_EU1 || MODE == EG_MSGA;
     for (int it = 0; it < n_my; ++it) {
       const int b = it & 1;
       const long long slot0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * PL::T;
-      int* r_src = reinterpret_cast<int*>(smem_dyn + PL::OFF_ROW + b * (PL::T * 6));
+      // row bookkeeping of this tile, published by the loaders (they are ahead: normally no wait at all).  Ring of NROWBUF: a
+      // loader can only be three tiles ahead of the slowest epilogue warp (stages -> accumulator buffers), see rowinfo().
+      int* r_src = reinterpret_cast<int*>(smem_dyn + PL::OFF_ROW + (it % PL::NROWBUF) * (PL::T * 6));
       short* r_dd = reinterpret_cast<short*>(r_src + PL::T);
-      if (NEED_ROWS) {
-        if (et < PL::T) {                                       // the first four epilogue warps: one row each
-          const int r = et;
-          const long long slot = slot0 + r;
-          int s = -1, dd = 0;
-          if (slot < a.EP) {
-            const int t64 = (int)(slot >> 6), mol = bt.etile_mol[t64];
-            const int n = bt.mol_n[mol], le = (int)(slot - ((long long)bt.mol_etile[mol] << 6));
-            if (le < n * (n - 1)) {
-              s = 0;
-              if (MODE == EG_MSGA) {
-                const int j = le / (n - 1), rem = le - j * (n - 1);
-                s = bt.mol_node[mol] + j;
-                const bool tail = rem == n - 2;
-                dd = (((r & 63) == 63 || tail) ? 1 : 0) | (tail ? 2 : 0) | (rem <= (r & 63) ? 4 : 0);
-              } else {
-                int i, j;
-                edge_src_dst(le, n, i, j);
-                s = bt.mol_node[mol] + i;
-                dd = j - i;
-              }
-            }
-          }
-          r_src[r] = s;
-          if (MODE == EG_MSGA) {
-            const unsigned em = __ballot_sync(0xffffffffu, dd & 1), tm = __ballot_sync(0xffffffffu, dd & 2), hm = __ballot_sync(0xffffffffu, dd & 4);
-            if (lane == 0) {
-              unsigned* masks = reinterpret_cast<unsigned*>(r_dd);
-              masks[(et >> 5) * 3 + 0] = em; masks[(et >> 5) * 3 + 1] = tm; masks[(et >> 5) * 3 + 2] = hm;
-            }
-          } else {
-            r_dd[r] = (short)dd;
-          }
-        }
-        asm volatile("bar.sync 2, 256;" ::: "memory");           // the eight epilogue warps (buffers alternate: one barrier per tile)
-      }
+      if (NEED_ROWS) tc::mbar_wait(&rows_full[it % PL::NROWBUF], (it / PL::NROWBUF) & 1);
       const bool active = MODE != EG_GATE || q == 0;
 #pragma unroll 1
       for (int mt = 0; mt < NMT; ++mt) {

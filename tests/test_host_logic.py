@@ -274,3 +274,69 @@ def test_operand_image_layout_contract_between_producer_and_consumer():
         want_lo = W.sw128_image_h16(lo[:, 64 * j:64 * j + 64]).view(np.uint8)
         assert np.array_equal(img[j * XSTAGE:j * XSTAGE + 16384], want_hi), j
         assert np.array_equal(img[j * XSTAGE + 16384:(j + 1) * XSTAGE], want_lo), j
+
+
+def test_sampler_options_schedules_are_evaluated_per_step_like_the_reference():
+    """CTMCVectorFieldB200._opts (host side of fm_integrate's options): the categorical-temperature / forward-weight /
+    inverse-temperature callables are evaluated once per step on the fp32 time grid exactly as the reference's step() would
+    (ctmc_vector_field.py:71-95,334,353,385,491) and handed over as per-step fp32 scalars; 'gat' needs both weight arrays."""
+    import ctypes as C
+    from types import SimpleNamespace
+    from flowmol_b200.vector_field import CTMCVectorFieldB200, build_cat_temp_schedule, build_fw_schedule
+    me = SimpleNamespace(eta=30.0, hc_thresh=0.9, cat_temperature=0.05, dfm_type='campbell',
+                         cat_temp_func=build_cat_temp_schedule(0.05), forward_weight_func=build_fw_schedule('beta'))
+    T = 9
+    o, keep = CTMCVectorFieldB200._opts(me, T, None, None, seed=7, mol_id_offset=3, tspan=None, cuda_graph=False)
+    assert o.n_timesteps == T and o.dfm_type == 0 and o.stochasticity == 30.0 and o.mol_id_offset == 3
+    assert not o.fw_host and not o.bw_host and not o.inv_temp_host
+    assert np.allclose(np.ctypeslib.as_array(o.tau_host, (T - 1,)), 0.05)
+    assert np.array_equal(np.ctypeslib.as_array(o.tspan_host, (T,)), torch.linspace(0, 1, T).numpy())
+    ctf, fwf, itf = build_cat_temp_schedule('decay', 0.8, 2), build_fw_schedule('beta', 0.25, 0.25, 10.0), (lambda t: 1.0 + 0.5 * t)
+    o, keep = CTMCVectorFieldB200._opts(me, T, 5.0, 0.0, 7, 0, None, False, 'gat', ctf, fwf, itf)
+    tt = torch.linspace(0, 1, T)
+    assert o.dfm_type == 1 and o.stochasticity == 5.0 and o.high_confidence_threshold == 0.0
+    tau = np.ctypeslib.as_array(o.tau_host, (T - 1,))
+    fw, bw = np.ctypeslib.as_array(o.fw_host, (T - 1,)), np.ctypeslib.as_array(o.bw_host, (T - 1,))
+    it = np.ctypeslib.as_array(o.inv_temp_host, (T - 1,))
+    for k in range(T - 1):
+        assert tau[k] == np.float32(0.8 * torch.pow(1 - tt[k], 2)) and it[k] == np.float32(1.0 + 0.5 * tt[k])
+        f = 1 + 10.0 * torch.pow(tt[k], 0.25) * torch.pow(1 - tt[k], 0.25)
+        assert fw[k] == np.float32(f) and bw[k] == np.float32(f - 1)
+    assert fw[0] == 1.0 and bw[0] == 0.0                      # t = 0: pure forward velocity
+    with pytest.raises(ValueError):
+        CTMCVectorFieldB200._opts(me, T, None, None, 7, 0, None, False, 'bogus')
+    if RL_available():
+        from oracle import ref_loader as RL
+        vf_cfg, sc_cfg = RL.read_vector_field_cfg("dev")
+        m = RL.build_reference_model(vf_cfg, sc_cfg, n_atom_types=6)
+        for k in range(T - 1):                                 # the reference's own default schedules (constructor defaults)
+            assert float(m.forward_weight_func(tt[k])) == float(fwf(tt[k]))
+            assert float(torch.as_tensor(m.cat_temp_func(tt[k]))) == float(torch.as_tensor(me.cat_temp_func(tt[k])))
+
+
+def RL_available():
+    from oracle import ref_loader as RL
+    return RL.available()
+
+
+def test_cli_prior_is_drawn_once_per_batch_and_sliced_per_rank():
+    """flowmol_b200/cli.py: noise that does not depend on the GPU count -- the COM-free prior positions are drawn for the whole
+    batch from one generator and every rank takes its contiguous slice (FlowMolB200.centered_normal / prior_from_x0)."""
+    from types import SimpleNamespace
+    from flowmol_b200.api import FlowMolB200
+    from flowmol_b200 import sharding as SH
+    n = np.array([5, 9, 3, 12, 7, 4])
+    x0 = FlowMolB200.centered_normal(n, torch.Generator().manual_seed(3))
+    assert torch.equal(x0, FlowMolB200.centered_normal(n, torch.Generator().manual_seed(3)))
+    noff = np.concatenate([[0], np.cumsum(n)])
+    for b in range(len(n)):                                   # every molecule is COM-free (priors.py:27-35)
+        assert x0[noff[b]:noff[b + 1]].mean(0).abs().max() < 1e-6
+    me = SimpleNamespace(n_atom_types=6, n_bond_types=4, fake_atoms=True)
+    parts = []
+    for lo, hi in SH.partition(n, 3):
+        pr = FlowMolB200.prior_from_x0(me, n[lo:hi], x0[noff[lo]:noff[hi]])
+        N, E = int(n[lo:hi].sum()), int((n[lo:hi] * (n[lo:hi] - 1)).sum())
+        assert pr['x_0'].shape == (N, 3) and pr['a_0'].shape == (N, 7) and pr['c_0'].shape == (N, 7) and pr['e_0'].shape == (E, 5)
+        assert (pr['a_0'].argmax(-1) == 6).all() and (pr['e_0'].argmax(-1) == 4).all() and pr['fake_atoms'] is True
+        parts.append(pr['x_0'])
+    assert torch.equal(torch.cat(parts), x0)

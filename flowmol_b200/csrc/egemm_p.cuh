@@ -84,6 +84,8 @@ k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
   constexpr int NIMG = IMG_IN ? ((MODE == EG_MSG0 || IS_EU) ? D::F / 64 : S / 64) : 0;
   static_assert(NIMG <= NSLAB, "image slabs are a prefix of K");
   constexpr int FIRST_CH = 2 * NIMG;                        // first chunk the loader warps convert
+  static_assert(!(MODE == EG_MSG0 || MODE == EG_EU1 || MODE == EG_MSGA) || FIRST_CH < NCH,
+                "modes whose epilogue needs the row bookkeeping must have a converted chunk: the loaders publish it from rowinfo()");
   constexpr int SH_W = 40;
   constexpr int LO_OFF = 16384;
   extern __shared__ __align__(1024) uint8_t smem_dyn[];

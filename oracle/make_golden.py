@@ -146,6 +146,46 @@ def gen_integrate(name, cfg_name, A, wseed, n_atoms, T, nseed):
     print(name, "N", N, "final a", out["a_1"][:10], "masked left", int((out["a_1"] == A).sum()))
 
 
+# dfm_type='gat' with non-default schedules (ctmc_vector_field.py:71-95,463-510): name, config, A, weight seed, sizes, T, noise seed
+CASES_GAT = [("itg_dev_gat_T12", "dev", 6, 11, [4, 9, 15], 12, 555)]
+GAT_SCHEDULES = dict(cat_temperature_schedule="decay", cat_temp_decay_max=0.8, cat_temp_decay_a=2.0,
+                     forward_weight_schedule="beta", fw_beta_a=0.25, fw_beta_b=0.25, fw_beta_max=10.0)
+
+
+def gen_integrate_gat(name, cfg_name, A, wseed, n_atoms, T, nseed):
+    """The verbatim reference with dfm_type='gat', its own 'decay' temperature and 'beta' forward-weight schedule builders."""
+    R = RL.load()
+    cfg, m, sd = _model(cfg_name, A, wseed)
+    gen = torch.Generator().manual_seed(2000 + nseed)
+    g, nbi, ebi, uem = RL.build_reference_graph(n_atoms, generator=gen)
+    N, U = g.num_nodes(), int(uem.sum())
+    g.ndata['a_0'] = R.priors.ctmc_masked_prior(N, A)
+    g.ndata['c_0'] = R.priors.ctmc_masked_prior(N, 6)
+    ep = R.priors.ctmc_masked_prior(U, 4)
+    e0 = torch.zeros(uem.shape[0], 5)
+    e0[uem] = ep
+    e0[~uem] = ep
+    g.edata['e_0'] = e0
+    x0 = g.ndata['x_0'].clone()
+    S = GAT_SCHEDULES
+    ctf = m.build_cat_temp_schedule(S["cat_temperature_schedule"], S["cat_temp_decay_max"], S["cat_temp_decay_a"])
+    fwf = m.build_fw_schedule(S["forward_weight_schedule"], S["fw_beta_a"], S["fw_beta_b"], S["fw_beta_max"])
+    with torch.no_grad(), RL.injected_noise(m, n_atoms, seed=nseed):
+        g2, traj = m.integrate(g, nbi, upper_edge_mask=uem, n_timesteps=T, visualize=True, dfm_type='gat',
+                               stochasticity=None, high_confidence_threshold=None, cat_temp_func=ctf, forward_weight_func=fwf)
+    out = {"config": cfg_name, "n_atom_types": A, "weight_seed": wseed, "n_atoms": np.array(n_atoms), "T": T,
+           "noise_seed": nseed, "weights_checksum": WT.weights_checksum(sd), "x_0": x0.numpy(), "dfm_type": "gat",
+           "x_1": g2.ndata['x_1'].numpy(), "a_1": g2.ndata['a_1'].argmax(-1).numpy(),
+           "c_1": g2.ndata['c_1'].argmax(-1).numpy(), "e_1": g2.edata['e_1'][uem].argmax(-1).numpy(),
+           "e_1_lower": g2.edata['e_1'][~uem].argmax(-1).numpy()}
+    out.update({k: np.array(v) for k, v in S.items()})
+    out["traj0.x"] = traj[0]['x'].numpy()
+    out["traj0.a"] = traj[0]['a'].argmax(-1).numpy()
+    out["traj0.a_1_pred"] = traj[0]['a_1_pred'].argmax(-1).numpy()          # the reference records p itself here: its argmax
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "N", N, "final a", out["a_1"][:10], "masked left", int((out["a_1"] == A).sum()))
+
+
 def gen_ctmc_cases():
     """campbell_step / purity_sampling on crafted states (h = 0, h = m, nothing masked, last step)."""
     R = RL.load()
@@ -212,6 +252,8 @@ def main():
         gen_forward(*c)
     for c in CASES_INTEGRATE:
         gen_integrate(*c)
+    for c in CASES_GAT:
+        gen_integrate_gat(*c)
     gen_ctmc_cases()
 
 

@@ -27,3 +27,15 @@ def model_from_golden(gd, dtype=torch.float32):
 def t(a, dtype=None):
     x = torch.from_numpy(np.asarray(a))
     return x if dtype is None else x.to(dtype)
+
+
+def golden_schedules(gd):
+    """(cat_temp_func, forward_weight_func) of a golden generated with non-default schedules (oracle/make_golden.py:GAT_SCHEDULES),
+    rebuilt with the product's host-side builders (flowmol_b200/vector_field.py == ctmc_vector_field.py:71-95)."""
+    from flowmol_b200.vector_field import build_cat_temp_schedule, build_fw_schedule
+    sched = str(gd["cat_temperature_schedule"])
+    ctf = build_cat_temp_schedule(sched if sched == "decay" else float(sched), float(gd["cat_temp_decay_max"]),
+                                  float(gd["cat_temp_decay_a"]))
+    fwf = build_fw_schedule(str(gd["forward_weight_schedule"]), float(gd["fw_beta_a"]), float(gd["fw_beta_b"]),
+                            float(gd["fw_beta_max"]))
+    return ctf, fwf

@@ -101,29 +101,6 @@ def test_trajectory_vs_reference_golden(name):
     np.testing.assert_allclose(out["x"], gd["x_1"], rtol=0, atol=1e-4)
 
 
-def test_gat_trajectory_vs_reference_golden():
-    """dfm_type='gat' + 'decay' temperature + 'beta' forward weights against the golden the verbatim reference produced
-    (oracle/make_golden.py:gen_integrate_gat): final state, and molecule 0's state / recorded endpoint at every step."""
-    gd = load_golden("itg_dev_gat_T12")
-    cfg, vf = model_for(gd)
-    n_atoms = gd["n_atoms"]
-    N, U = int(n_atoms.sum()), int((n_atoms * (n_atoms - 1) // 2).sum())
-    A = cfg.n_atom_types
-    ctf, fwf = golden_schedules(gd)
-    out = vf.integrate_tokens(n_atoms, t(gd["x_0"]), torch.full((N,), A), torch.full((N,), 6), torch.full((U,), 4),
-                              int(gd["T"]), seed=int(gd["noise_seed"]), traj=True, dfm_type='gat', cat_temp_func=ctf,
-                              forward_weight_func=fwf)
-    assert np.array_equal(out["a"].cpu().numpy(), gd["a_1"])
-    assert np.array_equal(out["c"].cpu().numpy(), gd["c_1"])
-    assert np.array_equal(out["e"].cpu().numpy(), gd["e_1"])
-    np.testing.assert_allclose(out["x"].cpu().numpy(), gd["x_1"], rtol=0, atol=1e-4)
-    n0 = int(n_atoms[0])
-    fr = {k: v.cpu().numpy() for k, v in out["traj"].items()}
-    assert np.array_equal(fr["a"][:, :n0], gd["traj0.a"])
-    assert np.array_equal(fr["a_1_pred"][:, :n0], gd["traj0.a_1_pred"])
-    np.testing.assert_allclose(fr["x"][:, :n0], gd["traj0.x"], rtol=0, atol=1e-4)
-
-
 def _oracle_vs_cuda_forward(cfg_name, A, n_atoms, wseed, seed):
     cfg, vf = cuda_model(cfg_name, A, wseed)
     om = O.OracleModel(cfg, WT.init_state_dict(cfg, wseed))
@@ -437,3 +414,26 @@ def test_fp16_operand_overflow_is_reported_not_silent():
     vf.set_option("tc_prec", 0)
     d = vf.forward_tokens(*args)
     assert torch.isfinite(d["a"]).all()
+
+
+def test_gat_trajectory_vs_reference_golden():
+    """dfm_type='gat' + 'decay' temperature + 'beta' forward weights against the golden the verbatim reference produced
+    (oracle/make_golden.py:gen_integrate_gat): final state, and molecule 0's state / recorded endpoint at every step."""
+    gd = load_golden("itg_dev_gat_T12")
+    cfg, vf = model_for(gd)
+    n_atoms = gd["n_atoms"]
+    N, U = int(n_atoms.sum()), int((n_atoms * (n_atoms - 1) // 2).sum())
+    A = cfg.n_atom_types
+    ctf, fwf = golden_schedules(gd)
+    out = vf.integrate_tokens(n_atoms, t(gd["x_0"]), torch.full((N,), A), torch.full((N,), 6), torch.full((U,), 4),
+                              int(gd["T"]), seed=int(gd["noise_seed"]), traj=True, dfm_type='gat', cat_temp_func=ctf,
+                              forward_weight_func=fwf)
+    assert np.array_equal(out["a"].cpu().numpy(), gd["a_1"])
+    assert np.array_equal(out["c"].cpu().numpy(), gd["c_1"])
+    assert np.array_equal(out["e"].cpu().numpy(), gd["e_1"])
+    np.testing.assert_allclose(out["x"].cpu().numpy(), gd["x_1"], rtol=0, atol=1e-4)
+    n0 = int(n_atoms[0])
+    fr = {k: v.cpu().numpy() for k, v in out["traj"].items()}
+    assert np.array_equal(fr["a"][:, :n0], gd["traj0.a"])
+    assert np.array_equal(fr["a_1_pred"][:, :n0], gd["traj0.a_1_pred"])
+    np.testing.assert_allclose(fr["x"][:, :n0], gd["traj0.x"], rtol=0, atol=1e-4)

@@ -15,6 +15,7 @@
 #include "egemm_tc.cuh"
 #include "egemm_p.cuh"
 #include "vec_stages.cuh"
+#include "vec_reg.cuh"
 #include "tc_test.cuh"
 
 namespace {
@@ -113,6 +114,7 @@ struct FmHandle {
   int conv_impl = 0;           // 0: fp32 CUDA-core k_conv_edge, 1: tcgen05 3xTF32 k_conv_edge_tc (flowmol3 dims only)
   int eg_persist = 1;          // tc_prec 1: persistent role-specialised k_egemm_p (1 CTA / SM, double-buffered accumulators)
   int eg_img = 1;              // k_egemm_p: consecutive tensor-core linears hand their activations over as fp16 (hi, lo) operand images
+  int vec_impl = 1;            // edge-row vector stages: 1 = register-resident warp units (vec_reg.cuh, needs the image chain), 0 = vec_stages.cuh
   int tc_prec = 0;             // operand format of k_egemm_tc: 0 = 3xTF32 images, 1 = scaled fp16 hi/lo images ("fp16x3")
   bool has_h16 = false;        // packed weights carry the fp16 images
   int* d_status = nullptr;     // device status word: bit 0 = an activation left the fp16 operand range (tc_prec 1)
@@ -247,7 +249,12 @@ int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
     const bool img = img_on(h);
     const size_t vsm = fm::VecSmem<D>::BYTES;
     const int vgrid = L.nET < 2 * h->n_sm ? L.nET : 2 * h->n_sm;     // persistent: 2 CTAs per SM, tiles strided
-    fm::k_vec_a<D><<<vgrid, fm::NT, vsm, st>>>(m, bt, l, x, v, VH, SH);
+    // register-resident vector stages (vec_reg.cuh): one warp per 16-row unit, VH holds VU = Vh_ext Wu (3 x 32 per row) instead
+    const bool vr = img && h->vec_impl == 1;
+    const int n_units = L.nET * (fm::TM / fm::UR);
+    const int vrgrid = (n_units + fm::NWARP - 1) / fm::NWARP < 2 * h->n_sm ? (n_units + fm::NWARP - 1) / fm::NWARP : 2 * h->n_sm;
+    if (!vr) fm::k_vec_a<D><<<vgrid, fm::NT, vsm, st>>>(m, bt, l, x, v, VH, SH);
+    else fm::k_vecr_a<D><<<vrgrid, fm::NT, 0, st>>>(m, bt, l, n_units, x, v, VH, SH);
     LAUNCH_OK(h);
     const int tcw[3] = {fm::C_MSG0_TCW, fm::C_MSG1_TCW, fm::C_MSG2_TCW}, tcg[3] = {fm::C_MSG0_TCG, fm::C_MSG1_TCG, fm::C_MSG2_TCG};
     const int gb[3] = {fm::C_MSG0_WHCP, fm::C_MSG1_WHCP, fm::C_MSG2_WHCP};
@@ -285,13 +292,18 @@ int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
       else launch_eg<D, fm::EG_GATE, 1>(h, (int)(L.EPA / 128), st, m, bt, ag);
       LAUNCH_OK(h);
       if (g < 2) {
-        fm::k_vec_b<D><<<vgrid, fm::NT, vsm, st>>>(bt, wptr(g == 0 ? fm::C_MSG0_WU : fm::C_MSG1_WU), (g == 0 ? D::H0 : D::V) + D::CP,
+        if (!vr)
+          fm::k_vec_b<D><<<vgrid, fm::NT, vsm, st>>>(bt, wptr(g == 0 ? fm::C_MSG0_WU : fm::C_MSG1_WU), (g == 0 ? D::H0 : D::V) + D::CP,
                                                      wptr(g == 0 ? fm::C_MSG1_WHCP : fm::C_MSG2_WHCP), 0, VH, SH, GT);
+        else
+          fm::k_vecr_b<D><<<vrgrid, fm::NT, 0, st>>>(bt, wptr(g == 0 ? fm::C_MSG1_WHCP : fm::C_MSG2_WHCP),
+                                                      wptr(g == 0 ? fm::C_MSG1_WU : fm::C_MSG2_WU), n_units, VH, SH, GT);
         LAUNCH_OK(h);
       }
       cur = outs[g];
     }
-    fm::k_vec_c<D><<<vgrid, fm::NT, vsm, st>>>(m, bt, l, h->fuse_agg ? D::S : 0, VH, GT, SA, M, partF, partL);
+    if (!vr) fm::k_vec_c<D><<<vgrid, fm::NT, vsm, st>>>(m, bt, l, h->fuse_agg ? D::S : 0, VH, GT, SA, M, partF, partL);
+    else fm::k_vecr_c<D><<<(L.nET + fm::NWARP - 1) / fm::NWARP, fm::NT, 0, st>>>(bt, VH, GT, M, partF, partL);
     LAUNCH_OK(h);
   }
   return 0;
@@ -483,6 +495,23 @@ void time_grid(int n, float* t) {
 
 float clamp01(float v) { return v < 0.f ? 0.f : (v > 1.f ? 1.f : v); }
 
+// campbell_step's jump probabilities of one step in the reference's fp32 arithmetic (ctmc_vector_field.py:430-434), linear
+// schedule: alpha_t = t, alpha_t' = 1 for every modality
+void step_probs(fm::StepScalars& sc, float t_i, float dt, float eta) {
+  sc.t_i = t_i;
+  sc.dt = dt;
+  for (int m = 0; m < 3; ++m) {
+    volatile float num = 1.0f + eta * t_i;
+    volatile float q = dt * num;
+    volatile float den = 1.0f - t_i;
+    sc.unmask_prob[m] = clamp01(q / den);
+    volatile float qm = dt * eta;
+    sc.mask_prob[m] = clamp01(qm);
+  }
+  sc.inj_u = nullptr;
+  sc.inj_n = 0;
+}
+
 int find_batch(FmHandle* h, void* ws, const Layout** L) {
   auto it = h->batches.find(ws);
   if (it == h->batches.end()) return fail("workspace has no batch: call fm_batch_init first");
@@ -669,17 +698,7 @@ int fm_integrate_traj(FmHandle* h, void* ws, float* x, uint8_t* a, uint8_t* c, u
     rc = dispatch_forward(h, ws, L, x, a, c, e, t_i, k == 1 ? nullptr : &prv, cur, -1, st);
     if (rc) break;
     fm::StepScalars sc;
-    sc.t_i = t_i;
-    sc.dt = s_i - t_i;
-    const float eta = o->stochasticity;
-    for (int m = 0; m < 3; ++m) {                                   // linear schedule: alpha_t = t, alpha_t' = 1
-      volatile float num = 1.0f + eta * t_i;
-      volatile float q = sc.dt * num;
-      volatile float den = 1.0f - t_i;
-      sc.unmask_prob[m] = clamp01(q / den);
-      volatile float qm = sc.dt * eta;
-      sc.mask_prob[m] = clamp01(qm);
-    }
+    step_probs(sc, t_i, s_i - t_i, o->stochasticity);
     sc.hc_thresh = o->high_confidence_threshold;
     sc.tau = o->tau_host ? o->tau_host[k - 1] : o->cat_temperature;
     sc.dfm_type = o->dfm_type;
@@ -824,6 +843,62 @@ int fm_time_egemm_msg(FmHandle* h, void* ws, int32_t layer, int32_t iters, float
   return 0;
 }
 
+// One campbell_step of the production step kernel on crafted inputs (tests/golden/ctmc_cases.npz: h = 0, h = m, m = 0, last step,
+// eta = 0): the atom-type modality of k_ctmc_step with K classes, the given sampling distribution p (not sharpened again) and
+// injected uniforms instead of Philox.  Host buffers; the other two modalities run on one-class dummies.
+int fm_debug_ctmc_step(const int32_t* n_atoms_host, int32_t B, int32_t K, const float* p_host, uint8_t* state_host, uint8_t* x1_host,
+                       const float* uniforms_host, float t_i, float dt, float eta, float hc_thresh, int32_t last_step, int device) {
+  if (!n_atoms_host || !p_host || !state_host || !x1_host || !uniforms_host || B < 1 || K < 1 || K > fm::KMAXC)
+    return fail("fm_debug_ctmc_step: bad argument");
+  CUDA_OK(cudaSetDevice(device));
+  std::vector<int> mol_n(B), mol_node(B), mol_u(B);
+  int N = 0, U = 0;
+  for (int b = 0; b < B; ++b) {
+    if (n_atoms_host[b] < 1) return fail("fm_debug_ctmc_step: empty molecule");
+    mol_n[b] = n_atoms_host[b]; mol_node[b] = N; mol_u[b] = U;
+    N += mol_n[b]; U += mol_n[b] * (mol_n[b] - 1) / 2;
+  }
+  int *d_n = nullptr, *d_node = nullptr, *d_u = nullptr;
+  float *d_p = nullptr, *d_one = nullptr, *d_x = nullptr, *d_px = nullptr, *d_inj = nullptr;
+  uint8_t *d_a = nullptr, *d_zero = nullptr, *d_x1 = nullptr;
+  const size_t big = (size_t)(N > U ? N : U) + 1;
+  CUDA_OK(cudaMalloc(&d_n, 4 * B)); CUDA_OK(cudaMalloc(&d_node, 4 * B)); CUDA_OK(cudaMalloc(&d_u, 4 * B));
+  CUDA_OK(cudaMalloc(&d_p, sizeof(float) * N * K)); CUDA_OK(cudaMalloc(&d_one, sizeof(float) * big));
+  CUDA_OK(cudaMalloc(&d_x, sizeof(float) * 3 * N)); CUDA_OK(cudaMalloc(&d_px, sizeof(float) * 3 * N)); CUDA_OK(cudaMalloc(&d_inj, sizeof(float) * 3 * N));
+  CUDA_OK(cudaMalloc(&d_a, N)); CUDA_OK(cudaMalloc(&d_zero, big)); CUDA_OK(cudaMalloc(&d_x1, N));
+  CUDA_OK(cudaMemcpy(d_n, mol_n.data(), 4 * B, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(d_node, mol_node.data(), 4 * B, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(d_u, mol_u.data(), 4 * B, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(d_p, p_host, sizeof(float) * N * K, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(d_inj, uniforms_host, sizeof(float) * 3 * N, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(d_a, state_host, N, cudaMemcpyHostToDevice));
+  std::vector<float> ones(big, 1.0f);
+  CUDA_OK(cudaMemcpy(d_one, ones.data(), sizeof(float) * big, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemset(d_zero, 0, big));
+  CUDA_OK(cudaMemset(d_x, 0, sizeof(float) * 3 * N));
+  CUDA_OK(cudaMemset(d_px, 0, sizeof(float) * 3 * N));
+  fm::BatchRT bt{};
+  bt.B = B; bt.N = N; bt.U = U;
+  bt.mol_n = d_n; bt.mol_node = d_node; bt.mol_u = d_u;
+  fm::StepScalars sc;
+  step_probs(sc, t_i, dt, eta);
+  sc.hc_thresh = hc_thresh;
+  sc.tau = 0.f;                          // p is used as given
+  sc.dfm_type = 0; sc.fw = 1.f; sc.bw = 0.f; sc.inv_temp = 1.f;
+  sc.last_step = last_step; sc.step_index = 1; sc.seed_lo = 0; sc.seed_hi = 0; sc.mol_id_offset = 0;
+  sc.inj_u = d_inj; sc.inj_n = N;
+  fm::TrajFrame tf{nullptr, nullptr, nullptr, nullptr, nullptr, d_x1, nullptr, nullptr};
+  // charges / bonds: one class with probability 1 on an unmasked state (a no-op for those modalities)
+  fm::k_ctmc_step<<<B, 256>>>(bt, K, 1, 1, d_px, d_p, d_one, d_one, d_x, d_a, d_zero, d_zero, sc, tf);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaDeviceSynchronize());
+  CUDA_OK(cudaMemcpy(state_host, d_a, N, cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(x1_host, d_x1, N, cudaMemcpyDeviceToHost));
+  cudaFree(d_n); cudaFree(d_node); cudaFree(d_u); cudaFree(d_p); cudaFree(d_one); cudaFree(d_x); cudaFree(d_px); cudaFree(d_inj);
+  cudaFree(d_a); cudaFree(d_zero); cudaFree(d_x1);
+  return 0;
+}
+
 int fm_set_option(FmHandle* h, const char* name, int32_t value) {
   if (!h || !name) return fail("fm_set_option: null argument");
   const std::string n(name);
@@ -843,6 +918,7 @@ int fm_set_option(FmHandle* h, const char* name, int32_t value) {
   if (n == "fuse_agg") { h->fuse_agg = value ? 1 : 0; return 0; }
   if (n == "eg_persist") { h->eg_persist = value ? 1 : 0; return 0; }
   if (n == "eg_img") { h->eg_img = value ? 1 : 0; return 0; }
+  if (n == "vec_impl") { h->vec_impl = value ? 1 : 0; return 0; }
   if (n == "tc_prec") {
     if (value < 0 || value > 1) return fail("fm_set_option: tc_prec must be 0 (3xTF32) or 1 (fp16x3)");
     if (value == 1 && !h->has_h16) return fail("fm_set_option: packed weights carry no fp16 operand images");
@@ -897,6 +973,7 @@ int fm_get_option(FmHandle* h, const char* name, int32_t* value) {
   if (std::string(name) == "tc_prec") { *value = h->tc_prec; return 0; }
   if (std::string(name) == "eg_persist") { *value = h->eg_persist; return 0; }
   if (std::string(name) == "eg_img") { *value = h->eg_img; return 0; }
+  if (std::string(name) == "vec_impl") { *value = h->vec_impl; return 0; }
   if (std::string(name) == "status") {      // synchronising read-and-clear of the device status word (see fm_check_status)
     int v = 0;
     CUDA_OK(cudaSetDevice(h->device));

@@ -22,10 +22,17 @@ struct StepScalars {
   int dfm_type;                          // 0 campbell, 1 gat (ctmc_vector_field.py:377-394,463-510)
   float fw, bw;                          // gat: forward weight of this step and the reference's `forward_weight - 1`
   float inv_temp;                        // factor of the position update (inv_temp_func(t_i), :334); 1 by default
+  const float* inj_u;                    // test hook (fm_debug_ctmc_step): [3][N] uniforms of the atom-type modality replacing Philox
+  int inj_n;                             //   (categorical draw, unmask draw, re-mask draw of node i at inj_u[k * inj_n + i]); NULL otherwise
 };
 
 // p = softmax(log(p_hat) / tau); returns max_k p_k ("purity")          (ctmc_vector_field.py:354-356)
 __device__ __forceinline__ float sharpen(const float* __restrict__ phat, int K, float tau, float* p) {
+  if (tau <= 0.f) {                      // test hook: p_hat already is the sampling distribution (campbell_step called directly)
+    float pur = 0.f;
+    for (int k = 0; k < K; ++k) { p[k] = phat[k]; pur = fmaxf(pur, p[k]); }
+    return pur;
+  }
   float mx = -INFINITY;
 #pragma unroll 4
   for (int k = 0; k < K; ++k) { p[k] = __fdiv_rn(logf(phat[k]), tau); mx = fmaxf(mx, p[k]); }
@@ -53,7 +60,8 @@ __device__ __forceinline__ int block_sum_int(int v, int* scratch /*NWARP ints*/)
 // (the reference's `<feat>_t` and `<feat>_1_pred` after the step, ctmc_vector_field.py:408-409 / 235-255)
 __device__ __forceinline__ void campbell_modality(const float* __restrict__ phat /*[cnt][K]*/, uint8_t* __restrict__ state,
                                                   int cnt, int K, int modality, uint32_t mol_gid, const StepScalars& sc,
-                                                  int* scratch, uint8_t* __restrict__ frame, uint8_t* __restrict__ x1_frame) {
+                                                  int* scratch, uint8_t* __restrict__ frame, uint8_t* __restrict__ x1_frame,
+                                                  int item0 = 0) {
   const float q_u = sc.unmask_prob[modality], q_m = sc.mask_prob[modality];
   float p[KMAXC];
   if (sc.dfm_type == 1) {
@@ -109,10 +117,14 @@ __device__ __forceinline__ void campbell_modality(const float* __restrict__ phat
     const int z = state[it];
     const float pur = sharpen(phat + (size_t)it * K, K, sc.tau, p);
     const Philox4 rnd = philox4x32_10((uint32_t)it, mol_gid, (uint32_t)sc.step_index, (uint32_t)modality, sc.seed_lo, sc.seed_hi);
+    float u_cat = u24(rnd.x), u_unmask = u24(rnd.y), u_mask = u24(rnd.z);
+    if (sc.inj_u && modality == 0) {
+      u_cat = sc.inj_u[item0 + it]; u_unmask = sc.inj_u[sc.inj_n + item0 + it]; u_mask = sc.inj_u[2 * sc.inj_n + item0 + it];
+    }
     // inverse-CDF categorical draw (shared definition with oracle/flowmol_oracle.py:sample_categorical)
     float c = 0.f, cum[KMAXC];
     for (int k = 0; k < K; ++k) { c = __fadd_rn(c, p[k]); cum[k] = c; }
-    const float thr = __fmul_rn(u24(rnd.x), c);
+    const float thr = __fmul_rn(u_cat, c);
     int x1 = 0;
     for (int k = 0; k < K; ++k) x1 += (cum[k] <= thr) ? 1 : 0;
     x1 = min(x1, K - 1);
@@ -120,9 +132,9 @@ __device__ __forceinline__ void campbell_modality(const float* __restrict__ phat
     float prob;
     if (sc.hc_thresh > 0.f) prob = masked ? (pur >= sc.hc_thresh ? ph : pl) : 0.f;
     else prob = masked ? q_u : 0.f;
-    const bool will_unmask = u24(rnd.y) < prob;
+    const bool will_unmask = u_unmask < prob;
     int zn = z;
-    if (!sc.last_step && (u24(rnd.z) < q_m) && !masked) zn = K;
+    if (!sc.last_step && (u_mask < q_m) && !masked) zn = K;
     if (will_unmask) zn = x1;
     state[it] = (uint8_t)zn;
     if (frame) frame[it] = (uint8_t)zn;
@@ -157,7 +169,7 @@ k_ctmc_step(const BatchRT bt, int A, int C, int EB, const float* __restrict__ px
     if (tf.x1) tf.x1[g] = px[g];
   }
   const uint32_t gid = (uint32_t)(mol + sc.mol_id_offset);
-  campbell_modality(pa + (size_t)nb * A, a_t + nb, n, A, 0, gid, sc, scratch, tf.a ? tf.a + nb : nullptr, tf.a1 ? tf.a1 + nb : nullptr);
+  campbell_modality(pa + (size_t)nb * A, a_t + nb, n, A, 0, gid, sc, scratch, tf.a ? tf.a + nb : nullptr, tf.a1 ? tf.a1 + nb : nullptr, nb);
   campbell_modality(pc + (size_t)nb * C, c_t + nb, n, C, 1, gid, sc, scratch, tf.c ? tf.c + nb : nullptr, tf.c1 ? tf.c1 + nb : nullptr);
   campbell_modality(pe + (size_t)ub * EB, e_t + ub, ucount, EB, 2, gid, sc, scratch, tf.e ? tf.e + ub : nullptr, tf.e1 ? tf.e1 + ub : nullptr);
 }

@@ -1,0 +1,413 @@
+// Register-resident vector-channel stages of the message GVPs (edge rows of the wide tensor-core pipeline).
+//
+// What the profiles said about vec_stages.cuh (profiles/r01s, r01y): k_vec_a/b/c are 26 % of a network evaluation and run at
+// 25-52 % of the HBM peak -- every 16-row block goes global -> registers -> shared -> (GEMM) -> shared -> (cross, norms) -> shared
+// -> (GEMM) -> shared -> global behind seven 64-thread barriers, and only the first of those phases has memory requests in flight.
+//
+// Here ONE WARP owns a unit of 16 rows (edges) end to end and nothing but the weights lives in shared memory:
+//   * an m16 MMA tile is the 16 rows of ONE xyz plane (not 16 consecutive (row, plane) pairs), the three planes are three tiles of
+//     the same warp: a thread then holds x, y and z of the same (row, column) -- norms and cross products are thread-local
+//     (the cross product's two column groups meet through one shuffle) -- and
+//   * the accumulator fragment of the first GEMM ([Vh | Vcp] = V [Wh | Wcp]) IS the A fragment of the second (Vu = Vh_ext Wu):
+//     c0..c3 of n-tiles 2j, 2j+1 are a0..a3 of k-step j, so the chain never leaves the register file;
+//   * the A operand of the first GEMM is loaded from global memory in fragment layout (a quad reads 32 contiguous bytes of a row),
+//     the next unit's rows are prefetched HBM -> L2 with one bulk-prefetch instruction each while this one computes.
+// No barriers, no activation tiles in shared memory, warps drift freely: memory requests of ~16 warps per SM overlap all the time.
+//
+// The global intermediates change with it: instead of VH (= [Vh | cross], 3 x 40 floats per row, consumed by the NEXT kernel's
+// Vu GEMM) a stage stores VU = Vh_ext Wu (3 x 32), i.e. both GEMMs of a GVP sit in the kernel that produced Vh, the kernel after
+// the gate linear starts with V' = gate * VU, and the last stage (k_vecr_c) has no GEMM at all.  Same arithmetic on the same
+// values in the same order as vec_stages.cuh (k_vecr_b / k_vecr_c: bit-identical; k_vecr_a orders K as v_src | x_diff so that its
+// fragment loads are aligned -- a different summation order inside the first MMA k-steps).
+//
+//   k_vecr_a : gather x / v of src;  Vh0 = [v_src | x_diff] [Wh | Wcp], cross, norms -> SH;  VU = Vh0_ext Wu      (message GVP 0)
+//   k_vecr_b : V' = GT * VU (GVP g);  Vh = V' [Wh | Wcp], cross, norms -> SH;  VU = Vh_ext Wu                      (GVP g + 1)
+//   k_vecr_c : V' = GT * VU (GVP 2), segment-sum over the in-edges of every destination -> M / partL / partF (vector columns)
+#pragma once
+#include "vec_stages.cuh"
+
+namespace fm {
+
+constexpr int VUW = 96;       // floats per row of VU: 3 planes x 32 vector channels
+constexpr int UR = 16;        // rows per unit (= one m16 tile per plane)
+
+struct VrUnit {
+  int nvalid;                 // live rows (a prefix of the unit)
+  int n, nb, le0;             // atoms / first node of the unit's molecule, local edge index of row 0
+};
+__device__ __forceinline__ VrUnit vr_unit(const BatchRT& bt, int unit) {
+  VrUnit u;
+  const int tile = unit >> 2, mol = __ldg(bt.etile_mol + tile);
+  u.n = __ldg(bt.mol_n + mol);
+  u.nb = __ldg(bt.mol_node + mol);
+  u.le0 = (tile - __ldg(bt.mol_etile + mol)) * TM + (unit & 3) * UR;
+  u.nvalid = max(0, min(UR, u.n * (u.n - 1) - u.le0));
+  return u;
+}
+
+// load_resident_h16 with an optional row rotation: rot1 != 0 puts source row 0 LAST (smem row k <- source row k + 1 for k < Kreal - 1,
+// smem row Kreal - 1 <- source row 0): message GVP 0 contracts over [v_src | x_diff] instead of the reference's [x_diff | v_src]
+__device__ __forceinline__ WH16 vr_load_w(float* dst, const float* __restrict__ src, int K, int Kreal, int np, int ld, int rot1, float* red) {
+  const int tid = threadIdx.x;
+  float mx = 0.f;
+  for (int i = tid; i < K * np; i += NT) mx = fmaxf(mx, fabsf(__ldg(src + i)));
+  mx = warp_max(mx);
+  if ((tid & 31) == 0) red[tid >> 5] = mx;
+  __syncthreads();
+  mx = 0.f;
+#pragma unroll
+  for (int w = 0; w < NWARP; ++w) mx = fmaxf(mx, red[w]);
+  __syncthreads();
+  const int e = mx >= 1e-30f ? (int)((__float_as_uint(mx) >> 23) & 0xffu) - 127 : 13;
+  const float scale = __uint_as_float((uint32_t)(127 + 13 - e) << 23), inv = __uint_as_float((uint32_t)(127 - 13 + e) << 23);
+  const int kp2 = ((K + 7) & ~7) >> 1;
+  uint32_t* hi = reinterpret_cast<uint32_t*>(dst);
+  uint32_t* lo = hi + kp2 * ld;
+  auto srow = [&](int k) { return rot1 ? (k < Kreal - 1 ? k + 1 : (k == Kreal - 1 ? 0 : k)) : k; };
+  for (int i = tid; i < kp2 * np; i += NT) {
+    const int r = i / np, n = i - r * np, k = 2 * r;
+    const float w0 = k < K ? __ldg(src + srow(k) * np + n) * scale : 0.f, w1 = k + 1 < K ? __ldg(src + srow(k + 1) * np + n) * scale : 0.f;
+    uint32_t h2, l2;
+    tc::split_h16x2(w0, w1, h2, l2);
+    hi[r * ld + n] = h2;
+    lo[r * ld + n] = l2;
+  }
+  return WH16{hi, lo, inv};
+}
+
+// D[p][nt] += A[p] W for the three planes p, one k-step of 16 (8): the same three products in the same order as warp_gemm_h16x3
+template <int NTL>
+__device__ __forceinline__ void vr_kstep16(float (&acc)[3][NTL][4], const uint32_t (&ah)[3][4], const uint32_t (&al)[3][4],
+                                           const uint32_t* __restrict__ Wh, const uint32_t* __restrict__ Wl, int ldw, int k0, int g, int t) {
+#pragma unroll
+  for (int nt = 0; nt < NTL; ++nt) {
+    uint32_t bh[2], bl[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int w = ((k0 >> 1) + t + 4 * i) * ldw + 8 * nt + g;
+      bh[i] = Wh[w]; bl[i] = Wl[w];
+    }
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+      mma_f16_16x8x16(acc[p][nt], al[p], bh);
+      mma_f16_16x8x16(acc[p][nt], ah[p], bl);
+      mma_f16_16x8x16(acc[p][nt], ah[p], bh);
+    }
+  }
+}
+template <int NTL>
+__device__ __forceinline__ void vr_kstep8(float (&acc)[3][NTL][4], const uint32_t (&ah)[3][2], const uint32_t (&al)[3][2],
+                                          const uint32_t* __restrict__ Wh, const uint32_t* __restrict__ Wl, int ldw, int k0, int g, int t) {
+#pragma unroll
+  for (int nt = 0; nt < NTL; ++nt) {
+    const int w = ((k0 >> 1) + t) * ldw + 8 * nt + g;
+    const uint32_t bh = Wh[w], bl = Wl[w];
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+      mma_f16_16x8x8(acc[p][nt], al[p], bh);
+      mma_f16_16x8x8(acc[p][nt], ah[p], bl);
+      mma_f16_16x8x8(acc[p][nt], ah[p], bh);
+    }
+  }
+}
+
+// The tail every stage shares: acc1 = [Vh | cross | 0] (already unscaled, cross products in place, columns >= hc zero) of the warp's
+// 16 rows x 3 planes -> norms to SH, Vu = Vh_ext Wu (K = hc padded to 40: k-steps 16, 16, 8) to VU.  NT1 >= 5 n-tiles.
+template <int NT1>
+__device__ __forceinline__ void vr_tail(float (&acc1)[3][NT1][4], const int hc, const WH16& wu, const size_t r0, const bool ok0, const bool ok1,
+                                        float* __restrict__ VU, float* __restrict__ SH) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  // gvp.py:14-21 sqrt(clamp(x^2 + y^2 + z^2, 1e-8)) per hidden vector channel; dead rows / padding columns store 0
+#pragma unroll
+  for (int nt = 0; nt < 5; ++nt)
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int col = 8 * nt + 2 * t;
+      const bool okr = hh ? ok1 : ok0;
+      float nn[2];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const float vx = acc1[0][nt][2 * hh + c], vy = acc1[1][nt][2 * hh + c], vz = acc1[2][nt][2 * hh + c];
+        const float q = __fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz));
+        nn[c] = (okr && col + c < hc) ? sqrt_pos(fmaxf(q, 1e-8f)) : 0.f;
+      }
+      *reinterpret_cast<float2*>(SH + (r0 + g + 8 * hh) * VHW + col) = make_float2(nn[0], nn[1]);
+    }
+  float acc2[3][4][4];
+#pragma unroll
+  for (int p = 0; p < 3; ++p)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc2[p][nt][i] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    uint32_t ah[3][4], al[3][4];
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+      tc::split_h16x2(acc1[p][2 * j][0], acc1[p][2 * j][1], ah[p][0], al[p][0]);
+      tc::split_h16x2(acc1[p][2 * j][2], acc1[p][2 * j][3], ah[p][1], al[p][1]);
+      tc::split_h16x2(acc1[p][2 * j + 1][0], acc1[p][2 * j + 1][1], ah[p][2], al[p][2]);
+      tc::split_h16x2(acc1[p][2 * j + 1][2], acc1[p][2 * j + 1][3], ah[p][3], al[p][3]);
+    }
+    vr_kstep16<4>(acc2, ah, al, wu.hi, wu.lo, WLD_U, 16 * j, g, t);
+  }
+  {
+    uint32_t ah[3][2], al[3][2];
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+      tc::split_h16x2(acc1[p][4][0], acc1[p][4][1], ah[p][0], al[p][0]);
+      tc::split_h16x2(acc1[p][4][2], acc1[p][4][3], ah[p][1], al[p][1]);
+    }
+    vr_kstep8<4>(acc2, ah, al, wu.hi, wu.lo, WLD_U, 32, g, t);
+  }
+  const float inv = wu.inv;
+#pragma unroll
+  for (int p = 0; p < 3; ++p)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh)
+        *reinterpret_cast<float2*>(VU + (r0 + g + 8 * hh) * VUW + p * 32 + 8 * nt + 2 * t) =
+            make_float2(acc2[p][nt][2 * hh] * inv, acc2[p][nt][2 * hh + 1] * inv);
+}
+
+// cross product of two 3-vectors with the roundings of torch.linalg.cross as vec_stage1 does them
+__device__ __forceinline__ void vr_cross(float ax, float ay, float az, float qx, float qy, float qz, float& rx, float& ry, float& rz) {
+  rx = __fsub_rn(__fmul_rn(ay, qz), __fmul_rn(az, qy));
+  ry = __fsub_rn(__fmul_rn(az, qx), __fmul_rn(ax, qz));
+  rz = __fsub_rn(__fmul_rn(ax, qy), __fmul_rn(ay, qx));
+}
+
+constexpr int VR_W1_WORDS = 2 * 20 * WLD_HCP;      // [Wh | Wcp] hi + lo, K <= 40
+constexpr int VR_W2_WORDS = 2 * 20 * WLD_U;        // Wu hi + lo, K <= 40
+
+template <class D>
+__global__ void __launch_bounds__(NT, 2)
+k_vecr_b(const BatchRT bt, const float* __restrict__ whcp, const float* __restrict__ wu, const int n_units,
+         float* __restrict__ VU, float* __restrict__ SH, const float* __restrict__ GT) {
+  static_assert(D::V == 32 && D::CP == 4, "fragment mapping: 32 vector channels, 4 cross-product features");
+  __shared__ __align__(16) float wsm[VR_W1_WORDS + VR_W2_WORDS];
+  __shared__ float red[NWARP];
+  const WH16 w1 = load_resident_h16(wsm, whcp, D::V, 32 * D::CPT_HC, WLD_HCP, red);
+  const WH16 w2 = load_resident_h16(wsm + VR_W1_WORDS, wu, pad4(D::V + D::CP), 32, WLD_U, red);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int nw = gridDim.x * NWARP;
+  for (int unit = blockIdx.x * NWARP + (threadIdx.x >> 5); unit < n_units; unit += nw) {
+    const VrUnit u = vr_unit(bt, unit);
+    const size_t r0 = (size_t)unit * UR;
+    if (lane == 0 && unit + nw < n_units) {
+      prefetch_l2(VU + (r0 + (size_t)nw * UR) * VUW, UR * VUW * 4);
+      prefetch_l2(GT + (r0 + (size_t)nw * UR) * 32, UR * 32 * 4);
+    }
+    const bool ok0 = g < u.nvalid, ok1 = g + 8 < u.nvalid;
+    // A fragments of V' = gate * VU straight from global memory: a0 (g, 2t) a1 (g + 8, 2t) a2 (g, 2t + 8) a3 (g + 8, 2t + 8)
+    float2 gv[2][4], vv[3][2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const size_t row = r0 + g + (i & 1) * 8;
+        const int col = 16 * ks + 2 * t + (i >> 1) * 8;
+        const bool ok = (i & 1) ? ok1 : ok0;
+        gv[ks][i] = ok ? *reinterpret_cast<const float2*>(GT + row * 32 + col) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+          vv[p][ks][i] = ok ? *reinterpret_cast<const float2*>(VU + row * VUW + p * 32 + col) : make_float2(0.f, 0.f);
+      }
+    float acc1[3][5][4];
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+#pragma unroll
+      for (int nt = 0; nt < 5; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc1[p][nt][i] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      uint32_t ah[3][4], al[3][4];
+#pragma unroll
+      for (int p = 0; p < 3; ++p)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          tc::split_h16x2(__fmul_rn(gv[ks][i].x, vv[p][ks][i].x), __fmul_rn(gv[ks][i].y, vv[p][ks][i].y), ah[p][i], al[p][i]);
+      vr_kstep16<5>(acc1, ah, al, w1.hi, w1.lo, WLD_HCP, 16 * ks, g, t);
+    }
+    {
+      const float inv = w1.inv;
+#pragma unroll
+      for (int p = 0; p < 3; ++p)
+#pragma unroll
+        for (int nt = 0; nt < 5; ++nt)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc1[p][nt][i] *= inv;
+    }
+    // cross products: n-tile 4 holds Vcp -- quads' lanes t = 0, 1 the columns 32 + 2t, 33 + 2t (first factors), lanes t + 2 the
+    // matching second factors 36 + 2t, 37 + 2t: one xor-2 exchange; the results replace the first factors, the rest becomes K padding
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float qx = __shfl_xor_sync(0xffffffffu, acc1[0][4][i], 2), qy = __shfl_xor_sync(0xffffffffu, acc1[1][4][i], 2),
+                  qz = __shfl_xor_sync(0xffffffffu, acc1[2][4][i], 2);
+      float rx, ry, rz;
+      vr_cross(acc1[0][4][i], acc1[1][4][i], acc1[2][4][i], qx, qy, qz, rx, ry, rz);
+      acc1[0][4][i] = t < 2 ? rx : 0.f;
+      acc1[1][4][i] = t < 2 ? ry : 0.f;
+      acc1[2][4][i] = t < 2 ? rz : 0.f;
+    }
+    vr_tail<5>(acc1, D::V + D::CP, w2, r0, ok0, ok1, VU, SH);
+  }
+}
+
+template <class D>
+__global__ void __launch_bounds__(NT, 2)
+k_vecr_a(const ModelRT m, const BatchRT bt, const int layer, const int n_units, const float* __restrict__ x, const float* __restrict__ v,
+         float* __restrict__ VU, float* __restrict__ SH) {
+  static_assert(D::V == 32 && D::CP == 4 && D::VIN0 == 33 && D::H0 == 33, "fragment mapping: [v_src(32) | x_diff], 4 cross-product features");
+  __shared__ __align__(16) float wsm[VR_W1_WORDS + VR_W2_WORDS];
+  __shared__ float red[NWARP];
+  __shared__ float xch[NWARP][UR * 3 * 8];                    // per warp: the 8 Vcp columns of its 16 rows x 3 planes
+  const WH16 w1 = vr_load_w(wsm, m.c(layer, C_MSG0_WHCP), pad4(D::VIN0), D::VIN0, 32 * D::CPT_HC0, WLD_HCP, 1, red);
+  const WH16 w2 = load_resident_h16(wsm + VR_W1_WORDS, m.c(layer, C_MSG0_WU), pad4(D::H0 + D::CP), 32, WLD_U, red);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3, warp = threadIdx.x >> 5;
+  float* xc = xch[warp];
+  const int nw = gridDim.x * NWARP;
+  constexpr int H = D::H0, HC = D::H0 + D::CP;                // 33, 37
+  for (int unit = blockIdx.x * NWARP + warp; unit < n_units; unit += nw) {
+    const VrUnit u = vr_unit(bt, unit);
+    const size_t r0 = (size_t)unit * UR;
+    const bool okr[2] = {g < u.nvalid, g + 8 < u.nvalid};
+    int src[2];
+    float ud[2][3];                                            // unit vector x_diff of this thread's two rows
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      src[hh] = u.nb;
+      ud[hh][0] = ud[hh][1] = ud[hh][2] = 0.f;
+      if (okr[hh]) {
+        int i, j;
+        edge_src_dst(u.le0 + g + 8 * hh, u.n, i, j);
+        src[hh] = u.nb + i;
+        float dx, dy, dz;
+        const float dist = pair_dist(x, src[hh], u.nb + j, dx, dy, dz);
+        ud[hh][0] = __fdiv_rn(dx, dist); ud[hh][1] = __fdiv_rn(dy, dist); ud[hh][2] = __fdiv_rn(dz, dist);
+      }
+    }
+    float2 vv[3][2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int col = 16 * ks + 2 * t + (i >> 1) * 8;
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+          vv[p][ks][i] = okr[i & 1] ? __ldg(reinterpret_cast<const float2*>(v + (size_t)src[i & 1] * 3 * D::V + p * D::V + col)) : make_float2(0.f, 0.f);
+      }
+    float acc1[3][6][4];
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+#pragma unroll
+      for (int nt = 0; nt < 6; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc1[p][nt][i] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      uint32_t ah[3][4], al[3][4];
+#pragma unroll
+      for (int p = 0; p < 3; ++p)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tc::split_h16x2(vv[p][ks][i].x, vv[p][ks][i].y, ah[p][i], al[p][i]);
+      vr_kstep16<6>(acc1, ah, al, w1.hi, w1.lo, WLD_HCP, 16 * ks, g, t);
+    }
+    {
+      // k = 32: x_diff (lane t = 0 of every quad), 33..39: K padding
+      uint32_t ah[3][2], al[3][2];
+#pragma unroll
+      for (int p = 0; p < 3; ++p)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) tc::split_h16x2(t == 0 ? ud[hh][p] : 0.f, 0.f, ah[p][hh], al[p][hh]);
+      vr_kstep8<6>(acc1, ah, al, w1.hi, w1.lo, WLD_HCP, 32, g, t);
+    }
+    {
+      const float inv = w1.inv;
+#pragma unroll
+      for (int p = 0; p < 3; ++p)
+#pragma unroll
+        for (int nt = 0; nt < 6; ++nt)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc1[p][nt][i] *= inv;
+    }
+    // cross products: Vcp = columns [33, 41) (n-tiles 4 and 5) -> per-warp exchange buffer -> the owners of columns 33..36 compute
+    __syncwarp();
+#pragma unroll
+    for (int nt = 4; nt < 6; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int col = 8 * nt + 2 * t + (i & 1), row = g + 8 * (i >> 1);
+        if (col >= H && col < H + 2 * D::CP) {
+#pragma unroll
+          for (int p = 0; p < 3; ++p) xc[(row * 3 + p) * 8 + (col - H)] = acc1[p][nt][i];
+        }
+      }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int col = 32 + 2 * t + (i & 1), row = g + 8 * (i >> 1);
+      if (col >= H && col < HC) {
+        const float* q = xc + (row * 3) * 8 + (col - H) + D::CP;
+        float rx, ry, rz;
+        vr_cross(acc1[0][4][i], acc1[1][4][i], acc1[2][4][i], q[0], q[8], q[16], rx, ry, rz);
+        acc1[0][4][i] = rx; acc1[1][4][i] = ry; acc1[2][4][i] = rz;
+      } else if (col >= HC) {
+        acc1[0][4][i] = 0.f; acc1[1][4][i] = 0.f; acc1[2][4][i] = 0.f;
+      }
+    }
+    vr_tail<6>(acc1, HC, w2, r0, okr[0], okr[1], VU, SH);
+  }
+}
+
+// V' = GT * VU of the last message GVP and its sum over the in-edges of every destination node (gvp.py:491-492, vector half):
+// one warp per 64-slot tile, lane = vector channel, the three planes in three accumulators; rows are dst-major, a segment that
+// is cut by the tile goes to partL (its head) / partF (a continuation) exactly as in k_vec_c / k_conv_edge.
+template <class D>
+__global__ void __launch_bounds__(NT)
+k_vecr_c(const BatchRT bt, const float* __restrict__ VU, const float* __restrict__ GT, float* __restrict__ M,
+         float* __restrict__ partF, float* __restrict__ partL) {
+  static_assert(D::V == 32, "lane = vector channel");
+  const int lane = threadIdx.x & 31, tile = blockIdx.x * NWARP + (threadIdx.x >> 5);
+  if (tile >= bt.n_edge_tiles) return;
+  const int mol = __ldg(bt.etile_mol + tile), n = __ldg(bt.mol_n + mol), nb = __ldg(bt.mol_node + mol);
+  const int le0 = (tile - __ldg(bt.mol_etile + mol)) * TM, nvalid = min(TM, n * (n - 1) - le0), deg = n - 1;
+  const size_t erow0 = (size_t)tile * TM;
+  int j = le0 / deg, rem = le0 - j * deg;                      // destination (local) and position inside its in-edge segment of row 0
+  bool head = rem == 0;                                        // the running segment started with the node's first in-edge
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  constexpr int CH = 8;
+  for (int rb = 0; rb < nvalid; rb += CH) {
+    float gbuf[CH], b0[CH], b1[CH], b2[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      const size_t r = erow0 + min(rb + k, nvalid - 1);
+      gbuf[k] = __ldg(GT + r * 32 + lane);
+      b0[k] = __ldg(VU + r * VUW + lane); b1[k] = __ldg(VU + r * VUW + 32 + lane); b2[k] = __ldg(VU + r * VUW + 64 + lane);
+    }
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      const int row = rb + k;
+      if (row < nvalid) {
+        a0 = __fadd_rn(a0, __fmul_rn(gbuf[k], b0[k]));
+        a1 = __fadd_rn(a1, __fmul_rn(gbuf[k], b1[k]));
+        a2 = __fadd_rn(a2, __fmul_rn(gbuf[k], b2[k]));
+        const bool tail = rem == deg - 1;
+        if (tail || row == nvalid - 1) {
+          float* dst = (head && tail) ? M + (size_t)(nb + j) * D::MW : (head ? partL + (size_t)tile * D::MW : partF + (size_t)tile * D::MW);
+          dst[D::S + lane] = a0; dst[D::S + 32 + lane] = a1; dst[D::S + 64 + lane] = a2;
+          a0 = a1 = a2 = 0.f;
+          head = true;                                         // the next segment (if any) starts at its node's first in-edge
+        }
+        if (tail) { rem = 0; ++j; } else ++rem;
+      }
+    }
+  }
+}
+
+}  // namespace fm

@@ -142,7 +142,8 @@ int fm_time_egemm_msg(FmHandle* h, void* workspace, int32_t layer, int32_t iters
  *          twice the MMA rate and half the weight-image bytes; activations must stay below 65504 in magnitude), 0 3xTF32;
  *          "eg_persist" = 1 (default) persistent k_egemm_p / 0 one-tile-per-CTA k_egemm_tc; "eg_img" = 1 (default) consecutive
  *          tensor-core linears hand their activations over as fp16 (hi, lo) operand images fetched by bulk TMA / 0 as fp32 rows
- *          converted by the consumer's loader warps (bit-identical results);
+ *          converted by the consumer's loader warps (bit-identical results); "vec_impl" = 1 (default) register-resident
+ *          vector stages of the message GVPs (one warp per 16 edges, csrc/vec_reg.cuh) / 0 shared-memory tile kernels;
  *          "tc_debug", "tc_trace", "tc_trace_mode": timing experiments.
  *          fm_get_option(h, "status", &v) synchronises the device and reads-and-clears the status word: bit 0 = an activation
  *          left the fp16 operand range since the last read (results invalid; switch to tc_prec 0).  fm_sample_host checks it. */
@@ -154,6 +155,14 @@ int fm_debug_read_trace(FmHandle* h, int64_t* out64_host);
  * returns, for up to `cap` launches, the csrc/api.cu line of the launch and its duration in ms (event to event, warm pipeline).
  * fm_set_option(h, "kprof", 0 or 1) clears the record. */
 int fm_debug_kprof(FmHandle* h, int32_t* lines_host, float* ms_host, int32_t cap, int32_t* n_out);
+/* test hook for CTMCVectorField.campbell_step + purity_sampling (ctmc_vector_field.py:414-461, flowmol/utils/ctmc_utils.py:4-35) as
+ * the production step kernel k_ctmc_step computes them: one step of ONE modality with `K` classes (mask index K) on `B` molecules
+ * with n_atoms_host[b] items each, the sampling distribution p_host [N][K] used as given (no temperature), uniforms_host [3][N] =
+ * (categorical draw, unmask draw, re-mask draw) in place of the Philox noise, the linear schedule's jump probabilities at
+ * (t_i, dt, eta).  state_host [N] is updated in place, x1_host [N] receives the sampled endpoint tokens.  Host buffers, synchronous. */
+int fm_debug_ctmc_step(const int32_t* n_atoms_host, int32_t n_molecules, int32_t K, const float* p_host, uint8_t* state_host,
+                       uint8_t* x1_host, const float* uniforms_host, float t_i, float dt, float eta, float hc_thresh,
+                       int32_t last_step, int device);
 /* number of kernels launched by the last fm_forward / fm_integrate call on this handle */
 int64_t fm_last_launch_count(FmHandle* h);
 

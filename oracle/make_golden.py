@@ -33,7 +33,22 @@ CASES_INTEGRATE = [
     ("itg_dev_T50", "dev", 6, 11, [5, 18, 12, 29, 3, 16, 21, 9], 50, 77),
     ("itg_flowmol3_T10", "flowmol3", 11, 12, [3, 12, 20], 10, 99),
     ("itg_flowmol3_T25", "flowmol3", 11, 12, [4, 30, 17], 25, 31337),
+    # SURVEY section 8c probe scales (round 2): GEOM-sized flowmol3 molecules, QM9-sized dev batches of 32 / 64, the largest GEOM
+    # molecule (181 atoms: several 128-row tiles per destination segment), and one full-length T = 250 trajectory
+    ("itg_flowmol3_geom8_T50", "flowmol3", 11, 12, [46, 44, 51, 38, 47, 46, 59, 42], 50, 4242),
+    ("itg_dev_qm9x32_T50", "dev", 6, 11, None, 50, 3232),
+    ("itg_dev_qm9x64_T100", "dev", 6, 11, None, 100, 6464),
+    ("itg_flowmol3_big_T25", "flowmol3", 11, 12, [64, 181], 25, 181),
+    ("itg_flowmol3_geom4_T250", "flowmol3", 11, 12, [46, 39, 52, 45], 250, 250250),
 ]
+
+
+def qm9_sizes(count, seed):
+    """QM9-sized molecule sizes for the `None` entries above: the reference's own histogram file, a seeded draw."""
+    n_map, counts = torch.load("/root/reference/data/qm9/train_data_n_atoms_histogram.pt")
+    gen = torch.Generator().manual_seed(seed)
+    idx = torch.multinomial(counts.float() / counts.sum().float(), count, replacement=True, generator=gen)
+    return [int(v) for v in n_map[idx]]
 
 
 def _model(cfg_name, A, wseed):
@@ -117,6 +132,8 @@ def gen_forward(name, cfg_name, A, wseed, n_atoms, taps):
 
 def gen_integrate(name, cfg_name, A, wseed, n_atoms, T, nseed):
     R = RL.load()
+    if n_atoms is None:
+        n_atoms = qm9_sizes(64 if "x64" in name else 32, nseed)
     cfg, m, sd = _model(cfg_name, A, wseed)
     gen = torch.Generator().manual_seed(2000 + nseed)
     g, nbi, ebi, uem = RL.build_reference_graph(n_atoms, generator=gen)
@@ -246,15 +263,21 @@ def gen_ctmc_cases():
 
 
 def main():
+    """`python -m oracle.make_golden [name ...]`: all fixtures, or only the named ones."""
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
+    only = set(sys.argv[1:])
     for c in CASES_FORWARD:
-        gen_forward(*c)
+        if not only or c[0] in only:
+            gen_forward(*c)
     for c in CASES_INTEGRATE:
-        gen_integrate(*c)
+        if not only or c[0] in only:
+            gen_integrate(*c)
     for c in CASES_GAT:
-        gen_integrate_gat(*c)
-    gen_ctmc_cases()
+        if not only or c[0] in only:
+            gen_integrate_gat(*c)
+    if not only or "ctmc_cases" in only:
+        gen_ctmc_cases()
 
 
 if __name__ == "__main__":

@@ -68,6 +68,23 @@ def load():
     return types.SimpleNamespace(**_loaded)
 
 
+def load_function_verbatim(relpath, func_name, namespace):
+    """Compile ONE top-level function of a reference file from its own source text, unmodified, into `namespace` -- for modules
+    whose import needs packages this image lacks (flowmol/analysis/molecule_builder.py imports rdkit at the top; its
+    `extract_moldata_from_graph` needs only torch and the graph container)."""
+    import ast
+    path = os.path.join(REF_ROOT, relpath)
+    with open(path) as f:
+        src = f.read()
+    tree = ast.parse(src)
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name == func_name:
+            code = compile(ast.Module(body=[node], type_ignores=[]), path, "exec")
+            exec(code, namespace)
+            return namespace[func_name]
+    raise KeyError(f"{func_name} not found in {path}")
+
+
 def read_vector_field_cfg(name):
     """`vector_field:` and `interpolant_scheduler:` blocks of configs/{dev,flowmol3}.yml (reference file)."""
     import yaml

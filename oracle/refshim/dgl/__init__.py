@@ -75,6 +75,21 @@ class DGLGraph:
             g.edata[k] = v.to(device)
         return g
 
+    def remove_nodes(self, nids):
+        """DGLGraph.remove_nodes: drops the nodes and their incident edges, relabels the remaining nodes in order, keeps the
+        feature rows of what remains (molecule_builder.py:231 uses it on one unbatched molecule)."""
+        nids = torch.as_tensor(nids).long()
+        keep = torch.ones(self._n, dtype=torch.bool, device=self._src.device)
+        keep[nids] = False
+        new_id = torch.cumsum(keep, 0) - 1
+        ek = keep[self._src] & keep[self._dst]
+        self._src, self._dst = new_id[self._src[ek]], new_id[self._dst[ek]]
+        self.ndata = _Frame({k: v[keep] for k, v in self.ndata.items()})
+        self.edata = _Frame({k: v[ek] for k, v in self.edata.items()})
+        self._n = int(keep.sum())
+        self._bnn = torch.tensor([self._n], device=self._src.device)
+        self._bne = torch.tensor([self._src.shape[0]], device=self._src.device)
+
     @contextlib.contextmanager
     def local_scope(self):
         nd, ed = _Frame(self.ndata), _Frame(self.edata)

@@ -36,6 +36,12 @@ WORKLOADS = {
     "qm9_1024": ("flowmol3", "qm9", 1024, 250, 1),
     "dev_qm9_32": ("dev", "qm9", 32, 50, 0),
 }
+# BASELINE.json configs[4], the graph-irregularity stress: GEOM-type model, 2048 molecules IN TOTAL (strong scaling: 2048 / N per
+# GPU), 250 timesteps, sizes either all equal to n ("sweep_n<n>") or uniform on {n/2 .. 3n/2} ("sweep_mix<n>"), n = 10 .. 80
+SWEEP_TOTAL = 2048
+for _n in (10, 20, 30, 40, 50, 60, 70, 80):
+    WORKLOADS[f"sweep_n{_n}"] = ("flowmol3", f"fixed:{_n}", SWEEP_TOTAL, 250, 4)
+    WORKLOADS[f"sweep_mix{_n}"] = ("flowmol3", f"uniform:{_n}", SWEEP_TOTAL, 250, 4)
 # matmul FLOPs of the reference per directed edge of one GVPConv message phase (624 502, flowmol3)
 CONV_EDGE_FLOP_PER_EDGE = {"flowmol3": 624502, "dev": 2 * (201 * 64 + 84 * 64 * 2 + 3 * 64 * 16) + 6 * (21 * 29 + 25 * 16 + 2 * (16 * 24 + 20 * 16))}
 # matmul FLOPs of one full network evaluation, flowmol3: per edge / per node
@@ -43,10 +49,21 @@ FWD_FLOP = {"flowmol3": (4874436, 6499384), "dev": (308680, 324660)}
 
 
 def draw_sizes(dataset, B, seed=1234, rank=0):
+    """Sizes of a synthetic batch: 'geom' / 'qm9' = the training-set histograms shipped with the reference
+    (data/*/train_data_n_atoms_histogram.pt), 'fixed:<n>' = all n atoms, 'uniform:<n>' = uniform on {n/2, .., 3n/2}."""
+    gen = torch.Generator().manual_seed(seed + 7919 * rank)
+    if dataset.startswith("fixed:"):
+        return np.full(B, int(dataset.split(":")[1]), dtype=np.int64)
+    if dataset.startswith("uniform:"):
+        n = int(dataset.split(":")[1])
+        return torch.randint(max(2, n // 2), n + n // 2 + 1, (B,), generator=gen).numpy().astype(np.int64)
     from flowmol_b200.api import n_atoms_histogram
     nmap, counts = n_atoms_histogram(dataset)
-    gen = torch.Generator().manual_seed(seed + 7919 * rank)
     return nmap[torch.multinomial(counts / counts.sum(), B, replacement=True, generator=gen)].numpy().astype(np.int64)
+
+
+def atom_types_of(dataset):
+    return 6 if dataset == "qm9" else 11          # QM9: C H N O F + fake; GEOM (and the sweep): 10 elements + fake
 
 
 def make_prior(n_atoms, A, seed):
@@ -109,7 +126,7 @@ def cpu_port_throughput(cfg_name, dataset, timesteps, budget_s=20.0, rank_seed=0
     from flowmol_b200.config import ModelConfig
     from oracle import flowmol_oracle as O
     cores = os.cpu_count() or 1
-    A = 11 if dataset == "geom" else 6
+    A = atom_types_of(dataset)
     cfg = ModelConfig.named(cfg_name, A)
     sd = WT.init_state_dict(cfg, 0)
     om = O.OracleModel(cfg, sd)
@@ -148,31 +165,103 @@ def cpu_port_throughput(cfg_name, dataset, timesteps, budget_s=20.0, rank_seed=0
                       f"({sec_per_eval:.3f} s each), extrapolated linearly to {timesteps} evaluations per molecule"}
 
 
+def cpu_full_trajectory(cfg_name, dataset, B, timesteps, repeats=3):
+    """the CPU path IN FULL on a configuration small enough for it (configs[0]: dev dims, 32 QM9-sized
+    molecules, 50 timesteps): complete `integrate` (all network evaluations + CTMC steps) of the oracle port, best of `repeats`;
+    where the reference tree is present (the build container, not the GPU box) the verbatim reference `CTMCVectorField.integrate`
+    is timed once beside it."""
+    from flowmol_b200 import weights as WT
+    from flowmol_b200.config import ModelConfig
+    from oracle import flowmol_oracle as O
+    A = atom_types_of(dataset)
+    cfg = ModelConfig.named(cfg_name, A)
+    sd = WT.init_state_dict(cfg, 0)
+    om = O.OracleModel(cfg, sd)
+    n_atoms = draw_sizes(dataset, B)
+    bt = O.make_batch(n_atoms)
+    x0, a0, c0, e0 = make_prior(n_atoms, A, 100)
+    a0, c0, e0 = a0.long(), c0.long(), e0.long()
+    cores = min(os.cpu_count() or 1, 16)
+    torch.set_num_threads(cores)
+    best = 1e30
+    with torch.no_grad():
+        for r in range(repeats):
+            t0 = time.perf_counter()
+            O.integrate(om, bt, x0, a0, c0, e0, timesteps, seed=1000 + r)
+            best = min(best, time.perf_counter() - t0)
+    out = {"value": B / best, "unit": "molecules/s", "cores": cores, "host_cpus": os.cpu_count(), "kind": "port",
+           "sample": f"the whole workload: {B} {dataset}-sized molecules (N={bt.N}, E={bt.E}), full {timesteps}-step integrate, "
+                     f"best of {repeats} ({best:.2f} s)"}
+    try:
+        from oracle import ref_loader as RL
+        if RL.available():
+            R = RL.load()
+            vf_cfg, sc_cfg = RL.read_vector_field_cfg(cfg_name)
+            m = RL.build_reference_model(vf_cfg, sc_cfg, n_atom_types=A)
+            m.load_state_dict(sd, strict=False)
+            g, nbi, ebi, uem = RL.build_reference_graph([int(v) for v in n_atoms], generator=torch.Generator().manual_seed(4))
+            Nn, Uu = g.num_nodes(), int(uem.sum())
+            g.ndata['a_0'] = R.priors.ctmc_masked_prior(Nn, A)
+            g.ndata['c_0'] = R.priors.ctmc_masked_prior(Nn, 6)
+            ep = R.priors.ctmc_masked_prior(Uu, 4)
+            e_0 = torch.zeros(uem.shape[0], 5)
+            e_0[uem] = ep
+            e_0[~uem] = ep
+            g.edata['e_0'] = e_0
+            with torch.no_grad():
+                t0 = time.perf_counter()
+                m.integrate(g, nbi, upper_edge_mask=uem, n_timesteps=timesteps, stochasticity=None, high_confidence_threshold=None)
+                dt = time.perf_counter() - t0
+            out["verbatim_reference"] = {"value": B / dt, "unit": "molecules/s", "seconds": dt,
+                                         "what": "the reference's own CTMCVectorField.integrate (flowmol/models/ctmc_vector_field.py:145-285), "
+                                                 "imported unmodified with the in-repo DGL / torch_scatter stand-ins, one run"}
+    except Exception as exc:                      # noqa: BLE001 -- the verbatim arm is a bonus, never a reason to lose the line
+        out["verbatim_reference"] = {"unavailable": f"{type(exc).__name__}: {exc}"}
+    return out
+
+
 def run_reference_arm(args, wl):
+    """`--impl reference`: the reference's CPU path on this box's host cores.  The reference is pure Python on DGL / pytorch-scatter /
+    Lightning / rdkit, none installable here, so the arm is the oracle PORT (oracle/flowmol_oracle.py, pinned bit-exactly to the
+    reference run verbatim): `impl_detail` says so.  configs[0] runs in full; the flowmol3 workloads time a bounded sample and
+    extrapolate linearly in network evaluations (stated in `cpu_baseline.sample`)."""
     cfg_name, dataset, B, T, _ = wl
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     vals = []
     for i in range(args.warmup + args.steps):
-        r = cpu_port_throughput(cfg_name, dataset, T, budget_s=max(3.0, 60.0 / max(1, args.warmup + args.steps)), rank_seed=0)
+        if args.workload == "dev_qm9_32":
+            r = cpu_full_trajectory(cfg_name, dataset, B, T, repeats=1)
+        else:
+            r = cpu_port_throughput(cfg_name, dataset, T, budget_s=max(3.0, 60.0 / max(1, args.warmup + args.steps)), rank_seed=0)
         if i >= args.warmup:
             vals.append(r)
     v = float(np.mean([r["value"] for r in vals]))
     cb = dict(vals[-1], value=v)
-    line = {"impl": "reference", "metric": f"molecules/sec @{T} steps ({dataset.upper()} batch)", "value": v,
+    line = {"impl": "reference", "impl_detail": "cpu_oracle_port (no GPU involved; n_gpus only mirrors the request)",
+            "metric": f"molecules/sec @{T} steps ({dataset.upper()} batch)", "value": v,
             "unit": "molecules/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1000.0 * B / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": 1000.0 * B / v, "higher_is_better": True, "scaling": scaling_of(args.workload), "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": config_dict(args.workload, wl, args.gpus),
             "cpu_baseline": cb, "e2e": {"value": v, "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
+def scaling_of(workload):
+    return "strong" if workload.startswith("sweep_") else "weak"
+
+
 def config_dict(name, wl, gpus):
     cfg_name, dataset, B, T, idx = wl
-    return {"workload": f"BASELINE.json configs[{idx}]: {dataset} sized molecules, {cfg_name} dims, {B} molecules per GPU, "
-                        f"{T} timesteps", "name": name, "molecules_per_gpu": B, "global_molecules": B * gpus, "timesteps": T,
-            "sizes": "n_atoms ~ train_data_n_atoms_histogram, one global draw torch.Generator().manual_seed(1234), contiguous cost-balanced ranges per rank",
+    strong = scaling_of(name) == "strong"
+    per_gpu, total = (B // gpus, B) if strong else (B, B * gpus)
+    sizes = {"geom": "n_atoms ~ data/geom_full_kekulized/train_data_n_atoms_histogram", "qm9": "n_atoms ~ data/qm9/train_data_n_atoms_histogram"}.get(
+        dataset, f"n_atoms {dataset.replace('fixed:', 'all = ').replace('uniform:', 'uniform on {n/2 .. 3n/2}, n = ')}")
+    return {"workload": f"BASELINE.json configs[{idx}]: {dataset} sized molecules, {cfg_name} dims, {total} molecules in total "
+                        f"({per_gpu} per GPU), {T} timesteps", "name": name, "molecules_per_gpu": per_gpu, "global_molecules": total,
+            "timesteps": T,
+            "sizes": sizes + ", one global draw torch.Generator().manual_seed(1234), contiguous cost-balanced ranges per rank",
             "weights": "random init (reference constructors' distributions), seed 0", "parallelism": f"molecule sharding x{gpus}",
             "l2": "inputs larger than L2 (edge hidden state alone is ~0.6 GB per evaluation at geom512); no flush needed"}
 
@@ -184,8 +273,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="geom512", choices=sorted(WORKLOADS))
+    ap.add_argument("--eg-cluster", type=int, default=None, help="k_egemm_p cluster size (1, 2, 4): multicast weight stream")
+    ap.add_argument("--vec-impl", type=int, default=None, help="1 register-resident vector stages (default), 0 shared-memory tile kernels")
     ap.add_argument("--timesteps", type=int, default=None, help="override the workload's timesteps (experiments only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-api-e2e", action="store_true", help="skip the extra pass through FlowMolB200.sample")
     ap.add_argument("--cuda-graph", type=int, default=0)
     ap.add_argument("--conv-impl", type=int, default=None, help="0 fp32 CUDA-core kernels, 2 wide tcgen05 pipeline (default where built)")
     ap.add_argument("--tc-prec", type=int, default=None, help="operand format of the tensor-core linears: 1 scaled fp16 hi/lo (default), 0 3xTF32")
@@ -207,17 +299,23 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    A = 11 if dataset == "geom" else 6
+    A = atom_types_of(dataset)
     cfg = ModelConfig.named(cfg_name, A)
     vf = CTMCVectorFieldB200(cfg, WT.init_state_dict(cfg, 0), device=dev)
+    strong = scaling_of(args.workload) == "strong"
+    B_global = B if strong else B * world              # strong scaling (the size sweep): the total is fixed, ranks share it
     if args.conv_impl is not None:
         vf.set_option("conv_impl", args.conv_impl)
     if args.tc_prec is not None:
         vf.set_option("tc_prec", args.tc_prec)
+    if args.eg_cluster is not None:
+        vf.set_option("eg_cluster", args.eg_cluster)
+    if args.vec_impl is not None:
+        vf.set_option("vec_impl", args.vec_impl)
     # one GLOBAL batch of B x world molecules, cut into contiguous cost-balanced ranges (flowmol_b200/sharding.py); global
     # molecule ids key the noise, so the molecules are the same at any world size
     from flowmol_b200 import sharding as SH
-    n_global = draw_sizes(dataset, B * world)
+    n_global = draw_sizes(dataset, B_global)
     ranges = SH.partition(n_global, world)
     lo, hi = ranges[rank]
     n_atoms = n_global[lo:hi]
@@ -263,10 +361,28 @@ def main():
         ms_total = timed(one_pass_device, args.steps)
     launches = vf.last_launches * args.steps
     ms_per_step = ms_total / args.steps
-    value = world * B / (ms_per_step / 1000.0)
+    value = B_global / (ms_per_step / 1000.0)
     one_pass_host(0)
     ms_e2e = timed(one_pass_host, args.steps) / args.steps
-    e2e_value = world * B / (ms_e2e / 1000.0)
+    e2e_value = B_global / (ms_e2e / 1000.0)
+    # the same pass through the reference-shaped public API (FlowMolB200.sample: graph construction, prior, integrate at the graph
+    # seam, D2H, one SampledMolecule per molecule) by wall clock, one pass on rank 0's share (informational: `e2e` is the C-ABI call)
+    e2e_api = None
+    if not args.no_api_e2e:
+        import flowmol_b200 as flowmol
+        model = flowmol.FlowMolB200.from_config(cfg_name, dataset="qm9" if dataset == "qm9" else "geom", seed=0, device=str(dev),
+                                                vector_field=vf)       # same weights (seed 0): adopt the built handle / workspace
+        torch.manual_seed(0)
+        nt = torch.from_numpy(n_atoms)
+        model.sample(nt[:8], n_timesteps=4)           # warm the Python path
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        mols = model.sample(nt, n_timesteps=T)
+        torch.cuda.synchronize()
+        dt_api = time.perf_counter() - t0
+        e2e_api = {"value": len(mols) * world / dt_api if not strong else len(mols) / dt_api, "unit": "molecules/s",
+                   "seconds": dt_api, "what": "model.sample(n_atoms, n_timesteps) wall clock on rank 0's share, scaled by the rank count "
+                                              "under weak scaling; includes graph build, prior sampling, D2H and molecule decode"}
     # roofline of the dominant kernel, timed live (CUDA events on its own stream) after a forward left valid state in the workspace
     peaks = {}
     try:
@@ -298,7 +414,11 @@ def main():
         modes = {"EG_MSG0": (4 * (F_ + 37) + 4 * S_, 2 * 197 * S_), "EG_MSG": (4 * 292 + 4 * S_, 2 * 292 * S_),
                  "EG_MSGA": (4 * 292 + 4 * S_, 2 * 292 * S_), "EG_GATE": (4 * S_ + 4 * 32, 2 * S_ * 32),
                  "EG_EU1": (4 * F_ + 4 * F_, 2 * 160 * F_), "EG_EU2": (4 * F_ + 4 * F_ + 4 * F_, 2 * F_ * F_)}
+        # the vector stages and their per-edge bytes (vec_reg.cuh: VU 384 B, SH 160 / 144 B, GT 128 B per edge)
+        modes.update({"k_vecr_a": (384 + 160, 0), "k_vecr_b": (384 + 128 + 384 + 160, 0), "k_vecr_c": (384 + 128, 0),
+                      "k_vec_a": (480 + 160, 0), "k_vec_b": (480 + 128 + 480 + 160, 0), "k_vec_c": (480 + 128, 0)})
         family = {}
+        fam_bytes, fam_ms, moved = 0.0, 0.0, 0.0
         for name_, (bpe, fpe) in modes.items():
             if name_ in prof:
                 cnt, ms_f = prof[name_]
@@ -306,23 +426,43 @@ def main():
                 family[name_] = {"launches_per_eval": cnt, "us_per_launch": us, "algorithmic_bytes_per_edge": bpe,
                                  "achieved_gbs": bpe * E / (us * 1e-6) / 1e9, "frac_of_hbm_peak": bpe * E / (us * 1e-6) / 1e9 / hbm_peak,
                                  "algorithmic_tflops": fpe * E / (us * 1e-6) / 1e12}
+                moved += bpe * E * cnt
+                if name_.startswith("EG_"):
+                    fam_bytes += bpe * E * cnt
+                    fam_ms += ms_f
+        # Headline: the whole k_egemm_p family of one evaluation, time-weighted (every edge-row launch of the persistent tcgen05
+        # linear: 51 % of an evaluation), not its best mode; the single-kernel EG_MSG number timed alone stays beside it.
+        achieved = fam_bytes / (fam_ms * 1e-3) / 1e9
         hbm_bytes = E * (292 + 256) * 4
-        achieved = hbm_bytes / (ms_k * 1e-3) / 1e9
         flops = 2 * 292 * 256 * E
         op_peak = bf16 if prec == 1 else tf32_peak
-        roofline = {"kernel": f"k_egemm_p<EG_MSG> (292->256 message linear of one GVP, {'fp16x3' if prec == 1 else '3xTF32'} tcgen05, "
-                              "operand images in and out, all edges)",
+        fe_, fn2 = FWD_FLOP[cfg_name]
+        alg_eval_bytes = 6100.0 * E + 40000.0 * N                    # irreducible bytes of a fully fused evaluation
+        alg_eval_flops = fe_ * E + fn2 * N
+        roofline = {"kernel": "k_egemm_p, all edge-row modes of one network evaluation, time-weighted (persistent tcgen05 linear, "
+                              f"{'fp16x3' if prec == 1 else '3xTF32'} operands, operand images between linears)",
                     "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "peak_kind": hbm_src, "algorithmic_bytes_per_launch": hbm_bytes, "ms_per_launch": ms_k,
-                    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this workload from the committed ncu capture
-                    # (profiles/r01s_ncu_full_egemm_p.csv: 1.405 + 1.170 GB; bench.py itself never runs under a profiler)
-                    "traffic": 2.575e9 if (args.workload == "geom512" and world == 1) else None,
-                    "tensor": {"algorithmic_flops_per_launch": flops, "achieved_tflops": flops / (ms_k * 1e-3) / 1e12,
-                               "peak_tflops": op_peak, "frac": flops / (ms_k * 1e-3) / 1e12 / op_peak,
-                               "note": "3 MMAs per fp32 product (error-compensated hi/lo operands): attainable ceiling = peak / 3"},
+                    "peak_kind": hbm_src, "algorithmic_bytes_per_launch": fam_bytes / max(1.0, sum(prof[k][0] for k in prof if k.startswith("EG_"))),
+                    "ms_per_launch": fam_ms / max(1.0, sum(prof[k][0] for k in prof if k.startswith("EG_"))),
+                    "traffic": None,        # bench.py never runs under a profiler: dram__bytes of the committed captures are in profiles/
+                    "single_kernel": {"kernel": "k_egemm_p<EG_MSG> alone on its stream (292->256 message linear, all edges)",
+                                      "ms_per_launch": ms_k, "algorithmic_bytes_per_launch": hbm_bytes,
+                                      "achieved_gbs": hbm_bytes / (ms_k * 1e-3) / 1e9, "frac": hbm_bytes / (ms_k * 1e-3) / 1e9 / hbm_peak,
+                                      "algorithmic_flops_per_launch": flops, "achieved_tflops": flops / (ms_k * 1e-3) / 1e12,
+                                      "tensor_frac_of_x3_ceiling": flops / (ms_k * 1e-3) / 1e12 / (op_peak / 3.0)},
+                    "whole_evaluation": {
+                        "ms_event_to_event": fwd_ms,
+                        "bytes_moved_by_the_listed_kernels": moved, "moved_gbs": moved / (fwd_ms * 1e-3) / 1e9,
+                        "moved_frac_of_hbm_peak": moved / (fwd_ms * 1e-3) / 1e9 / hbm_peak,
+                        "algorithmic_bytes_fused": alg_eval_bytes, "moved_over_algorithmic": moved / alg_eval_bytes,
+                        "algorithmic_frac_of_hbm_peak": alg_eval_bytes / (fwd_ms * 1e-3) / 1e9 / hbm_peak,
+                        "algorithmic_flops": alg_eval_flops, "algorithmic_tflops": alg_eval_flops / (fwd_ms * 1e-3) / 1e12,
+                        "tensor_frac_of_x3_ceiling": alg_eval_flops / (fwd_ms * 1e-3) / 1e12 / (op_peak / 3.0),
+                        "note": "SURVEY 8d: fused, the evaluation is compute-bound (about 800 FLOP per irreducible HBM byte); this build "
+                                "keeps activations between linears in HBM, so its kernels are HBM-bound and `moved_over_algorithmic` "
+                                "is the price of not fusing the GVP chain"},
                     "family": family,
                     "kernel_ms_per_eval": {k: round(t_, 4) for k, (c_, t_) in sorted(prof.items(), key=lambda kv: -kv[1][1])},
-                    "eval_ms_event_to_event": fwd_ms,
                     "message_pass": {"what": "whole message phase of one conv layer (10 launches: 3 vec + 6 egemm + segment-sum)",
                                      "ms": ms_pass, "algorithmic_tflops": CONV_EDGE_FLOP_PER_EDGE[cfg_name] * E / (ms_pass * 1e-3) / 1e12}}
     else:
@@ -337,19 +477,21 @@ def main():
     fe, fn_ = FWD_FLOP[cfg_name]
     total_flops = (fe * E + fn_ * N) * T * world
     line = {"metric": f"molecules/sec @{T} steps ({dataset.upper()} batch)", "value": value, "unit": "molecules/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling_of(args.workload),
             "vs_baseline": None,
             "dtype": ("f32 (tensor-core linears as error-compensated " + ("scaled fp16 hi/lo x3" if prec == 1 else "3xTF32") +
                       " on tcgen05, fp32 accumulate)") if impl == 2 else "f32",
             "data": "synthetic", "config": config_dict(args.workload, wl, world),
-            "e2e": {"value": e2e_value, "unit": "molecules/s", "h2d_bytes_per_step": int(N * 12 + 2 * N + U + 4 * B),
+            "e2e": {"value": e2e_value, "unit": "molecules/s", "h2d_bytes_per_step": int(N * 12 + 2 * N + U + 4 * len(n_atoms)),
                     "d2h_bytes_per_step": int(N * 12 + 2 * N + U), "ms_per_step": ms_e2e},
+            "e2e_api": e2e_api,
             "gpu_launches": int(launches), "roofline": roofline,
             "model_tflops": total_flops / (ms_per_step * 1e-3) / 1e12, "batch": {"N": N, "E": E, "U": U}}
     if rank == 0:
         line["clocks"] = clk.summary()
         if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_port_throughput(cfg_name, dataset, T)
+            line["cpu_baseline"] = (cpu_full_trajectory(cfg_name, dataset, B, T) if args.workload == "dev_qm9_32"
+                                    else cpu_port_throughput(cfg_name, dataset, T))
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -56,6 +56,7 @@ SYMBOLS = {
     "fm_debug_tc_gemm": (c_i32, [c_vp, c_vp, c_i32, c_vp, c_i32, c_i32]),
     "fm_time_egemm_msg": (c_i32, [c_vp, c_vp, c_i32, c_i32, C.POINTER(c_f32), c_vp]),
     "fm_time_conv_edge": (c_i32, [c_vp, c_vp, c_i32, c_i32, C.POINTER(c_f32), c_vp]),
+    "fm_decode": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "fm_debug_ctmc_step": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_f32, c_f32, c_f32, c_f32, c_i32, c_i32]),
 }
 

@@ -75,6 +75,26 @@ class SampledMolecule:
             if build_ep_traj and 'x_1_pred' in traj_frames:
                 self.ep_traj_mols = self.process_traj_frames(traj_frames, ep_traj=True)
 
+    @classmethod
+    def from_decoded(cls, positions, atom_tokens, charges, bond_types, bond_src, bond_dst, atom_type_map, fake_atoms=True,
+                     explicit_aromaticity=False):
+        """A molecule from the arrays the device-side decode (fm_decode) produced: surviving atoms only, renumbered bonds."""
+        self = cls.__new__(cls)
+        atom_type_map = list(atom_type_map)
+        symbols_all = atom_type_map + (['Sn'] if fake_atoms else []) + ['Se']
+        self.positions = positions
+        self.atom_types = [symbols_all[int(t)] for t in atom_tokens]
+        self.atom_charges = charges.to(torch.int64)
+        self.bond_types = bond_types.to(torch.int64)
+        self.bond_src_idxs = bond_src.to(torch.int64)
+        self.bond_dst_idxs = bond_dst.to(torch.int64)
+        self.num_atoms = int(positions.shape[0])
+        self.atom_type_map = atom_type_map
+        self.fake_atoms, self.explicit_aromaticity, self.align_traj = fake_atoms, explicit_aromaticity, True
+        self.rdkit_mol = self.build_molecule()
+        self.traj_frames, self.traj_mols, self.ep_traj_mols = None, None, None
+        return self
+
     def process_traj_frames(self, traj_frames, ep_traj=False):
         """molecule_builder.py:156-214: every frame decoded like a final molecule, fake atoms shown (as 'Sn'), positions
         rigidly aligned to the last frame.  Returns SampledMolecule objects (their `.rdkit_mol` is set when rdkit is present)."""
@@ -139,7 +159,7 @@ class FlowMolB200:
     canonical_feat_order = ['x', 'a', 'c', 'e']
 
     def __init__(self, atom_type_map, vector_field_config, state_dict, n_atoms_hist=None, dataset="geom",
-                 default_n_timesteps=250, fake_atom_p=0.3, explicit_aromaticity=False, device="cuda:0"):
+                 default_n_timesteps=250, fake_atom_p=0.3, explicit_aromaticity=False, device="cuda:0", vector_field=None):
         self.atom_type_map = list(atom_type_map)
         self.fake_atoms = fake_atom_p > 0
         self.explicit_aromaticity = explicit_aromaticity
@@ -152,13 +172,28 @@ class FlowMolB200:
         self.vector_field = None
         self.n_atoms_map, counts = n_atoms_hist if n_atoms_hist is not None else n_atoms_histogram(dataset)
         self.n_atoms_dist = torch.distributions.Categorical(probs=counts / counts.sum())       # flowmol.py:461-466
-        if torch.cuda.is_available():
+        if vector_field is not None:                      # adopt an already built device model (same config and weights)
+            self.vector_field = vector_field
+            self._device = str(vector_field.device)
+        elif torch.cuda.is_available():
             self._materialise(device)
 
     # -- construction ------------------------------------------------------------------------------------------------------
     @classmethod
     def from_checkpoint(cls, ckpt_path, device="cuda:0", **load_kwargs):
         sd, hp = WT.state_dict_from_checkpoint(ckpt_path)
+        # the kernels hard-wire what every shipped config uses: the CTMC parameterisation, the linear
+        # interpolant (alpha = t, alpha' = 1) for all four modalities and 6 charge classes.  Anything else must not load silently.
+        param = hp.get("parameterization", "ctmc")
+        if param != "ctmc":
+            raise NotImplementedError(f"checkpoint parameterization {param!r}: only 'ctmc' is built (flowmol.py:190-193)")
+        sched = (hp.get("interpolant_scheduler_config") or {}).get("schedule_type", "linear")
+        kinds = set(sched.values()) if isinstance(sched, dict) else {sched}
+        if kinds != {"linear"}:
+            raise NotImplementedError(f"checkpoint interpolant schedule {sched!r}: only the linear schedule is built "
+                                      "(interpolant_scheduler.py:148-154)")
+        if int(hp.get("n_atom_charges", 6)) != 6 or hp.get("exclude_charges", False):
+            raise NotImplementedError("checkpoint needs n_atom_charges == 6 and exclude_charges == False")
         hist = None
         if load_kwargs.get("n_atoms_hist_file"):
             n, c = torch.load(load_kwargs["n_atoms_hist_file"])
@@ -169,12 +204,13 @@ class FlowMolB200:
                    explicit_aromaticity=hp.get("explicit_aromaticity", False), device=device)
 
     @classmethod
-    def from_config(cls, name="flowmol3", dataset="geom", seed=0, device="cuda:0"):
+    def from_config(cls, name="flowmol3", dataset="geom", seed=0, device="cuda:0", vector_field=None):
         """Random-init weights of a named reference config (no checkpoint is reachable offline)."""
         from .config import NAMED_VECTOR_FIELDS
         amap = GEOM_ATOM_MAP if dataset == "geom" else QM9_ATOM_MAP
         cfg = ModelConfig.named(name, len(amap) + 1)
-        return cls(amap, NAMED_VECTOR_FIELDS[name], WT.init_state_dict(cfg, seed), dataset=dataset, device=device)
+        return cls(amap, NAMED_VECTOR_FIELDS[name], WT.init_state_dict(cfg, seed), dataset=dataset, device=device,
+                   vector_field=vector_field)
 
     def _materialise(self, device):
         self.vector_field = CTMCVectorFieldB200(self.cfg, self._state_dict, device=device)
@@ -233,6 +269,38 @@ class FlowMolB200:
         nbi = torch.arange(len(n)).repeat_interleave(n)
         return x - (torch.zeros(len(n), 3).index_add_(0, nbi, x) / n[:, None].float())[nbi]
 
+    device_decode = True       # sample(): token-level integrate + fm_decode on the device (False: the graph-level seam + host decode)
+
+    def _sample_tokens(self, g, n_timesteps, stochasticity, high_confidence_threshold, seed=None, mol_id_offset=0, **kwargs):
+        """The body of `sample` without one-hot round trips: the prior's tokens (argmax of the one-hots, on the device), the
+        token-level trajectory, the decode kernel, one D2H of compact arrays, then one SampledMolecule per molecule by slicing."""
+        vf = self.vector_field
+        uem = g.upper_edge_mask()
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())       # like vector_field.integrate: torch's global RNG decides
+        e0 = g.edata['e_0']
+        out = vf.integrate_tokens(g.n_atoms.numpy(), g.ndata['x_0'], g.ndata['a_0'].argmax(-1), g.ndata['c_0'].argmax(-1),
+                                  e0[uem.to(e0.device)].argmax(-1), n_timesteps, seed, stochasticity, high_confidence_threshold,
+                                  mol_id_offset, kwargs.pop('tspan', None), kwargs.pop('cuda_graph', False),
+                                  dfm_type=kwargs.pop('dfm_type', None), cat_temp_func=kwargs.pop('cat_temp_func', None),
+                                  forward_weight_func=kwargs.pop('forward_weight_func', None), inv_temp_func=kwargs.pop('inv_temp_func', None))
+        fake_token = len(self.atom_type_map) if self.fake_atoms else -1
+        d = vf.decode_tokens(g.n_atoms.numpy(), out['x'], out['a'], out['c'], out['e'], fake_token)
+        n = g.n_atoms.numpy()
+        noff = np.concatenate([[0], np.cumsum(n)])
+        uoff = np.concatenate([[0], np.cumsum(n * (n - 1) // 2)])
+        keep = d['atom_new'] >= 0
+        x_kept, a_kept, ch_kept = d['x'][keep], d['a'][keep], d['charge'][keep]
+        koff = np.concatenate([[0], np.cumsum(d['mol_kept'].numpy())])
+        nbonds = d['mol_bonds'].numpy()
+        mols = []
+        for b in range(len(n)):
+            ks, bs = slice(koff[b], koff[b + 1]), slice(uoff[b], uoff[b] + nbonds[b])
+            mols.append(SampledMolecule.from_decoded(x_kept[ks], a_kept[ks].tolist(), ch_kept[ks], d['bond_type'][bs], d['bond_src'][bs],
+                                                     d['bond_dst'][bs], self.atom_type_map, fake_atoms=self.fake_atoms,
+                                                     explicit_aromaticity=self.explicit_aromaticity))
+        return mols
+
     @torch.no_grad()
     def sample(self, n_atoms, n_timesteps=None, device="cuda:0", stochasticity=None, high_confidence_threshold=None,
                xt_traj=False, ep_traj=False, prior=None, **kwargs):
@@ -254,6 +322,8 @@ class FlowMolB200:
             elif not prior['fake_atoms'] and self.fake_atoms:
                 a0 = torch.cat([torch.zeros(a0.shape[0], 1, device=dev), a0], dim=-1)
             g.ndata['a_0'] = a0
+        if not visualize and self.device_decode:
+            return self._sample_tokens(g, n_timesteps, stochasticity, high_confidence_threshold, **kwargs)
         itg = self.vector_field.integrate(g, g.node_batch_idx(), upper_edge_mask=g.upper_edge_mask(), n_timesteps=n_timesteps,
                                           visualize=visualize, stochasticity=stochasticity,
                                           high_confidence_threshold=high_confidence_threshold, **kwargs)

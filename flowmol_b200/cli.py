@@ -103,8 +103,19 @@ def main(argv=None):
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device(device))
-    if args.seed is not None:
-        torch.manual_seed(args.seed)                                     # test.py:70-71 (seed_everything)
+    # test.py:70-71 seeds everything only when --seed is given and draws fresh randomness otherwise.  Here every rank must draw the
+    # same sizes and the same noise, so an unseeded run picks ONE random base seed on rank 0, broadcasts it and prints it.
+    base_seed = args.seed
+    if base_seed is None:
+        base_seed = int.from_bytes(os.urandom(7), "little")
+        if world > 1:
+            import torch.distributed as dist
+            box = [base_seed]
+            dist.broadcast_object_list(box, src=0)
+            base_seed = int(box[0])
+        if rank == 0:
+            print(f"no --seed given: using base seed {base_seed} (pass --seed {base_seed} to reproduce this run)")
+    torch.manual_seed(base_seed)
     if args.config is not None:
         model = api.FlowMolB200.from_config(args.config, dataset=args.dataset, seed=0, device=device)
         out_dir = Path(".")
@@ -115,7 +126,7 @@ def main(argv=None):
     model = model.cuda(local).eval()
     # all sizes up front (every rank draws the same list: same torch seed), then cost-aware batches, each sharded over the ranks
     if args.n_atoms_per_mol is None:
-        g = torch.Generator().manual_seed(args.seed if args.seed is not None else int(time.time()) if world == 1 else 0)
+        g = torch.Generator().manual_seed(base_seed)
         n_atoms = model.n_atoms_map[torch.multinomial(model.n_atoms_dist.probs.float(), args.n_mols, replacement=True, generator=g)]
     else:
         n_atoms = torch.full((args.n_mols,), args.n_atoms_per_mol, dtype=torch.long)
@@ -125,7 +136,7 @@ def main(argv=None):
     molecules = [None] * args.n_mols
     # noise that does not depend on the GPU count: one generator (same state on every rank) draws, per batch, the Philox seed of
     # the CTMC noise and the prior positions of the WHOLE batch; a rank integrates its slice with mol_id_offset = its first molecule
-    ngen = torch.Generator().manual_seed((args.seed if args.seed is not None else 0) + 0x5EED)
+    ngen = torch.Generator().manual_seed(base_seed + 0x5EED)
     torch.cuda.synchronize()
     start = time.time()
     for bi, idx in enumerate(batches):

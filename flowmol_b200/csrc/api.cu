@@ -114,6 +114,8 @@ struct FmHandle {
   int conv_impl = 0;           // 0: fp32 CUDA-core k_conv_edge, 1: tcgen05 3xTF32 k_conv_edge_tc (flowmol3 dims only)
   int eg_persist = 1;          // tc_prec 1: persistent role-specialised k_egemm_p (1 CTA / SM, double-buffered accumulators)
   int eg_img = 1;              // k_egemm_p: consecutive tensor-core linears hand their activations over as fp16 (hi, lo) operand images
+  int eg_cluster = 1;          // k_egemm_p on edge rows: CTAs per thread-block cluster sharing one multicast weight stream (1, 2, 4)
+  int eg_clusters_seen = 0;    // cudaOccupancyMaxActiveClusters of the last cluster kernel configured (diagnostics)
   int vec_impl = 1;            // edge-row vector stages: 1 = register-resident warp units (vec_reg.cuh, needs the image chain), 0 = vec_stages.cuh
   int tc_prec = 0;             // operand format of k_egemm_tc: 0 = 3xTF32 images, 1 = scaled fp16 hi/lo images ("fp16x3")
   bool has_h16 = false;        // packed weights carry the fp16 images
@@ -211,11 +213,43 @@ inline void prof_mark(FmHandle* h, int line, cudaStream_t st) {
 
 // operand-image hand-over between consecutive linears: only k_egemm_p knows it (callers pass IMG != 0 only when img_on(h))
 inline bool img_on(const FmHandle* h) { return h->eg_img && h->tc_prec == 1 && h->eg_persist && h->eg_nh == 1 && h->eg_nh_gate == 1 && h->fuse_agg; }
+// k_egemm_p as thread-block clusters of CL CTAs that share one multicast weight stream (egemm_p.cuh).  The grid is the number of
+// clusters the device can hold at once (cudaOccupancyMaxActiveClusters: a cluster lives inside one GPC) times CL.
+template <class D, int MODE, int IMG, int CL>
+void launch_egp_cluster(FmHandle* h, int n_tiles, cudaStream_t st, const fm::ModelRT& m, const fm::BatchRT& bt, const fm::EgArgs& a) {
+  auto kern = fm::k_egemm_p<D, MODE, IMG, CL>;
+  static int max_clusters = -1;                 // per instantiation; every rank of a job drives the same kind of device
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(fm::EgpPlan::THREADS);
+  cfg.dynamicSmemBytes = fm::EgpPlan::SMEM_BYTES;
+  cfg.stream = st;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  if (max_clusters < 0) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES);
+    cfg.gridDim = dim3(CL * (h->n_sm / CL));
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) n = 1;
+    max_clusters = n;
+    h->eg_clusters_seen = n;
+  }
+  const int want = (n_tiles + CL - 1) / CL;
+  cfg.gridDim = dim3(CL * (want < max_clusters ? want : max_clusters));
+  cudaLaunchKernelEx(&cfg, kern, m, bt, a, n_tiles);
+}
+
 template <class D, int MODE, int NH, int IMG = 0>
 void launch_eg(FmHandle* h, int grid, cudaStream_t st, const fm::ModelRT& m, const fm::BatchRT& bt, fm::EgArgs a) {
   using PL = fm::EgPlan<NH>;
   a.status = h->d_status;
   if (NH == 1 && h->tc_prec == 1 && h->eg_persist) {      // `grid` = number of 128-row tiles
+    if constexpr (IMG == (fm::EGI_IN | fm::EGI_OUT)) {     // the edge-row linears of the image chain: optional cluster launch
+      if (h->eg_cluster == 2 && !(a.flags & fm::EGF_NODE_ROWS)) { launch_egp_cluster<D, MODE, IMG, 2>(h, grid, st, m, bt, a); return; }
+      if (h->eg_cluster == 4 && !(a.flags & fm::EGF_NODE_ROWS)) { launch_egp_cluster<D, MODE, IMG, 4>(h, grid, st, m, bt, a); return; }
+    }
     fm::k_egemm_p<D, MODE, IMG><<<grid < h->n_sm ? grid : h->n_sm, fm::EgpPlan::THREADS, fm::EgpPlan::SMEM_BYTES, st>>>(m, bt, a, grid);
     return;
   }
@@ -778,6 +812,22 @@ int fm_sample_host(FmHandle* h, const int32_t* n_atoms, int32_t B, float* x_host
   return rc;
 }
 
+int fm_decode(FmHandle* h, void* ws, const uint8_t* a, const uint8_t* c, const uint8_t* e, int32_t fake_atom_token,
+              int32_t* atom_new, int8_t* charge, int32_t* mol_kept, int32_t* bond_src, int32_t* bond_dst, uint8_t* bond_type,
+              int32_t* mol_bonds, void* stream) {
+  if (!h || !ws || !a || !c || !e || !atom_new || !charge || !mol_kept || !bond_src || !bond_dst || !bond_type || !mol_bonds)
+    return fail("fm_decode: null argument");
+  const Layout* Lp;
+  if (find_batch(h, ws, &Lp)) return -1;
+  CUDA_OK(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const fm::BatchRT bt = batch_rt(ws, *Lp);
+  fm::k_decode<<<Lp->B, 256, 0, st>>>(bt, a, c, e, fake_atom_token, h->cfg.n_bond_types, atom_new, charge, mol_kept, bond_src, bond_dst,
+                                      bond_type, mol_bonds);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int fm_workspace_tensor(FmHandle* h, void* ws, const char* name, void** ptr, size_t* n_floats) {
   if (!h || !ws || !name || !ptr || !n_floats) return fail("fm_workspace_tensor: null argument");
   const Layout* Lp;
@@ -919,6 +969,11 @@ int fm_set_option(FmHandle* h, const char* name, int32_t value) {
   if (n == "eg_persist") { h->eg_persist = value ? 1 : 0; return 0; }
   if (n == "eg_img") { h->eg_img = value ? 1 : 0; return 0; }
   if (n == "vec_impl") { h->vec_impl = value ? 1 : 0; return 0; }
+  if (n == "eg_cluster") {
+    if (value != 1 && value != 2 && value != 4) return fail("fm_set_option: eg_cluster must be 1, 2 or 4");
+    h->eg_cluster = value;
+    return 0;
+  }
   if (n == "tc_prec") {
     if (value < 0 || value > 1) return fail("fm_set_option: tc_prec must be 0 (3xTF32) or 1 (fp16x3)");
     if (value == 1 && !h->has_h16) return fail("fm_set_option: packed weights carry no fp16 operand images");
@@ -974,6 +1029,8 @@ int fm_get_option(FmHandle* h, const char* name, int32_t* value) {
   if (std::string(name) == "eg_persist") { *value = h->eg_persist; return 0; }
   if (std::string(name) == "eg_img") { *value = h->eg_img; return 0; }
   if (std::string(name) == "vec_impl") { *value = h->vec_impl; return 0; }
+  if (std::string(name) == "eg_cluster") { *value = h->eg_cluster; return 0; }
+  if (std::string(name) == "eg_clusters_seen") { *value = h->eg_clusters_seen; return 0; }
   if (std::string(name) == "status") {      // synchronising read-and-clear of the device status word (see fm_check_status)
     int v = 0;
     CUDA_OK(cudaSetDevice(h->device));

@@ -174,4 +174,68 @@ k_ctmc_step(const BatchRT bt, int A, int C, int EB, const float* __restrict__ px
   campbell_modality(pe + (size_t)ub * EB, e_t + ub, ucount, EB, 2, gid, sc, scratch, tf.e ? tf.e + ub : nullptr, tf.e1 ? tf.e1 + ub : nullptr);
 }
 
+// ---- finalisation on the device (flowmol/models/flowmol.py:564-587 -> flowmol/analysis/molecule_builder.py:217-265) ------------------------
+// extract_moldata_from_graph as one launch, one CTA per molecule: atoms whose type is the fake-atom token are dropped and the rest
+// renumbered in order (atom_new[i] = new index or -1), charge = token - 2, and the bond list = upper-triangle edges in the reference's
+// order whose order is neither 0 nor the mask token and whose two atoms survive, compacted per molecule at offset mol_u[b] with the
+// renumbered (src < dst) indices.  The host then slices compact arrays instead of looping over one-hot graphs.
+__device__ __forceinline__ int block_excl_scan_flag(bool flag, int* scratch /* >= 33 ints */, int& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const unsigned bal = __ballot_sync(0xffffffffu, flag);
+  const int in_warp = __popc(bal & ((1u << lane) - 1u));
+  __syncthreads();                                     // previous use of scratch is over
+  if (lane == 0) scratch[warp] = __popc(bal);
+  __syncthreads();
+  int before = 0, tot = 0;
+  for (int w = 0; w < nw; ++w) { const int c = scratch[w]; if (w < warp) before += c; tot += c; }
+  total = tot;
+  return before + in_warp;
+}
+
+__global__ void __launch_bounds__(256)
+k_decode(const BatchRT bt, const uint8_t* __restrict__ a, const uint8_t* __restrict__ c, const uint8_t* __restrict__ e, int fake_token,
+         int mask_bond, int* __restrict__ atom_new, int8_t* __restrict__ charge, int* __restrict__ mol_kept,
+         int* __restrict__ bond_src, int* __restrict__ bond_dst, uint8_t* __restrict__ bond_type, int* __restrict__ mol_bonds) {
+  __shared__ int scratch[40];
+  __shared__ int new_idx[2048];                        // n <= 2000 (fm_batch_init)
+  const int mol = blockIdx.x, n = bt.mol_n[mol], nb = bt.mol_node[mol], ub = bt.mol_u[mol], ucount = n * (n - 1) / 2;
+  int base = 0;
+  for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+    const int i = i0 + threadIdx.x;
+    const bool keep = i < n && (int)a[nb + i] != fake_token;
+    int tot;
+    const int pos = block_excl_scan_flag(keep, scratch, tot);
+    if (i < n) {
+      const int v = keep ? base + pos : -1;
+      new_idx[i] = v;
+      atom_new[nb + i] = v;
+      charge[nb + i] = (int8_t)((int)c[nb + i] - 2);
+    }
+    base += tot;
+  }
+  if (threadIdx.x == 0) mol_kept[mol] = base;
+  __syncthreads();
+  int bbase = 0;
+  for (int l0 = 0; l0 < ucount; l0 += blockDim.x) {
+    const int lu = l0 + threadIdx.x;
+    int i = 0, j = 0, btp = 0;
+    bool sel = false;
+    if (lu < ucount) {
+      upper_ij(lu, n, i, j);
+      btp = e[ub + lu];
+      if (btp == mask_bond) btp = 0;
+      sel = btp != 0 && new_idx[i] >= 0 && new_idx[j] >= 0;
+    }
+    int tot;
+    const int pos = block_excl_scan_flag(sel, scratch, tot);
+    if (sel) {
+      bond_src[ub + bbase + pos] = new_idx[i];
+      bond_dst[ub + bbase + pos] = new_idx[j];
+      bond_type[ub + bbase + pos] = (uint8_t)btp;
+    }
+    bbase += tot;
+  }
+  if (threadIdx.x == 0) mol_bonds[mol] = bbase;
+}
+
 }  // namespace fm

@@ -56,7 +56,25 @@ struct EgpPlan {
 // same function of the same fp32 value on either side of HBM, so the results are bit-identical to the fp32 hand-over.
 enum EgImg : int { EGI_IN = 1, EGI_OUT = 2 };
 
-template <class D, int MODE, int IMG = 0>
+// CL: thread-block cluster size (launch attribute).  What ncu says about the message linears (profiles/r01s, r02): 6.6 KB of L2 -> SM
+// traffic per cycle, the measured fabric cap of the chip, and more than half of it is every CTA re-streaming the same 320 KB of
+// weight images for every 128-edge tile.  With CL > 1 the CTAs of a cluster walk the weight stream together: unit u is fetched
+// from L2 ONCE by CTA u % CL as a multicast bulk copy that lands in the ring slot of all CL CTAs (each CTA's w_full barrier
+// expects the bytes itself), a slot is refilled when the MMAs of ALL CL CTAs have released it (tcgen05.commit multicast onto the
+// peers' w_empty barriers, arrival count CL).  The MMAs themselves stay cta_group::1; tiles, activations, accumulators and
+// epilogues are private to each CTA.  A CTA with one tile less than its peers still takes part in the last round of the weight
+// protocol (waits for the units, releases them, issues its share of the copies).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+}
+
+template <class D, int MODE, int IMG = 0, int CL = 1>
 __global__ void __launch_bounds__(EgpPlan::THREADS, 1)
 k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) {
   using PL = EgpPlan;
@@ -98,8 +116,13 @@ k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
   constexpr bool NEED_ROWS = MODE == EG_MSG0 || MODE == EG_EU1 || MODE == EG_MSGA;      // the epilogue needs per-row node indices
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_my = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  // rounds of the weight protocol: the tile count of the cluster's first CTA (the largest of the cluster; n_my <= n_cl <= n_my + 1)
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+  const int cfirst = (int)blockIdx.x - (int)crank;
+  const int n_cl = CL > 1 ? ((cfirst < n_tiles) ? (n_tiles - 1 - cfirst) / (int)gridDim.x + 1 : 0) : n_my;
+  constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
   if (tid == 0) {
-    for (int i = 0; i < RING; ++i) { tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < RING; ++i) { tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], CL); }
     for (int i = 0; i < NST; ++i) { tc::mbar_init(&x_full[i], PL::NLW); tc::mbar_init(&x_empty[i], NMT); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], NMT); tc::mbar_init(&acc_empty[i], PL::NEW); }
     for (int i = 0; i < PL::NROWBUF; ++i) tc::mbar_init(&rows_full[i], PL::NLW);
@@ -108,6 +131,7 @@ k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
   if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
   tc::tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();          // the peers' barriers exist before anything is multicast at them
   tc::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
@@ -115,12 +139,14 @@ k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
     // ---- weight producer ---------------------------------------------------------------------------------------------------------
     if (lane == 0) {
       uint32_t u = 0;
-      for (int it = 0; it < n_my; ++it) {
+      for (int it = 0; it < n_cl; ++it) {
         for (uint32_t k = 0; k < NU; ++k, ++u) {
           const uint32_t sl = u % RING, use = u / RING;
-          if (use > 0) tc::mbar_wait(&w_empty[sl], (use - 1) & 1);
+          if (use > 0) tc::mbar_wait(&w_empty[sl], (use - 1) & 1);            // CL > 1: released by every CTA of the cluster
           tc::mbar_arrive_expect_tx(&w_full[sl], UNIT_BYTES);
-          tc::bulk_g2s(ring + sl * UNIT_BYTES, reinterpret_cast<const uint8_t*>(a.units) + (size_t)k * UNIT_BYTES, UNIT_BYTES, &w_full[sl]);
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(a.units) + (size_t)k * UNIT_BYTES;
+          if (CL == 1) tc::bulk_g2s(ring + sl * UNIT_BYTES, src, UNIT_BYTES, &w_full[sl]);
+          else if (u % CL == crank) tc::bulk_g2s_multicast(ring + sl * UNIT_BYTES, src, UNIT_BYTES, &w_full[sl], CMASK);
         }
       }
     }
@@ -153,7 +179,7 @@ k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
                 tc::umma_f16(d, dw, tc::desc_sw128_lo(xh + 2 * ks), idesc, 1u);
               }
             }
-            tc::umma_commit(&w_empty[sl]);
+            if (CL == 1) tc::umma_commit(&w_empty[sl]); else tc::umma_commit_multicast(&w_empty[sl], CMASK);
           }
           tc::mbar_wait(&w_full[sl + 1], ph);
           tc::tc_fence_after();
@@ -162,13 +188,26 @@ k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
 #pragma unroll
             for (uint32_t ks = 0; ks < 4; ++ks)
               if (ks < ksteps) tc::umma_f16(d, tc::desc_sw128_lo(wl + 2 * ks), tc::desc_sw128_lo(xh + 2 * ks), idesc, 1u);
-            tc::umma_commit(&w_empty[sl + 1]);
+            if (CL == 1) tc::umma_commit(&w_empty[sl + 1]); else tc::umma_commit_multicast(&w_empty[sl + 1], CMASK);
             tc::umma_commit(&x_empty[st]);
           }
           sl += 2 * NMT;
           if (sl >= RING) { sl -= RING; ph ^= 1; }
         }
         if (leader) tc::umma_commit(&acc_full[b]);
+      }
+      if (CL > 1 && n_cl > n_my) {
+        // one tile less than the cluster's first CTA: take the last round's weight units and release them untouched
+        for (int j = 0; j < NSLAB; ++j) {
+#pragma unroll
+          for (int hl = 0; hl < 2; ++hl) {
+            tc::mbar_wait(&w_full[sl + hl], ph);
+            tc::tc_fence_after();
+            if (leader) tc::umma_commit_multicast(&w_empty[sl + hl], CMASK);
+          }
+          sl += 2 * NMT;
+          if (sl >= RING) { sl -= RING; ph ^= 1; }
+        }
       }
     }
   } else if (warp < PL::W_EPI0) {
@@ -508,6 +547,7 @@ k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
   }
   tc::tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();          // no peer copy / commit may still be aimed at this CTA's shared memory when it exits
   if (warp == 1) tc::tmem_dealloc(tmem, 512);
 }
 

@@ -75,40 +75,66 @@ __device__ __forceinline__ WH16 vr_load_w(float* dst, const float* __restrict__ 
   return WH16{hi, lo, inv};
 }
 
-// D[p][nt] += A[p] W for the three planes p, one k-step of 16 (8): the same three products in the same order as warp_gemm_h16x3
+// D[p][nt] += A[p] W for the three planes p, one k-step of 16 (8): per accumulator the same three products in the same order as
+// warp_gemm_h16x3 (a_lo b_hi, a_hi b_lo, a_hi b_hi).  ncu (profiles/r02b): with ~4 warps per scheduler the stages spent 2 issue
+// slots per instruction waiting on fixed-latency dependencies -- the three HMMAs of one accumulator back to back -- so the products
+// are issued round-robin over the NTL x 3 accumulators (dependent HMMAs are NTL * 3 instructions apart) and the asm statements are
+// not volatile (pure functions of their operands: ptxas may interleave them with the splits and loads around them).
+__device__ __forceinline__ void vr_mma16(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void vr_mma8(float (&d)[4], const uint32_t (&a)[2], const uint32_t b) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%0, %1, %2, %3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(b));
+}
 template <int NTL>
 __device__ __forceinline__ void vr_kstep16(float (&acc)[3][NTL][4], const uint32_t (&ah)[3][4], const uint32_t (&al)[3][4],
                                            const uint32_t* __restrict__ Wh, const uint32_t* __restrict__ Wl, int ldw, int k0, int g, int t) {
+  uint32_t bh[NTL][2], bl[NTL][2];
 #pragma unroll
-  for (int nt = 0; nt < NTL; ++nt) {
-    uint32_t bh[2], bl[2];
+  for (int nt = 0; nt < NTL; ++nt)
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int w = ((k0 >> 1) + t + 4 * i) * ldw + 8 * nt + g;
-      bh[i] = Wh[w]; bl[i] = Wl[w];
+      bh[nt][i] = Wh[w]; bl[nt][i] = Wl[w];
     }
 #pragma unroll
-    for (int p = 0; p < 3; ++p) {
-      mma_f16_16x8x16(acc[p][nt], al[p], bh);
-      mma_f16_16x8x16(acc[p][nt], ah[p], bl);
-      mma_f16_16x8x16(acc[p][nt], ah[p], bh);
-    }
-  }
+  for (int nt = 0; nt < NTL; ++nt)
+#pragma unroll
+    for (int p = 0; p < 3; ++p) vr_mma16(acc[p][nt], al[p], bh[nt]);
+#pragma unroll
+  for (int nt = 0; nt < NTL; ++nt)
+#pragma unroll
+    for (int p = 0; p < 3; ++p) vr_mma16(acc[p][nt], ah[p], bl[nt]);
+#pragma unroll
+  for (int nt = 0; nt < NTL; ++nt)
+#pragma unroll
+    for (int p = 0; p < 3; ++p) vr_mma16(acc[p][nt], ah[p], bh[nt]);
 }
 template <int NTL>
 __device__ __forceinline__ void vr_kstep8(float (&acc)[3][NTL][4], const uint32_t (&ah)[3][2], const uint32_t (&al)[3][2],
                                           const uint32_t* __restrict__ Wh, const uint32_t* __restrict__ Wl, int ldw, int k0, int g, int t) {
+  uint32_t bh[NTL], bl[NTL];
 #pragma unroll
   for (int nt = 0; nt < NTL; ++nt) {
     const int w = ((k0 >> 1) + t) * ldw + 8 * nt + g;
-    const uint32_t bh = Wh[w], bl = Wl[w];
-#pragma unroll
-    for (int p = 0; p < 3; ++p) {
-      mma_f16_16x8x8(acc[p][nt], al[p], bh);
-      mma_f16_16x8x8(acc[p][nt], ah[p], bl);
-      mma_f16_16x8x8(acc[p][nt], ah[p], bh);
-    }
+    bh[nt] = Wh[w]; bl[nt] = Wl[w];
   }
+#pragma unroll
+  for (int nt = 0; nt < NTL; ++nt)
+#pragma unroll
+    for (int p = 0; p < 3; ++p) vr_mma8(acc[p][nt], al[p], bh[nt]);
+#pragma unroll
+  for (int nt = 0; nt < NTL; ++nt)
+#pragma unroll
+    for (int p = 0; p < 3; ++p) vr_mma8(acc[p][nt], ah[p], bl[nt]);
+#pragma unroll
+  for (int nt = 0; nt < NTL; ++nt)
+#pragma unroll
+    for (int p = 0; p < 3; ++p) vr_mma8(acc[p][nt], ah[p], bh[nt]);
 }
 
 // The tail every stage shares: acc1 = [Vh | cross | 0] (already unscaled, cross products in place, columns >= hc zero) of the warp's

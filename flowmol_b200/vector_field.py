@@ -352,6 +352,31 @@ class CTMCVectorFieldB200:
             out.append(d)
         return out
 
+    def decode_tokens(self, n_atoms, x, a, c, e_upper, fake_atom_token=-1):
+        """FlowMol.sample's finalisation (flowmol.py:564-587 -> molecule_builder.py:217-265) on the device: final token state ->
+        compact per-molecule arrays; ONE D2H of those.  Returns CPU tensors: 'x' [N,3], 'a' [N] tokens, 'charge' [N] int8,
+        'atom_new' [N] int32 (index after dropping fake atoms, -1 = dropped), 'mol_kept' [B], 'bond_src' / 'bond_dst' [U] int32 and
+        'bond_type' [U] uint8 (molecule b's bonds at [u_off[b], u_off[b] + mol_bonds[b])), 'mol_bonds' [B]."""
+        n = self._prepare(n_atoms)
+        dev = self.device
+        N, U, B = int(n.sum()), int((n.astype(np.int64) * (n - 1) // 2).sum()), len(n)
+        a = a.to(dev, torch.uint8).contiguous()
+        c = c.to(dev, torch.uint8).contiguous()
+        e = e_upper.to(dev, torch.uint8).contiguous()
+        i32 = dict(dtype=torch.int32, device=dev)
+        out = {'atom_new': torch.empty(N, **i32), 'charge': torch.empty(N, dtype=torch.int8, device=dev),
+               'mol_kept': torch.empty(B, **i32), 'bond_src': torch.empty(max(U, 1), **i32), 'bond_dst': torch.empty(max(U, 1), **i32),
+               'bond_type': torch.empty(max(U, 1), dtype=torch.uint8, device=dev), 'mol_bonds': torch.empty(B, **i32)}
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.fm_decode(self._h, self._ws.data_ptr(), a.data_ptr(), c.data_ptr(), e.data_ptr(), int(fake_atom_token),
+                                          out['atom_new'].data_ptr(), out['charge'].data_ptr(), out['mol_kept'].data_ptr(),
+                                          out['bond_src'].data_ptr(), out['bond_dst'].data_ptr(), out['bond_type'].data_ptr(),
+                                          out['mol_bonds'].data_ptr(), self._stream()))
+        host = {k: v.cpu() for k, v in out.items()}
+        host['x'] = x.detach().to(torch.float32).cpu()
+        host['a'] = a.cpu()
+        return host
+
     def sample_host(self, n_atoms, x0, a0, c0, e0_upper, n_timesteps, seed, stochasticity=None,
                     high_confidence_threshold=None, mol_id_offset=0, tspan=None, cuda_graph=False):
         """Host (pinned) buffers in, host buffers out: H2D + batch descriptor + trajectory + D2H inside one C call.

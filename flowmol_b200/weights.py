@@ -131,11 +131,14 @@ class _Stub:
         self.__dict__.update(state if isinstance(state, dict) else {})
 
 
-def state_dict_from_checkpoint(path):
+def state_dict_from_checkpoint(path, allow_unsafe_pickle=None):
     """Read a Lightning `.ckpt` ({'state_dict': {'vector_field.<name>': tensor}, 'hyper_parameters': {...}}).
 
     Returns (state_dict without the `vector_field.` prefix, hyper_parameters dict)."""
+    import os
     import pickle
+    if allow_unsafe_pickle is None:
+        allow_unsafe_pickle = os.environ.get("FLOWMOL_B200_UNSAFE_CKPT", "0") == "1"
 
     class _Unpickler(pickle.Unpickler):
         def find_class(self, module, name):
@@ -152,9 +155,38 @@ def state_dict_from_checkpoint(path):
     for attr in dir(pickle):
         if not hasattr(_Pickle, attr):
             setattr(_Pickle, attr, getattr(pickle, attr))
-    ckpt = torch.load(path, map_location="cpu", weights_only=False, pickle_module=_Pickle)
+    # First the safe loader (tensors + plain containers + the few pathlib types Lightning hyper-parameters carry).  A checkpoint
+    # that pickles other classes (e.g. from packages this image lacks) is only read with the stubbing unpickler -- which, like any
+    # pickle load, executes code from the file -- when the caller opts in; stubbed classes are reported.
+    import pathlib
+    import warnings
+    try:
+        with torch.serialization.safe_globals([pathlib.PosixPath, pathlib.Path, pathlib.PurePosixPath, pathlib.PurePath]):
+            ckpt = torch.load(path, map_location="cpu", weights_only=True)
+    except Exception as exc:                    # noqa: BLE001 -- torch raises UnpicklingError / RuntimeError depending on the cause
+        if not allow_unsafe_pickle:
+            raise RuntimeError(f"{path}: not loadable with torch.load(weights_only=True) ({type(exc).__name__}: {exc}); pass "
+                               "allow_unsafe_pickle=True (or set FLOWMOL_B200_UNSAFE_CKPT=1) only for checkpoints you trust") from exc
+        stubbed = []
+
+        class _Reporting(_Unpickler):
+            def find_class(self, module, name):
+                cls = super().find_class(module, name)
+                if cls is _Stub:
+                    stubbed.append(f"{module}.{name}")
+                return cls
+        _Pickle.Unpickler = _Reporting
+        _Pickle.load = staticmethod(lambda f, **k: _Reporting(f, **k).load())
+        ckpt = torch.load(path, map_location="cpu", weights_only=False, pickle_module=_Pickle)
+        if stubbed:
+            warnings.warn(f"{path}: classes not importable here were replaced by empty stubs: {sorted(set(stubbed))}")
     sd = OrderedDict((k[len("vector_field."):], v) for k, v in ckpt["state_dict"].items() if k.startswith("vector_field."))
     hp = dict(ckpt.get("hyper_parameters", {}))
+    for key, kinds in (("atom_type_map", (list, tuple)), ("vector_field_config", (dict,))):
+        if key in hp and not isinstance(hp[key], kinds):
+            raise TypeError(f"{path}: hyper-parameter {key!r} has type {type(hp[key]).__name__}, expected {kinds[0].__name__}")
+    if "n_atoms_hist_file" in hp and not isinstance(hp["n_atoms_hist_file"], (str, os.PathLike)):
+        raise TypeError(f"{path}: hyper-parameter 'n_atoms_hist_file' is not a path")
     return sd, hp
 
 

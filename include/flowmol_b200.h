@@ -16,6 +16,8 @@
  *                            flowmol/models/flowmol.py:557
  *   fm_integrate_traj        the same with visualize=True: per-step frames of the state and of the predicted / sampled endpoint
  *                            (ctmc_vector_field.py:187-202,235-283), written on the device by the step kernel
+ *   fm_decode                the decode at the end of FlowMol.sample (flowmol.py:564-587, molecule_builder.py:217-265): argmax
+ *                            state -> surviving atoms, charges, compact bond lists, on the device
  *   fm_sample_host           FlowMol.sample(n_atoms, n_timesteps, prior=...) from host buffers to host buffers
  *                            (flowmol.py:489-589 minus rdkit), i.e. integrate + the H2D / D2H around it
  *
@@ -120,6 +122,17 @@ int fm_integrate_traj(FmHandle* h, void* workspace, float* x, uint8_t* a, uint8_
 int fm_sample_host(FmHandle* h, const int32_t* n_atoms_host, int32_t n_molecules, float* x_host, uint8_t* a_host,
                    uint8_t* c_host, uint8_t* e_upper_host, const FmSampleOpts* opts, void* workspace,
                    size_t workspace_bytes, void* stream);
+
+/* finalisation on the device: FlowMol.sample's decode (flowmol/models/flowmol.py:564-587 -> extract_moldata_from_graph,
+ * flowmol/analysis/molecule_builder.py:217-265) of the batch last initialised on `workspace`, from final token state (device) to
+ * compact per-molecule arrays (device): atom_new [N] = index of the atom after fake atoms (token == fake_atom_token; pass -1 for a
+ * model without fake atoms) are dropped, or -1; charge [N] = charge token - 2; mol_kept [B] = surviving atoms; the bond list of
+ * molecule b (upper-triangle edges in the reference's order whose order is neither 0 nor the mask token n_bond_types and whose atoms
+ * both survive, renumbered src < dst) sits at bond_src / bond_dst / bond_type [mol_u[b] .. mol_u[b] + mol_bonds[b]) where
+ * mol_u[b] = sum over earlier molecules of n(n-1)/2 (so every output array has the size of the corresponding input). */
+int fm_decode(FmHandle* h, void* workspace, const uint8_t* a, const uint8_t* c, const uint8_t* e_upper, int32_t fake_atom_token,
+              int32_t* atom_new, int8_t* charge, int32_t* mol_kept, int32_t* bond_src, int32_t* bond_dst, uint8_t* bond_type,
+              int32_t* mol_bonds, void* stream);
 
 /* introspection for tests: device pointer + size (floats) of a named workspace tensor after fm_batch_init:
  * "s" [N,S], "v" [N,3,V], "x" [N,3], "ef" [EP,F] (internal padded dst-major order), "P", "M" */

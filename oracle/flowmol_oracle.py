@@ -361,7 +361,7 @@ def gat_step(p, xt, alpha_t, alpha_t_prime, forward_weight, dt, mask_index, u_ca
 
 def integrate(model, bt, x0, a0, c0, e0_upper, n_timesteps, seed, eta=None, hc_thresh=None, tau=0.05,
               mol_id_offset=0, record=None, dfm_type='campbell', cat_temp_func=None, forward_weight_func=None,
-              inv_temp_func=None):
+              inv_temp_func=None, tspan=None):
     """flowmol/models/ctmc_vector_field.py:145-411 (integrate + step), dfm_type='campbell', linear schedule
     (alpha_t = t, alpha_t' = 1: flowmol/models/interpolant_scheduler.py:148-154), inv_temp = 1.
 
@@ -370,7 +370,8 @@ def integrate(model, bt, x0, a0, c0, e0_upper, n_timesteps, seed, eta=None, hc_t
     cfg = model.cfg
     eta = cfg.stochasticity if eta is None else eta
     hc_thresh = cfg.high_confidence_threshold if hc_thresh is None else hc_thresh
-    t = torch.linspace(0, 1, n_timesteps)              # fp32, as the reference
+    t = torch.linspace(0, 1, n_timesteps) if tspan is None else tspan.float()     # ctmc_vector_field.py:169-172 (fp32)
+    n_timesteps = int(t.shape[0])
     x_t = x0.clone().float()
     a_t, c_t, e_t = a0.clone(), c0.clone(), e0_upper.clone()
     prev = None

@@ -176,6 +176,24 @@ def test_lightning_checkpoint_ingestion_and_molecule_decode(tmp_path):
     assert sizes.min() >= 3 and sizes.max() <= 181
     with pytest.raises(ValueError):
         load_pretrained("nope")
+    # options the kernels do not implement must be refused at load time, not sampled with the wrong coefficients
+    for bad in ({"parameterization": "dirichlet"}, {"n_atom_charges": 5}, {"exclude_charges": True},
+                {"interpolant_scheduler_config": {"schedule_type": {"x": "cosine", "a": "linear", "c": "linear", "e": "linear"}}}):
+        ck2 = dict(ck, hyper_parameters={**ck["hyper_parameters"], **bad})
+        torch.save(ck2, d / "bad.ckpt")
+        with pytest.raises(NotImplementedError):
+            FlowMolB200.from_checkpoint(d / "bad.ckpt", device="cpu")
+    ok = dict(ck, hyper_parameters={**ck["hyper_parameters"], "parameterization": "ctmc", "n_atom_charges": 6,
+                                    "interpolant_scheduler_config": {"schedule_type": {k: "linear" for k in "xace"}}})
+    torch.save(ok, d / "ok.ckpt")
+    assert FlowMolB200.from_checkpoint(d / "ok.ckpt", device="cpu").n_atom_types == 11
+    # a checkpoint that pickles a class is not read by the safe loader unless the caller opts in
+    import argparse
+    torch.save(dict(ck, callbacks={"x": argparse.Namespace(a=1)}), d / "cls.ckpt")
+    with pytest.raises(RuntimeError, match="weights_only"):
+        WT.state_dict_from_checkpoint(d / "cls.ckpt")
+    sd2, _ = WT.state_dict_from_checkpoint(d / "cls.ckpt", allow_unsafe_pickle=True)
+    assert all(torch.equal(sd2[k], sd[k]) for k in sd)
     # decode: 4 atoms, atom 2 is a fake atom (index 10), bonds 0-1 single, 0-2 (to the fake atom) double, 1-3 masked
     x = np.arange(12, dtype=np.float32).reshape(4, 3)
     a = np.array([0, 3, 10, 1])

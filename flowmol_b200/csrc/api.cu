@@ -14,6 +14,7 @@
 #include "conv_tc.cuh"
 #include "egemm_tc.cuh"
 #include "egemm_p.cuh"
+#include "egemm_e.cuh"
 #include "vec_stages.cuh"
 #include "vec_reg.cuh"
 #include "tc_test.cuh"
@@ -114,6 +115,8 @@ struct FmHandle {
   int conv_impl = 0;           // 0: fp32 CUDA-core k_conv_edge, 1: tcgen05 3xTF32 k_conv_edge_tc (flowmol3 dims only)
   int eg_persist = 1;          // tc_prec 1: persistent role-specialised k_egemm_p (1 CTA / SM, double-buffered accumulators)
   int eg_img = 1;              // k_egemm_p: consecutive tensor-core linears hand their activations over as fp16 (hi, lo) operand images
+  int eg_orient = 0;           // message linears MSG0 / MSG of the image chain: 0 = features on M (k_egemm_p, default), 1 = edges on M
+                               // (k_egemm_e: bit-identical, measured slower -- MSG0 750 vs 588 us, MSG 591 vs 547 us, profiles/r02d)
   int eg_cluster = 1;          // k_egemm_p on edge rows: CTAs per thread-block cluster sharing one multicast weight stream (1, 2, 4)
   int eg_clusters_seen = 0;    // cudaOccupancyMaxActiveClusters of the last cluster kernel configured (diagnostics)
   int vec_impl = 1;            // edge-row vector stages: 1 = register-resident warp units (vec_reg.cuh, needs the image chain), 0 = vec_stages.cuh
@@ -190,6 +193,8 @@ int set_smem_attrs() {
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_EU2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_LIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_MSGA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_e<D, fm::EG_MSG0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgePlan::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_e<D, fm::EG_MSG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgePlan::SMEM_BYTES));
     constexpr int IO = fm::EGI_IN | fm::EGI_OUT;
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_MSG0, IO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_MSG, IO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
@@ -300,7 +305,12 @@ int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
         constexpr int IO = fm::EGI_IN | fm::EGI_OUT;
         a.in_img = g == 0 ? at<float>(ws, L.EFI) : cur;
         a.out_img = outs[g];
-        if (g == 0) {
+        if (g < 2 && h->eg_orient == 1 && h->eg_cluster == 1) {      // edges-on-M orientation (egemm_e.cuh)
+          a.status = h->d_status;
+          const int grid_e = gt < h->n_sm ? gt : h->n_sm;
+          if (g == 0) fm::k_egemm_e<D, fm::EG_MSG0><<<grid_e, fm::EgePlan::THREADS, fm::EgePlan::SMEM_BYTES, st>>>(m, bt, a, gt);
+          else fm::k_egemm_e<D, fm::EG_MSG><<<grid_e, fm::EgePlan::THREADS, fm::EgePlan::SMEM_BYTES, st>>>(m, bt, a, gt);
+        } else if (g == 0) {
           launch_eg<D, fm::EG_MSG0, 1, IO>(h, gt, st, m, bt, a);
         } else if (g == 1) {
           launch_eg<D, fm::EG_MSG, 1, IO>(h, gt, st, m, bt, a);
@@ -607,7 +617,7 @@ int fm_create(const FmConfig* cfg, const float* w_host, size_t n_floats, const i
                c.n_hidden_scalars + 3 * c.n_vec_channels};
   CUDA_OK(cudaMalloc(&h->d_w, n_floats * sizeof(float)));
   CUDA_OK(cudaMalloc(&h->d_off, n_off * sizeof(long long)));
-  CUDA_OK(cudaMalloc(&h->d_table, sizeof(float) * (c.n_bond_types + 1) * c.n_hidden_edge_feats));
+  CUDA_OK(cudaMalloc(&h->d_table, sizeof(float) * 2 * (c.n_bond_types + 1) * c.n_hidden_edge_feats));   // edge-embedding table + its image under the SC residual's first linear
   CUDA_OK(cudaMalloc(&h->d_status, sizeof(int)));
   CUDA_OK(cudaMemset(h->d_status, 0, sizeof(int)));
   CUDA_OK(cudaMemcpy(h->d_w, w_host, n_floats * sizeof(float), cudaMemcpyHostToDevice));
@@ -969,6 +979,7 @@ int fm_set_option(FmHandle* h, const char* name, int32_t value) {
   if (n == "eg_persist") { h->eg_persist = value ? 1 : 0; return 0; }
   if (n == "eg_img") { h->eg_img = value ? 1 : 0; return 0; }
   if (n == "vec_impl") { h->vec_impl = value ? 1 : 0; return 0; }
+  if (n == "eg_orient") { h->eg_orient = value ? 1 : 0; return 0; }
   if (n == "eg_cluster") {
     if (value != 1 && value != 2 && value != 4) return fail("fm_set_option: eg_cluster must be 1, 2 or 4");
     h->eg_cluster = value;
@@ -1029,6 +1040,7 @@ int fm_get_option(FmHandle* h, const char* name, int32_t* value) {
   if (std::string(name) == "eg_persist") { *value = h->eg_persist; return 0; }
   if (std::string(name) == "eg_img") { *value = h->eg_img; return 0; }
   if (std::string(name) == "vec_impl") { *value = h->vec_impl; return 0; }
+  if (std::string(name) == "eg_orient") { *value = h->eg_orient; return 0; }
   if (std::string(name) == "eg_cluster") { *value = h->eg_cluster; return 0; }
   if (std::string(name) == "eg_clusters_seen") { *value = h->eg_clusters_seen; return 0; }
   if (std::string(name) == "status") {      // synchronising read-and-clear of the device status word (see fm_check_status)

@@ -256,6 +256,21 @@ __global__ void k_edge_table(const ModelRT m, float* __restrict__ table) {
     var /= D::F;
     table[tok * D::F + tid] = (h1[tid] - mean) / sqrtf(var + 1e-5f) * m.g(G_EEMB_LN_W)[tid] + m.g(G_EEMB_LN_B)[tid];
   }
+  // Second table (self-conditioning models): the part of the edge residual MLP's first linear that multiplies the embedded edge
+  // features (self_conditioning.py:70-78: cat[e_feats, e_1_pred, rbf differences]) takes one of n_bond_types + 1 values as well:
+  // T1[tok] = b1 + table[tok] . W1[0:F, :].  k_edge_init then contracts only the F + 4 + R -> 4 + R per-edge columns (-44 % of its
+  // MACs; a different fp32 summation order for those F terms, inside the parity budget like the node-side folds).
+  if (m.self_cond) {
+    __syncthreads();
+    if (tid < D::F) h0[tid] = table[tok * D::F + tid];
+    __syncthreads();
+    if (tid < D::F) {
+      const float* w1 = m.g(G_SCE0_W);
+      float a = 0.f;
+      for (int k = 0; k < D::F; ++k) a = fmaf(h0[k], w1[k * NP + tid], a);
+      table[(m.EB + 1 + tok) * D::F + tid] = a + m.g(G_SCE0_B)[tid];
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -294,52 +309,56 @@ k_edge_init(const ModelRT m, const BatchRT bt, const float* __restrict__ x_t, co
     sm.src[tid] = p0; sm.dst[tid] = p1; sm.aux[tid] = tok; sm.dist[tid] = dd; sm.G[tid] = d1;
   }
   __syncthreads();
+  // self-conditioning residual on the edge features (self_conditioning.py:70-82).  The embedded edge features are one of
+  // n_bond_types + 1 table rows, so their share of the first linear is the precomputed T1[tok] (k_edge_table); the per-edge
+  // operand is only [e_1_pred (EB) | rbf(d_1) - rbf(d_t) (R)].
   const int EB = m.EB;
-  const int K = D::F + EB + D::R, KP = pad4(K);
-  for (int idx = tid; idx < TM * KP; idx += NT) {
-    const int row = idx / KP, c = idx - row * KP;
-    float v = 0.f;
-    if (sm.src[row] >= 0) {
-      if (c < D::F) v = m.eemb_table[sm.aux[row] * D::F + c];
-      else if (has_prev) {
-        if (c < D::F + EB) v = prev.e[(size_t)(ub + lu0 + row) * EB + (c - D::F)];
+  const int K = EB + D::R, KP = pad4(K);
+  const float* tab = m.eemb_table;
+  const float* tab1 = m.eemb_table + (size_t)(EB + 1) * D::F;
+  float out[1][RPW][D::CPT_F];
+  if (has_prev) {
+    for (int idx = tid; idx < TM * KP; idx += NT) {
+      const int row = idx / KP, c = idx - row * KP;
+      float v = 0.f;
+      if (sm.src[row] >= 0) {
+        if (c < EB) v = prev.e[(size_t)(ub + lu0 + row) * EB + c];
         else if (c < K) {
-          const float mu = m.g(G_RBF_MU)[c - D::F - EB], sigma = m.rbf_dmax / (float)D::R;
+          const float mu = m.g(G_RBF_MU)[c - EB], sigma = m.rbf_dmax / (float)D::R;
           v = __fsub_rn(rbf_f(sm.G[row], mu, sigma), rbf_f(sm.dist[row], mu, sigma));   // d_edge_1 - d_edge_t
         }
       }
+      sm.Xs[row * XE + c] = v;
     }
-    sm.Xs[row * XE + c] = v;
-  }
-  float out[1][RPW][D::CPT_F];
-  if (has_prev) {
     float acc[1][RPW][D::CPT_F];
-    tile_gemm<1, D::CPT_F, RPW, WST>(sm.Xs, XE, 0, KP, m.g(G_SCE0_W), sm.wstage, acc);
-    {
-      const float* b = m.g(G_SCE0_B);
+    tile_gemm<1, D::CPT_F, RPW, WST>(sm.Xs, XE, 0, KP, m.g(G_SCE0_W) + (size_t)D::F * (D::CPT_F * 32), sm.wstage, acc);
 #pragma unroll
-      for (int r = 0; r < RPW; ++r)
+    for (int r = 0; r < RPW; ++r) {
+      const int tok = sm.aux[warp * RPW + r];
 #pragma unroll
-        for (int c = 0; c < D::CPT_F; ++c) {
-          const int col = ColMap<D::CPT_F>::col(lane, c);
-          sm.Xs[(warp * RPW + r) * XE + KP + col] = silu_f(acc[0][r][c] + b[col]);
-        }
+      for (int c = 0; c < D::CPT_F; ++c) {
+        const int col = ColMap<D::CPT_F>::col(lane, c);
+        sm.Xs[(warp * RPW + r) * XE + KP + col] = silu_f(acc[0][r][c] + tab1[tok * D::F + col]);
+      }
     }
     tile_gemm<1, D::CPT_F, RPW, WST>(sm.Xs + KP, XE, 0, D::F, m.g(G_SCE2_W), sm.wstage, acc);
     const float* b = m.g(G_SCE2_B);
 #pragma unroll
-    for (int r = 0; r < RPW; ++r)
+    for (int r = 0; r < RPW; ++r) {
+      const int tok = sm.aux[warp * RPW + r];
 #pragma unroll
       for (int c = 0; c < D::CPT_F; ++c) {
         const int col = ColMap<D::CPT_F>::col(lane, c);
-        out[0][r][c] = __fadd_rn(sm.Xs[(warp * RPW + r) * XE + col], silu_f(acc[0][r][c] + b[col]));
+        out[0][r][c] = __fadd_rn(tab[tok * D::F + col], silu_f(acc[0][r][c] + b[col]));
       }
+    }
   } else {
-    __syncthreads();
 #pragma unroll
-    for (int r = 0; r < RPW; ++r)
+    for (int r = 0; r < RPW; ++r) {
+      const int tok = sm.aux[warp * RPW + r];
 #pragma unroll
-      for (int c = 0; c < D::CPT_F; ++c) out[0][r][c] = sm.Xs[(warp * RPW + r) * XE + ColMap<D::CPT_F>::col(lane, c)];
+      for (int c = 0; c < D::CPT_F; ++c) out[0][r][c] = tab[tok * D::F + ColMap<D::CPT_F>::col(lane, c)];
+    }
   }
   // mirrored store (self_conditioning.py:79-82)
 #pragma unroll

@@ -96,6 +96,9 @@ class CTMCVectorFieldB200:
         self._ws = None
         self._ws_key = None
         self.last_launches = 0
+        # fp16x3 operands need |activation| < 65504; nobody knows the range of a given trained checkpoint.  When the device status
+        # word reports an overflow, the call is repeated once with 3xTF32 operands (no range limit) and the handle stays there.
+        self.auto_fallback = True
 
     def __del__(self):
         try:
@@ -156,13 +159,32 @@ class CTMCVectorFieldB200:
         return int(v.value)
 
     def check_status(self):
-        """Synchronising read-and-clear of the device status word; raises if an activation left the fp16 operand range of the
-        tensor-core linears (|x| >= 65504 with tc_prec 1) -- the results of that call are invalid, re-run with tc_prec 0."""
-        with torch.cuda.device(self.device):
-            st = self.get_option("status")
-        if st & 1:
+        """Read-and-clear of the device status word; raises if an activation left the fp16 operand range of the tensor-core
+        linears (|x| >= 65504 with tc_prec 1) -- the results of that call are invalid."""
+        if self._status_fired():
             raise RuntimeError("flowmol_b200: an activation left the fp16 operand range of the tensor-core linears; "
                                "call set_option('tc_prec', 0) (3xTF32 operands) and re-run")
+
+    def _status_fired(self):
+        with torch.cuda.device(self.device):
+            return bool(self.get_option("status") & 1)
+
+    def _guarded(self, run):
+        """run() -> result; on an fp16-operand overflow: with auto_fallback, switch the handle to 3xTF32 operands (with a warning)
+        and run once more; otherwise raise."""
+        out = run()
+        if not self._status_fired():
+            return out
+        if self.auto_fallback and self.get_option("tc_prec") == 1:
+            import warnings
+            warnings.warn("flowmol_b200: an activation left the fp16 operand range (|x| >= 65504); repeating the call with 3xTF32 "
+                          "operands and keeping them for this model (set_option('tc_prec', 1) switches back)")
+            self.set_option("tc_prec", 0)
+            out = run()
+            if not self._status_fired():
+                return out
+        raise RuntimeError("flowmol_b200: an activation left the fp16 operand range of the tensor-core linears; "
+                           "call set_option('tc_prec', 0) (3xTF32 operands) and re-run")
 
     def kernel_profile(self, n_atoms, x_t, a_idx, c_idx, e_idx_upper, t=0.3, prev=None, n_forwards=1):
         """In-situ per-kernel timing of `n_forwards` network evaluations: fm_debug_kprof records a CUDA event after every launch
@@ -246,13 +268,15 @@ class CTMCVectorFieldB200:
             prev = {k: prev[k].to(dev, torch.float32).contiguous() for k in 'xace'}
             pv = self._pred_struct(prev)
         po = self._pred_struct(out)
-        with torch.cuda.device(dev):
-            _lib.check(self.lib.fm_forward(self._h, self._ws.data_ptr(), x_t.data_ptr(), a.data_ptr(), c.data_ptr(),
-                                           e.data_ptr(), float(t), C.byref(pv) if pv is not None else None, C.byref(po),
-                                           int(stop_after_conv), self._stream()))
-        self.last_launches = int(self.lib.fm_last_launch_count(self._h))
-        self.check_status()
-        return out
+
+        def run():
+            with torch.cuda.device(dev):
+                _lib.check(self.lib.fm_forward(self._h, self._ws.data_ptr(), x_t.data_ptr(), a.data_ptr(), c.data_ptr(),
+                                               e.data_ptr(), float(t), C.byref(pv) if pv is not None else None, C.byref(po),
+                                               int(stop_after_conv), self._stream()))
+            self.last_launches = int(self.lib.fm_last_launch_count(self._h))
+            return out
+        return self._guarded(run)
 
     def _opts(self, n_timesteps, stochasticity, high_confidence_threshold, seed, mol_id_offset, tspan, cuda_graph,
               dfm_type=None, cat_temp_func=None, forward_weight_func=None, inv_temp_func=None):
@@ -302,15 +326,13 @@ class CTMCVectorFieldB200:
         (tokens sampled by campbell_step) -- written by the step kernel itself, no host round trips."""
         n = self._prepare(n_atoms)
         dev = self.device
-        x = x0.to(dev, torch.float32).contiguous().clone()
-        a = a0.to(dev, torch.uint8).contiguous().clone()
-        c = c0.to(dev, torch.uint8).contiguous().clone()
-        e = e0_upper.to(dev, torch.uint8).contiguous().clone()
+        x_in, a_in = x0.to(dev, torch.float32).contiguous(), a0.to(dev, torch.uint8).contiguous()
+        c_in, e_in = c0.to(dev, torch.uint8).contiguous(), e0_upper.to(dev, torch.uint8).contiguous()
         o, keep = self._opts(n_timesteps, stochasticity, high_confidence_threshold, seed, mol_id_offset, tspan, cuda_graph,
                              dfm_type, cat_temp_func, forward_weight_func, inv_temp_func)
         frames, tr = None, None
         if traj:
-            T, N, U = int(o.n_timesteps), x.shape[0], e.shape[0]
+            T, N, U = int(o.n_timesteps), x_in.shape[0], e_in.shape[0]
             u8 = dict(dtype=torch.uint8, device=dev)
             frames = {'x': torch.empty(T, N, 3, device=dev), 'a': torch.empty(T, N, **u8), 'c': torch.empty(T, N, **u8),
                       'e': torch.empty(T, U, **u8), 'x_1_pred': torch.empty(T - 1, N, 3, device=dev),
@@ -319,13 +341,15 @@ class CTMCVectorFieldB200:
             tr = _lib.FmTraj(x=frames['x'].data_ptr(), a=frames['a'].data_ptr(), c=frames['c'].data_ptr(), e=frames['e'].data_ptr(),
                              x1=frames['x_1_pred'].data_ptr(), a1=frames['a_1_pred'].data_ptr(),
                              c1=frames['c_1_pred'].data_ptr(), e1=frames['e_1_pred'].data_ptr())
-        with torch.cuda.device(dev):
-            _lib.check(self.lib.fm_integrate_traj(self._h, self._ws.data_ptr(), x.data_ptr(), a.data_ptr(), c.data_ptr(),
-                                                  e.data_ptr(), C.byref(o), C.byref(tr) if tr is not None else None,
-                                                  self._stream()))
-        self.last_launches = int(self.lib.fm_last_launch_count(self._h))
-        self.check_status()
-        out = {'x': x, 'a': a, 'c': c, 'e': e}
+        def run():
+            x, a, c, e = x_in.clone(), a_in.clone(), c_in.clone(), e_in.clone()       # the trajectory updates its state in place
+            with torch.cuda.device(dev):
+                _lib.check(self.lib.fm_integrate_traj(self._h, self._ws.data_ptr(), x.data_ptr(), a.data_ptr(), c.data_ptr(),
+                                                      e.data_ptr(), C.byref(o), C.byref(tr) if tr is not None else None,
+                                                      self._stream()))
+            self.last_launches = int(self.lib.fm_last_launch_count(self._h))
+            return {'x': x, 'a': a, 'c': c, 'e': e}
+        out = self._guarded(run)
         if traj:
             out['traj'] = frames
         return out
@@ -391,10 +415,21 @@ class CTMCVectorFieldB200:
             self._ws = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
         self._ws_key = n.tobytes()
         o, ts = self._opts(n_timesteps, stochasticity, high_confidence_threshold, seed, mol_id_offset, tspan, cuda_graph)
+        retry = self.auto_fallback and self.get_option("tc_prec") == 1
+        saved = [t_.clone() for t_ in (x0, a0, c0, e0_upper)] if retry else None      # the call overwrites its host buffers
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.fm_sample_host(self._h, n.ctypes.data, len(n), x0.data_ptr(), a0.data_ptr(), c0.data_ptr(),
-                                               e0_upper.data_ptr(), C.byref(o), self._ws.data_ptr(), self._ws.numel(),
-                                               self._stream()))
+            rc = self.lib.fm_sample_host(self._h, n.ctypes.data, len(n), x0.data_ptr(), a0.data_ptr(), c0.data_ptr(),
+                                         e0_upper.data_ptr(), C.byref(o), self._ws.data_ptr(), self._ws.numel(), self._stream())
+            if rc != 0 and retry and b"fp16 operand range" in self.lib.fm_last_error():
+                import warnings
+                warnings.warn("flowmol_b200: an activation left the fp16 operand range (|x| >= 65504); repeating the call with 3xTF32 "
+                              "operands and keeping them for this model")
+                self.set_option("tc_prec", 0)
+                for dst_, src_ in zip((x0, a0, c0, e0_upper), saved):
+                    dst_.copy_(src_)
+                rc = self.lib.fm_sample_host(self._h, n.ctypes.data, len(n), x0.data_ptr(), a0.data_ptr(), c0.data_ptr(),
+                                             e0_upper.data_ptr(), C.byref(o), self._ws.data_ptr(), self._ws.numel(), self._stream())
+            _lib.check(rc)
         self.last_launches = int(self.lib.fm_last_launch_count(self._h))
         return {'x': x0, 'a': a0, 'c': c0, 'e': e0_upper}
 

@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -q -x -m gpu -s -k "agree" > gpurun_out/r02d_pytest_agree.txt 2>&1; echo "agree rc=$?"; grep -E "parity\] (edges|impl 2)|passed|failed|Error" gpurun_out/r02d_pytest_agree.txt | tail
+timeout 600 python tools/gpu_kprof.py 3 > gpurun_out/r02d_kprof.txt 2>&1; head -12 gpurun_out/r02d_kprof.txt
+timeout 1500 python -m pytest tests -q -x -m gpu -s > gpurun_out/r02d_pytest_gpu.txt 2>&1; echo "pytest rc=$?"; grep -E "passed|failed|Error" gpurun_out/r02d_pytest_gpu.txt | tail -3

@@ -117,6 +117,8 @@ struct FmHandle {
   int eg_img = 1;              // k_egemm_p: consecutive tensor-core linears hand their activations over as fp16 (hi, lo) operand images
   int eg_orient = 0;           // message linears MSG0 / MSG of the image chain: 0 = features on M (k_egemm_p, default), 1 = edges on M
                                // (k_egemm_e: bit-identical, measured slower -- MSG0 750 vs 588 us, MSG 591 vs 547 us, profiles/r02d)
+  int eg_fuse_gate = 1;        // GVP 1 / 2 of the message pass: gate linear inside the scalar linear's kernel (k_egemm_g; needs the image chain
+                               // and the register-resident vector stages); aggregation pieces become 32 rows
   int eg_cluster = 1;          // k_egemm_p on edge rows: CTAs per thread-block cluster sharing one multicast weight stream (1, 2, 4)
   int eg_clusters_seen = 0;    // cudaOccupancyMaxActiveClusters of the last cluster kernel configured (diagnostics)
   int vec_impl = 1;            // edge-row vector stages: 1 = register-resident warp units (vec_reg.cuh, needs the image chain), 0 = vec_stages.cuh
@@ -193,6 +195,8 @@ int set_smem_attrs() {
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_EU2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_LIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_MSGA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_g<D, fm::EG_MSG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EggPlan::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_g<D, fm::EG_MSGA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EggPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_e<D, fm::EG_MSG0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgePlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_e<D, fm::EG_MSG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgePlan::SMEM_BYTES));
     constexpr int IO = fm::EGI_IN | fm::EGI_OUT;
@@ -218,6 +222,8 @@ inline void prof_mark(FmHandle* h, int line, cudaStream_t st) {
 
 // operand-image hand-over between consecutive linears: only k_egemm_p knows it (callers pass IMG != 0 only when img_on(h))
 inline bool img_on(const FmHandle* h) { return h->eg_img && h->tc_prec == 1 && h->eg_persist && h->eg_nh == 1 && h->eg_nh_gate == 1 && h->fuse_agg; }
+// gate-fused message linears (egemm_e.cuh:k_egemm_g): on top of the image chain and the register-resident vector stages
+inline bool gate_fused(const FmHandle* h) { return img_on(h) && h->vec_impl == 1 && h->eg_fuse_gate == 1 && h->eg_cluster == 1 && h->conv_impl == 2; }
 // k_egemm_p as thread-block clusters of CL CTAs that share one multicast weight stream (egemm_p.cuh).  The grid is the number of
 // clusters the device can hold at once (cudaOccupancyMaxActiveClusters: a cluster lives inside one GPC) times CL.
 template <class D, int MODE, int IMG, int CL>
@@ -290,6 +296,7 @@ int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
     const int vgrid = L.nET < 2 * h->n_sm ? L.nET : 2 * h->n_sm;     // persistent: 2 CTAs per SM, tiles strided
     // register-resident vector stages (vec_reg.cuh): one warp per 16-row unit, VH holds VU = Vh_ext Wu (3 x 32 per row) instead
     const bool vr = img && h->vec_impl == 1;
+    const bool gf = gate_fused(h);
     const int n_units = L.nET * (fm::TM / fm::UR);
     const int vrgrid = (n_units + fm::NWARP - 1) / fm::NWARP < 2 * h->n_sm ? (n_units + fm::NWARP - 1) / fm::NWARP : 2 * h->n_sm;
     if (!vr) fm::k_vec_a<D><<<vgrid, fm::NT, vsm, st>>>(m, bt, l, x, v, VH, SH);
@@ -305,6 +312,13 @@ int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
         constexpr int IO = fm::EGI_IN | fm::EGI_OUT;
         a.in_img = g == 0 ? at<float>(ws, L.EFI) : cur;
         a.out_img = outs[g];
+        if (g >= 1 && gf) {                                          // scalar linear + gate linear in one kernel (egemm_e.cuh)
+          a.status = h->d_status;
+          a.g_units = wptr(tc_c(h, tcg[g])); a.g_bias = wptr(gb[g] + fm::GV_BG); a.g_out = GT;
+          const int grid_g = gt < h->n_sm ? gt : h->n_sm;
+          if (g == 1) fm::k_egemm_g<D, fm::EG_MSG><<<grid_g, fm::EggPlan::THREADS, fm::EggPlan::SMEM_BYTES, st>>>(m, bt, a, gt);
+          else fm::k_egemm_g<D, fm::EG_MSGA><<<grid_g, fm::EggPlan::THREADS, fm::EggPlan::SMEM_BYTES, st>>>(m, bt, a, gt);
+        } else
         if (g < 2 && h->eg_orient == 1 && h->eg_cluster == 1) {      // edges-on-M orientation (egemm_e.cuh)
           a.status = h->d_status;
           const int grid_e = gt < h->n_sm ? gt : h->n_sm;
@@ -329,12 +343,14 @@ int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
         else launch_eg<D, fm::EG_MSG, 1>(h, gt, st, m, bt, a);
       }
       LAUNCH_OK(h);
-      fm::EgArgs ag{wptr(tc_c(h, tcg[g])), wptr(gb[g] + fm::GV_BG), outs[g], nullptr, nullptr, nullptr, GT, nullptr, nullptr, L.EP, h->trace_mode == 2 ? h->d_trace : nullptr, h->trace_cta, 0, h->tc_debug};
-      ag.in_img = outs[g];
-      if (img) launch_eg<D, fm::EG_GATE, 1, fm::EGI_IN>(h, (int)(L.EPA / 128), st, m, bt, ag);
-      else if (h->eg_nh_gate == 2) launch_eg<D, fm::EG_GATE, 2>(h, (int)(L.EPA / 256), st, m, bt, ag);
-      else launch_eg<D, fm::EG_GATE, 1>(h, (int)(L.EPA / 128), st, m, bt, ag);
-      LAUNCH_OK(h);
+      if (!(g >= 1 && gf)) {
+        fm::EgArgs ag{wptr(tc_c(h, tcg[g])), wptr(gb[g] + fm::GV_BG), outs[g], nullptr, nullptr, nullptr, GT, nullptr, nullptr, L.EP, h->trace_mode == 2 ? h->d_trace : nullptr, h->trace_cta, 0, h->tc_debug};
+        ag.in_img = outs[g];
+        if (img) launch_eg<D, fm::EG_GATE, 1, fm::EGI_IN>(h, (int)(L.EPA / 128), st, m, bt, ag);
+        else if (h->eg_nh_gate == 2) launch_eg<D, fm::EG_GATE, 2>(h, (int)(L.EPA / 256), st, m, bt, ag);
+        else launch_eg<D, fm::EG_GATE, 1>(h, (int)(L.EPA / 128), st, m, bt, ag);
+        LAUNCH_OK(h);
+      }
       if (g < 2) {
         if (!vr)
           fm::k_vec_b<D><<<vgrid, fm::NT, vsm, st>>>(bt, wptr(g == 0 ? fm::C_MSG0_WU : fm::C_MSG1_WU), (g == 0 ? D::H0 : D::V) + D::CP,
@@ -347,7 +363,7 @@ int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
       cur = outs[g];
     }
     if (!vr) fm::k_vec_c<D><<<vgrid, fm::NT, vsm, st>>>(m, bt, l, h->fuse_agg ? D::S : 0, VH, GT, SA, M, partF, partL);
-    else fm::k_vecr_c<D><<<(L.nET + fm::NWARP - 1) / fm::NWARP, fm::NT, 0, st>>>(bt, VH, GT, M, partF, partL);
+    else fm::k_vecr_c<D><<<(L.nET * (gf ? 2 : 1) + fm::NWARP - 1) / fm::NWARP, fm::NT, 0, st>>>(bt, gf ? 32 : fm::TM, VH, GT, M, partF, partL);
     LAUNCH_OK(h);
   }
   return 0;
@@ -457,6 +473,7 @@ int run_pass(FmHandle* h, void* ws, const Layout& L, const float* x_t, const uin
     if (h->conv_impl == 2) {
       int rc = conv_wide<D>(h, ws, L, bt, l, st);
       if (rc) return rc;
+      if (gate_fused(h)) agg_rows = 32;          // k_egemm_g<EG_MSGA> / k_vecr_c write 32-row aggregation pieces
     } else if (agg_rows == fm::TM) {
       fm::k_conv_edge<D><<<L.nET, fm::NT, smem, st>>>(m, bt, l, x, v, ef, P, Q, vd, M, partF, partL);
       LAUNCH_OK(h);
@@ -980,6 +997,7 @@ int fm_set_option(FmHandle* h, const char* name, int32_t value) {
   if (n == "eg_img") { h->eg_img = value ? 1 : 0; return 0; }
   if (n == "vec_impl") { h->vec_impl = value ? 1 : 0; return 0; }
   if (n == "eg_orient") { h->eg_orient = value ? 1 : 0; return 0; }
+  if (n == "eg_fuse_gate") { h->eg_fuse_gate = value ? 1 : 0; return 0; }
   if (n == "eg_cluster") {
     if (value != 1 && value != 2 && value != 4) return fail("fm_set_option: eg_cluster must be 1, 2 or 4");
     h->eg_cluster = value;
@@ -1041,6 +1059,7 @@ int fm_get_option(FmHandle* h, const char* name, int32_t* value) {
   if (std::string(name) == "eg_img") { *value = h->eg_img; return 0; }
   if (std::string(name) == "vec_impl") { *value = h->vec_impl; return 0; }
   if (std::string(name) == "eg_orient") { *value = h->eg_orient; return 0; }
+  if (std::string(name) == "eg_fuse_gate") { *value = h->eg_fuse_gate; return 0; }
   if (std::string(name) == "eg_cluster") { *value = h->eg_cluster; return 0; }
   if (std::string(name) == "eg_clusters_seen") { *value = h->eg_clusters_seen; return 0; }
   if (std::string(name) == "status") {      // synchronising read-and-clear of the device status word (see fm_check_status)

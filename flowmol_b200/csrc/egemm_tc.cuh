@@ -69,6 +69,9 @@ struct EgArgs {
   int* status;               // PREC 1: bit 0 is set when an activation leaves the fp16 operand range (|x| >= ACT_LIMIT_H16)
   const float* in_img;       // k_egemm_p<.., EGI_IN>: fp16 (hi, lo) operand images of the leading k-slabs (egemm_p.cuh)
   float* out_img;            // k_egemm_p<.., EGI_OUT>: where the output's operand images go
+  const float* g_units;      // k_egemm_g: weight images of the GVP's gate linear (the EG_GATE units), its bias and the gate rows [EPA][32]
+  const float* g_bias;
+  float* g_out;
 };
 
 // EG_MSGA: one finished segment sum of feature f.  Deliberately not inlined: the call sits behind a rarely taken branch in a

@@ -396,14 +396,18 @@ k_vecr_a(const ModelRT m, const BatchRT bt, const int layer, const int n_units, 
 // is cut by the tile goes to partL (its head) / partF (a continuation) exactly as in k_vec_c / k_conv_edge.
 template <class D>
 __global__ void __launch_bounds__(NT)
-k_vecr_c(const BatchRT bt, const float* __restrict__ VU, const float* __restrict__ GT, float* __restrict__ M,
-         float* __restrict__ partF, float* __restrict__ partL) {
+k_vecr_c(const BatchRT bt, const int piece_rows /* 64 or 32: rows per aggregation piece (k_node_pre's agg_rows) */,
+         const float* __restrict__ VU, const float* __restrict__ GT, float* __restrict__ M, float* __restrict__ partF,
+         float* __restrict__ partL) {
   static_assert(D::V == 32, "lane = vector channel");
-  const int lane = threadIdx.x & 31, tile = blockIdx.x * NWARP + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31, piece = blockIdx.x * NWARP + (threadIdx.x >> 5);
+  const int ppt = TM / piece_rows, tile = piece / ppt;          // pieces per 64-slot tile
   if (tile >= bt.n_edge_tiles) return;
   const int mol = __ldg(bt.etile_mol + tile), n = __ldg(bt.mol_n + mol), nb = __ldg(bt.mol_node + mol);
-  const int le0 = (tile - __ldg(bt.mol_etile + mol)) * TM, nvalid = min(TM, n * (n - 1) - le0), deg = n - 1;
-  const size_t erow0 = (size_t)tile * TM;
+  const int le0 = (tile - __ldg(bt.mol_etile + mol)) * TM + (piece - tile * ppt) * piece_rows;
+  const int nvalid = min(piece_rows, n * (n - 1) - le0), deg = n - 1;
+  if (nvalid <= 0) return;
+  const size_t erow0 = (size_t)piece * piece_rows;
   int j = le0 / deg, rem = le0 - j * deg;                      // destination (local) and position inside its in-edge segment of row 0
   bool head = rem == 0;                                        // the running segment started with the node's first in-edge
   float a0 = 0.f, a1 = 0.f, a2 = 0.f;
@@ -425,7 +429,7 @@ k_vecr_c(const BatchRT bt, const float* __restrict__ VU, const float* __restrict
         a2 = __fadd_rn(a2, __fmul_rn(gbuf[k], b2[k]));
         const bool tail = rem == deg - 1;
         if (tail || row == nvalid - 1) {
-          float* dst = (head && tail) ? M + (size_t)(nb + j) * D::MW : (head ? partL + (size_t)tile * D::MW : partF + (size_t)tile * D::MW);
+          float* dst = (head && tail) ? M + (size_t)(nb + j) * D::MW : (head ? partL + (size_t)piece * D::MW : partF + (size_t)piece * D::MW);
           dst[D::S + lane] = a0; dst[D::S + 32 + lane] = a1; dst[D::S + 64 + lane] = a2;
           a0 = a1 = a2 = 0.f;
           head = true;                                         // the next segment (if any) starts at its node's first in-edge

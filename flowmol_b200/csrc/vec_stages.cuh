@@ -465,15 +465,18 @@ k_node_pre(const ModelRT m, const BatchRT bt, int layer, int agg_rows, float* __
   // element exposed one L2 round trip per piece and column: 235 us for 24 k nodes, profiles/r01q.)
   auto piece0 = [&](int t0, int t1, int g, int col) { return t0 == t1 ? M[(size_t)g * D::MW + col] : partL[(size_t)t0 * D::MW + col]; };
   auto piece1 = [&](int t0, int t1, int col) { return t1 > t0 ? partF[(size_t)(t0 + 1) * D::MW + col] : -0.0f; };
+  // third piece, branch-free as well: with 32-row aggregation pieces (gate-fused message linears) a GEOM-sized node (45 in-edges)
+  // spans two or three pieces, and the data-dependent loop below was k_node_pre's critical path (101 -> 182 us, profiles/r02f)
+  auto piece2 = [&](int t0, int t1, int col) { return t1 > t0 + 1 ? partF[(size_t)(t0 + 2) * D::MW + col] : -0.0f; };
   auto finish = [&](int row, int t0, int t1, int col, float msg) {
-    for (int t = t0 + 2; t <= t1; ++t) msg = __fadd_rn(msg, partF[(size_t)t * D::MW + col]);
+    for (int t = t0 + 3; t <= t1; ++t) msg = __fadd_rn(msg, partF[(size_t)t * D::MW + col]);
     const float div = sm.dist[row];
     return div != 0.f ? __fdiv_rn(msg, div) : msg;
   };
   constexpr int RG = 2;                                     // rows per group: 2 x 8 columns x 3 loads in flight per lane
   const int lane = tid & 31;
   for (int r0 = 0; r0 < RPW; r0 += RG) {
-    float sv[RG][D::CPT_S], a0[RG][D::CPT_S], a1[RG][D::CPT_S];
+    float sv[RG][D::CPT_S], a0[RG][D::CPT_S], a1[RG][D::CPT_S], a2[RG][D::CPT_S];
 #pragma unroll
     for (int rr = 0; rr < RG; ++rr) {
       const int row = warp * RPW + r0 + rr, g = min(g0 + row, bt.N - 1);      // dead rows read a live row and are not stored
@@ -484,6 +487,7 @@ k_node_pre(const ModelRT m, const BatchRT bt, int layer, int agg_rows, float* __
         sv[rr][c] = s[(size_t)g * D::S + col];
         a0[rr][c] = piece0(t0, t1, g, col);
         a1[rr][c] = piece1(t0, t1, col);
+        a2[rr][c] = piece2(t0, t1, col);
       }
     }
 #pragma unroll
@@ -494,12 +498,12 @@ k_node_pre(const ModelRT m, const BatchRT bt, int layer, int agg_rows, float* __
       float* srow = s + (size_t)g * D::S;
       row_scalar_layernorm<D>(srow, m.c(layer, C_LN_MSG_W), m.c(layer, C_LN_MSG_B), [&](int col) {
         const int c = col >> 5;
-        return __fadd_rn(sv[rr][c], finish(row, t0, t1, col, __fadd_rn(a0[rr][c], a1[rr][c])));
+        return __fadd_rn(sv[rr][c], finish(row, t0, t1, col, __fadd_rn(__fadd_rn(a0[rr][c], a1[rr][c]), a2[rr][c])));
       });
     }
   }
   for (int i0 = tid; i0 < TM * 3 * D::V; i0 += 4 * NT) {
-    float vv[4], b0[4], b1[4];
+    float vv[4], b0[4], b1[4], b2[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {                            // 4 x 3 loads in flight
       const int idx = i0 + k * NT, row = idx / (3 * D::V), pc = idx - row * 3 * D::V, g = min(g0 + row, bt.N - 1);
@@ -507,12 +511,13 @@ k_node_pre(const ModelRT m, const BatchRT bt, int layer, int agg_rows, float* __
       vv[k] = v[(size_t)g * 3 * D::V + pc];
       b0[k] = piece0(t0, t1, g, D::S + pc);
       b1[k] = piece1(t0, t1, D::S + pc);
+      b2[k] = piece2(t0, t1, D::S + pc);
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int idx = i0 + k * NT, row = idx / (3 * D::V), pc = idx - row * 3 * D::V, g = g0 + row;
       float val = 0.f;
-      if (g < bt.N) val = __fadd_rn(vv[k], finish(row, sm.dst[row], sm.aux[row], D::S + pc, __fadd_rn(b0[k], b1[k])));
+      if (g < bt.N) val = __fadd_rn(vv[k], finish(row, sm.dst[row], sm.aux[row], D::S + pc, __fadd_rn(__fadd_rn(b0[k], b1[k]), b2[k])));
       sm.Va[(row * 3 + pc / D::V) * D::LDVA + (pc % D::V)] = val;
     }
   }

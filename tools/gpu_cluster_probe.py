@@ -13,6 +13,7 @@ vf = CTMCVectorFieldB200(cfg, WT.init_state_dict(cfg, 0))
 n_atoms = draw_sizes("geom", 512)
 x0, a0, c0, e0 = make_prior(n_atoms, 11, 100)
 ref = None
+vf.set_option("eg_fuse_gate", 0)          # cluster launches exist for the un-fused chain only
 for cl in (1, 2, 4, 1):
     vf.set_option("eg_cluster", cl)
     d0 = vf.forward_tokens(n_atoms, x0, a0, c0, e0, 0.0, None)

@@ -384,7 +384,7 @@ struct EggPlan {
   static constexpr int OFF_PARK = OFF_WG + WG_BYTES;
   static constexpr int OFF_ROW = OFF_PARK + PARK_BYTES;     // NROWBUF x int row[T]
   static constexpr int OFF_BAR = OFF_ROW + NROWBUF * T * 4;
-  static constexpr int NBAR = 4 + 2 * NST + 4 + NROWBUF + 2 + 2 + 1;
+  static constexpr int NBAR = 8 + 2 * NST + 4 + NROWBUF + 2 + 2 + 1;
   static constexpr int BYTES = OFF_BAR + NBAR * 8 + 16;
   static constexpr size_t SMEM_BYTES = BYTES;
   static_assert(BYTES <= 232448, "227 KB of shared memory per CTA");
@@ -436,14 +436,14 @@ k_egemm_g(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
   uint8_t* wg = smem_dyn + PL::OFF_WG;
   uint8_t* park = smem_dyn + PL::OFF_PARK;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_dyn + PL::OFF_BAR);
-  uint64_t *w_full = bars, *w_empty = bars + 2, *x_full = bars + 4, *x_empty = x_full + NST;
+  uint64_t *w_full = bars, *w_empty = bars + 4, *x_full = bars + 8, *x_empty = x_full + NST;
   uint64_t *acc_full = x_empty + NST, *acc_empty = acc_full + 2, *rows_full = acc_empty + 2;
   uint64_t *a_ready = rows_full + PL::NROWBUF, *gate_full = a_ready + 2, *wg_full = gate_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wg_full + 1);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_my = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 4; ++i) { tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < NST; ++i) { tc::mbar_init(&x_full[i], PL::NLW); tc::mbar_init(&x_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&acc_full[i], 1);
@@ -468,16 +468,18 @@ k_egemm_g(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
         tc::mbar_arrive_expect_tx(wg_full, PL::WG_BYTES);
         for (int u = 0; u < 8; ++u) tc::bulk_g2s(wg + u * 4096, reinterpret_cast<const uint8_t*>(a.g_units) + (size_t)u * 4096, 4096, wg_full);
       }
+      // the four 16 KB units of a k-slab in stream order (f 0..127 hi, f 0..127 lo, f 128..255 hi, f 128..255 lo), each with its own
+      // barrier pair: a unit is refilled as soon as ITS MMAs are done.  (A first version moved the two hi / lo units as one 32 KB
+      // tile for N = 256 MMAs: only two refills in flight, tensor pipe 49 % busy, the epilogue warps waiting -- profiles/r02g.)
       uint32_t g = 0;
       for (int it = 0; it < n_my; ++it) {
         for (int j = 0; j < NSLAB; ++j, ++g) {
           const uint8_t* src = reinterpret_cast<const uint8_t*>(a.units) + (size_t)(4 * j) * TC_UNIT;
 #pragma unroll
-          for (int hl = 0; hl < 2; ++hl) {
-            if (g > 0) tc::mbar_wait(&w_empty[hl], (g - 1) & 1);
-            tc::mbar_arrive_expect_tx(&w_full[hl], 2 * TC_UNIT);
-            tc::bulk_g2s(ring + (2 * hl) * TC_UNIT, src + hl * TC_UNIT, TC_UNIT, &w_full[hl]);
-            tc::bulk_g2s(ring + (2 * hl + 1) * TC_UNIT, src + (2 + hl) * TC_UNIT, TC_UNIT, &w_full[hl]);
+          for (int u = 0; u < 4; ++u) {
+            if (g > 0) tc::mbar_wait(&w_empty[u], (g - 1) & 1);
+            tc::mbar_arrive_expect_tx(&w_full[u], TC_UNIT);
+            tc::bulk_g2s(ring + u * TC_UNIT, src + u * TC_UNIT, TC_UNIT, &w_full[u]);
           }
         }
       }
@@ -485,39 +487,43 @@ k_egemm_g(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
   } else if (warp == 1) {
     // ---- main MMA issuer ---------------------------------------------------------------------------------------------------------------
     const bool leader = tc::elect_one();
-    const uint32_t idesc = tc::idesc_f16(128, 256);
-    const uint32_t w_hi = tc::smem_u32(ring) >> 4, w_lo = w_hi + ((2 * TC_UNIT) >> 4), x_lo = tc::smem_u32(xst) >> 4;
+    const uint32_t idesc = tc::idesc_f16(128, 128);          // two N = 128 MMAs per k-step and product: one per 128-feature weight unit
+    const uint32_t w_base = tc::smem_u32(ring) >> 4, x_lo = tc::smem_u32(xst) >> 4;
     uint32_t g = 0;
     for (int it = 0; it < n_my; ++it) {
       const int b = it & 1;
       if (it >= 2) { tc::mbar_wait(&acc_empty[b], ((it >> 1) - 1) & 1); tc::tc_fence_after(); }
-      const uint32_t d = tmem + (uint32_t)(b * 256);
       for (int j = 0; j < NSLAB; ++j, ++g) {
         const uint32_t st = g % NST, ksteps = (j == NSLAB - 1) ? LAST_KSTEPS : 4;
         tc::mbar_wait(&x_full[st], (g / NST) & 1);
         const uint32_t xh = x_lo + st * (PL::XSTAGE >> 4), xl = xh + (LO_OFF >> 4);
-        tc::mbar_wait(&w_full[0], g & 1);
-        tc::tc_fence_after();
-        if (leader) {
 #pragma unroll
-          for (uint32_t ks = 0; ks < 4; ++ks) {
-            if (ks < ksteps) {
-              const uint64_t dw = tc::desc_sw128_lo(w_hi + 2 * ks);
-              tc::umma_f16(d, tc::desc_sw128_lo(xl + 2 * ks), dw, idesc, (j > 0 || ks > 0) ? 1u : 0u);
-              tc::umma_f16(d, tc::desc_sw128_lo(xh + 2 * ks), dw, idesc, 1u);
+        for (uint32_t ft = 0; ft < 2; ++ft) {
+          const uint32_t d = tmem + (uint32_t)(b * 256) + ft * 128;
+          const uint32_t wh = w_base + (2 * ft) * (TC_UNIT >> 4), wl = wh + (TC_UNIT >> 4);
+          tc::mbar_wait(&w_full[2 * ft], g & 1);
+          tc::tc_fence_after();
+          if (leader) {
+#pragma unroll
+            for (uint32_t ks = 0; ks < 4; ++ks) {
+              if (ks < ksteps) {
+                const uint64_t dw = tc::desc_sw128_lo(wh + 2 * ks);
+                tc::umma_f16(d, tc::desc_sw128_lo(xl + 2 * ks), dw, idesc, (j > 0 || ks > 0) ? 1u : 0u);
+                tc::umma_f16(d, tc::desc_sw128_lo(xh + 2 * ks), dw, idesc, 1u);
+              }
             }
+            tc::umma_commit(&w_empty[2 * ft]);
           }
-          tc::umma_commit(&w_empty[0]);
-        }
-        tc::mbar_wait(&w_full[1], g & 1);
-        tc::tc_fence_after();
-        if (leader) {
+          tc::mbar_wait(&w_full[2 * ft + 1], g & 1);
+          tc::tc_fence_after();
+          if (leader) {
 #pragma unroll
-          for (uint32_t ks = 0; ks < 4; ++ks)
-            if (ks < ksteps) tc::umma_f16(d, tc::desc_sw128_lo(xh + 2 * ks), tc::desc_sw128_lo(w_lo + 2 * ks), idesc, 1u);
-          tc::umma_commit(&w_empty[1]);
-          tc::umma_commit(&x_empty[st]);
+            for (uint32_t ks = 0; ks < 4; ++ks)
+              if (ks < ksteps) tc::umma_f16(d, tc::desc_sw128_lo(xh + 2 * ks), tc::desc_sw128_lo(wl + 2 * ks), idesc, 1u);
+            tc::umma_commit(&w_empty[2 * ft + 1]);
+          }
         }
+        if (leader) tc::umma_commit(&x_empty[st]);
       }
       if (leader) tc::umma_commit(&acc_full[b]);
     }

@@ -15,6 +15,7 @@
 #include "egemm_tc.cuh"
 #include "egemm_p.cuh"
 #include "egemm_e.cuh"
+#include "egemm_c.cuh"
 #include "vec_stages.cuh"
 #include "vec_reg.cuh"
 #include "tc_test.cuh"
@@ -121,6 +122,7 @@ struct FmHandle {
                                // and the register-resident vector stages); aggregation pieces become 32 rows
   int eg_cluster = 1;          // k_egemm_p on edge rows: CTAs per thread-block cluster sharing one multicast weight stream (1, 2, 4)
   int eg_clusters_seen = 0;    // cudaOccupancyMaxActiveClusters of the last cluster kernel configured (diagnostics)
+  int eu_fuse = 1;             // EdgeUpdate: both linears + LayerNorm in one kernel, hidden activations in tensor memory (egemm_c.cuh)
   int vec_impl = 1;            // edge-row vector stages: 1 = register-resident warp units (vec_reg.cuh, needs the image chain), 0 = vec_stages.cuh
   int tc_prec = 0;             // operand format of k_egemm_tc: 0 = 3xTF32 images, 1 = scaled fp16 hi/lo images ("fp16x3")
   bool has_h16 = false;        // packed weights carry the fp16 images
@@ -197,6 +199,7 @@ int set_smem_attrs() {
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_MSGA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_g<D, fm::EG_MSG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EggPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_g<D, fm::EG_MSGA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EggPlan::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_c<D, fm::CH_EU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgcPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_e<D, fm::EG_MSG0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgePlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_e<D, fm::EG_MSG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgePlan::SMEM_BYTES));
     constexpr int IO = fm::EGI_IN | fm::EGI_OUT;
@@ -496,6 +499,16 @@ int run_pass(FmHandle* h, void* ws, const Layout& L, const float* x_t, const uin
           auto uptr = [&](int id) { return h->d_w + h->off_h[fm::G_COUNT + m.L * fm::C_COUNT + upd * fm::U_COUNT + id]; };
           float* H = at<float>(ws, L.SA);
           const int gt = (int)(L.EPA / 128);
+          if (img_on(h) && h->eu_fuse && h->vec_impl == 1) {   // EU1 -> SiLU -> EU2 -> residual + LayerNorm in one kernel (egemm_c.cuh)
+            fm::EgArgs ac{uptr(tc_u(h, fm::U_EUPD_TC1)), uptr(fm::U_EUPD_B2), ef, nullptr, EAB, x, ef, uptr(fm::U_EUPD_LN_W), uptr(fm::U_EUPD_LN_B), L.EP, nullptr, 0, 0, h->tc_debug};
+            ac.status = h->d_status;
+            ac.in_img = at<float>(ws, L.EFI); ac.out_img = at<float>(ws, L.EFI);
+            ac.g_units = uptr(tc_u(h, fm::U_EUPD_TC2));
+            fm::k_egemm_c<D, fm::CH_EU><<<gt < h->n_sm ? gt : h->n_sm, fm::EgcPlan::THREADS, fm::EgcPlan::SMEM_BYTES, st>>>(m, bt, ac, gt);
+            LAUNCH_OK(h);
+            done = true;
+          }
+          if (!done) {
           fm::EgArgs a1{uptr(tc_u(h, fm::U_EUPD_TC1)), nullptr, ef, nullptr, EAB, x, H, nullptr, nullptr, L.EP, h->trace_mode == 3 ? h->d_trace : nullptr, h->trace_cta, 0, h->tc_debug};
           a1.in_img = at<float>(ws, L.EFI); a1.out_img = H;
           if (img_on(h)) launch_eg<D, fm::EG_EU1, 1, fm::EGI_IN | fm::EGI_OUT>(h, gt, st, m, bt, a1);
@@ -507,6 +520,7 @@ int run_pass(FmHandle* h, void* ws, const Layout& L, const float* x_t, const uin
           else launch_eg<D, fm::EG_EU2, 1>(h, gt, st, m, bt, a2);
           LAUNCH_OK(h);
           done = true;
+          }
         }
       }
       if (!done) { fm::k_edge_update<D><<<L.nET, fm::NT, smem, st>>>(m, bt, upd, x, EAB, ef); LAUNCH_OK(h); }
@@ -998,6 +1012,7 @@ int fm_set_option(FmHandle* h, const char* name, int32_t value) {
   if (n == "vec_impl") { h->vec_impl = value ? 1 : 0; return 0; }
   if (n == "eg_orient") { h->eg_orient = value ? 1 : 0; return 0; }
   if (n == "eg_fuse_gate") { h->eg_fuse_gate = value ? 1 : 0; return 0; }
+  if (n == "eu_fuse") { h->eu_fuse = value ? 1 : 0; return 0; }
   if (n == "eg_cluster") {
     if (value != 1 && value != 2 && value != 4) return fail("fm_set_option: eg_cluster must be 1, 2 or 4");
     h->eg_cluster = value;
@@ -1060,6 +1075,7 @@ int fm_get_option(FmHandle* h, const char* name, int32_t* value) {
   if (std::string(name) == "vec_impl") { *value = h->vec_impl; return 0; }
   if (std::string(name) == "eg_orient") { *value = h->eg_orient; return 0; }
   if (std::string(name) == "eg_fuse_gate") { *value = h->eg_fuse_gate; return 0; }
+  if (std::string(name) == "eu_fuse") { *value = h->eu_fuse; return 0; }
   if (std::string(name) == "eg_cluster") { *value = h->eg_cluster; return 0; }
   if (std::string(name) == "eg_clusters_seen") { *value = h->eg_clusters_seen; return 0; }
   if (std::string(name) == "status") {      // synchronising read-and-clear of the device status word (see fm_check_status)

@@ -399,6 +399,18 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
       "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&f)[32]) {
+  uint32_t lo[16], hi[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { lo[i] = __float_as_uint(f[i]); hi[i] = __float_as_uint(f[16 + i]); }
+  tmem_st16(taddr, lo);
+  tmem_st16(taddr + 16, hi);
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // D[tmem] (+)= A[tmem] . B[smem]^T, kind::f16: A = M lanes x 8 columns of packed fp16 pairs (16 k values)
 __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -478,6 +490,7 @@ k_egemm_g(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             if (g > 0) tc::mbar_wait(&w_empty[u], (g - 1) & 1);
+            if (a.dbg & 1) { tc::mbar_arrive_expect_tx(&w_full[u], 0u); continue; }
             tc::mbar_arrive_expect_tx(&w_full[u], TC_UNIT);
             tc::bulk_g2s(ring + u * TC_UNIT, src + u * TC_UNIT, TC_UNIT, &w_full[u]);
           }
@@ -506,7 +519,7 @@ k_egemm_g(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
           if (leader) {
 #pragma unroll
             for (uint32_t ks = 0; ks < 4; ++ks) {
-              if (ks < ksteps) {
+              if (ks < ksteps && !(a.dbg & 2)) {
                 const uint64_t dw = tc::desc_sw128_lo(wh + 2 * ks);
                 tc::umma_f16(d, tc::desc_sw128_lo(xl + 2 * ks), dw, idesc, (j > 0 || ks > 0) ? 1u : 0u);
                 tc::umma_f16(d, tc::desc_sw128_lo(xh + 2 * ks), dw, idesc, 1u);
@@ -519,7 +532,7 @@ k_egemm_g(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
           if (leader) {
 #pragma unroll
             for (uint32_t ks = 0; ks < 4; ++ks)
-              if (ks < ksteps) tc::umma_f16(d, tc::desc_sw128_lo(xh + 2 * ks), tc::desc_sw128_lo(wl + 2 * ks), idesc, 1u);
+              if (ks < ksteps && !(a.dbg & 2)) tc::umma_f16(d, tc::desc_sw128_lo(xh + 2 * ks), tc::desc_sw128_lo(wl + 2 * ks), idesc, 1u);
             tc::umma_commit(&w_empty[2 * ft + 1]);
           }
         }
@@ -542,6 +555,7 @@ k_egemm_g(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
         uint32_t first = 0;
 #pragma unroll
         for (uint32_t c = 0; c < 8; ++c) {
+          if (a.dbg & 16) break;
           const uint32_t sl = c >> 1;                                         // k-slab of the gate weights
 #pragma unroll
           for (uint32_t k2 = 0; k2 < 2; ++k2) {
@@ -619,9 +633,12 @@ k_egemm_g(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
           if (lane == 0) {
             if (warp == PL::W_LOAD0) {
               const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
+              if (a.dbg & 4) tc::mbar_arrive_expect_tx(&x_full[st], 0u);
+              else {
               tc::mbar_arrive_expect_tx(&x_full[st], PL::XSTAGE);
               tc::bulk_g2s(xst + st * PL::XSTAGE, reinterpret_cast<const uint8_t*>(a.in_img) + ((size_t)tile * NIMG + s) * PL::XSTAGE,
                            PL::XSTAGE, &x_full[st]);
+              }
             } else {
               asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&x_full[st])) : "memory");
             }
@@ -682,6 +699,7 @@ k_egemm_g(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
       float* gp = a.g_out + (size_t)slot * 32;
 #pragma unroll
       for (int i8 = 0; i8 < 4; ++i8) {
+        if (a.dbg & (8 | 32)) break;
         float o[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = sigmoid_fast(gacc[8 * i8 + e] * g_unscale + __ldg(a.g_bias + 8 * i8 + e));
@@ -714,6 +732,10 @@ k_egemm_g(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
         float acc[32];
         tc::tmem_ld32(cb + (uint32_t)(c * 32), acc);
         tc::tmem_ld_wait();
+        if (a.dbg & 8) {
+          if (s == 0 && hf == 0 && it > 0) gate_epilogue(it - 1);
+          continue;
+        }
         uint32_t h2[16], l2[16];
 #pragma unroll
         for (int i4 = 0; i4 < 8; ++i4) {
@@ -745,7 +767,7 @@ k_egemm_g(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
           tmem_st16(cb + (uint32_t)(c * 32), h2);                 // in place: 16 columns of (hi, hi) pairs, 16 columns of (lo, lo) pairs
           tmem_st16(cb + (uint32_t)(c * 32 + 16), l2);
         }
-        if (MODE == EG_MSG) {
+        if (MODE == EG_MSG && !(a.dbg & 32)) {
           uint8_t* ob = reinterpret_cast<uint8_t*>(a.out_img) + ((size_t)tile * (S / 64) + s) * PL::XSTAGE + (size_t)row * 128;
 #pragma unroll
           for (int pr_ = 0; pr_ < 2; ++pr_) {
@@ -759,7 +781,7 @@ k_egemm_g(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
             st_global_256(ob + LO_OFF + pos * 16, swap ? lb : la, swap ? la : lb);
           }
         }
-        if (AGG) {
+        if (AGG && !(a.dbg & 64)) {
           // scalar messages summed over the in-edges of every destination (gvp.py:491): per segment of this warp's 32 rows one masked
           // transposing reduction -- lane i ends up with feature 32 c + i summed over the segment's rows -- stored as a 32-row piece
           const long long t32 = (tile * PL::T + q * 32) >> 5;

@@ -18,6 +18,7 @@
 #include "egemm_c.cuh"
 #include "vec_stages.cuh"
 #include "vec_reg.cuh"
+#include "edge_reg.cuh"
 #include "tc_test.cuh"
 
 namespace {
@@ -122,6 +123,8 @@ struct FmHandle {
                                // and the register-resident vector stages); aggregation pieces become 32 rows
   int eg_cluster = 1;          // k_egemm_p on edge rows: CTAs per thread-block cluster sharing one multicast weight stream (1, 2, 4)
   int eg_clusters_seen = 0;    // cudaOccupancyMaxActiveClusters of the last cluster kernel configured (diagnostics)
+  int edge_reg = 1;            // upper-edge MLPs (edge self-conditioning residual, bond-order head) as register-resident warp kernels (edge_reg.cuh)
+  int node_img = 1;            // node-row GVP chains: operand images between the three scalar linears (as on edge rows)
   int eu_fuse = 1;             // EdgeUpdate: both linears + LayerNorm in one kernel, hidden activations in tensor memory (egemm_c.cuh)
   int vec_impl = 1;            // edge-row vector stages: 1 = register-resident warp units (vec_reg.cuh, needs the image chain), 0 = vec_stages.cuh
   int tc_prec = 0;             // operand format of k_egemm_tc: 0 = 3xTF32 images, 1 = scaled fp16 hi/lo images ("fp16x3")
@@ -199,12 +202,16 @@ int set_smem_attrs() {
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_MSGA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_g<D, fm::EG_MSG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EggPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_g<D, fm::EG_MSGA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EggPlan::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_edge_head_r<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EdgeRegSmem<D>::HEAD_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_edge_init_r<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EdgeRegSmem<D>::INIT_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_c<D, fm::CH_EU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgcPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_e<D, fm::EG_MSG0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgePlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_e<D, fm::EG_MSG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgePlan::SMEM_BYTES));
     constexpr int IO = fm::EGI_IN | fm::EGI_OUT;
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_MSG0, IO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_MSG, IO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_MSG, fm::EGI_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_MSG, fm::EGI_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_MSGA, IO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_GATE, fm::EGI_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_EU1, IO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
@@ -387,14 +394,23 @@ int node_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
     const size_t vsm = fm::VecSmem<D>::BYTES;
     const int gt = (int)(L.NPA / 128);
     using PL = fm::EgPlan<1>;
-    auto scalar = [&](const float* units, const float* bias, const float* in, float* out) {
+    // hand-over between the three GVPs of a chain as operand images, like the edge rows (node_img): GVP 0 reads fp32 rows and writes
+    // images, GVP 1 reads and writes images, GVP 2 reads images and writes fp32 rows (k_node_mid / nobody reads them as images)
+    const bool nimg = img_on(h) && h->node_img;
+    auto scalar = [&](const float* units, const float* bias, const float* in, float* out, int g) {
       fm::EgArgs a{units, bias, in, SH, nullptr, nullptr, out, nullptr, nullptr, (long long)L.N, nullptr, 0, fm::EGF_NODE_ROWS, 0};
-      launch_eg<D, fm::EG_MSG, 1>(h, gt, st, m, bt, a);
+      a.in_img = in; a.out_img = out;
+      if (!nimg) launch_eg<D, fm::EG_MSG, 1>(h, gt, st, m, bt, a);
+      else if (g == 0) launch_eg<D, fm::EG_MSG, 1, fm::EGI_OUT>(h, gt, st, m, bt, a);
+      else if (g == 1) launch_eg<D, fm::EG_MSG, 1, fm::EGI_IN | fm::EGI_OUT>(h, gt, st, m, bt, a);
+      else launch_eg<D, fm::EG_MSG, 1, fm::EGI_IN>(h, gt, st, m, bt, a);
     };
-    auto gate = [&](const float* units, const float* bias, const float* in, int identity) {
+    auto gate = [&](const float* units, const float* bias, const float* in, int identity, int g) {
       fm::EgArgs a{units, bias, in, nullptr, nullptr, nullptr, GT, nullptr, nullptr, (long long)L.N, nullptr, 0,
                    fm::EGF_NODE_ROWS | (identity ? fm::EGF_IDENTITY : 0), 0};
-      launch_eg<D, fm::EG_GATE, 1>(h, gt, st, m, bt, a);
+      a.in_img = in;
+      if (nimg && g < 2) launch_eg<D, fm::EG_GATE, 1, fm::EGI_IN>(h, gt, st, m, bt, a);
+      else launch_eg<D, fm::EG_GATE, 1>(h, gt, st, m, bt, a);
     };
     auto linear = [&](const float* units, const float* bias, float* out) {
       fm::EgArgs a{units, bias, s, nullptr, nullptr, nullptr, out, nullptr, nullptr, (long long)L.N, nullptr, 0, fm::EGF_NODE_ROWS, 0};
@@ -408,8 +424,8 @@ int node_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
     const float* cur = s;
     float* outs[3] = {SA, SB, SA};
     for (int g = 0; g < 3; ++g) {
-      scalar(wptr(l, tc_c(h, utw[g])), wptr(l, ub[g] + fm::GV_B), cur, outs[g]); LAUNCH_OK(h);
-      gate(wptr(l, tc_c(h, utg[g])), wptr(l, ub[g] + fm::GV_BG), outs[g], 0); LAUNCH_OK(h);
+      scalar(wptr(l, tc_c(h, utw[g])), wptr(l, ub[g] + fm::GV_B), cur, outs[g], g); LAUNCH_OK(h);
+      gate(wptr(l, tc_c(h, utg[g])), wptr(l, ub[g] + fm::GV_BG), outs[g], 0, g); LAUNCH_OK(h);
       if (g < 2) {
         fm::k_vec_b<D><<<vgrid, fm::NT, vsm, st>>>(bt, wptr(l, ub[g] + fm::GV_WU), D::V + D::CP, wptr(l, ub[g + 1] + fm::GV_WHCP), 1, VH, SH, GT);
         LAUNCH_OK(h);
@@ -425,8 +441,8 @@ int node_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
       const int pb[3] = {fm::U_POS0_WHCP, fm::U_POS1_WHCP, fm::U_POS2_WHCP};
       cur = s;
       for (int g = 0; g < 3; ++g) {
-        scalar(uptr(tc_u(h, ptw[g])), uptr(pb[g] + fm::GV_B), cur, outs[g]); LAUNCH_OK(h);
-        gate(uptr(tc_u(h, ptg[g])), uptr(pb[g] + fm::GV_BG), outs[g], g == 2); LAUNCH_OK(h);
+        scalar(uptr(tc_u(h, ptw[g])), uptr(pb[g] + fm::GV_B), cur, outs[g], g); LAUNCH_OK(h);
+        gate(uptr(tc_u(h, ptg[g])), uptr(pb[g] + fm::GV_BG), outs[g], g == 2, g); LAUNCH_OK(h);
         if (g < 2) {
           fm::k_vec_b<D><<<vgrid, fm::NT, vsm, st>>>(bt, uptr(pb[g] + fm::GV_WU), D::V + D::CP, uptr(pb[g + 1] + fm::GV_WHCP), 1, VH, SH, GT);
           LAUNCH_OK(h);
@@ -454,6 +470,20 @@ int run_pass(FmHandle* h, void* ws, const Layout& L, const float* x_t, const uin
   fm::k_node_embed<D><<<L.nNT, fm::NT, smem, st>>>(m, bt, x_t, a_t, c_t, t, prev, has_prev, s, v, P);
   LAUNCH_OK(h);
   if (m.use_dst) { fm::k_dst_proj<D><<<L.nNT, fm::NT, smem, st>>>(m, bt, 0, s, v, Q, vd); LAUNCH_OK(h); }
+  bool edge_done = false;
+  int er_grid = 0;
+  if constexpr (D::S == 256 && D::V == 32 && D::SD == 0 && D::F == 128 && D::R == 32) {
+    // register-resident upper-edge kernels (edge_reg.cuh): 16-row units, one warp each, 2 CTAs per SM
+    const int n_units = L.nUT * (fm::TM / fm::UR), want = (n_units + fm::NWARP - 1) / fm::NWARP;
+    er_grid = want < 2 * h->n_sm ? want : 2 * h->n_sm;
+    if (h->edge_reg && has_prev && m.self_cond && h->conv_impl == 2 && img_on(h) && h->vec_impl == 1 && m.EB <= 7) {
+      // self-conditioning residual + both output formats (fp32 rows, operand images) in one kernel; dead rows were zeroed by fm_batch_init
+      fm::k_edge_init_r<D><<<er_grid, fm::NT, fm::EdgeRegSmem<D>::INIT_BYTES, st>>>(m, bt, n_units, x_t, e_t, prev, ef, at<float>(ws, L.EFI));
+      LAUNCH_OK(h);
+      edge_done = true;
+    }
+  }
+  if (!edge_done) {
   fm::k_edge_init<D><<<L.nUT, fm::NT, fm::EdgeSmem<D>::BYTES, st>>>(m, bt, x_t, e_t, prev, has_prev, ef);
   LAUNCH_OK(h);
   if constexpr (D::S == 256 && D::V == 32 && D::SD == 0 && D::F == 128) {
@@ -462,6 +492,7 @@ int run_pass(FmHandle* h, void* ws, const Layout& L, const float* x_t, const uin
       fm::k_ef_image<D><<<nt < 4 * h->n_sm ? nt : 4 * h->n_sm, 256, 0, st>>>(bt, ef, at<float>(ws, L.EFI), L.EP, nt);
       LAUNCH_OK(h);
     }
+  }
   }
   CUDA_OK(cudaMemcpyAsync(x, x_t, sizeof(float) * 3 * L.N, cudaMemcpyDeviceToDevice, st));
   for (int l = 0; l < m.L; ++l) {
@@ -529,8 +560,18 @@ int run_pass(FmHandle* h, void* ws, const Layout& L, const float* x_t, const uin
   }
   fm::k_node_head<D><<<L.nNT, fm::NT, smem, st>>>(m, bt, s, out.a, out.c);
   LAUNCH_OK(h);
-  fm::k_edge_head<D><<<L.nUT, fm::NT, fm::EdgeSmem<D>::BYTES, st>>>(m, bt, ef, out.e);
-  LAUNCH_OK(h);
+  bool head_done = false;
+  if constexpr (D::S == 256 && D::V == 32 && D::SD == 0 && D::F == 128 && D::R == 32) {
+    if (h->edge_reg && m.EB <= 8) {
+      fm::k_edge_head_r<D><<<er_grid, fm::NT, fm::EdgeRegSmem<D>::HEAD_BYTES, st>>>(m, bt, L.nUT * (fm::TM / fm::UR), ef, out.e);
+      LAUNCH_OK(h);
+      head_done = true;
+    }
+  }
+  if (!head_done) {
+    fm::k_edge_head<D><<<L.nUT, fm::NT, fm::EdgeSmem<D>::BYTES, st>>>(m, bt, ef, out.e);
+    LAUNCH_OK(h);
+  }
   fm::k_com<<<(L.B + 7) / 8, 256, 0, st>>>(bt, x, out.x, remove_com);
   LAUNCH_OK(h);
   return 0;
@@ -711,6 +752,10 @@ int fm_batch_init(FmHandle* h, const int32_t* n_atoms, int32_t B, void* ws, size
   CUDA_OK(up(L.mol_n, mol_n)); CUDA_OK(up(L.mol_node, mol_node)); CUDA_OK(up(L.mol_u, mol_u));
   CUDA_OK(up(L.mol_etile, mol_et)); CUDA_OK(up(L.mol_utile, mol_ut)); CUDA_OK(up(L.etile_mol, et_mol));
   CUDA_OK(up(L.utile_mol, ut_mol)); CUDA_OK(up(L.node_mol, node_mol));
+  // edge-feature rows and their operand images: the padding slots of every molecule's block are never written by k_edge_init_r
+  // (it stores live rows only) and every linear computes whole 128-row tiles -- start them as zeros, not as allocator garbage
+  CUDA_OK(cudaMemsetAsync(at<char>(ws, L.ef), 0, 4ull * (size_t)L.EPA * h->dyn.F, st));
+  if (h->dyn.S == 256 && h->dyn.SD == 0) CUDA_OK(cudaMemsetAsync(at<char>(ws, L.EFI), 0, 4ull * (size_t)L.EPA * h->dyn.F, st));
   CUDA_OK(cudaStreamSynchronize(st));      // the host vectors die here
   h->batches[ws] = L;
   return 0;
@@ -1013,6 +1058,8 @@ int fm_set_option(FmHandle* h, const char* name, int32_t value) {
   if (n == "eg_orient") { h->eg_orient = value ? 1 : 0; return 0; }
   if (n == "eg_fuse_gate") { h->eg_fuse_gate = value ? 1 : 0; return 0; }
   if (n == "eu_fuse") { h->eu_fuse = value ? 1 : 0; return 0; }
+  if (n == "node_img") { h->node_img = value ? 1 : 0; return 0; }
+  if (n == "edge_reg") { h->edge_reg = value ? 1 : 0; return 0; }
   if (n == "eg_cluster") {
     if (value != 1 && value != 2 && value != 4) return fail("fm_set_option: eg_cluster must be 1, 2 or 4");
     h->eg_cluster = value;
@@ -1076,6 +1123,8 @@ int fm_get_option(FmHandle* h, const char* name, int32_t* value) {
   if (std::string(name) == "eg_orient") { *value = h->eg_orient; return 0; }
   if (std::string(name) == "eg_fuse_gate") { *value = h->eg_fuse_gate; return 0; }
   if (std::string(name) == "eu_fuse") { *value = h->eu_fuse; return 0; }
+  if (std::string(name) == "node_img") { *value = h->node_img; return 0; }
+  if (std::string(name) == "edge_reg") { *value = h->edge_reg; return 0; }
   if (std::string(name) == "eg_cluster") { *value = h->eg_cluster; return 0; }
   if (std::string(name) == "eg_clusters_seen") { *value = h->eg_clusters_seen; return 0; }
   if (std::string(name) == "status") {      // synchronising read-and-clear of the device status word (see fm_check_status)

@@ -16,6 +16,7 @@
 #include "egemm_p.cuh"
 #include "egemm_e.cuh"
 #include "egemm_c.cuh"
+#include "egemm_g2.cuh"
 #include "vec_stages.cuh"
 #include "vec_reg.cuh"
 #include "edge_reg.cuh"
@@ -123,6 +124,7 @@ struct FmHandle {
                                // and the register-resident vector stages); aggregation pieces become 32 rows
   int eg_cluster = 1;          // k_egemm_p on edge rows: CTAs per thread-block cluster sharing one multicast weight stream (1, 2, 4)
   int eg_clusters_seen = 0;    // cudaOccupancyMaxActiveClusters of the last cluster kernel configured (diagnostics)
+  int eg_pair = 0;             // gate-fused message linears on CTA pairs (tcgen05 cta_group::2, egemm_g2.cuh)
   int edge_reg = 1;            // upper-edge MLPs (edge self-conditioning residual, bond-order head) as register-resident warp kernels (edge_reg.cuh)
   int node_img = 1;            // node-row GVP chains: operand images between the three scalar linears (as on edge rows)
   int eu_fuse = 1;             // EdgeUpdate: both linears + LayerNorm in one kernel, hidden activations in tensor memory (egemm_c.cuh)
@@ -202,6 +204,8 @@ int set_smem_attrs() {
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_MSGA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_g<D, fm::EG_MSG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EggPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_g<D, fm::EG_MSGA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EggPlan::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_g2<D, fm::EG_MSG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EggPlan::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_g2<D, fm::EG_MSGA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EggPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_edge_head_r<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EdgeRegSmem<D>::HEAD_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_edge_init_r<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EdgeRegSmem<D>::INIT_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_c<D, fm::CH_EU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgcPlan::SMEM_BYTES));
@@ -326,6 +330,11 @@ int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
           a.status = h->d_status;
           a.g_units = wptr(tc_c(h, tcg[g])); a.g_bias = wptr(gb[g] + fm::GV_BG); a.g_out = GT;
           const int grid_g = gt < h->n_sm ? gt : h->n_sm;
+          if (h->eg_pair && gt % 2 == 0 && h->n_sm >= 2) {             // CTA pairs on one weight stream (egemm_g2.cuh)
+            const int grid_p = 2 * (gt / 2 < h->n_sm / 2 ? gt / 2 : h->n_sm / 2);
+            if (g == 1) fm::k_egemm_g2<D, fm::EG_MSG><<<grid_p, fm::EggPlan::THREADS, fm::EggPlan::SMEM_BYTES, st>>>(m, bt, a, gt);
+            else fm::k_egemm_g2<D, fm::EG_MSGA><<<grid_p, fm::EggPlan::THREADS, fm::EggPlan::SMEM_BYTES, st>>>(m, bt, a, gt);
+          } else
           if (g == 1) fm::k_egemm_g<D, fm::EG_MSG><<<grid_g, fm::EggPlan::THREADS, fm::EggPlan::SMEM_BYTES, st>>>(m, bt, a, gt);
           else fm::k_egemm_g<D, fm::EG_MSGA><<<grid_g, fm::EggPlan::THREADS, fm::EggPlan::SMEM_BYTES, st>>>(m, bt, a, gt);
         } else
@@ -1060,6 +1069,7 @@ int fm_set_option(FmHandle* h, const char* name, int32_t value) {
   if (n == "eu_fuse") { h->eu_fuse = value ? 1 : 0; return 0; }
   if (n == "node_img") { h->node_img = value ? 1 : 0; return 0; }
   if (n == "edge_reg") { h->edge_reg = value ? 1 : 0; return 0; }
+  if (n == "eg_pair") { h->eg_pair = value ? 1 : 0; return 0; }
   if (n == "eg_cluster") {
     if (value != 1 && value != 2 && value != 4) return fail("fm_set_option: eg_cluster must be 1, 2 or 4");
     h->eg_cluster = value;
@@ -1125,6 +1135,7 @@ int fm_get_option(FmHandle* h, const char* name, int32_t* value) {
   if (std::string(name) == "eu_fuse") { *value = h->eu_fuse; return 0; }
   if (std::string(name) == "node_img") { *value = h->node_img; return 0; }
   if (std::string(name) == "edge_reg") { *value = h->edge_reg; return 0; }
+  if (std::string(name) == "eg_pair") { *value = h->eg_pair; return 0; }
   if (std::string(name) == "eg_cluster") { *value = h->eg_cluster; return 0; }
   if (std::string(name) == "eg_clusters_seen") { *value = h->eg_clusters_seen; return 0; }
   if (std::string(name) == "status") {      // synchronising read-and-clear of the device status word (see fm_check_status)

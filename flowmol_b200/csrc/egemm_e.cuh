@@ -713,6 +713,10 @@ k_egemm_g(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
     for (int it = 0; it < n_my; ++it) {
       const int b = it & 1;
       const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
+      // Gate rows of the PREVIOUS tile first: its accumulator buffer is the one the main MMAs of tile it + 1 need, and they can only
+      // start once these four warps have read G out of it.  (Done one chunk into this tile -- i.e. after acc_full of THIS tile -- the
+      // main issuer could never run ahead: MMAs alone took 420 us per launch against a tensor floor of ~260 us, profiles/r02i.)
+      if (hf == 0 && it > 0) gate_epilogue(it - 1);
       // MSGA: this lane's row: destination node and whether it is the node's first / last in-edge; segments of the warp's 32 rows
       int info = -1;
       unsigned seg_ends = 0;
@@ -732,10 +736,7 @@ k_egemm_g(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
         float acc[32];
         tc::tmem_ld32(cb + (uint32_t)(c * 32), acc);
         tc::tmem_ld_wait();
-        if (a.dbg & 8) {
-          if (s == 0 && hf == 0 && it > 0) gate_epilogue(it - 1);
-          continue;
-        }
+        if (a.dbg & 8) continue;
         uint32_t h2[16], l2[16];
 #pragma unroll
         for (int i4 = 0; i4 < 8; ++i4) {
@@ -801,7 +802,6 @@ k_egemm_g(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
             lo = hi_ + 1;
           }
         }
-        if (s == 0 && hf == 0 && it > 0) gate_epilogue(it - 1);   // one chunk into this tile: the gate MMAs of the last one are done
       }
       tmem_st_wait();
       tc::tc_fence_before();

@@ -56,6 +56,10 @@ struct EgpPlan {
 // same function of the same fp32 value on either side of HBM, so the results are bit-identical to the fp32 hand-over.
 enum EgImg : int { EGI_IN = 1, EGI_OUT = 2 };
 
+// (Measured and dropped, profiles/r02w: a cp.async.bulk.prefetch.L2 of the operand images two tiles ahead of every CTA made every
+// mode SLOWER -- GATE 214 -> 264 us, MSG 687 -> 741 us: the stream is already deep enough for the DRAM controllers and the
+// prefetched lines compete with the output stream for L2.)
+
 // CL: thread-block cluster size (launch attribute).  What ncu says about the message linears (profiles/r01s, r02): 6.6 KB of L2 -> SM
 // traffic per cycle, the measured fabric cap of the chip, and more than half of it is every CTA re-streaming the same 320 KB of
 // weight images for every 128-edge tile.  With CL > 1 the CTAs of a cluster walk the weight stream together: unit u is fetched

@@ -10,6 +10,8 @@ from flowmol_b200.vector_field import CTMCVectorFieldB200
 from bench import draw_sizes, make_prior
 cfg = ModelConfig.named("flowmol3", 11)
 vf = CTMCVectorFieldB200(cfg, WT.init_state_dict(cfg, 0))
+for kv in filter(None, os.environ.get("FM_OPTS", "").split(",")):      # e.g. FM_OPTS=eg_pair=0,eu_fuse=0
+    vf.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 n_atoms = draw_sizes("geom", 512)
 x0, a0, c0, e0 = make_prior(n_atoms, 11, 100)
 nf = int(sys.argv[1]) if len(sys.argv) > 1 else 3

@@ -12,7 +12,7 @@ NCCL gather of the results to rank 0, inside the timed region.
 
 Printed JSON line (rank 0): metric/value/unit/..., `e2e` (same metric through fm_sample_host with pinned HOST buffers:
 H2D of the prior + batch descriptor + trajectory + D2H of the result inside the timed region), `roofline` for the dominant
-kernel (k_egemm_p: HBM-bound, timed live with CUDA events on its stream, per-mode numbers from in-pipeline events),
+kernel family (the persistent tcgen05 linears k_egemm_p / _g / _c: timed live with CUDA events, per-mode numbers from in-pipeline events),
 `cpu_baseline` (the CPU oracle port on a bounded sample),
 `clocks`, `gpu_launches`.
 """
@@ -411,14 +411,20 @@ def main():
         # algorithmic HBM bytes per edge (fp32 rows read + written; per-node operands gathered from L2 are not counted) and matmul
         # FLOP per edge of every mode
         F_, S_ = 128, 256
-        modes = {"EG_MSG0": (4 * (F_ + 37) + 4 * S_, 2 * 197 * S_), "EG_MSG": (4 * 292 + 4 * S_, 2 * 292 * S_),
-                 "EG_MSGA": (4 * 292 + 4 * S_, 2 * 292 * S_), "EG_GATE": (4 * S_ + 4 * 32, 2 * S_ * 32),
-                 "EG_EU1": (4 * F_ + 4 * F_, 2 * 160 * F_), "EG_EU2": (4 * F_ + 4 * F_ + 4 * F_, 2 * F_ * F_)}
+        gate_fused = vf.get_option("eg_fuse_gate") == 1 and prof.get("EG_GATE", (0, 0))[0] <= 6.5
+        modes = {"EG_MSG0": (4 * (F_ + 37) + 4 * S_, 2 * 197 * S_), "EG_GATE": (4 * S_ + 4 * 32, 2 * S_ * 32),
+                 "EG_EU1": (4 * F_ + 4 * F_, 2 * 160 * F_), "EG_EU2": (4 * F_ + 4 * F_ + 4 * F_, 2 * F_ * F_),
+                 # EdgeUpdate in one kernel (egemm_c.cuh): image in, fp32 residual in, fp32 rows + image out; both linears
+                 "k_egemm_c": (4 * F_ * 4, 2 * 160 * F_ + 2 * F_ * F_)}
+        if gate_fused:      # k_egemm_g: the gate linear rides along (+ 128 B of gate rows); GVP 2 writes no activation at all
+            modes.update({"EG_MSG": (4 * 292 + 4 * S_ + 4 * 32, 2 * 292 * S_ + 2 * S_ * 32), "EG_MSGA": (4 * 292 + 4 * 32, 2 * 292 * S_ + 2 * S_ * 32)})
+        else:
+            modes.update({"EG_MSG": (4 * 292 + 4 * S_, 2 * 292 * S_), "EG_MSGA": (4 * 292 + 4 * S_, 2 * 292 * S_)})
         # the vector stages and their per-edge bytes (vec_reg.cuh: VU 384 B, SH 160 / 144 B, GT 128 B per edge)
         modes.update({"k_vecr_a": (384 + 160, 0), "k_vecr_b": (384 + 128 + 384 + 160, 0), "k_vecr_c": (384 + 128, 0),
                       "k_vec_a": (480 + 160, 0), "k_vec_b": (480 + 128 + 480 + 160, 0), "k_vec_c": (480 + 128, 0)})
         family = {}
-        fam_bytes, fam_ms, moved = 0.0, 0.0, 0.0
+        fam_bytes, fam_ms, moved, fam_launches = 0.0, 0.0, 0.0, 0.0
         for name_, (bpe, fpe) in modes.items():
             if name_ in prof:
                 cnt, ms_f = prof[name_]
@@ -427,9 +433,10 @@ def main():
                                  "achieved_gbs": bpe * E / (us * 1e-6) / 1e9, "frac_of_hbm_peak": bpe * E / (us * 1e-6) / 1e9 / hbm_peak,
                                  "algorithmic_tflops": fpe * E / (us * 1e-6) / 1e12}
                 moved += bpe * E * cnt
-                if name_.startswith("EG_"):
+                if name_.startswith("EG_") or name_ == "k_egemm_c":
                     fam_bytes += bpe * E * cnt
                     fam_ms += ms_f
+                    fam_launches += cnt
         # Headline: the whole k_egemm_p family of one evaluation, time-weighted (every edge-row launch of the persistent tcgen05
         # linear: 51 % of an evaluation), not its best mode; the single-kernel EG_MSG number timed alone stays beside it.
         achieved = fam_bytes / (fam_ms * 1e-3) / 1e9
@@ -439,11 +446,12 @@ def main():
         fe_, fn2 = FWD_FLOP[cfg_name]
         alg_eval_bytes = 6100.0 * E + 40000.0 * N                    # irreducible bytes of a fully fused evaluation
         alg_eval_flops = fe_ * E + fn2 * N
-        roofline = {"kernel": "k_egemm_p, all edge-row modes of one network evaluation, time-weighted (persistent tcgen05 linear, "
-                              f"{'fp16x3' if prec == 1 else '3xTF32'} operands, operand images between linears)",
+        roofline = {"kernel": "persistent tcgen05 linears (k_egemm_p / k_egemm_g / k_egemm_c), all edge-row launches of one network evaluation, "
+                              f"time-weighted ({'fp16x3' if prec == 1 else '3xTF32'} operands, operand images between linears, gate linears and "
+                              "EdgeUpdate fused in-kernel through tensor memory)",
                     "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "peak_kind": hbm_src, "algorithmic_bytes_per_launch": fam_bytes / max(1.0, sum(prof[k][0] for k in prof if k.startswith("EG_"))),
-                    "ms_per_launch": fam_ms / max(1.0, sum(prof[k][0] for k in prof if k.startswith("EG_"))),
+                    "peak_kind": hbm_src, "algorithmic_bytes_per_launch": fam_bytes / max(1.0, fam_launches),
+                    "ms_per_launch": fam_ms / max(1.0, fam_launches),
                     "traffic": None,        # bench.py never runs under a profiler: dram__bytes of the committed captures are in profiles/
                     "single_kernel": {"kernel": "k_egemm_p<EG_MSG> alone on its stream (292->256 message linear, all edges)",
                                       "ms_per_launch": ms_k, "algorithmic_bytes_per_launch": hbm_bytes,
@@ -463,7 +471,7 @@ def main():
                                 "is the price of not fusing the GVP chain"},
                     "family": family,
                     "kernel_ms_per_eval": {k: round(t_, 4) for k, (c_, t_) in sorted(prof.items(), key=lambda kv: -kv[1][1])},
-                    "message_pass": {"what": "whole message phase of one conv layer (10 launches: 3 vec + 6 egemm + segment-sum)",
+                    "message_pass": {"what": "whole message phase of one conv layer (8 launches: 4 vector stages, MSG0, GATE, MSG + gate, MSGA + gate + segment-sum)",
                                      "ms": ms_pass, "algorithmic_tflops": CONV_EDGE_FLOP_PER_EDGE[cfg_name] * E / (ms_pass * 1e-3) / 1e12}}
     else:
         flops = CONV_EDGE_FLOP_PER_EDGE[cfg_name] * E

@@ -274,6 +274,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="geom512", choices=sorted(WORKLOADS))
     ap.add_argument("--eg-cluster", type=int, default=None, help="k_egemm_p cluster size (1, 2, 4): multicast weight stream")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE", help="fm_set_option before the run (A/B measurements), e.g. --opt pdl=0")
     ap.add_argument("--vec-impl", type=int, default=None, help="1 register-resident vector stages (default), 0 shared-memory tile kernels")
     ap.add_argument("--timesteps", type=int, default=None, help="override the workload's timesteps (experiments only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -310,6 +311,8 @@ def main():
         vf.set_option("tc_prec", args.tc_prec)
     if args.eg_cluster is not None:
         vf.set_option("eg_cluster", args.eg_cluster)
+    for kv in args.opt:
+        vf.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     if args.vec_impl is not None:
         vf.set_option("vec_impl", args.vec_impl)
     # one GLOBAL batch of B x world molecules, cut into contiguous cost-balanced ranges (flowmol_b200/sharding.py); global

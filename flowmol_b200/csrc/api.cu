@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <string>
+#include <utility>
 #include <unordered_map>
 #include <vector>
 
@@ -124,6 +125,7 @@ struct FmHandle {
                                // and the register-resident vector stages); aggregation pieces become 32 rows
   int eg_cluster = 1;          // k_egemm_p on edge rows: CTAs per thread-block cluster sharing one multicast weight stream (1, 2, 4)
   int eg_clusters_seen = 0;    // cudaOccupancyMaxActiveClusters of the last cluster kernel configured (diagnostics)
+  int pdl = 0;                 // programmatic dependent launch of every pipeline kernel (launch_k); measured 3 % slower end to end (profiles/r02z): off
   int eg_pair = 0;             // gate-fused message linears on CTA pairs (tcgen05 cta_group::2, egemm_g2.cuh)
   int edge_reg = 1;            // upper-edge MLPs (edge self-conditioning residual, bond-order head) as register-resident warp kernels (edge_reg.cuh)
   int node_img = 1;            // node-row GVP chains: operand images between the three scalar linears (as on edge rows)
@@ -224,6 +226,23 @@ int set_smem_attrs() {
   return 0;
 }
 
+
+// Kernel launch, optionally as a programmatic dependent launch (option "pdl"; default off: measured 7573 vs 7339 ms per 250-step
+// trajectory, profiles/r02z -- the kernels fill the SMs' shared memory, so a dependent CTA cannot become resident before its
+// predecessor's CTA on that SM has exited, and the early-launched grid only adds scheduling work): the kernel's CTAs may start while its predecessor
+// in the stream drains; every kernel begins with pdl_launch(); ... pdl_wait() (common.cuh) before it touches activation data.
+template <class... KArgs, class... Args>
+inline void launch_k(FmHandle* h, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = (h && h->pdl) ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
+
 // k_egemm_tc in the operand precision selected on the handle
 // in-situ per-launch timing (option "kprof"): an event after every launch; consecutive differences are the launches' durations in
 // the warm pipeline (what ncu's serialised cold-cache replays cannot show).  Line 0 = start marker.
@@ -275,11 +294,11 @@ void launch_eg(FmHandle* h, int grid, cudaStream_t st, const fm::ModelRT& m, con
       if (h->eg_cluster == 2 && !(a.flags & fm::EGF_NODE_ROWS)) { launch_egp_cluster<D, MODE, IMG, 2>(h, grid, st, m, bt, a); return; }
       if (h->eg_cluster == 4 && !(a.flags & fm::EGF_NODE_ROWS)) { launch_egp_cluster<D, MODE, IMG, 4>(h, grid, st, m, bt, a); return; }
     }
-    fm::k_egemm_p<D, MODE, IMG><<<grid < h->n_sm ? grid : h->n_sm, fm::EgpPlan::THREADS, fm::EgpPlan::SMEM_BYTES, st>>>(m, bt, a, grid);
+    launch_k(h, fm::k_egemm_p<D, MODE, IMG>, grid < h->n_sm ? grid : h->n_sm, fm::EgpPlan::THREADS, fm::EgpPlan::SMEM_BYTES, st, m, bt, a, grid);
     return;
   }
-  if (h->tc_prec) fm::k_egemm_tc<D, MODE, NH, 1><<<grid, PL::THREADS, PL::SMEM_BYTES, st>>>(m, bt, a);
-  else fm::k_egemm_tc<D, MODE, NH, 0><<<grid, PL::THREADS, PL::SMEM_BYTES, st>>>(m, bt, a);
+  if (h->tc_prec) launch_k(h, fm::k_egemm_tc<D, MODE, NH, 1>, grid, PL::THREADS, PL::SMEM_BYTES, st, m, bt, a);
+  else launch_k(h, fm::k_egemm_tc<D, MODE, NH, 0>, grid, PL::THREADS, PL::SMEM_BYTES, st, m, bt, a);
 }
 // id of a tensor-core image entry in the selected precision (the fp16 twins follow the TF32 entries, weight_layout.py)
 inline int tc_c(const FmHandle* h, int id) { return id + (h->tc_prec ? (int)fm::C_MSG0_TCW_H - (int)fm::C_MSG0_TCW : 0); }
@@ -313,8 +332,8 @@ int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
     const bool gf = gate_fused(h);
     const int n_units = L.nET * (fm::TM / fm::UR);
     const int vrgrid = (n_units + fm::NWARP - 1) / fm::NWARP < 2 * h->n_sm ? (n_units + fm::NWARP - 1) / fm::NWARP : 2 * h->n_sm;
-    if (!vr) fm::k_vec_a<D><<<vgrid, fm::NT, vsm, st>>>(m, bt, l, x, v, VH, SH);
-    else fm::k_vecr_a<D><<<vrgrid, fm::NT, 0, st>>>(m, bt, l, n_units, x, v, VH, SH);
+    if (!vr) launch_k(h, fm::k_vec_a<D>, vgrid, fm::NT, vsm, st, m, bt, l, x, v, VH, SH);
+    else launch_k(h, fm::k_vecr_a<D>, vrgrid, fm::NT, 0, st, m, bt, l, n_units, x, v, VH, SH);
     LAUNCH_OK(h);
     const int tcw[3] = {fm::C_MSG0_TCW, fm::C_MSG1_TCW, fm::C_MSG2_TCW}, tcg[3] = {fm::C_MSG0_TCG, fm::C_MSG1_TCG, fm::C_MSG2_TCG};
     const int gb[3] = {fm::C_MSG0_WHCP, fm::C_MSG1_WHCP, fm::C_MSG2_WHCP};
@@ -332,17 +351,17 @@ int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
           const int grid_g = gt < h->n_sm ? gt : h->n_sm;
           if (h->eg_pair && gt % 2 == 0 && h->n_sm >= 2) {             // CTA pairs on one weight stream (egemm_g2.cuh)
             const int grid_p = 2 * (gt / 2 < h->n_sm / 2 ? gt / 2 : h->n_sm / 2);
-            if (g == 1) fm::k_egemm_g2<D, fm::EG_MSG><<<grid_p, fm::EggPlan::THREADS, fm::EggPlan::SMEM_BYTES, st>>>(m, bt, a, gt);
-            else fm::k_egemm_g2<D, fm::EG_MSGA><<<grid_p, fm::EggPlan::THREADS, fm::EggPlan::SMEM_BYTES, st>>>(m, bt, a, gt);
+            if (g == 1) launch_k(h, fm::k_egemm_g2<D, fm::EG_MSG>, grid_p, fm::EggPlan::THREADS, fm::EggPlan::SMEM_BYTES, st, m, bt, a, gt);
+            else launch_k(h, fm::k_egemm_g2<D, fm::EG_MSGA>, grid_p, fm::EggPlan::THREADS, fm::EggPlan::SMEM_BYTES, st, m, bt, a, gt);
           } else
-          if (g == 1) fm::k_egemm_g<D, fm::EG_MSG><<<grid_g, fm::EggPlan::THREADS, fm::EggPlan::SMEM_BYTES, st>>>(m, bt, a, gt);
-          else fm::k_egemm_g<D, fm::EG_MSGA><<<grid_g, fm::EggPlan::THREADS, fm::EggPlan::SMEM_BYTES, st>>>(m, bt, a, gt);
+          if (g == 1) launch_k(h, fm::k_egemm_g<D, fm::EG_MSG>, grid_g, fm::EggPlan::THREADS, fm::EggPlan::SMEM_BYTES, st, m, bt, a, gt);
+          else launch_k(h, fm::k_egemm_g<D, fm::EG_MSGA>, grid_g, fm::EggPlan::THREADS, fm::EggPlan::SMEM_BYTES, st, m, bt, a, gt);
         } else
         if (g < 2 && h->eg_orient == 1 && h->eg_cluster == 1) {      // edges-on-M orientation (egemm_e.cuh)
           a.status = h->d_status;
           const int grid_e = gt < h->n_sm ? gt : h->n_sm;
-          if (g == 0) fm::k_egemm_e<D, fm::EG_MSG0><<<grid_e, fm::EgePlan::THREADS, fm::EgePlan::SMEM_BYTES, st>>>(m, bt, a, gt);
-          else fm::k_egemm_e<D, fm::EG_MSG><<<grid_e, fm::EgePlan::THREADS, fm::EgePlan::SMEM_BYTES, st>>>(m, bt, a, gt);
+          if (g == 0) launch_k(h, fm::k_egemm_e<D, fm::EG_MSG0>, grid_e, fm::EgePlan::THREADS, fm::EgePlan::SMEM_BYTES, st, m, bt, a, gt);
+          else launch_k(h, fm::k_egemm_e<D, fm::EG_MSG>, grid_e, fm::EgePlan::THREADS, fm::EgePlan::SMEM_BYTES, st, m, bt, a, gt);
         } else if (g == 0) {
           launch_eg<D, fm::EG_MSG0, 1, IO>(h, gt, st, m, bt, a);
         } else if (g == 1) {
@@ -372,17 +391,17 @@ int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
       }
       if (g < 2) {
         if (!vr)
-          fm::k_vec_b<D><<<vgrid, fm::NT, vsm, st>>>(bt, wptr(g == 0 ? fm::C_MSG0_WU : fm::C_MSG1_WU), (g == 0 ? D::H0 : D::V) + D::CP,
+          launch_k(h, fm::k_vec_b<D>, vgrid, fm::NT, vsm, st, bt, wptr(g == 0 ? fm::C_MSG0_WU : fm::C_MSG1_WU), (g == 0 ? D::H0 : D::V) + D::CP,
                                                      wptr(g == 0 ? fm::C_MSG1_WHCP : fm::C_MSG2_WHCP), 0, VH, SH, GT);
         else
-          fm::k_vecr_b<D><<<vrgrid, fm::NT, 0, st>>>(bt, wptr(g == 0 ? fm::C_MSG1_WHCP : fm::C_MSG2_WHCP),
+          launch_k(h, fm::k_vecr_b<D>, vrgrid, fm::NT, 0, st, bt, wptr(g == 0 ? fm::C_MSG1_WHCP : fm::C_MSG2_WHCP),
                                                       wptr(g == 0 ? fm::C_MSG1_WU : fm::C_MSG2_WU), n_units, VH, SH, GT);
         LAUNCH_OK(h);
       }
       cur = outs[g];
     }
-    if (!vr) fm::k_vec_c<D><<<vgrid, fm::NT, vsm, st>>>(m, bt, l, h->fuse_agg ? D::S : 0, VH, GT, SA, M, partF, partL);
-    else fm::k_vecr_c<D><<<(L.nET * (gf ? 2 : 1) + fm::NWARP - 1) / fm::NWARP, fm::NT, 0, st>>>(bt, gf ? 32 : fm::TM, VH, GT, M, partF, partL);
+    if (!vr) launch_k(h, fm::k_vec_c<D>, vgrid, fm::NT, vsm, st, m, bt, l, h->fuse_agg ? D::S : 0, VH, GT, SA, M, partF, partL);
+    else launch_k(h, fm::k_vecr_c<D>, (L.nET * (gf ? 2 : 1) + fm::NWARP - 1) / fm::NWARP, fm::NT, 0, st, bt, gf ? 32 : fm::TM, VH, GT, M, partF, partL);
     LAUNCH_OK(h);
   }
   return 0;
@@ -426,7 +445,7 @@ int node_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
       launch_eg<D, fm::EG_LIN, 1>(h, gt, st, m, bt, a);
     };
     const int vgrid = L.nNT < 2 * h->n_sm ? L.nNT : 2 * h->n_sm;
-    fm::k_node_pre<D><<<L.nNT, fm::NT, vsm, st>>>(m, bt, l, agg_rows, s, v, M, partF, partL, VH, SH);
+    launch_k(h, fm::k_node_pre<D>, L.nNT, fm::NT, vsm, st, m, bt, l, agg_rows, s, v, M, partF, partL, VH, SH);
     LAUNCH_OK(h);
     const int utw[3] = {fm::C_UPD0_TCW, fm::C_UPD1_TCW, fm::C_UPD2_TCW}, utg[3] = {fm::C_UPD0_TCG, fm::C_UPD1_TCG, fm::C_UPD2_TCG};
     const int ub[3] = {fm::C_UPD0_WHCP, fm::C_UPD1_WHCP, fm::C_UPD2_WHCP};
@@ -436,12 +455,12 @@ int node_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
       scalar(wptr(l, tc_c(h, utw[g])), wptr(l, ub[g] + fm::GV_B), cur, outs[g], g); LAUNCH_OK(h);
       gate(wptr(l, tc_c(h, utg[g])), wptr(l, ub[g] + fm::GV_BG), outs[g], 0, g); LAUNCH_OK(h);
       if (g < 2) {
-        fm::k_vec_b<D><<<vgrid, fm::NT, vsm, st>>>(bt, wptr(l, ub[g] + fm::GV_WU), D::V + D::CP, wptr(l, ub[g + 1] + fm::GV_WHCP), 1, VH, SH, GT);
+        launch_k(h, fm::k_vec_b<D>, vgrid, fm::NT, vsm, st, bt, wptr(l, ub[g] + fm::GV_WU), D::V + D::CP, wptr(l, ub[g + 1] + fm::GV_WHCP), 1, VH, SH, GT);
         LAUNCH_OK(h);
       }
       cur = outs[g];
     }
-    fm::k_node_mid<D><<<L.nNT, fm::NT, vsm, st>>>(m, bt, l, upd, s, v, SA, VH, SH, GT);
+    launch_k(h, fm::k_node_mid<D>, L.nNT, fm::NT, vsm, st, m, bt, l, upd, s, v, SA, VH, SH, GT);
     LAUNCH_OK(h);
     if (has_next) { linear(wptr(l + 1, tc_c(h, fm::C_WSRC_TC)), wptr(l + 1, fm::C_BSRC), P); LAUNCH_OK(h); }
     if (upd >= 0) {
@@ -453,12 +472,12 @@ int node_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
         scalar(uptr(tc_u(h, ptw[g])), uptr(pb[g] + fm::GV_B), cur, outs[g], g); LAUNCH_OK(h);
         gate(uptr(tc_u(h, ptg[g])), uptr(pb[g] + fm::GV_BG), outs[g], g == 2, g); LAUNCH_OK(h);
         if (g < 2) {
-          fm::k_vec_b<D><<<vgrid, fm::NT, vsm, st>>>(bt, uptr(pb[g] + fm::GV_WU), D::V + D::CP, uptr(pb[g + 1] + fm::GV_WHCP), 1, VH, SH, GT);
+          launch_k(h, fm::k_vec_b<D>, vgrid, fm::NT, vsm, st, bt, uptr(pb[g] + fm::GV_WU), D::V + D::CP, uptr(pb[g + 1] + fm::GV_WHCP), 1, VH, SH, GT);
           LAUNCH_OK(h);
         }
         cur = outs[g];
       }
-      fm::k_node_post<D><<<L.nNT, fm::NT, vsm, st>>>(m, bt, upd, x, VH, GT);
+      launch_k(h, fm::k_node_post<D>, L.nNT, fm::NT, vsm, st, m, bt, upd, x, VH, GT);
       LAUNCH_OK(h);
     }
   }
@@ -476,9 +495,9 @@ int run_pass(FmHandle* h, void* ws, const Layout& L, const float* x_t, const uin
   float *s = at<float>(ws, L.s), *v = at<float>(ws, L.v), *x = at<float>(ws, L.x), *P = at<float>(ws, L.P);
   float *Q = at<float>(ws, L.Q), *vd = at<float>(ws, L.vd), *EAB = at<float>(ws, L.EAB), *M = at<float>(ws, L.M);
   float *partF = at<float>(ws, L.partF), *partL = at<float>(ws, L.partL), *ef = at<float>(ws, L.ef);
-  fm::k_node_embed<D><<<L.nNT, fm::NT, smem, st>>>(m, bt, x_t, a_t, c_t, t, prev, has_prev, s, v, P);
+  launch_k(h, fm::k_node_embed<D>, L.nNT, fm::NT, smem, st, m, bt, x_t, a_t, c_t, t, prev, has_prev, s, v, P);
   LAUNCH_OK(h);
-  if (m.use_dst) { fm::k_dst_proj<D><<<L.nNT, fm::NT, smem, st>>>(m, bt, 0, s, v, Q, vd); LAUNCH_OK(h); }
+  if (m.use_dst) { launch_k(h, fm::k_dst_proj<D>, L.nNT, fm::NT, smem, st, m, bt, 0, s, v, Q, vd); LAUNCH_OK(h); }
   bool edge_done = false;
   int er_grid = 0;
   if constexpr (D::S == 256 && D::V == 32 && D::SD == 0 && D::F == 128 && D::R == 32) {
@@ -487,18 +506,18 @@ int run_pass(FmHandle* h, void* ws, const Layout& L, const float* x_t, const uin
     er_grid = want < 2 * h->n_sm ? want : 2 * h->n_sm;
     if (h->edge_reg && has_prev && m.self_cond && h->conv_impl == 2 && img_on(h) && h->vec_impl == 1 && m.EB <= 7) {
       // self-conditioning residual + both output formats (fp32 rows, operand images) in one kernel; dead rows were zeroed by fm_batch_init
-      fm::k_edge_init_r<D><<<er_grid, fm::NT, fm::EdgeRegSmem<D>::INIT_BYTES, st>>>(m, bt, n_units, x_t, e_t, prev, ef, at<float>(ws, L.EFI));
+      launch_k(h, fm::k_edge_init_r<D>, er_grid, fm::NT, fm::EdgeRegSmem<D>::INIT_BYTES, st, m, bt, n_units, x_t, e_t, prev, ef, at<float>(ws, L.EFI));
       LAUNCH_OK(h);
       edge_done = true;
     }
   }
   if (!edge_done) {
-  fm::k_edge_init<D><<<L.nUT, fm::NT, fm::EdgeSmem<D>::BYTES, st>>>(m, bt, x_t, e_t, prev, has_prev, ef);
+  launch_k(h, fm::k_edge_init<D>, L.nUT, fm::NT, fm::EdgeSmem<D>::BYTES, st, m, bt, x_t, e_t, prev, has_prev, ef);
   LAUNCH_OK(h);
   if constexpr (D::S == 256 && D::V == 32 && D::SD == 0 && D::F == 128) {
     if (h->conv_impl == 2 && img_on(h)) {        // entry of the operand-image chain (egemm_p.cuh)
       const int nt = (int)(L.EPA / 128);
-      fm::k_ef_image<D><<<nt < 4 * h->n_sm ? nt : 4 * h->n_sm, 256, 0, st>>>(bt, ef, at<float>(ws, L.EFI), L.EP, nt);
+      launch_k(h, fm::k_ef_image<D>, nt < 4 * h->n_sm ? nt : 4 * h->n_sm, 256, 0, st, bt, ef, at<float>(ws, L.EFI), L.EP, nt);
       LAUNCH_OK(h);
     }
   }
@@ -508,7 +527,7 @@ int run_pass(FmHandle* h, void* ws, const Layout& L, const float* x_t, const uin
     int agg_rows = fm::TM;
     if constexpr (D::S == 256 && D::V == 32 && D::SD == 0) {
       if (h->conv_impl == 1) {
-        fm::k_conv_edge_tc<D><<<2 * L.nET, fm::NT, fm::TcPlan<D>::SMEM_BYTES, st>>>(m, bt, l, x, v, ef, P, M, partF, partL, h->tc_debug);
+        launch_k(h, fm::k_conv_edge_tc<D>, 2 * L.nET, fm::NT, fm::TcPlan<D>::SMEM_BYTES, st, m, bt, l, x, v, ef, P, M, partF, partL, h->tc_debug);
         agg_rows = fm::TCT;
         LAUNCH_OK(h);
       }
@@ -518,7 +537,7 @@ int run_pass(FmHandle* h, void* ws, const Layout& L, const float* x_t, const uin
       if (rc) return rc;
       if (gate_fused(h)) agg_rows = 32;          // k_egemm_g<EG_MSGA> / k_vecr_c write 32-row aggregation pieces
     } else if (agg_rows == fm::TM) {
-      fm::k_conv_edge<D><<<L.nET, fm::NT, smem, st>>>(m, bt, l, x, v, ef, P, Q, vd, M, partF, partL);
+      launch_k(h, fm::k_conv_edge<D>, L.nET, fm::NT, smem, st, m, bt, l, x, v, ef, P, Q, vd, M, partF, partL);
       LAUNCH_OK(h);
     }
     int upd = -1;
@@ -528,10 +547,10 @@ int run_pass(FmHandle* h, void* ws, const Layout& L, const float* x_t, const uin
       int rc = node_wide<D>(h, ws, L, bt, l, upd, has_next, agg_rows, st);
       if (rc) return rc;
     } else {
-      fm::k_node_update<D><<<L.nNT, fm::NT, smem, st>>>(m, bt, l, upd, has_next, agg_rows, s, v, x, M, partF, partL, P, EAB);
+      launch_k(h, fm::k_node_update<D>, L.nNT, fm::NT, smem, st, m, bt, l, upd, has_next, agg_rows, s, v, x, M, partF, partL, P, EAB);
       LAUNCH_OK(h);
     }
-    if (m.use_dst && has_next) { fm::k_dst_proj<D><<<L.nNT, fm::NT, smem, st>>>(m, bt, l + 1, s, v, Q, vd); LAUNCH_OK(h); }
+    if (m.use_dst && has_next) { launch_k(h, fm::k_dst_proj<D>, L.nNT, fm::NT, smem, st, m, bt, l + 1, s, v, Q, vd); LAUNCH_OK(h); }
     if (upd >= 0) {
       bool done = false;
       if constexpr (D::S == 256 && D::V == 32 && D::SD == 0 && D::F == 128) {
@@ -544,7 +563,7 @@ int run_pass(FmHandle* h, void* ws, const Layout& L, const float* x_t, const uin
             ac.status = h->d_status;
             ac.in_img = at<float>(ws, L.EFI); ac.out_img = at<float>(ws, L.EFI);
             ac.g_units = uptr(tc_u(h, fm::U_EUPD_TC2));
-            fm::k_egemm_c<D, fm::CH_EU><<<gt < h->n_sm ? gt : h->n_sm, fm::EgcPlan::THREADS, fm::EgcPlan::SMEM_BYTES, st>>>(m, bt, ac, gt);
+            launch_k(h, fm::k_egemm_c<D, fm::CH_EU>, gt < h->n_sm ? gt : h->n_sm, fm::EgcPlan::THREADS, fm::EgcPlan::SMEM_BYTES, st, m, bt, ac, gt);
             LAUNCH_OK(h);
             done = true;
           }
@@ -563,25 +582,25 @@ int run_pass(FmHandle* h, void* ws, const Layout& L, const float* x_t, const uin
           }
         }
       }
-      if (!done) { fm::k_edge_update<D><<<L.nET, fm::NT, smem, st>>>(m, bt, upd, x, EAB, ef); LAUNCH_OK(h); }
+      if (!done) { launch_k(h, fm::k_edge_update<D>, L.nET, fm::NT, smem, st, m, bt, upd, x, EAB, ef); LAUNCH_OK(h); }
     }
     if (l == stop_after) return 0;
   }
-  fm::k_node_head<D><<<L.nNT, fm::NT, smem, st>>>(m, bt, s, out.a, out.c);
+  launch_k(h, fm::k_node_head<D>, L.nNT, fm::NT, smem, st, m, bt, s, out.a, out.c);
   LAUNCH_OK(h);
   bool head_done = false;
   if constexpr (D::S == 256 && D::V == 32 && D::SD == 0 && D::F == 128 && D::R == 32) {
     if (h->edge_reg && m.EB <= 8) {
-      fm::k_edge_head_r<D><<<er_grid, fm::NT, fm::EdgeRegSmem<D>::HEAD_BYTES, st>>>(m, bt, L.nUT * (fm::TM / fm::UR), ef, out.e);
+      launch_k(h, fm::k_edge_head_r<D>, er_grid, fm::NT, fm::EdgeRegSmem<D>::HEAD_BYTES, st, m, bt, L.nUT * (fm::TM / fm::UR), ef, out.e);
       LAUNCH_OK(h);
       head_done = true;
     }
   }
   if (!head_done) {
-    fm::k_edge_head<D><<<L.nUT, fm::NT, fm::EdgeSmem<D>::BYTES, st>>>(m, bt, ef, out.e);
+    launch_k(h, fm::k_edge_head<D>, L.nUT, fm::NT, fm::EdgeSmem<D>::BYTES, st, m, bt, ef, out.e);
     LAUNCH_OK(h);
   }
-  fm::k_com<<<(L.B + 7) / 8, 256, 0, st>>>(bt, x, out.x, remove_com);
+  launch_k(h, fm::k_com, (L.B + 7) / 8, 256, 0, st, bt, x, out.x, remove_com);
   LAUNCH_OK(h);
   return 0;
 }
@@ -851,7 +870,7 @@ int fm_integrate_traj(FmHandle* h, void* ws, float* x, uint8_t* a, uint8_t* c, u
       if (traj->c1) tf.c1 = traj->c1 + (size_t)(k - 1) * N;
       if (traj->e1) tf.e1 = traj->e1 + (size_t)(k - 1) * U;
     }
-    fm::k_ctmc_step<<<L.B, 256, 0, st>>>(bt, h->rt.A, h->rt.C, h->rt.EB, cur.x, cur.a, cur.c, cur.e, x, a, c, e, sc, tf);
+    launch_k(h, fm::k_ctmc_step, L.B, 256, 0, st, bt, h->rt.A, h->rt.C, h->rt.EB, cur.x, cur.a, cur.c, cur.e, x, a, c, e, sc, tf);
     ++h->launches;
     if (cudaGetLastError() != cudaSuccess) rc = fail("k_ctmc_step launch failed");
   }
@@ -917,7 +936,7 @@ int fm_decode(FmHandle* h, void* ws, const uint8_t* a, const uint8_t* c, const u
   CUDA_OK(cudaSetDevice(h->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const fm::BatchRT bt = batch_rt(ws, *Lp);
-  fm::k_decode<<<Lp->B, 256, 0, st>>>(bt, a, c, e, fake_atom_token, h->cfg.n_bond_types, atom_new, charge, mol_kept, bond_src, bond_dst,
+  launch_k(h, fm::k_decode, Lp->B, 256, 0, st, bt, a, c, e, fake_atom_token, h->cfg.n_bond_types, atom_new, charge, mol_kept, bond_src, bond_dst,
                                       bond_type, mol_bonds);
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -1070,6 +1089,7 @@ int fm_set_option(FmHandle* h, const char* name, int32_t value) {
   if (n == "node_img") { h->node_img = value ? 1 : 0; return 0; }
   if (n == "edge_reg") { h->edge_reg = value ? 1 : 0; return 0; }
   if (n == "eg_pair") { h->eg_pair = value ? 1 : 0; return 0; }
+  if (n == "pdl") { h->pdl = value ? 1 : 0; return 0; }
   if (n == "eg_cluster") {
     if (value != 1 && value != 2 && value != 4) return fail("fm_set_option: eg_cluster must be 1, 2 or 4");
     h->eg_cluster = value;
@@ -1136,6 +1156,7 @@ int fm_get_option(FmHandle* h, const char* name, int32_t* value) {
   if (std::string(name) == "node_img") { *value = h->node_img; return 0; }
   if (std::string(name) == "edge_reg") { *value = h->edge_reg; return 0; }
   if (std::string(name) == "eg_pair") { *value = h->eg_pair; return 0; }
+  if (std::string(name) == "pdl") { *value = h->pdl; return 0; }
   if (std::string(name) == "eg_cluster") { *value = h->eg_cluster; return 0; }
   if (std::string(name) == "eg_clusters_seen") { *value = h->eg_clusters_seen; return 0; }
   if (std::string(name) == "status") {      // synchronising read-and-clear of the device status word (see fm_check_status)
@@ -1204,11 +1225,11 @@ int fm_time_conv_edge(FmHandle* h, void* ws, int32_t layer, int32_t iters, float
       int rc = conv_wide<fm::DimsFlowmol3>(h, ws, L, bt, layer, st);
       if (rc) return rc;
     } else if (h->variant == 0 && h->conv_impl == 1)
-      fm::k_conv_edge_tc<fm::DimsFlowmol3><<<2 * L.nET, fm::NT, fm::TcPlan<fm::DimsFlowmol3>::SMEM_BYTES, st>>>(h->rt, bt, layer, x, v, ef, P, M, partF, partL, h->tc_debug);
+      launch_k(h, fm::k_conv_edge_tc<fm::DimsFlowmol3>, 2 * L.nET, fm::NT, fm::TcPlan<fm::DimsFlowmol3>::SMEM_BYTES, st, h->rt, bt, layer, x, v, ef, P, M, partF, partL, h->tc_debug);
     else if (h->variant == 0)
-      fm::k_conv_edge<fm::DimsFlowmol3><<<L.nET, fm::NT, fm::DimsFlowmol3::SMEM_BYTES, st>>>(h->rt, bt, layer, x, v, ef, P, Q, vd, M, partF, partL);
+      launch_k(h, fm::k_conv_edge<fm::DimsFlowmol3>, L.nET, fm::NT, fm::DimsFlowmol3::SMEM_BYTES, st, h->rt, bt, layer, x, v, ef, P, Q, vd, M, partF, partL);
     else
-      fm::k_conv_edge<fm::DimsDev><<<L.nET, fm::NT, fm::DimsDev::SMEM_BYTES, st>>>(h->rt, bt, layer, x, v, ef, P, Q, vd, M, partF, partL);
+      launch_k(h, fm::k_conv_edge<fm::DimsDev>, L.nET, fm::NT, fm::DimsDev::SMEM_BYTES, st, h->rt, bt, layer, x, v, ef, P, Q, vd, M, partF, partL);
   }
   CUDA_OK(cudaEventRecord(e1, st));
   CUDA_OK(cudaEventSynchronize(e1));

@@ -27,6 +27,14 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+// ---- programmatic dependent launch ---------------------------------------------------------------------------------------------------
+// Every kernel of the pipeline is launched with cudaLaunchAttributeProgrammaticStreamSerialization (api.cu:launch_k): its CTAs may
+// become resident while the kernel before it in the stream is still draining, run their prologue (barrier init, tensor-memory
+// allocation, weight split) and then block in pdl_wait() until the predecessor has completed and its writes are visible.  Nothing
+// that reads or writes activation data may come before pdl_wait(); pdl_launch() lets the NEXT kernel's CTAs start early in turn.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- math (accurate versions: the parity bar is the reference's fp32 noise floor) ---------------------------------
 // 1 / v for v in [1, inf]: MUFU.RCP (1 ulp), branch-free.  The IEEE division / __frcp_rn compile to a call with a slow path
 // behind a reconvergence barrier, which serialises unrolled epilogues into one ~130-cycle dependent chain per element

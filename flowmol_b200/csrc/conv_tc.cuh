@@ -147,6 +147,8 @@ __global__ void __launch_bounds__(NT, 1)
 k_conv_edge_tc(const ModelRT m, const BatchRT bt, int layer, const float* __restrict__ x, const float* __restrict__ v,
                const float* __restrict__ ef, const float* __restrict__ P, float* __restrict__ M, float* __restrict__ partF,
                float* __restrict__ partL, int dbg) {
+  pdl_launch();
+  pdl_wait();
   using PL = TcPlan<D>;
   static_assert(D::S == 256 && D::V == 32 && D::SD == 0, "k_conv_edge_tc is specialised for the flowmol3 dimensions");
   extern __shared__ uint8_t smem_dyn[];

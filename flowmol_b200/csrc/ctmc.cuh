@@ -155,6 +155,8 @@ k_ctmc_step(const BatchRT bt, int A, int C, int EB, const float* __restrict__ px
             const float* __restrict__ pc, const float* __restrict__ pe, float* __restrict__ x_t,
             uint8_t* __restrict__ a_t, uint8_t* __restrict__ c_t, uint8_t* __restrict__ e_t, const StepScalars sc,
             const TrajFrame tf) {
+  pdl_launch();
+  pdl_wait();
   __shared__ int scratch[32];
   const int mol = blockIdx.x;
   const int n = bt.mol_n[mol], nb = bt.mol_node[mol], ub = bt.mol_u[mol], ucount = n * (n - 1) / 2;
@@ -196,6 +198,8 @@ __global__ void __launch_bounds__(256)
 k_decode(const BatchRT bt, const uint8_t* __restrict__ a, const uint8_t* __restrict__ c, const uint8_t* __restrict__ e, int fake_token,
          int mask_bond, int* __restrict__ atom_new, int8_t* __restrict__ charge, int* __restrict__ mol_kept,
          int* __restrict__ bond_src, int* __restrict__ bond_dst, uint8_t* __restrict__ bond_type, int* __restrict__ mol_bonds) {
+  pdl_launch();
+  pdl_wait();
   __shared__ int scratch[40];
   __shared__ int new_idx[2048];                        // n <= 2000 (fm_batch_init)
   const int mol = blockIdx.x, n = bt.mol_n[mol], nb = bt.mol_node[mol], ub = bt.mol_u[mol], ucount = n * (n - 1) / 2;

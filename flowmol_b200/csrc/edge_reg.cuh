@@ -102,6 +102,8 @@ struct EdgeRegSmem {
 template <class D>
 __global__ void __launch_bounds__(NT, 2)
 k_edge_head_r(const ModelRT m, const BatchRT bt, const int n_units, const float* __restrict__ ef, float* __restrict__ pe) {
+  pdl_launch();
+  pdl_wait();
   static_assert(D::F == 128, "16 n-tiles / 8 k-steps");
   constexpr int F = D::F;
   extern __shared__ __align__(16) float er_smem[];
@@ -196,6 +198,8 @@ template <class D>
 __global__ void __launch_bounds__(NT, 2)
 k_edge_init_r(const ModelRT m, const BatchRT bt, const int n_units, const float* __restrict__ x_t, const uint8_t* __restrict__ e_t,
               const PredPtr prev, float* __restrict__ ef, float* __restrict__ img) {
+  pdl_launch();
+  pdl_wait();
   static_assert(D::F == 128 && D::R == 32, "16 n-tiles; 32 radial basis functions");
   constexpr int F = D::F;
   extern __shared__ __align__(16) float er_smem[];

@@ -85,6 +85,8 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&v)[4])
 template <class D, int MODE>
 __global__ void __launch_bounds__(EgcPlan::THREADS, 1)
 k_egemm_c(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) {
+  pdl_launch();
+  pdl_wait();
   using PL = EgcPlan;
   static_assert(MODE == CH_EU, "chain modes");
   static_assert(D::F == 128 && D::R == 32, "hidden width 128 = one N = 128 MMA; rbf chunk = 32 k values");

@@ -53,6 +53,8 @@ __device__ __forceinline__ void st_global_256(void* p, uint4 lo, uint4 hi) {
 template <class D, int MODE>
 __global__ void __launch_bounds__(EgePlan::THREADS, 1)
 k_egemm_e(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) {
+  pdl_launch();
+  pdl_wait();
   using PL = EgePlan;
   static_assert(MODE == EG_MSG0 || MODE == EG_MSG, "edges-on-M orientation: the first two message linears (image in, image out)");
   static_assert(D::S == 256 && D::F % 64 == 0, "256 output features = one N = 256 MMA");
@@ -426,6 +428,8 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
 template <class D, int MODE>
 __global__ void __launch_bounds__(EggPlan::THREADS, 1)
 k_egemm_g(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) {
+  pdl_launch();
+  pdl_wait();
   using PL = EggPlan;
   static_assert(MODE == EG_MSG || MODE == EG_MSGA, "gate-fused message linears of GVP 1 (image out) and GVP 2 (segment sum)");
   static_assert(D::S == 256, "256 output features = one N = 256 MMA, eight 32-feature chunks");

@@ -82,6 +82,8 @@ __device__ __forceinline__ void mbar_wait_cl(uint64_t* bar, uint32_t parity) {
 template <class D, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EggPlan::THREADS, 1)
 k_egemm_g2(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) {
+  pdl_launch();
+  pdl_wait();
   using PL = EggPlan;
   static_assert(MODE == EG_MSG || MODE == EG_MSGA, "gate-fused message linears of GVP 1 (image out) and GVP 2 (segment sum)");
   static_assert(D::S == 256, "256 output features = one N = 256 MMA, eight 32-feature chunks");

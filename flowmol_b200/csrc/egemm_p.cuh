@@ -81,6 +81,8 @@ __device__ __forceinline__ void cluster_sync_all() {
 template <class D, int MODE, int IMG = 0, int CL = 1>
 __global__ void __launch_bounds__(EgpPlan::THREADS, 1)
 k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) {
+  pdl_launch();
+  pdl_wait();
   using PL = EgpPlan;
   constexpr int S = D::S;
   constexpr bool IMG_IN = (IMG & EGI_IN) != 0, IMG_OUT = (IMG & EGI_OUT) != 0;
@@ -560,6 +562,8 @@ k_egemm_p(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
 // every row of a tile -- never see uninitialised data there.
 template <class D>
 __global__ void __launch_bounds__(256) k_ef_image(const BatchRT bt, float* __restrict__ ef, float* __restrict__ img, long long EP, int n_tiles) {
+  pdl_launch();
+  pdl_wait();
   static_assert(D::F % 64 == 0, "image slabs are 64 k values");
   constexpr int F4 = D::F / 4;
   __shared__ int ok_row[128];

@@ -90,6 +90,8 @@ __device__ __noinline__ void eg_store_segment(float* __restrict__ M, float* __re
 template <class D, int MODE, int NH, int PREC>
 __global__ void __launch_bounds__(EgPlan<NH>::THREADS, NH == 1 ? 2 : 1)
 k_egemm_tc(const ModelRT m, const BatchRT bt, const EgArgs a) {
+  pdl_launch();
+  pdl_wait();
   using PL = EgPlan<NH>;
   constexpr int EG_T = PL::T, EG_XSTAGE = PL::XSTAGE;
   constexpr int LO_OFF = NH * 16384;                          // offset of the lo images inside a stage

@@ -101,6 +101,8 @@ __global__ void __launch_bounds__(NT, 1)
 k_node_embed(const ModelRT m, const BatchRT bt, const float* __restrict__ x_t, const uint8_t* __restrict__ a_t,
              const uint8_t* __restrict__ c_t, float t, const PredPtr prev, int has_prev,
              float* __restrict__ s_out, float* __restrict__ v_out, float* __restrict__ P0) {
+  pdl_launch();
+  pdl_wait();
   extern __shared__ __align__(16) float smem_raw[];
   Smem<D> sm(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -229,6 +231,8 @@ k_node_embed(const ModelRT m, const BatchRT bt, const float* __restrict__ x_t, c
 // ------------------------------------------------------------------------------------------------------------------
 template <class D>
 __global__ void k_edge_table(const ModelRT m, float* __restrict__ table) {
+  pdl_launch();
+  pdl_wait();
   __shared__ float h0[D::F], h1[D::F];
   const int tok = blockIdx.x, tid = threadIdx.x;
   const float* emb = m.g(G_EMB_E) + tok * D::TOK;
@@ -280,6 +284,8 @@ template <class D>
 __global__ void __launch_bounds__(NT, 2)
 k_edge_init(const ModelRT m, const BatchRT bt, const float* __restrict__ x_t, const uint8_t* __restrict__ e_t,
             const PredPtr prev, int has_prev, float* __restrict__ ef) {
+  pdl_launch();
+  pdl_wait();
   extern __shared__ __align__(16) float smem_raw[];
   Smem<D> sm = EdgeSmem<D>::carve(smem_raw);
   constexpr int XE = EdgeSmem<D>::XE, WST = EdgeSmem<D>::WST;
@@ -409,6 +415,8 @@ __global__ void __launch_bounds__(NT, 1)
 k_conv_edge(const ModelRT m, const BatchRT bt, int layer, const float* __restrict__ x, const float* __restrict__ v,
             const float* __restrict__ ef, const float* __restrict__ P, const float* __restrict__ Q,
             const float* __restrict__ vd, float* __restrict__ M, float* __restrict__ partF, float* __restrict__ partL) {
+  pdl_launch();
+  pdl_wait();
   extern __shared__ __align__(16) float smem_raw[];
   Smem<D> sm(smem_raw);
   const int tid = threadIdx.x;
@@ -578,6 +586,8 @@ k_node_update(const ModelRT m, const BatchRT bt, int layer, int updater /* -1: n
               int has_next, int agg_rows, float* __restrict__ s, float* __restrict__ v, float* __restrict__ x,
               const float* __restrict__ M, const float* __restrict__ partF, const float* __restrict__ partL,
               float* __restrict__ Pnext, float* __restrict__ EAB) {
+  pdl_launch();
+  pdl_wait();
   extern __shared__ __align__(16) float smem_raw[];
   Smem<D> sm(smem_raw);
   const int tid = threadIdx.x;
@@ -666,6 +676,8 @@ template <class D>
 __global__ void __launch_bounds__(NT, 1)
 k_dst_proj(const ModelRT m, const BatchRT bt, int layer, const float* __restrict__ s, const float* __restrict__ v,
            float* __restrict__ Q, float* __restrict__ vd) {
+  pdl_launch();
+  pdl_wait();
   if constexpr (D::SD > 0) {
     extern __shared__ __align__(16) float smem_raw[];
     Smem<D> sm(smem_raw);
@@ -707,6 +719,8 @@ template <class D>
 __global__ void __launch_bounds__(NT, 1)
 k_edge_update(const ModelRT m, const BatchRT bt, int updater, const float* __restrict__ x, const float* __restrict__ EAB,
               float* __restrict__ ef) {
+  pdl_launch();
+  pdl_wait();
   extern __shared__ __align__(16) float smem_raw[];
   Smem<D> sm(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -801,6 +815,8 @@ __device__ __forceinline__ float lane_softmax(float logit, int lane, int lo, int
 template <class D>
 __global__ void __launch_bounds__(NT, 1)
 k_node_head(const ModelRT m, const BatchRT bt, const float* __restrict__ s, float* __restrict__ pa, float* __restrict__ pc) {
+  pdl_launch();
+  pdl_wait();
   extern __shared__ __align__(16) float smem_raw[];
   Smem<D> sm(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -841,6 +857,8 @@ k_node_head(const ModelRT m, const BatchRT bt, const float* __restrict__ s, floa
 template <class D>
 __global__ void __launch_bounds__(NT, 2)
 k_edge_head(const ModelRT m, const BatchRT bt, const float* __restrict__ ef, float* __restrict__ pe) {
+  pdl_launch();
+  pdl_wait();
   extern __shared__ __align__(16) float smem_raw[];
   Smem<D> sm = EdgeSmem<D>::carve(smem_raw);
   constexpr int XE = EdgeSmem<D>::XE, WST = EdgeSmem<D>::WST;
@@ -898,6 +916,8 @@ k_edge_head(const ModelRT m, const BatchRT bt, const float* __restrict__ ef, flo
 
 // COM removal: x_hat = x - mean_mol(x)   (vector_field.py:347-350); one warp per molecule
 __global__ void k_com(const BatchRT bt, const float* __restrict__ x, float* __restrict__ px, int remove_com) {
+  pdl_launch();
+  pdl_wait();
   const int mol = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (mol >= bt.B) return;
   const int n = bt.mol_n[mol], nb = bt.mol_node[mol];

@@ -9,6 +9,8 @@ constexpr int TCT_M = 128, TCT_N = 64;
 
 __global__ void __launch_bounds__(128, 1) k_tc_gemm_test(const float* __restrict__ W, const float* __restrict__ X, int K,
                                                          float* __restrict__ out /*[128][64]*/, int passes /*1 or 3*/) {
+  pdl_launch();
+  pdl_wait();
   extern __shared__ __align__(1024) uint8_t tsm[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base;
@@ -77,6 +79,8 @@ __global__ void __launch_bounds__(128, 1) k_tc_gemm_test(const float* __restrict
 // geometry of the TF32 slabs.  `w_scale` is the power-of-two weight scale the host packer would choose.
 __global__ void __launch_bounds__(128, 1) k_tc_gemm_test_h16(const float* __restrict__ W, const float* __restrict__ X, int K,
                                                              float* __restrict__ out /*[128][64]*/, float w_scale) {
+  pdl_launch();
+  pdl_wait();
   extern __shared__ __align__(1024) uint8_t tsm[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base;

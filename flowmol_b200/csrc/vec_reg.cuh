@@ -212,6 +212,8 @@ template <class D>
 __global__ void __launch_bounds__(NT, 2)
 k_vecr_b(const BatchRT bt, const float* __restrict__ whcp, const float* __restrict__ wu, const int n_units,
          float* __restrict__ VU, float* __restrict__ SH, const float* __restrict__ GT) {
+  pdl_launch();
+  pdl_wait();
   static_assert(D::V == 32 && D::CP == 4, "fragment mapping: 32 vector channels, 4 cross-product features");
   __shared__ __align__(16) float wsm[VR_W1_WORDS + VR_W2_WORDS];
   __shared__ float red[NWARP];
@@ -288,6 +290,8 @@ template <class D>
 __global__ void __launch_bounds__(NT, 2)
 k_vecr_a(const ModelRT m, const BatchRT bt, const int layer, const int n_units, const float* __restrict__ x, const float* __restrict__ v,
          float* __restrict__ VU, float* __restrict__ SH) {
+  pdl_launch();
+  pdl_wait();
   static_assert(D::V == 32 && D::CP == 4 && D::VIN0 == 33 && D::H0 == 33, "fragment mapping: [v_src(32) | x_diff], 4 cross-product features");
   __shared__ __align__(16) float wsm[VR_W1_WORDS + VR_W2_WORDS];
   __shared__ float red[NWARP];
@@ -399,6 +403,8 @@ __global__ void __launch_bounds__(NT)
 k_vecr_c(const BatchRT bt, const int piece_rows /* 64 or 32: rows per aggregation piece (k_node_pre's agg_rows) */,
          const float* __restrict__ VU, const float* __restrict__ GT, float* __restrict__ M, float* __restrict__ partF,
          float* __restrict__ partL) {
+  pdl_launch();
+  pdl_wait();
   static_assert(D::V == 32, "lane = vector channel");
   const int lane = threadIdx.x & 31, piece = blockIdx.x * NWARP + (threadIdx.x >> 5);
   const int ppt = TM / piece_rows, tile = piece / ppt;          // pieces per 64-slot tile

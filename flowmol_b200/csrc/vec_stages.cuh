@@ -253,6 +253,8 @@ template <class D>
 __global__ void __launch_bounds__(NT, 2)
 k_vec_a(const ModelRT m, const BatchRT bt, int layer, const float* __restrict__ x, const float* __restrict__ v,
         float* __restrict__ VH, float* __restrict__ SH) {
+  pdl_launch();
+  pdl_wait();
   extern __shared__ __align__(16) float smem_raw[];
   Smem<D> sm = VecSmem<D>::carve(smem_raw);
   const int tid = threadIdx.x, pair = tid >> 6, pt = tid & (PT - 1), e0 = pair * PE;
@@ -317,6 +319,8 @@ template <class D>
 __global__ void __launch_bounds__(NT, 2)
 k_vec_b(const BatchRT bt, const float* __restrict__ wu, int hc_prev, const float* __restrict__ whcp, int node_rows,
         float* __restrict__ VH, float* __restrict__ SH, const float* __restrict__ GT) {
+  pdl_launch();
+  pdl_wait();
   extern __shared__ __align__(16) float smem_raw[];
   Smem<D> sm = VecSmem<D>::carve(smem_raw);
   // [pad8(hc_prev)][32 (+8)] words, then [V][64 (+8)] words
@@ -338,6 +342,8 @@ __global__ void __launch_bounds__(NT, 2)
 k_vec_c(const ModelRT m, const BatchRT bt, int layer, int first_col /* S when k_egemm_tc<EG_MSGA> reduced the scalar columns */,
         const float* __restrict__ VH, const float* __restrict__ GT, const float* __restrict__ Smsg, float* __restrict__ M,
         float* __restrict__ partF, float* __restrict__ partL) {
+  pdl_launch();
+  pdl_wait();
   extern __shared__ __align__(16) float smem_raw[];
   Smem<D> sm = VecSmem<D>::carve(smem_raw);
   const int tid = threadIdx.x;
@@ -439,6 +445,8 @@ __global__ void __launch_bounds__(NT, 2)
 k_node_pre(const ModelRT m, const BatchRT bt, int layer, int agg_rows, float* __restrict__ s, float* __restrict__ v,
            const float* __restrict__ M, const float* __restrict__ partF, const float* __restrict__ partL,
            float* __restrict__ VH, float* __restrict__ SH) {
+  pdl_launch();
+  pdl_wait();
   extern __shared__ __align__(16) float smem_raw[];
   Smem<D> sm = VecSmem<D>::carve(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -533,6 +541,8 @@ template <class D>
 __global__ void __launch_bounds__(NT, 2)
 k_node_mid(const ModelRT m, const BatchRT bt, int layer, int updater, float* __restrict__ s, float* __restrict__ v,
            const float* __restrict__ S3, float* __restrict__ VH, float* __restrict__ SH, const float* __restrict__ GT) {
+  pdl_launch();
+  pdl_wait();
   extern __shared__ __align__(16) float smem_raw[];
   Smem<D> sm = VecSmem<D>::carve(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -567,6 +577,8 @@ template <class D>
 __global__ void __launch_bounds__(NT, 2)
 k_node_post(const ModelRT m, const BatchRT bt, int updater, float* __restrict__ x, const float* __restrict__ VH,
             const float* __restrict__ GT) {
+  pdl_launch();
+  pdl_wait();
   extern __shared__ __align__(16) float smem_raw[];
   Smem<D> sm = VecSmem<D>::carve(smem_raw);
   const int tid = threadIdx.x;

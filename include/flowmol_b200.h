@@ -158,6 +158,14 @@ int fm_time_egemm_msg(FmHandle* h, void* workspace, int32_t layer, int32_t iters
  *          converted by the consumer's loader warps (bit-identical results); "vec_impl" = 1 (default) register-resident
  *          vector stages of the message GVPs (one warp per 16 edges, csrc/vec_reg.cuh) / 0 shared-memory tile kernels;
  *          "tc_debug", "tc_trace", "tc_trace_mode": timing experiments.
+ *          "eg_fuse_gate" = 1 (default): the gate linear of message GVPs 1 / 2 runs inside the scalar linear's kernel (k_egemm_g, A
+ *          operand in tensor memory); "eu_fuse" = 1 (default): EdgeUpdate (both linears, residual, LayerNorm) in one kernel
+ *          (k_egemm_c); "node_img" = 1 (default): operand images between the node-row linears (bit-identical to 0);
+ *          "edge_reg" = 1 (default): upper-edge MLPs as register-resident warp kernels (edge_reg.cuh) instead of the fp32 tile
+ *          kernels; "eg_pair" = 1: gate-fused linears on CTA pairs (tcgen05 cta_group::2, bit-identical, measured slower:
+ *          default 0); "eg_orient" = 1: edges-on-M k_egemm_e for MSG0 / MSG without gate fusion; "tc_debug": knock-out timing
+ *          bits of k_egemm_g / k_egemm_c (results are garbage; tools/gpu_knockout.py); "pdl" = 1: programmatic dependent launch of
+ *          every pipeline kernel (measured 3 % slower end to end: default 0);
  *          fm_get_option(h, "status", &v) synchronises the device and reads-and-clears the status word: bit 0 = an activation
  *          left the fp16 operand range since the last read (results invalid; switch to tc_prec 0).  fm_sample_host checks it. */
 int fm_set_option(FmHandle* h, const char* name, int32_t value);

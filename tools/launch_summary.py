@@ -8,7 +8,9 @@ for row in rows:
     k = row['Kernel Name']
     name = k.split('<')[0].replace('void ', '').split('(')[0].replace('fm::', '')
     m = re.search(r'>, \(?(?:fm::EgMode|int)?\)?(\d+)(?:, (?:\(int\))?(\d+))?(?:, (?:\(int\))?(\d+))?>\(', k)
-    if 'egemm' in name and m:
+    if "egemm_c" in name and m:
+        name += "<EU>"
+    elif "egemm" in name and m:
         name += f"<{MODES.get(int(m.group(1)), m.group(1))}" + (f",img{m.group(2)}" if 'egemm_p' in name and m.group(2) not in (None, '0') else "") + ">"
     name += " g=" + row.get('Grid Size', '?').strip('()').split(',')[0]
     v = float(row['Metric Value'])

@@ -21,7 +21,7 @@ for line in out.split("\n"):
             w = want.match(m.group(1))
             if w:
                 hist[name][w.group(0)] += 1
-keep = [k for k in hist if re.search(r"k_egemm_[peg]<|k_vecr|k_vec_[abc]|k_ctmc|k_decode|k_node_(pre|mid)|k_conv_edge", k)]
+keep = [k for k in hist if re.search(r"k_egemm_(p|e|g|g2|c)<|k_vecr|k_vec_[abc]|k_ctmc|k_decode|k_node_(pre|mid)|k_conv_edge|k_edge_(init|head)_r", k)]
 for k in sorted(keep):
     c = hist[k]
     print(f"{k}: {c['total']} instructions; " + ", ".join(f"{op} x{n}" for op, n in sorted(c.items()) if op != "total"))

@@ -425,7 +425,9 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       : "memory");
 }
 
-template <class D, int MODE>
+// IN_IMG = 0: the leading S k values arrive as fp32 rows `in_s` and are converted by the loaders (node rows, first GVP of a chain);
+// OUT_F32 = 1: s' leaves as fp32 rows `out` instead of operand images (node rows, last GVP of a chain: k_node_mid reads them).
+template <class D, int MODE, int IN_IMG = 1, int OUT_F32 = 0>
 __global__ void __launch_bounds__(EggPlan::THREADS, 1)
 k_egemm_g(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) {
   pdl_launch();
@@ -439,9 +441,10 @@ k_egemm_g(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
   constexpr int NCH = (K + 31) / 32;
   constexpr int LAST_KSTEPS = ((K - 1) % 64) / 16 + 1;
   constexpr int NST = PL::NST;
-  constexpr int NIMG = S / 64;
+  constexpr int NIMG = IN_IMG ? S / 64 : 0;
   constexpr int FIRST_CH = 2 * NIMG;
   static_assert(FIRST_CH < NCH, "the loaders publish the row bookkeeping from their first converted chunk");
+  static_assert(!(OUT_F32 || !IN_IMG) || MODE == EG_MSG, "fp32 rows in / out: node-row chains (no segment sum)");
   constexpr int SH_W = 40;
   constexpr int LO_OFF = 16384;
   constexpr bool AGG = MODE == EG_MSGA;
@@ -593,7 +596,9 @@ k_egemm_g(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
       const int r = wrow0 + lane;
       const long long slot = f_slot0 + r;
       int ok = 0, info = -1;
-      if (slot < a.EP) {
+      if (a.flags & EGF_NODE_ROWS) {
+        ok = slot < a.EP;                                       // EP = number of nodes
+      } else if (slot < a.EP) {
         const int t64 = (int)(slot >> 6), mol = bt.etile_mol[t64];
         const int n = bt.mol_n[mol], le = (int)(slot - ((long long)bt.mol_etile[mol] << 6));
         if (le < n * (n - 1)) {
@@ -619,8 +624,12 @@ k_egemm_g(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
         const long long sl_ = f_slot0 + wrow0 + rl;
         const bool ok = __shfl_sync(0xffffffffu, r_ok, rl) != 0;
         float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int k0 = (j - S / 32) * 32 + ch * 4;
-        if (ok && k0 < SH_W) val = *(reinterpret_cast<const float4*>(a.in_sh + (size_t)sl_ * SH_W + k0));
+        if (!IN_IMG && j < S / 32) {
+          if (ok) val = *(reinterpret_cast<const float4*>(a.in_s + (size_t)sl_ * S + j * 32) + ch);
+        } else {
+          const int k0 = (j - S / 32) * 32 + ch * 4;
+          if (ok && k0 < SH_W) val = *(reinterpret_cast<const float4*>(a.in_sh + (size_t)sl_ * SH_W + k0));
+        }
         buf[i] = val;
       }
     };
@@ -706,7 +715,10 @@ k_egemm_g(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
         if (a.dbg & (8 | 32)) break;
         float o[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = sigmoid_fast(gacc[8 * i8 + e] * g_unscale + __ldg(a.g_bias + 8 * i8 + e));
+        for (int e = 0; e < 8; ++e) {
+          const float zg = gacc[8 * i8 + e] * g_unscale + __ldg(a.g_bias + 8 * i8 + e);
+          o[e] = (a.flags & EGF_IDENTITY) ? zg : sigmoid_fast(zg);
+        }
         st_global_256(gp + 8 * i8, make_uint4(__float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3])),
                       make_uint4(__float_as_uint(o[4]), __float_as_uint(o[5]), __float_as_uint(o[6]), __float_as_uint(o[7])));
       }
@@ -772,6 +784,14 @@ k_egemm_g(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
           tmem_st16(cb + (uint32_t)(c * 32), h2);                 // in place: 16 columns of (hi, hi) pairs, 16 columns of (lo, lo) pairs
           tmem_st16(cb + (uint32_t)(c * 32 + 16), l2);
         }
+        if (OUT_F32) {
+          float* op = a.out + ((size_t)tile * PL::T + row) * S + c * 32;
+#pragma unroll
+          for (int i8 = 0; i8 < 4; ++i8)
+            st_global_256(op + 8 * i8,
+                          make_uint4(__float_as_uint(acc[8 * i8]), __float_as_uint(acc[8 * i8 + 1]), __float_as_uint(acc[8 * i8 + 2]), __float_as_uint(acc[8 * i8 + 3])),
+                          make_uint4(__float_as_uint(acc[8 * i8 + 4]), __float_as_uint(acc[8 * i8 + 5]), __float_as_uint(acc[8 * i8 + 6]), __float_as_uint(acc[8 * i8 + 7])));
+        } else
         if (MODE == EG_MSG && !(a.dbg & 32)) {
           uint8_t* ob = reinterpret_cast<uint8_t*>(a.out_img) + ((size_t)tile * (S / 64) + s) * PL::XSTAGE + (size_t)row * 128;
 #pragma unroll

@@ -211,7 +211,7 @@ class CTMCVectorFieldB200:
             for back in range(0, 4):                       # the launch is on the LAUNCH_OK line or just above it
                 tx = src[line - 1 - back]
                 m = (re.search(r"launch_eg<D, fm::(EG_\w+), \d", tx) or re.search(r"fm::(k_\w+)<", tx)
-                     or re.search(r"\b(scalar|gate|linear)\(", tx))
+                     or re.search(r"\b(scalar|gate|linear|sgate)\(", tx))
                 if m:
                     return m.group(1) if m.group(1).startswith(("EG_", "k_")) else "node_" + m.group(1)
             return f"line{line}"

@@ -45,6 +45,7 @@ struct Layout {
   size_t mol_n, mol_node, mol_u, mol_etile, mol_utile, etile_mol, utile_mol, node_mol;
   size_t s, v, x, P, Q, vd, EAB, M, partF, partL, ef;
   size_t SA, SB, VH, SH, GT;   // wide tensor-core pipeline intermediates (per padded edge slot, rounded up to 256 slots)
+  size_t SHI;                  // vector norms of message GVPs 1 / 2 as the last k-slab's operand images (k_vecr_b -> k_egemm_g): 256 B per slot
   size_t EFI;                  // fp16 (hi, lo) operand images of the edge features (egemm_p.cuh), same bytes as ef
   long long EPA = 0;
   long long NPA = 0;           // node rows rounded up to 256
@@ -85,6 +86,7 @@ Layout make_layout(const Dyn& d, const int32_t* n_atoms, int B) {
   L.EFI = take(wide ? 4ull * (size_t)L.EPA * d.F : 0);
   L.SA = take(4ull * wide * d.S); L.SB = take(4ull * wide * d.S); L.VH = take(4ull * wide * 120); L.SH = take(4ull * wide * 40);
   L.GT = take(4ull * wide * 32);
+  L.SHI = take(wide ? 256ull * (size_t)L.EPA : 0);
   for (int k = 0; k < 3; ++k) {
     L.pred[k][0] = take(4ull * N * 3); L.pred[k][1] = take(4ull * N * d.A); L.pred[k][2] = take(4ull * N * d.C);
     L.pred[k][3] = take(4ull * (size_t)U * d.EB);
@@ -125,6 +127,7 @@ struct FmHandle {
                                // and the register-resident vector stages); aggregation pieces become 32 rows
   int eg_cluster = 1;          // k_egemm_p on edge rows: CTAs per thread-block cluster sharing one multicast weight stream (1, 2, 4)
   int eg_clusters_seen = 0;    // cudaOccupancyMaxActiveClusters of the last cluster kernel configured (diagnostics)
+  int sh_img = 1;              // norms of message GVPs 1 / 2 as operand images: every k-slab of k_egemm_g is a bulk copy
   int node_fuse_gate = 1;      // node-row GVPs: scalar + gate linear in one k_egemm_g launch
   int pdl = 0;                 // programmatic dependent launch of every pipeline kernel (launch_k); measured 3 % slower end to end (profiles/r02z): off
   int eg_pair = 0;             // gate-fused message linears on CTA pairs (tcgen05 cta_group::2, egemm_g2.cuh)
@@ -207,6 +210,8 @@ int set_smem_attrs() {
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_MSGA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_g<D, fm::EG_MSG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EggPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_g<D, fm::EG_MSGA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EggPlan::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_g<D, fm::EG_MSG, 1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EggPlan::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_g<D, fm::EG_MSGA, 1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EggPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_g<D, fm::EG_MSG, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EggPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_g<D, fm::EG_MSG, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EggPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_g2<D, fm::EG_MSG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EggPlan::SMEM_BYTES));
@@ -333,6 +338,8 @@ int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
     // register-resident vector stages (vec_reg.cuh): one warp per 16-row unit, VH holds VU = Vh_ext Wu (3 x 32 per row) instead
     const bool vr = img && h->vec_impl == 1;
     const bool gf = gate_fused(h);
+    const bool shi = gf && h->sh_img && !h->eg_pair;           // norms of GVP 1 / 2 handed over as operand images (k_vecr_b -> k_egemm_g)
+    float* SHI = at<float>(ws, L.SHI);
     const int n_units = L.nET * (fm::TM / fm::UR);
     const int vrgrid = (n_units + fm::NWARP - 1) / fm::NWARP < 2 * h->n_sm ? (n_units + fm::NWARP - 1) / fm::NWARP : 2 * h->n_sm;
     if (!vr) launch_k(h, fm::k_vec_a<D>, vgrid, fm::NT, vsm, st, m, bt, l, x, v, VH, SH);
@@ -356,6 +363,11 @@ int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
             const int grid_p = 2 * (gt / 2 < h->n_sm / 2 ? gt / 2 : h->n_sm / 2);
             if (g == 1) launch_k(h, fm::k_egemm_g2<D, fm::EG_MSG>, grid_p, fm::EggPlan::THREADS, fm::EggPlan::SMEM_BYTES, st, m, bt, a, gt);
             else launch_k(h, fm::k_egemm_g2<D, fm::EG_MSGA>, grid_p, fm::EggPlan::THREADS, fm::EggPlan::SMEM_BYTES, st, m, bt, a, gt);
+          } else
+          if (shi) {
+            a.sh_img = SHI;
+            if (g == 1) launch_k(h, fm::k_egemm_g<D, fm::EG_MSG, 1, 0, 1>, grid_g, fm::EggPlan::THREADS, fm::EggPlan::SMEM_BYTES, st, m, bt, a, gt);
+            else launch_k(h, fm::k_egemm_g<D, fm::EG_MSGA, 1, 0, 1>, grid_g, fm::EggPlan::THREADS, fm::EggPlan::SMEM_BYTES, st, m, bt, a, gt);
           } else
           if (g == 1) launch_k(h, fm::k_egemm_g<D, fm::EG_MSG>, grid_g, fm::EggPlan::THREADS, fm::EggPlan::SMEM_BYTES, st, m, bt, a, gt);
           else launch_k(h, fm::k_egemm_g<D, fm::EG_MSGA>, grid_g, fm::EggPlan::THREADS, fm::EggPlan::SMEM_BYTES, st, m, bt, a, gt);
@@ -398,7 +410,8 @@ int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
                                                      wptr(g == 0 ? fm::C_MSG1_WHCP : fm::C_MSG2_WHCP), 0, VH, SH, GT);
         else
           launch_k(h, fm::k_vecr_b<D>, vrgrid, fm::NT, 0, st, bt, wptr(g == 0 ? fm::C_MSG1_WHCP : fm::C_MSG2_WHCP),
-                                                      wptr(g == 0 ? fm::C_MSG1_WU : fm::C_MSG2_WU), n_units, VH, SH, GT);
+                                                      wptr(g == 0 ? fm::C_MSG1_WU : fm::C_MSG2_WU), n_units, VH, SH, GT,
+                                                      shi ? SHI : (float*)nullptr);
         LAUNCH_OK(h);
       }
       cur = outs[g];
@@ -807,6 +820,7 @@ int fm_batch_init(FmHandle* h, const int32_t* n_atoms, int32_t B, void* ws, size
   // (it stores live rows only) and every linear computes whole 128-row tiles -- start them as zeros, not as allocator garbage
   CUDA_OK(cudaMemsetAsync(at<char>(ws, L.ef), 0, 4ull * (size_t)L.EPA * h->dyn.F, st));
   if (h->dyn.S == 256 && h->dyn.SD == 0) CUDA_OK(cudaMemsetAsync(at<char>(ws, L.EFI), 0, 4ull * (size_t)L.EPA * h->dyn.F, st));
+  if (h->dyn.S == 256 && h->dyn.SD == 0) CUDA_OK(cudaMemsetAsync(at<char>(ws, L.SHI), 0, 256ull * (size_t)L.EPA, st));   // k columns >= 40 are never written
   CUDA_OK(cudaStreamSynchronize(st));      // the host vectors die here
   h->batches[ws] = L;
   return 0;
@@ -1114,6 +1128,7 @@ int fm_set_option(FmHandle* h, const char* name, int32_t value) {
   if (n == "eg_pair") { h->eg_pair = value ? 1 : 0; return 0; }
   if (n == "pdl") { h->pdl = value ? 1 : 0; return 0; }
   if (n == "node_fuse_gate") { h->node_fuse_gate = value ? 1 : 0; return 0; }
+  if (n == "sh_img") { h->sh_img = value ? 1 : 0; return 0; }
   if (n == "eg_cluster") {
     if (value != 1 && value != 2 && value != 4) return fail("fm_set_option: eg_cluster must be 1, 2 or 4");
     h->eg_cluster = value;
@@ -1182,6 +1197,7 @@ int fm_get_option(FmHandle* h, const char* name, int32_t* value) {
   if (std::string(name) == "eg_pair") { *value = h->eg_pair; return 0; }
   if (std::string(name) == "pdl") { *value = h->pdl; return 0; }
   if (std::string(name) == "node_fuse_gate") { *value = h->node_fuse_gate; return 0; }
+  if (std::string(name) == "sh_img") { *value = h->sh_img; return 0; }
   if (std::string(name) == "eg_cluster") { *value = h->eg_cluster; return 0; }
   if (std::string(name) == "eg_clusters_seen") { *value = h->eg_clusters_seen; return 0; }
   if (std::string(name) == "status") {      // synchronising read-and-clear of the device status word (see fm_check_status)

@@ -427,7 +427,9 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
 
 // IN_IMG = 0: the leading S k values arrive as fp32 rows `in_s` and are converted by the loaders (node rows, first GVP of a chain);
 // OUT_F32 = 1: s' leaves as fp32 rows `out` instead of operand images (node rows, last GVP of a chain: k_node_mid reads them).
-template <class D, int MODE, int IN_IMG = 1, int OUT_F32 = 0>
+// SH_IMG = 1: the vector norms (the last k-slab) arrive as operand images too (`sh_img`, written by k_vecr_b): the loaders convert
+// nothing, every k-slab of a tile is one bulk copy (knock-out timing: the conversion cost ~40 us per launch, profiles/r03d).
+template <class D, int MODE, int IN_IMG = 1, int OUT_F32 = 0, int SH_IMG = 0>
 __global__ void __launch_bounds__(EggPlan::THREADS, 1)
 k_egemm_g(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) {
   pdl_launch();
@@ -441,9 +443,10 @@ k_egemm_g(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
   constexpr int NCH = (K + 31) / 32;
   constexpr int LAST_KSTEPS = ((K - 1) % 64) / 16 + 1;
   constexpr int NST = PL::NST;
-  constexpr int NIMG = IN_IMG ? S / 64 : 0;
-  constexpr int FIRST_CH = 2 * NIMG;
-  static_assert(FIRST_CH < NCH, "the loaders publish the row bookkeeping from their first converted chunk");
+  static_assert(!SH_IMG || IN_IMG, "norms as images: only on top of the image chain");
+  constexpr int NIMG = IN_IMG ? S / 64 + (SH_IMG ? 1 : 0) : 0;
+  constexpr int FIRST_CH = SH_IMG ? NCH : 2 * NIMG;
+  static_assert(SH_IMG || FIRST_CH < NCH, "the loaders publish the row bookkeeping from their first converted chunk");
   static_assert(!(OUT_F32 || !IN_IMG) || MODE == EG_MSG, "fp32 rows in / out: node-row chains (no segment sum)");
   constexpr int SH_W = 40;
   constexpr int LO_OFF = 16384;
@@ -635,7 +638,7 @@ k_egemm_g(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
     };
     float4 cur[8], nxt[8];
     float amax = 0.f;
-    if (n_my > 0) { rowinfo(0); fetch(FIRST_CH, cur); }
+    if (n_my > 0) { rowinfo(0); if (!SH_IMG) fetch(FIRST_CH, cur); }
     uint32_t g = 0;
     for (int it = 0; it < n_my; ++it) {
 #pragma unroll
@@ -649,14 +652,16 @@ k_egemm_g(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
               if (a.dbg & 4) tc::mbar_arrive_expect_tx(&x_full[st], 0u);
               else {
               tc::mbar_arrive_expect_tx(&x_full[st], PL::XSTAGE);
-              tc::bulk_g2s(xst + st * PL::XSTAGE, reinterpret_cast<const uint8_t*>(a.in_img) + ((size_t)tile * NIMG + s) * PL::XSTAGE,
-                           PL::XSTAGE, &x_full[st]);
+              const uint8_t* srcp = (SH_IMG && s == NIMG - 1) ? reinterpret_cast<const uint8_t*>(a.sh_img) + (size_t)tile * PL::XSTAGE
+                                                              : reinterpret_cast<const uint8_t*>(a.in_img) + ((size_t)tile * (S / 64) + s) * PL::XSTAGE;
+              tc::bulk_g2s(xst + st * PL::XSTAGE, srcp, PL::XSTAGE, &x_full[st]);
               }
             } else {
               asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&x_full[st])) : "memory");
             }
           }
           __syncwarp();
+          if (SH_IMG && s == NSLAB - 1 && it + 1 < n_my) rowinfo(it + 1);      // MSGA: the next tile's destination bookkeeping
           continue;
         }
         uint8_t* hi = xst + st * PL::XSTAGE;

@@ -72,6 +72,7 @@ struct EgArgs {
   const float* g_units;      // k_egemm_g: weight images of the GVP's gate linear (the EG_GATE units), its bias and the gate rows [EPA][32]
   const float* g_bias;
   float* g_out;
+  const float* sh_img;       // k_egemm_g<.., SH_IMG>: the vector norms as the last k-slab's operand images (written by k_vecr_b), one 32 KB block per tile
 };
 
 // EG_MSGA: one finished segment sum of feature f.  Deliberately not inlined: the call sits behind a rarely taken branch in a

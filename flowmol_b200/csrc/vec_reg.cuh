@@ -141,9 +141,10 @@ __device__ __forceinline__ void vr_kstep8(float (&acc)[3][NTL][4], const uint32_
 // 16 rows x 3 planes -> norms to SH, Vu = Vh_ext Wu (K = hc padded to 40: k-steps 16, 16, 8) to VU.  NT1 >= 5 n-tiles.
 template <int NT1>
 __device__ __forceinline__ void vr_tail(float (&acc1)[3][NT1][4], const int hc, const WH16& wu, const size_t r0, const bool ok0, const bool ok1,
-                                        float* __restrict__ VU, float* __restrict__ SH) {
+                                        float* __restrict__ VU, float* __restrict__ SH, float* __restrict__ SHI = nullptr) {
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   // gvp.py:14-21 sqrt(clamp(x^2 + y^2 + z^2, 1e-8)) per hidden vector channel; dead rows / padding columns store 0
+  uint32_t wh[5][2], wl[5][2];                               // SHI: packed (hi, hi) / (lo, lo) words of this lane's two columns per n-tile and row
 #pragma unroll
   for (int nt = 0; nt < 5; ++nt)
 #pragma unroll
@@ -157,8 +158,38 @@ __device__ __forceinline__ void vr_tail(float (&acc1)[3][NT1][4], const int hc, 
         const float q = __fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz));
         nn[c] = (okr && col + c < hc) ? sqrt_pos(fmaxf(q, 1e-8f)) : 0.f;
       }
-      *reinterpret_cast<float2*>(SH + (r0 + g + 8 * hh) * VHW + col) = make_float2(nn[0], nn[1]);
+      if (SHI) tc::split_h16x2(nn[0] * tc::ACT_SCALE_H16, nn[1] * tc::ACT_SCALE_H16, wh[nt][hh], wl[nt][hh]);
+      else *reinterpret_cast<float2*>(SH + (r0 + g + 8 * hh) * VHW + col) = make_float2(nn[0], nn[1]);
     }
+  if (SHI) {
+    // The norms as the LAST k-slab of the next scalar linear's operand images (egemm_p.cuh): per 128-row tile one 32 KB block
+    // [hi 16 KB | lo 16 KB], row r = 128 bytes, 16-byte piece p (8 k values) at position p ^ (r % 8); columns >= 40 stay zero
+    // (fm_batch_init).  A quad holds piece nt of a row as four 4-byte words: a 4 x 4 word transpose inside the quad (four shuffles)
+    // gives lane t all 16 bytes of piece t, so pieces 0..3 leave as ONE 16-byte store per lane (full sectors); piece 4 as words.
+    // (Stored word by word the stage was 29 % slower: 20 partial-sector stores per lane, profiles/r03e.)
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const size_t slot = r0 + g + 8 * hh;
+      const uint32_t r = (uint32_t)(slot & 127), r7 = r & 7u;
+      uint8_t* rowb = reinterpret_cast<uint8_t*>(SHI) + (slot >> 7) * 32768 + r * 128;
+#pragma unroll
+      for (int hl = 0; hl < 2; ++hl) {
+        uint32_t x0 = hl ? wl[0][hh] : wh[0][hh], x1 = hl ? wl[1][hh] : wh[1][hh], x2 = hl ? wl[2][hh] : wh[2][hh], x3 = hl ? wl[3][hh] : wh[3][hh];
+        {   // 2 x 2 blocks: swap the off-diagonal words with the xor-1 partner
+          const uint32_t s01 = (t & 1) ? x0 : x1, s23 = (t & 1) ? x2 : x3;
+          const uint32_t q01 = __shfl_xor_sync(0xffffffffu, s01, 1), q23 = __shfl_xor_sync(0xffffffffu, s23, 1);
+          if (t & 1) { x0 = q01; x2 = q23; } else { x1 = q01; x3 = q23; }
+        }
+        {   // swap the off-diagonal 2 x 2 blocks with the xor-2 partner
+          const uint32_t sa = (t & 2) ? x0 : x2, sb = (t & 2) ? x1 : x3;
+          const uint32_t qa = __shfl_xor_sync(0xffffffffu, sa, 2), qb = __shfl_xor_sync(0xffffffffu, sb, 2);
+          if (t & 2) { x0 = qa; x1 = qb; } else { x2 = qa; x3 = qb; }
+        }
+        *reinterpret_cast<uint4*>(rowb + hl * 16384 + (((uint32_t)t ^ r7) << 4)) = make_uint4(x0, x1, x2, x3);
+        *reinterpret_cast<uint32_t*>(rowb + hl * 16384 + ((4u ^ r7) << 4) + 4 * t) = hl ? wl[4][hh] : wh[4][hh];
+      }
+    }
+  }
   float acc2[3][4][4];
 #pragma unroll
   for (int p = 0; p < 3; ++p)
@@ -211,7 +242,7 @@ constexpr int VR_W2_WORDS = 2 * 20 * WLD_U;        // Wu hi + lo, K <= 40
 template <class D>
 __global__ void __launch_bounds__(NT, 2)
 k_vecr_b(const BatchRT bt, const float* __restrict__ whcp, const float* __restrict__ wu, const int n_units,
-         float* __restrict__ VU, float* __restrict__ SH, const float* __restrict__ GT) {
+         float* __restrict__ VU, float* __restrict__ SH, const float* __restrict__ GT, float* __restrict__ SHI) {
   pdl_launch();
   pdl_wait();
   static_assert(D::V == 32 && D::CP == 4, "fragment mapping: 32 vector channels, 4 cross-product features");
@@ -282,7 +313,7 @@ k_vecr_b(const BatchRT bt, const float* __restrict__ whcp, const float* __restri
       acc1[1][4][i] = t < 2 ? ry : 0.f;
       acc1[2][4][i] = t < 2 ? rz : 0.f;
     }
-    vr_tail<5>(acc1, D::V + D::CP, w2, r0, ok0, ok1, VU, SH);
+    vr_tail<5>(acc1, D::V + D::CP, w2, r0, ok0, ok1, VU, SH, SHI);
   }
 }
 

@@ -18,6 +18,7 @@
 #include "egemm_e.cuh"
 #include "egemm_c.cuh"
 #include "egemm_g2.cuh"
+#include "egemm_h.cuh"
 #include "vec_stages.cuh"
 #include "vec_reg.cuh"
 #include "edge_reg.cuh"
@@ -127,6 +128,7 @@ struct FmHandle {
                                // and the register-resident vector stages); aggregation pieces become 32 rows
   int eg_cluster = 1;          // k_egemm_p on edge rows: CTAs per thread-block cluster sharing one multicast weight stream (1, 2, 4)
   int eg_clusters_seen = 0;    // cudaOccupancyMaxActiveClusters of the last cluster kernel configured (diagnostics)
+  int eg_epi12 = 1;            // gate-fused edge-row linears with twelve epilogue warps (k_egemm_h; needs sh_img)
   int sh_img = 1;              // norms of message GVPs 1 / 2 as operand images: every k-slab of k_egemm_g is a bulk copy
   int node_fuse_gate = 1;      // node-row GVPs: scalar + gate linear in one k_egemm_g launch
   int pdl = 0;                 // programmatic dependent launch of every pipeline kernel (launch_k); measured 3 % slower end to end (profiles/r02z): off
@@ -210,6 +212,8 @@ int set_smem_attrs() {
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_p<D, fm::EG_MSGA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgpPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_g<D, fm::EG_MSG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EggPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_g<D, fm::EG_MSGA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EggPlan::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_h<D, fm::EG_MSG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EghPlan::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_h<D, fm::EG_MSGA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EghPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_g<D, fm::EG_MSG, 1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EggPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_g<D, fm::EG_MSGA, 1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EggPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_g<D, fm::EG_MSG, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EggPlan::SMEM_BYTES));
@@ -363,6 +367,11 @@ int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
             const int grid_p = 2 * (gt / 2 < h->n_sm / 2 ? gt / 2 : h->n_sm / 2);
             if (g == 1) launch_k(h, fm::k_egemm_g2<D, fm::EG_MSG>, grid_p, fm::EggPlan::THREADS, fm::EggPlan::SMEM_BYTES, st, m, bt, a, gt);
             else launch_k(h, fm::k_egemm_g2<D, fm::EG_MSGA>, grid_p, fm::EggPlan::THREADS, fm::EggPlan::SMEM_BYTES, st, m, bt, a, gt);
+          } else
+          if (shi && h->eg_epi12) {                                    // all-image inputs: twelve epilogue warps (egemm_h.cuh)
+            a.sh_img = SHI;
+            if (g == 1) launch_k(h, fm::k_egemm_h<D, fm::EG_MSG>, grid_g, fm::EghPlan::THREADS, fm::EghPlan::SMEM_BYTES, st, m, bt, a, gt);
+            else launch_k(h, fm::k_egemm_h<D, fm::EG_MSGA>, grid_g, fm::EghPlan::THREADS, fm::EghPlan::SMEM_BYTES, st, m, bt, a, gt);
           } else
           if (shi) {
             a.sh_img = SHI;
@@ -1129,6 +1138,7 @@ int fm_set_option(FmHandle* h, const char* name, int32_t value) {
   if (n == "pdl") { h->pdl = value ? 1 : 0; return 0; }
   if (n == "node_fuse_gate") { h->node_fuse_gate = value ? 1 : 0; return 0; }
   if (n == "sh_img") { h->sh_img = value ? 1 : 0; return 0; }
+  if (n == "eg_epi12") { h->eg_epi12 = value ? 1 : 0; return 0; }
   if (n == "eg_cluster") {
     if (value != 1 && value != 2 && value != 4) return fail("fm_set_option: eg_cluster must be 1, 2 or 4");
     h->eg_cluster = value;
@@ -1198,6 +1208,7 @@ int fm_get_option(FmHandle* h, const char* name, int32_t* value) {
   if (std::string(name) == "pdl") { *value = h->pdl; return 0; }
   if (std::string(name) == "node_fuse_gate") { *value = h->node_fuse_gate; return 0; }
   if (std::string(name) == "sh_img") { *value = h->sh_img; return 0; }
+  if (std::string(name) == "eg_epi12") { *value = h->eg_epi12; return 0; }
   if (std::string(name) == "eg_cluster") { *value = h->eg_cluster; return 0; }
   if (std::string(name) == "eg_clusters_seen") { *value = h->eg_clusters_seen; return 0; }
   if (std::string(name) == "status") {      // synchronising read-and-clear of the device status word (see fm_check_status)

@@ -186,7 +186,16 @@ __device__ __forceinline__ void vr_tail(float (&acc1)[3][NT1][4], const int hc, 
           if (t & 2) { x0 = qa; x1 = qb; } else { x2 = qa; x3 = qb; }
         }
         *reinterpret_cast<uint4*>(rowb + hl * 16384 + (((uint32_t)t ^ r7) << 4)) = make_uint4(x0, x1, x2, x3);
-        *reinterpret_cast<uint32_t*>(rowb + hl * 16384 + ((4u ^ r7) << 4) + 4 * t) = hl ? wl[4][hh] : wh[4][hh];
+        // piece 4 (columns 32..39) shares its 32-byte sector with the all-zero piece 5: the quad writes the whole sector (8 bytes per
+        // lane), so that no sector of the image is ever written partially
+        {
+          const uint32_t w4 = hl ? wl[4][hh] : wh[4][hh];
+          const int q0 = (lane & ~3) + 2 * (t & 1);
+          const uint32_t wa = __shfl_sync(0xffffffffu, w4, q0), wb = __shfl_sync(0xffffffffu, w4, q0 + 1);
+          const uint32_t p4 = 4u ^ r7;                        // position of piece 4; its sector starts at position p4 & ~1
+          const bool mine = (uint32_t)(t >> 1) == (p4 & 1u);
+          *reinterpret_cast<uint2*>(rowb + hl * 16384 + ((p4 & ~1u) << 4) + 8 * t) = mine ? make_uint2(wa, wb) : make_uint2(0u, 0u);
+        }
       }
     }
   }

@@ -45,9 +45,23 @@ __device__ __forceinline__ VrUnit vr_unit(const BatchRT& bt, int unit) {
   return u;
 }
 
+// Channel permutation of the fragment layouts.  In an m16n8k16 fragment a thread owns logical k (or n) positions 2t, 2t + 1 and
+// 2t + 8, 2t + 9 of every group of 16: read straight from memory that is two 8-byte accesses per row and group, and a warp
+// instruction touches 8 rows x 32 bytes -- the vector stages ran at 56-64 % LSU-wavefront utilisation moving 33 bytes per wavefront
+// (profiles/r02_ncu_full_other.csv).  The contraction does not care which physical channel sits at which logical position as long
+// as the other operand agrees, and the weights are re-laid out in shared memory once per CTA anyway: logical position
+// 16 m + 8 h + 2 t + c  <->  physical channel 16 m + 4 t + 2 h + c.  A thread's four positions of a group are then FOUR CONSECUTIVE
+// channels: one 16-byte access, a quad covers 64 contiguous bytes of the row, half the memory instructions.  Memory layouts stay
+// in natural channel order (k_vecr_c and the scalar linears read them unchanged).
+__device__ __forceinline__ int vr_logical_of(int pc) { return (pc & ~15) | (((pc >> 1) & 1) << 3) | (((pc >> 2) & 3) << 1) | (pc & 1); }
+__device__ __forceinline__ int vr_physical_of(int lc) { return (lc & ~15) | (((lc >> 1) & 3) << 2) | (((lc >> 3) & 1) << 1) | (lc & 1); }
+
 // load_resident_h16 with an optional row rotation: rot1 != 0 puts source row 0 LAST (smem row k <- source row k + 1 for k < Kreal - 1,
 // smem row Kreal - 1 <- source row 0): message GVP 0 contracts over [v_src | x_diff] instead of the reference's [x_diff | v_src]
-__device__ __forceinline__ WH16 vr_load_w(float* dst, const float* __restrict__ src, int K, int Kreal, int np, int ld, int rot1, float* red) {
+// permK > 0: logical k rows [0, permK) hold the source rows of the permuted physical channels (A operand read as 16-byte groups);
+// permN > 0: logical columns [0, permN) hold the permuted physical output channels (C fragment stored as 16-byte groups)
+__device__ __forceinline__ WH16 vr_load_w(float* dst, const float* __restrict__ src, int K, int Kreal, int np, int ld, int rot1, float* red,
+                                          int permK = 0, int permN = 0) {
   const int tid = threadIdx.x;
   float mx = 0.f;
   for (int i = tid; i < K * np; i += NT) mx = fmaxf(mx, fabsf(__ldg(src + i)));
@@ -63,10 +77,14 @@ __device__ __forceinline__ WH16 vr_load_w(float* dst, const float* __restrict__ 
   const int kp2 = ((K + 7) & ~7) >> 1;
   uint32_t* hi = reinterpret_cast<uint32_t*>(dst);
   uint32_t* lo = hi + kp2 * ld;
-  auto srow = [&](int k) { return rot1 ? (k < Kreal - 1 ? k + 1 : (k == Kreal - 1 ? 0 : k)) : k; };
+  auto srow = [&](int k) {
+    if (k < permK) k = vr_physical_of(k);
+    return rot1 ? (k < Kreal - 1 ? k + 1 : (k == Kreal - 1 ? 0 : k)) : k;
+  };
   for (int i = tid; i < kp2 * np; i += NT) {
     const int r = i / np, n = i - r * np, k = 2 * r;
-    const float w0 = k < K ? __ldg(src + srow(k) * np + n) * scale : 0.f, w1 = k + 1 < K ? __ldg(src + srow(k + 1) * np + n) * scale : 0.f;
+    const int sn = n < permN ? vr_physical_of(n) : n;          // smem (logical) column n <- source column
+    const float w0 = k < K ? __ldg(src + srow(k) * np + sn) * scale : 0.f, w1 = k + 1 < K ? __ldg(src + srow(k + 1) * np + sn) * scale : 0.f;
     uint32_t h2, l2;
     tc::split_h16x2(w0, w1, h2, l2);
     hi[r * ld + n] = h2;
@@ -227,15 +245,18 @@ __device__ __forceinline__ void vr_tail(float (&acc1)[3][NT1][4], const int hc, 
     }
     vr_kstep8<4>(acc2, ah, al, wu.hi, wu.lo, WLD_U, 32, g, t);
   }
+  // Wu's columns sit in shared memory in the permuted order (vr_load_w, permN): n-tiles 2 m, 2 m + 1 hold the four consecutive
+  // output channels 16 m + 4 t .. + 3 of this thread -- one 16-byte store per plane, group and row
   const float inv = wu.inv;
 #pragma unroll
   for (int p = 0; p < 3; ++p)
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
+    for (int mg = 0; mg < 2; ++mg)
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh)
-        *reinterpret_cast<float2*>(VU + (r0 + g + 8 * hh) * VUW + p * 32 + 8 * nt + 2 * t) =
-            make_float2(acc2[p][nt][2 * hh] * inv, acc2[p][nt][2 * hh + 1] * inv);
+        *reinterpret_cast<float4*>(VU + (r0 + g + 8 * hh) * VUW + p * 32 + 16 * mg + 4 * t) =
+            make_float4(acc2[p][2 * mg][2 * hh] * inv, acc2[p][2 * mg][2 * hh + 1] * inv, acc2[p][2 * mg + 1][2 * hh] * inv,
+                        acc2[p][2 * mg + 1][2 * hh + 1] * inv);
 }
 
 // cross product of two 3-vectors with the roundings of torch.linalg.cross as vec_stage1 does them
@@ -257,8 +278,8 @@ k_vecr_b(const BatchRT bt, const float* __restrict__ whcp, const float* __restri
   static_assert(D::V == 32 && D::CP == 4, "fragment mapping: 32 vector channels, 4 cross-product features");
   __shared__ __align__(16) float wsm[VR_W1_WORDS + VR_W2_WORDS];
   __shared__ float red[NWARP];
-  const WH16 w1 = load_resident_h16(wsm, whcp, D::V, 32 * D::CPT_HC, WLD_HCP, red);
-  const WH16 w2 = load_resident_h16(wsm + VR_W1_WORDS, wu, pad4(D::V + D::CP), 32, WLD_U, red);
+  const WH16 w1 = vr_load_w(wsm, whcp, D::V, D::V, 32 * D::CPT_HC, WLD_HCP, 0, red, /*permK=*/D::V, 0);
+  const WH16 w2 = vr_load_w(wsm + VR_W1_WORDS, wu, pad4(D::V + D::CP), pad4(D::V + D::CP), 32, WLD_U, 0, red, 0, /*permN=*/32);
   __syncthreads();
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int nw = gridDim.x * NWARP;
@@ -270,19 +291,20 @@ k_vecr_b(const BatchRT bt, const float* __restrict__ whcp, const float* __restri
       prefetch_l2(GT + (r0 + (size_t)nw * UR) * 32, UR * 32 * 4);
     }
     const bool ok0 = g < u.nvalid, ok1 = g + 8 < u.nvalid;
-    // A fragments of V' = gate * VU straight from global memory: a0 (g, 2t) a1 (g + 8, 2t) a2 (g, 2t + 8) a3 (g + 8, 2t + 8)
-    float2 gv[2][4], vv[3][2][4];
+    // A fragments of V' = gate * VU straight from global memory.  Permuted channel order (vr_load_w, permK): the thread's logical
+    // positions 2t, 2t + 1 (a0 / a1) and 2t + 8, 2t + 9 (a2 / a3) of k-step ks are the physical channels 16 ks + 4t .. + 3
+    float4 gq[2][2], vq[3][2][2];
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const size_t row = r0 + g + (i & 1) * 8;
-        const int col = 16 * ks + 2 * t + (i >> 1) * 8;
-        const bool ok = (i & 1) ? ok1 : ok0;
-        gv[ks][i] = ok ? *reinterpret_cast<const float2*>(GT + row * 32 + col) : make_float2(0.f, 0.f);
+      for (int hh = 0; hh < 2; ++hh) {
+        const size_t row = r0 + g + hh * 8;
+        const int col = 16 * ks + 4 * t;
+        const bool ok = hh ? ok1 : ok0;
+        gq[ks][hh] = ok ? *reinterpret_cast<const float4*>(GT + row * 32 + col) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int p = 0; p < 3; ++p)
-          vv[p][ks][i] = ok ? *reinterpret_cast<const float2*>(VU + row * VUW + p * 32 + col) : make_float2(0.f, 0.f);
+          vq[p][ks][hh] = ok ? *reinterpret_cast<const float4*>(VU + row * VUW + p * 32 + col) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     float acc1[3][5][4];
 #pragma unroll
@@ -297,8 +319,11 @@ k_vecr_b(const BatchRT bt, const float* __restrict__ whcp, const float* __restri
 #pragma unroll
       for (int p = 0; p < 3; ++p)
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          tc::split_h16x2(__fmul_rn(gv[ks][i].x, vv[p][ks][i].x), __fmul_rn(gv[ks][i].y, vv[p][ks][i].y), ah[p][i], al[p][i]);
+        for (int hh = 0; hh < 2; ++hh) {
+          const float4 gg = gq[ks][hh], vw = vq[p][ks][hh];
+          tc::split_h16x2(__fmul_rn(gg.x, vw.x), __fmul_rn(gg.y, vw.y), ah[p][hh], al[p][hh]);
+          tc::split_h16x2(__fmul_rn(gg.z, vw.z), __fmul_rn(gg.w, vw.w), ah[p][2 + hh], al[p][2 + hh]);
+        }
       vr_kstep16<5>(acc1, ah, al, w1.hi, w1.lo, WLD_HCP, 16 * ks, g, t);
     }
     {
@@ -336,8 +361,8 @@ k_vecr_a(const ModelRT m, const BatchRT bt, const int layer, const int n_units, 
   __shared__ __align__(16) float wsm[VR_W1_WORDS + VR_W2_WORDS];
   __shared__ float red[NWARP];
   __shared__ float xch[NWARP][UR * 3 * 8];                    // per warp: the 8 Vcp columns of its 16 rows x 3 planes
-  const WH16 w1 = vr_load_w(wsm, m.c(layer, C_MSG0_WHCP), pad4(D::VIN0), D::VIN0, 32 * D::CPT_HC0, WLD_HCP, 1, red);
-  const WH16 w2 = load_resident_h16(wsm + VR_W1_WORDS, m.c(layer, C_MSG0_WU), pad4(D::H0 + D::CP), 32, WLD_U, red);
+  const WH16 w1 = vr_load_w(wsm, m.c(layer, C_MSG0_WHCP), pad4(D::VIN0), D::VIN0, 32 * D::CPT_HC0, WLD_HCP, 1, red, /*permK=*/D::V, 0);
+  const WH16 w2 = vr_load_w(wsm + VR_W1_WORDS, m.c(layer, C_MSG0_WU), pad4(D::H0 + D::CP), pad4(D::H0 + D::CP), 32, WLD_U, 0, red, 0, /*permN=*/32);
   __syncthreads();
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3, warp = threadIdx.x >> 5;
   float* xc = xch[warp];
@@ -362,15 +387,15 @@ k_vecr_a(const ModelRT m, const BatchRT bt, const int layer, const int n_units, 
         ud[hh][0] = __fdiv_rn(dx, dist); ud[hh][1] = __fdiv_rn(dy, dist); ud[hh][2] = __fdiv_rn(dz, dist);
       }
     }
-    float2 vv[3][2][4];
+    float4 vq[3][2][2];                                        // permuted channel order: 16 bytes = the thread's four positions of a k-step
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int col = 16 * ks + 2 * t + (i >> 1) * 8;
+      for (int hh = 0; hh < 2; ++hh) {
+        const int col = 16 * ks + 4 * t;
 #pragma unroll
         for (int p = 0; p < 3; ++p)
-          vv[p][ks][i] = okr[i & 1] ? __ldg(reinterpret_cast<const float2*>(v + (size_t)src[i & 1] * 3 * D::V + p * D::V + col)) : make_float2(0.f, 0.f);
+          vq[p][ks][hh] = okr[hh] ? __ldg(reinterpret_cast<const float4*>(v + (size_t)src[hh] * 3 * D::V + p * D::V + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     float acc1[3][6][4];
 #pragma unroll
@@ -385,7 +410,10 @@ k_vecr_a(const ModelRT m, const BatchRT bt, const int layer, const int n_units, 
 #pragma unroll
       for (int p = 0; p < 3; ++p)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) tc::split_h16x2(vv[p][ks][i].x, vv[p][ks][i].y, ah[p][i], al[p][i]);
+        for (int hh = 0; hh < 2; ++hh) {
+          tc::split_h16x2(vq[p][ks][hh].x, vq[p][ks][hh].y, ah[p][hh], al[p][hh]);
+          tc::split_h16x2(vq[p][ks][hh].z, vq[p][ks][hh].w, ah[p][2 + hh], al[p][2 + hh]);
+        }
       vr_kstep16<6>(acc1, ah, al, w1.hi, w1.lo, WLD_HCP, 16 * ks, g, t);
     }
     {

@@ -112,7 +112,7 @@ k_edge_head_r(const ModelRT m, const BatchRT bt, const int n_units, const float*
   float* b1s = w2s + EdgeRegSmem<D>::W_OUT8;
   float* b2s = b1s + F;
   float* red = b2s + 32;
-  const WH16 w1 = load_resident_h16(w1s, m.g(G_EHEAD0_W), F, F, ER_LD, red);
+  const WH16 w1 = vr_load_w(w1s, m.g(G_EHEAD0_W), F, F, F, ER_LD, 0, red, /*permK=*/F, 0);     // permuted k order: 16-byte A loads (vec_reg.cuh)
   const WH16 w2 = load_resident_h16(w2s, m.g(G_EHEAD2_W), F, 32, ER_LD8, red);
   for (int i = threadIdx.x; i < F; i += NT) b1s[i] = m.g(G_EHEAD0_B)[i];
   if (threadIdx.x < 32) b2s[threadIdx.x] = m.g(G_EHEAD2_B)[threadIdx.x];
@@ -139,17 +139,19 @@ k_edge_head_r(const ModelRT m, const BatchRT bt, const int n_units, const float*
       for (int i = 0; i < 4; ++i) acc1[nt][i] = 0.f;
 #pragma unroll 2
     for (int ks = 0; ks < F / 16; ++ks) {
-      // A fragment of ef[i->j] + ef[j->i] straight from global memory: a0 (g, 2t) a1 (g + 8, 2t) a2 (g, 2t + 8) a3 (g + 8, 2t + 8)
+      // A fragment of ef[i->j] + ef[j->i] straight from global memory; permuted k order: the thread's positions 2t, 2t + 1 (a0 / a1)
+      // and 2t + 8, 2t + 9 (a2 / a3) of this k-step are the four consecutive features 16 ks + 4t .. + 3
       uint32_t ah[4], al[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int hh = i & 1, col = 16 * ks + 2 * t + (i >> 1) * 8;
-        float2 s = make_float2(0.f, 0.f);
+      for (int hh = 0; hh < 2; ++hh) {
+        const int col = 16 * ks + 4 * t;
+        float4 sm4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (okr[hh]) {
-          const float2 a = *reinterpret_cast<const float2*>(r0p[hh] + col), b = *reinterpret_cast<const float2*>(r1p[hh] + col);
-          s = make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y));
+          const float4 a = *reinterpret_cast<const float4*>(r0p[hh] + col), b = *reinterpret_cast<const float4*>(r1p[hh] + col);
+          sm4 = make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
         }
-        tc::split_h16x2(s.x, s.y, ah[i], al[i]);
+        tc::split_h16x2(sm4.x, sm4.y, ah[hh], al[hh]);
+        tc::split_h16x2(sm4.z, sm4.w, ah[2 + hh], al[2 + hh]);
       }
       er_kstep16<16>(acc1, ah, al, w1.hi, w1.lo, ER_LD, 16 * ks, 0, g, t);
     }
@@ -211,7 +213,8 @@ k_edge_init_r(const ModelRT m, const BatchRT bt, const int n_units, const float*
   const int EB = m.EB;
   // rows [F, F + EB + R) of the first linear multiply the per-edge operand [e_1_pred | rbf differences]; image padded to 48 k values
   const WH16 w1 = er_load_w(w1s, m.g(G_SCE0_W) + (size_t)F * F, EB + D::R, 48, F, ER_LD, red);
-  const WH16 w2 = load_resident_h16(w2s, m.g(G_SCE2_W), F, F, ER_LD, red);
+  // second linear: output columns in the permuted order of vec_reg.cuh (a thread's values of n-tiles 2 m, 2 m + 1 = four consecutive channels)
+  const WH16 w2 = vr_load_w(w2s, m.g(G_SCE2_W), F, F, F, ER_LD, 0, red, 0, /*permN=*/F);
   for (int i = threadIdx.x; i < 2 * 8 * F; i += NT) {
     const int half = i / (8 * F), r = (i - half * 8 * F) / F, c = i % F;
     tabs[i] = r <= EB ? m.eemb_table[(size_t)(half * (EB + 1) + r) * F + c] : 0.f;
@@ -291,7 +294,7 @@ k_edge_init_r(const ModelRT m, const BatchRT bt, const int n_units, const float*
       for (int dir = 0; dir < 2; ++dir) {
         const long long slot = dir ? p1[hh] : p0[hh];
         rowp[hh][dir] = ef + (size_t)slot * F;
-        imgp[hh][dir] = reinterpret_cast<uint8_t*>(img) + (size_t)(slot >> 7) * (F / 64) * 32768 + (size_t)(slot & 127) * 128 + 4 * t;
+        imgp[hh][dir] = reinterpret_cast<uint8_t*>(img) + (size_t)(slot >> 7) * (F / 64) * 32768 + (size_t)(slot & 127) * 128;
         r7[hh][dir] = (int)(slot & 7);
       }
     // second linear in two halves of 64 output features; out = table[tok] + SiLU(. + b2), mirrored to both directed edges
@@ -305,24 +308,27 @@ k_edge_init_r(const ModelRT m, const BatchRT bt, const int n_units, const float*
 #pragma unroll
       for (int j = 0; j < 8; ++j) er_kstep16<8>(acc2, fh[j], fl[j], w2.hi, w2.lo, ER_LD, 16 * j, 64 * half, g, t);
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        const int col = 64 * half + 8 * nt + 2 * t;
-        const float2 bb = *reinterpret_cast<const float2*>(b2s + col);
+      for (int mm = 0; mm < 4; ++mm) {
+        const int col = 64 * half + 16 * mm + 4 * t;              // this thread's four consecutive output channels of n-tiles 2 mm, 2 mm + 1
+        const float4 bb = *reinterpret_cast<const float4*>(b2s + col);
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           if (!okr[hh]) continue;
-          const float2 tb = *reinterpret_cast<const float2*>(tabs + tok[hh] * F + col);
-          const float z0 = acc2[nt][2 * hh] * w2.inv + bb.x, z1 = acc2[nt][2 * hh + 1] * w2.inv + bb.y;
+          const float4 tb = *reinterpret_cast<const float4*>(tabs + tok[hh] * F + col);
+          const float z0 = acc2[2 * mm][2 * hh] * w2.inv + bb.x, z1 = acc2[2 * mm][2 * hh + 1] * w2.inv + bb.y;
+          const float z2 = acc2[2 * mm + 1][2 * hh] * w2.inv + bb.z, z3 = acc2[2 * mm + 1][2 * hh + 1] * w2.inv + bb.w;
           const float o0 = __fadd_rn(tb.x, z0 * sigmoid_fast(z0)), o1 = __fadd_rn(tb.y, z1 * sigmoid_fast(z1));
-          uint32_t h2, l2;
-          tc::split_h16x2(o0, o1, h2, l2);
+          const float o2 = __fadd_rn(tb.z, z2 * sigmoid_fast(z2)), o3 = __fadd_rn(tb.w, z3 * sigmoid_fast(z3));
+          uint32_t ha, la, hb, lb;
+          tc::split_h16x2(o0, o1, ha, la);
+          tc::split_h16x2(o2, o3, hb, lb);
+          const int piece = 2 * mm + (t >> 1);                     // 16-byte piece (8 k values) of the row inside k-slab `half`
 #pragma unroll
           for (int dir = 0; dir < 2; ++dir) {
-            *reinterpret_cast<float2*>(rowp[hh][dir] + col) = make_float2(o0, o1);
-            // image: k-slab `half`, this n-tile is the row's 16-byte piece nt, stored at piece position nt ^ (row % 8)
-            uint8_t* ib = imgp[hh][dir] + half * 32768 + ((nt ^ r7[hh][dir]) << 4);
-            *reinterpret_cast<uint32_t*>(ib) = h2;
-            *reinterpret_cast<uint32_t*>(ib + 16384) = l2;
+            *reinterpret_cast<float4*>(rowp[hh][dir] + col) = make_float4(o0, o1, o2, o3);
+            uint8_t* ib = imgp[hh][dir] + half * 32768 + ((piece ^ r7[hh][dir]) << 4) + 8 * (t & 1);
+            *reinterpret_cast<uint2*>(ib) = make_uint2(ha, hb);
+            *reinterpret_cast<uint2*>(ib + 16384) = make_uint2(la, lb);
           }
         }
       }

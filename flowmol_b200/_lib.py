@@ -57,6 +57,7 @@ SYMBOLS = {
     "fm_time_egemm_msg": (c_i32, [c_vp, c_vp, c_i32, c_i32, C.POINTER(c_f32), c_vp]),
     "fm_time_conv_edge": (c_i32, [c_vp, c_vp, c_i32, c_i32, C.POINTER(c_f32), c_vp]),
     "fm_decode": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "fm_debug_tmem_shapes": (c_i32, [c_vp, c_i32]),
     "fm_debug_ctmc_step": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_f32, c_f32, c_f32, c_f32, c_i32, c_i32]),
 }
 

@@ -128,6 +128,7 @@ struct FmHandle {
                                // and the register-resident vector stages); aggregation pieces become 32 rows
   int eg_cluster = 1;          // k_egemm_p on edge rows: CTAs per thread-block cluster sharing one multicast weight stream (1, 2, 4)
   int eg_clusters_seen = 0;    // cudaOccupancyMaxActiveClusters of the last cluster kernel configured (diagnostics)
+  int eg_perm = 1;             // k_egemm_h<MSG> with permuted output features: image stores re-read from tensor memory (16-byte pieces)
   int eg_epi12 = 1;            // gate-fused edge-row linears with twelve epilogue warps (k_egemm_h; needs sh_img)
   int sh_img = 1;              // norms of message GVPs 1 / 2 as operand images: every k-slab of k_egemm_g is a bulk copy
   int node_fuse_gate = 1;      // node-row GVPs: scalar + gate linear in one k_egemm_g launch
@@ -213,6 +214,7 @@ int set_smem_attrs() {
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_g<D, fm::EG_MSG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EggPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_g<D, fm::EG_MSGA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EggPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_h<D, fm::EG_MSG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EghPlan::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_h<D, fm::EG_MSG, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EghPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_h<D, fm::EG_MSGA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EghPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_g<D, fm::EG_MSG, 1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EggPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_g<D, fm::EG_MSGA, 1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EggPlan::SMEM_BYTES));
@@ -370,6 +372,11 @@ int conv_wide(FmHandle* h, void* ws, const Layout& L, const fm::BatchRT& bt, int
           } else
           if (shi && h->eg_epi12) {                                    // all-image inputs: twelve epilogue warps (egemm_h.cuh)
             a.sh_img = SHI;
+            if (g == 1 && h->eg_perm && h->off_h[fm::G_COUNT + l * fm::C_COUNT + fm::C_MSG1_TCW_HP] >= 0) {
+              // output features permuted inside every 32-chunk: image stores from the packed words in tensor memory, 16 bytes per lane
+              a.units = wptr(fm::C_MSG1_TCW_HP); a.bias = wptr(fm::C_MSG1_BP); a.g_units = wptr(fm::C_MSG1_TCG_HP);
+              launch_k(h, fm::k_egemm_h<D, fm::EG_MSG, 1>, grid_g, fm::EghPlan::THREADS, fm::EghPlan::SMEM_BYTES, st, m, bt, a, gt);
+            } else
             if (g == 1) launch_k(h, fm::k_egemm_h<D, fm::EG_MSG>, grid_g, fm::EghPlan::THREADS, fm::EghPlan::SMEM_BYTES, st, m, bt, a, gt);
             else launch_k(h, fm::k_egemm_h<D, fm::EG_MSGA>, grid_g, fm::EghPlan::THREADS, fm::EghPlan::SMEM_BYTES, st, m, bt, a, gt);
           } else
@@ -1139,6 +1146,7 @@ int fm_set_option(FmHandle* h, const char* name, int32_t value) {
   if (n == "node_fuse_gate") { h->node_fuse_gate = value ? 1 : 0; return 0; }
   if (n == "sh_img") { h->sh_img = value ? 1 : 0; return 0; }
   if (n == "eg_epi12") { h->eg_epi12 = value ? 1 : 0; return 0; }
+  if (n == "eg_perm") { h->eg_perm = value ? 1 : 0; return 0; }
   if (n == "eg_cluster") {
     if (value != 1 && value != 2 && value != 4) return fail("fm_set_option: eg_cluster must be 1, 2 or 4");
     h->eg_cluster = value;
@@ -1209,6 +1217,7 @@ int fm_get_option(FmHandle* h, const char* name, int32_t* value) {
   if (std::string(name) == "node_fuse_gate") { *value = h->node_fuse_gate; return 0; }
   if (std::string(name) == "sh_img") { *value = h->sh_img; return 0; }
   if (std::string(name) == "eg_epi12") { *value = h->eg_epi12; return 0; }
+  if (std::string(name) == "eg_perm") { *value = h->eg_perm; return 0; }
   if (std::string(name) == "eg_cluster") { *value = h->eg_cluster; return 0; }
   if (std::string(name) == "eg_clusters_seen") { *value = h->eg_clusters_seen; return 0; }
   if (std::string(name) == "status") {      // synchronising read-and-clear of the device status word (see fm_check_status)
@@ -1251,6 +1260,20 @@ int fm_debug_tc_gemm(const float* w_host, const float* x_host, int32_t K, float*
   CUDA_OK(cudaDeviceSynchronize());
   CUDA_OK(cudaMemcpy(out_host, dout, sizeof(float) * 128 * 64, cudaMemcpyDeviceToHost));
   cudaFree(dw); cudaFree(dx); cudaFree(dout);
+  return 0;
+}
+
+// probe of the tcgen05.ld shapes (tc_test.cuh:k_tmem_shape_probe): out_host int32 [128][16]
+int fm_debug_tmem_shapes(int32_t* out_host, int device) {
+  if (!out_host) return fail("fm_debug_tmem_shapes: bad argument");
+  CUDA_OK(cudaSetDevice(device));
+  int* d = nullptr;
+  CUDA_OK(cudaMalloc(&d, sizeof(int) * 128 * 16));
+  fm::k_tmem_shape_probe<<<1, 128>>>(d);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaDeviceSynchronize());
+  CUDA_OK(cudaMemcpy(out_host, d, sizeof(int) * 128 * 16, cudaMemcpyDeviceToHost));
+  cudaFree(d);
   return 0;
 }
 

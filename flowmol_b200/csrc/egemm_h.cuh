@@ -40,13 +40,28 @@ struct EghPlan {
   static_assert(OFF_PARK % 1024 == 0 && OFF_WG % 1024 == 0, "operand tiles are 1024-byte aligned");
 };
 
-template <class D, int MODE>
+// 16 lanes x 128 bits, four repeats: thread T receives rows T / 4 and T / 4 + 8 of the 16 lanes, column 4 n + T % 4 of repeat n
+// (registers 2 n, 2 n + 1) -- measured mapping, tools/gpu_tmem_shapes.py
+__device__ __forceinline__ void tmem_ld_16x128b_x4(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x128b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
+
+// PERM = 1 (EG_MSG, option eg_perm): the weight units / bias / gate units arrive with the output features permuted inside every
+// 32-feature chunk (weights.py:feature_perm).  The epilogue arithmetic is unchanged (it works on accumulator columns), the packed
+// fp16 (hi | lo) words it writes back into tensor memory are the gate GEMM's A operand as before -- and ALSO the source of the
+// image stores: re-read with the 16x128b shape a thread's four words of a row are one 16-byte piece of the operand image, a
+// quad writes 64 contiguous bytes of a row and a warp instruction touches 8 rows instead of 32 (the image stores were 193 of the
+// epilogue's 477 us, LSU-wavefront bound: profiles/r03c).
+template <class D, int MODE, int PERM = 0>
 __global__ void __launch_bounds__(EghPlan::THREADS, 1)
 k_egemm_h(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) {
   pdl_launch();
   pdl_wait();
   using PL = EghPlan;
   static_assert(MODE == EG_MSG || MODE == EG_MSGA, "gate-fused message linears of GVP 1 (image out) and GVP 2 (segment sum)");
+  static_assert(!PERM || MODE == EG_MSG, "permuted features: the linear that writes operand images");
   static_assert(D::S == 256, "256 output features, eight 32-feature chunks");
   constexpr int S = D::S;
   constexpr int K = D::K1;
@@ -323,6 +338,42 @@ k_egemm_h(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
           tmem_st16(cb + (uint32_t)(c * 32), h2);                 // in place: 16 columns of (hi, hi) pairs, 16 columns of (lo, lo) pairs
           tmem_st16(cb + (uint32_t)(c * 32 + 16), l2);
         }
+        if (MODE == EG_MSG && PERM && !(a.dbg & 32)) {
+          uint8_t* slab = reinterpret_cast<uint8_t*>(a.out_img) + ((size_t)tile * (S / 64) + s) * PL::XSTAGE;
+          if (c == 7) {
+            // parked chunk: its words never reach tensor memory; piece j (physical features 8 j .. 8 j + 7 of the chunk) = the words
+            // of the accumulator columns 8 n + 2 j, + 1 (n = 0..3): row-per-thread stores as before, two pieces per 32 bytes
+            uint8_t* ob = slab + (size_t)row * 128;
+#pragma unroll
+            for (int pr_ = 0; pr_ < 2; ++pr_) {
+              const uint32_t p0 = (uint32_t)(ch_ * 4 + 2 * pr_), pos = (p0 ^ x7) & ~1u;
+              const bool swap = (x7 & 1u) != 0;
+              const int j0 = 2 * pr_, j1 = 2 * pr_ + 1;
+              const uint4 ha = make_uint4(h2[j0], h2[4 + j0], h2[8 + j0], h2[12 + j0]), hb = make_uint4(h2[j1], h2[4 + j1], h2[8 + j1], h2[12 + j1]);
+              const uint4 la = make_uint4(l2[j0], l2[4 + j0], l2[8 + j0], l2[12 + j0]), lb = make_uint4(l2[j1], l2[4 + j1], l2[8 + j1], l2[12 + j1]);
+              st_global_256(ob + pos * 16, swap ? hb : ha, swap ? ha : hb);
+              st_global_256(ob + LO_OFF + pos * 16, swap ? lb : la, swap ? la : lb);
+            }
+          } else {
+            tmem_st_wait();
+            const int tq = lane & 3, rq = lane >> 2;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const uint32_t ta = tmem + ((uint32_t)(q * 32 + 16 * half) << 16) + (uint32_t)(b * 256 + c * 32);
+              uint32_t wh_[8], wl_[8];
+              tmem_ld_16x128b_x4(ta, wh_);
+              tmem_ld_16x128b_x4(ta + 16, wl_);
+              tc::tmem_ld_wait();
+#pragma unroll
+              for (int r8 = 0; r8 < 2; ++r8) {
+                const int rr_ = q * 32 + 16 * half + rq + 8 * r8;                         // row of the tile
+                uint8_t* dstp = slab + (size_t)rr_ * 128 + ((((uint32_t)(ch_ * 4 + tq)) ^ (uint32_t)(rr_ & 7)) << 4);
+                *reinterpret_cast<uint4*>(dstp) = make_uint4(wh_[r8], wh_[2 + r8], wh_[4 + r8], wh_[6 + r8]);
+                *reinterpret_cast<uint4*>(dstp + LO_OFF) = make_uint4(wl_[r8], wl_[2 + r8], wl_[4 + r8], wl_[6 + r8]);
+              }
+            }
+          }
+        } else
         if (MODE == EG_MSG && !(a.dbg & 32)) {
           uint8_t* ob = reinterpret_cast<uint8_t*>(a.out_img) + ((size_t)tile * (S / 64) + s) * PL::XSTAGE + (size_t)row * 128;
 #pragma unroll

@@ -143,4 +143,49 @@ __global__ void __launch_bounds__(128, 1) k_tc_gemm_test_h16(const float* __rest
   if (warp == 0) tc::tmem_dealloc(tm, 64);
 }
 
+
+// Probe of the tcgen05.ld shapes: every TMEM (lane, column) cell of a 128 x 32 block holds lane * 256 + column (written with the
+// 32x32b shape whose mapping is known: thread = lane); every warp then reads lanes [32 w, 32 w + 16) with 16x256b.x2 / 16x128b.x2 /
+// 16x64b.x2 and reports the cells its registers received: out[warp][lane][0..7] = 16x256b, [8..11] = 16x128b, [12..13] = 16x64b.
+__global__ void __launch_bounds__(128, 1) k_tmem_shape_probe(int* __restrict__ out) {
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 0) tc::tmem_alloc(&tmem_base, 32);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_base;
+  const uint32_t la = (uint32_t)(warp * 32) << 16;
+  uint32_t v[16];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = (uint32_t)((warp * 32 + lane) * 256 + h * 16 + i);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(tmem + la + h * 16),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
+        "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+  }
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  uint32_t a[8], b[4], c[2];
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7])
+               : "r"(tmem + la));
+  asm volatile("tcgen05.ld.sync.aligned.16x128b.x2.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]) : "r"(tmem + la));
+  asm volatile("tcgen05.ld.sync.aligned.16x64b.x2.b32 {%0, %1}, [%2];\n" : "=r"(c[0]), "=r"(c[1]) : "r"(tmem + la));
+  tc::tmem_ld_wait();
+  int* o = out + (warp * 32 + lane) * 16;
+  for (int i = 0; i < 8; ++i) o[i] = (int)a[i];
+  for (int i = 0; i < 4; ++i) o[8 + i] = (int)b[i];
+  for (int i = 0; i < 2; ++i) o[12 + i] = (int)c[i];
+  o[14] = o[15] = 0;
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 32);
+}
+
 }  // namespace fm

@@ -344,6 +344,16 @@ def tc_units_h16(w_fk, rows_per_unit):
     return np.concatenate(chunks)
 
 
+def feature_perm(n):
+    """perm[lf] = physical feature held by accumulator column lf.  Inside every chunk of 32: lf = 8 n + 2 t + c  ->  8 t + 2 n + c
+    (n, t in 0..3): read back from tensor memory with the 16x128b shape (thread t of a quad: packed column 4 n + t), a thread's four
+    words are then the physical pairs 4 t .. 4 t + 3 = one 16-byte piece of the operand image (csrc/egemm_h.cuh)."""
+    lf = np.arange(n)
+    c32, r = lf // 32 * 32, lf % 32
+    nn, t, c = r // 8, (r % 8) // 2, r % 2
+    return c32 + 8 * t + 2 * nn + c
+
+
 def _pack_gvp(P, base, sd, p, w_rows=None):
     """GVP under state_dict prefix `p` -> 6 consecutive entries starting at id `base`.
     [Wh | Wcp] are fused into one operand (they multiply the same input); `w_rows` selects/reorders the rows of the
@@ -430,7 +440,13 @@ def pack(cfg: ModelConfig, sd):
                     P.raw(c("MSG0_TCW_H"), tc_units_h16(wt[:, rows_edge_h], 128))
                 else:
                     P.tc(c(f"MSG{i}_TCW"), c(f"MSG{i}_TCW_H"), wt, 128)
-                P.tc(c(f"MSG{i}_TCG"), c(f"MSG{i}_TCG_H"), _np(sd, f"{p}.edge_message.{i}.scalar_to_vector_gates.weight"), 32)
+                wg = _np(sd, f"{p}.edge_message.{i}.scalar_to_vector_gates.weight")
+                P.tc(c(f"MSG{i}_TCG"), c(f"MSG{i}_TCG_H"), wg, 32)
+                if i == 1:
+                    perm = feature_perm(S)
+                    P.raw(c("MSG1_TCW_HP"), tc_units_h16(wt[perm, :], 128))
+                    P.raw(c("MSG1_TCG_HP"), tc_units_h16(wg[:, perm], 32))
+                    P.vec(c("MSG1_BP"), _np(sd, f"{p}.edge_message.1.to_feats_out.0.bias")[perm])
         for i in range(3):
             _pack_gvp(P, c(f"UPD{i}_WHCP"), sd, f"{p}.node_update.{i}")
         if S % 128 == 0 and V <= 32 and 2 * F == S:      # node pipeline on the tensor cores (node rows through k_egemm_tc)

@@ -146,6 +146,9 @@ int fm_time_conv_edge(FmHandle* h, void* workspace, int32_t layer, int32_t iters
  * passes = 1 (plain TF32) or 3 (error-compensated 3xTF32) */
 int fm_debug_tc_gemm(const float* w_host, const float* x_host, int32_t K, float* out_host, int32_t passes, int device);
 /* same, for the dominant kernel of the default flowmol3 pipeline: the 292 -> 256 message linear k_egemm_tc<EG_MSG> (GVP 1) */
+/* probe of the tcgen05.ld shapes 16x256b / 16x128b / 16x64b: which (TMEM lane, column) every register of every thread receives
+ * (out_host int32 [128][16]: cell = lane * 256 + column; [0..7] 16x256b.x2, [8..11] 16x128b.x2, [12..13] 16x64b.x2) */
+int fm_debug_tmem_shapes(int32_t* out_host, int device);
 int fm_time_egemm_msg(FmHandle* h, void* workspace, int32_t layer, int32_t iters, float* ms_avg, void* stream);
 /* options: "conv_impl" = 0 fp32 CUDA-core message kernel (bit-for-bit the reference's fp32 arithmetic up to summation order),
  *          1 fused tcgen05 3xTF32 message kernel (experimental), 2 wide tcgen05 3xTF32 pipeline (default for the flowmol3

@@ -128,6 +128,7 @@ struct FmHandle {
                                // and the register-resident vector stages); aggregation pieces become 32 rows
   int eg_cluster = 1;          // k_egemm_p on edge rows: CTAs per thread-block cluster sharing one multicast weight stream (1, 2, 4)
   int eg_clusters_seen = 0;    // cudaOccupancyMaxActiveClusters of the last cluster kernel configured (diagnostics)
+  int eu_quad = 1;             // k_egemm_c with four threads per row in the epilogues (permuted features)
   int eg_perm = 1;             // k_egemm_h<MSG> with permuted output features: image stores re-read from tensor memory (16-byte pieces)
   int eg_epi12 = 1;            // gate-fused edge-row linears with twelve epilogue warps (k_egemm_h; needs sh_img)
   int sh_img = 1;              // norms of message GVPs 1 / 2 as operand images: every k-slab of k_egemm_g is a bulk copy
@@ -225,6 +226,7 @@ int set_smem_attrs() {
     CUDA_OK(cudaFuncSetAttribute(fm::k_edge_head_r<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EdgeRegSmem<D>::HEAD_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_edge_init_r<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EdgeRegSmem<D>::INIT_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_c<D, fm::CH_EU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgcPlan::SMEM_BYTES));
+    CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_c<D, fm::CH_EU, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgcPlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_e<D, fm::EG_MSG0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgePlan::SMEM_BYTES));
     CUDA_OK(cudaFuncSetAttribute(fm::k_egemm_e<D, fm::EG_MSG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EgePlan::SMEM_BYTES));
     constexpr int IO = fm::EGI_IN | fm::EGI_OUT;
@@ -615,6 +617,11 @@ int run_pass(FmHandle* h, void* ws, const Layout& L, const float* x_t, const uin
             ac.status = h->d_status;
             ac.in_img = at<float>(ws, L.EFI); ac.out_img = at<float>(ws, L.EFI);
             ac.g_units = uptr(tc_u(h, fm::U_EUPD_TC2));
+            if (h->eu_quad && h->off_h[fm::G_COUNT + m.L * fm::C_COUNT + upd * fm::U_COUNT + fm::U_EUPD_TC1_HP] >= 0) {
+              // four threads per row in both epilogues: permuted hidden / output features (egemm_c.cuh, QL)
+              ac.units = uptr(fm::U_EUPD_TC1_HP); ac.g_units = uptr(fm::U_EUPD_TC2_HP);
+              launch_k(h, fm::k_egemm_c<D, fm::CH_EU, 1>, gt < h->n_sm ? gt : h->n_sm, fm::EgcPlan::THREADS, fm::EgcPlan::SMEM_BYTES, st, m, bt, ac, gt);
+            } else
             launch_k(h, fm::k_egemm_c<D, fm::CH_EU>, gt < h->n_sm ? gt : h->n_sm, fm::EgcPlan::THREADS, fm::EgcPlan::SMEM_BYTES, st, m, bt, ac, gt);
             LAUNCH_OK(h);
             done = true;
@@ -1147,6 +1154,7 @@ int fm_set_option(FmHandle* h, const char* name, int32_t value) {
   if (n == "sh_img") { h->sh_img = value ? 1 : 0; return 0; }
   if (n == "eg_epi12") { h->eg_epi12 = value ? 1 : 0; return 0; }
   if (n == "eg_perm") { h->eg_perm = value ? 1 : 0; return 0; }
+  if (n == "eu_quad") { h->eu_quad = value ? 1 : 0; return 0; }
   if (n == "eg_cluster") {
     if (value != 1 && value != 2 && value != 4) return fail("fm_set_option: eg_cluster must be 1, 2 or 4");
     h->eg_cluster = value;
@@ -1218,6 +1226,7 @@ int fm_get_option(FmHandle* h, const char* name, int32_t* value) {
   if (std::string(name) == "sh_img") { *value = h->sh_img; return 0; }
   if (std::string(name) == "eg_epi12") { *value = h->eg_epi12; return 0; }
   if (std::string(name) == "eg_perm") { *value = h->eg_perm; return 0; }
+  if (std::string(name) == "eu_quad") { *value = h->eu_quad; return 0; }
   if (std::string(name) == "eg_cluster") { *value = h->eg_cluster; return 0; }
   if (std::string(name) == "eg_clusters_seen") { *value = h->eg_clusters_seen; return 0; }
   if (std::string(name) == "status") {      // synchronising read-and-clear of the device status word (see fm_check_status)

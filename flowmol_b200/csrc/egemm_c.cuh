@@ -82,7 +82,44 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&v)[4])
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
 }
 
-template <class D, int MODE>
+// tcgen05.ld / st shapes with FOUR THREADS PER ROW (measured mapping, tools/gpu_tmem_shapes.py).  The address names the first of 16
+// lanes; thread T holds rows T / 4 and T / 4 + 8 of them.
+//   16x256b.xN: columns 8 n + 2 (T % 4) + {0, 1} of repeat n: registers 4 n + {0, 1} (row T / 4), 4 n + {2, 3} (row T / 4 + 8)
+//   16x128b.xN: column 4 n + T % 4 of repeat n: registers 2 n (row T / 4), 2 n + 1 (row T / 4 + 8)
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, float (&v)[16]) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
+                 "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, float (&v)[32]) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
+        "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]),
+        "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]),
+        "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st_16x128b_x4(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.16x128b.x4.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+
+// QL = 1 ("quad layout", option eu_quad): both epilogues work with FOUR THREADS PER ROW.  With one thread per row every 32-byte
+// access of a warp touches 32 different 128-byte lines and the kernel was bound by LSU wavefronts (65 % of peak, profiles/r02_summary).
+// The hidden features of linear 1 and the output features of linear 2 arrive PERMUTED (weights.py:quad_perm; packed entries
+// EUPD_TC1_HP / EUPD_TC2_HP): accumulator column 8 n + 2 t + c holds physical feature 32 (n / 4) + 8 t + 2 (n % 4) + c, so that the
+// thread T % 4 = t of a row's quad owns the 8 consecutive features 32 j + 8 t .. + 7 of every group j of 32.  Every global access
+// of the epilogues (EA[src], EB[dst], the residual, the fp32 rows, the 16-byte pieces of the operand images) is then one 32- or
+// 16-byte access per lane with the quad covering 128 (64) CONTIGUOUS bytes of the row: a warp instruction touches 8 rows.
+// h goes back to tensor memory IN PLACE with the 16x128b shape (packed k-pair column 4 n + t of its group of 32).
+template <class D, int MODE, int QL = 0>
 __global__ void __launch_bounds__(EgcPlan::THREADS, 1)
 k_egemm_c(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) {
   pdl_launch();
@@ -324,6 +361,82 @@ k_egemm_c(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&x_full[st])) : "memory");
       }
     }
+  } else if (QL && warp < PL::W_E2) {
+    // ---- epilogue 1, four threads per row: h = SiLU(D1 * unscale + EA[src] + EB[dst]) -> packed fp16 (hi | lo) in tensor memory ------------------
+    const int q = warp & 3, tq = lane & 3, rq = lane >> 2;
+    const float unscale = a.units[(size_t)NU1 * (TC_UNIT / 4)];
+    float omax = 0.f;
+    for (int it = 0; it < n_my; ++it) {
+      const int b = it & 1;
+      tc::mbar_wait(&rows_full[it % PL::NROWBUF], (it / PL::NROWBUF) & 1);
+      const uint8_t* rb = smem_dyn + PL::OFF_ROW + (it % PL::NROWBUF) * PL::ROWBYTES;
+      // this thread's four rows: (half, r8) -> row 32 q + 16 half + lane / 4 + 8 r8; EA[src] / EB[dst] at its 8 features of every group
+      const float *pa[2][2], *pb[2][2];
+#pragma unroll
+      for (int half = 0; half < 2; ++half)
+#pragma unroll
+        for (int r8 = 0; r8 < 2; ++r8) {
+          const int r = q * 32 + 16 * half + rq + 8 * r8;
+          const int sn = max(reinterpret_cast<const int*>(rb)[r], 0);
+          const int dn = sn + (int)reinterpret_cast<const short*>(rb + PL::T * 4)[r];
+          pa[half][r8] = a.P + (size_t)sn * 2 * F + 8 * tq;
+          pb[half][r8] = a.P + (size_t)dn * 2 * F + F + 8 * tq;
+        }
+      // step = (half, group j of 32 features): one 16x256b.x4 load, 2 rows x (EA, EB) x 32 bytes, one step of loads in flight ahead
+      float4 ca[2][2], cbv[2][2], na[2][2], nbv[2][2];
+      auto gather = [&](int step, float4 (&ea)[2][2], float4 (&eb)[2][2]) {
+        const int half = step >> 2, j = step & 3;
+#pragma unroll
+        for (int r8 = 0; r8 < 2; ++r8) {
+          ld_global_256(pa[half][r8] + 32 * j, ea[r8][0], ea[r8][1]);
+          ld_global_256(pb[half][r8] + 32 * j, eb[r8][0], eb[r8][1]);
+        }
+      };
+      gather(0, ca, cbv);
+      tc::mbar_wait(&d1_full[b], (it >> 1) & 1);
+      tc::tc_fence_after();
+#pragma unroll
+      for (int step = 0; step < 8; ++step) {
+        const int half = step >> 2, j = step & 3;
+        const uint32_t cbh = tmem + ((uint32_t)(q * 32 + 16 * half) << 16) + (uint32_t)(b * 256);
+        float acc[16];
+        tmem_ld_16x256b_x4(cbh + (uint32_t)(32 * j), acc);
+        if (step + 1 < 8) gather(step + 1, na, nbv);
+        tc::tmem_ld_wait();
+        uint32_t hw[8], lw[8];
+        if (!(a.dbg & 8)) {
+#pragma unroll
+          for (int r8 = 0; r8 < 2; ++r8) {
+            const float ea[8] = {ca[r8][0].x, ca[r8][0].y, ca[r8][0].z, ca[r8][0].w, ca[r8][1].x, ca[r8][1].y, ca[r8][1].z, ca[r8][1].w};
+            const float eb[8] = {cbv[r8][0].x, cbv[r8][0].y, cbv[r8][0].z, cbv[r8][0].w, cbv[r8][1].x, cbv[r8][1].y, cbv[r8][1].z, cbv[r8][1].w};
+#pragma unroll
+            for (int n4 = 0; n4 < 4; ++n4) {                    // repeat n4: accumulator columns 32 j + 8 n4 + 2 t + {0, 1} = features 32 j + 8 t + 2 n4 + {0, 1}
+              float o[2];
+#pragma unroll
+              for (int c = 0; c < 2; ++c) {
+                const float z = acc[4 * n4 + 2 * r8 + c] * unscale + __fadd_rn(ea[2 * n4 + c], eb[2 * n4 + c]);
+                o[c] = z * sigmoid_fast(z);
+                omax = fmaxf(omax, fabsf(o[c]));
+              }
+              tc::split_h16x2(o[0], o[1], hw[2 * n4 + r8], lw[2 * n4 + r8]);
+            }
+          }
+          // in place, as the one-thread-per-row epilogue: the 32 accumulator columns of group j become 16 columns of hi pairs and 16 of
+          // lo pairs (packed k-pair column 4 n4 + t of the group); every column of the group has been read by this step's load
+          tmem_st_16x128b_x4(cbh + (uint32_t)(32 * j), hw);
+          tmem_st_16x128b_x4(cbh + (uint32_t)(32 * j + 16), lw);
+        }
+#pragma unroll
+        for (int r8 = 0; r8 < 2; ++r8)
+#pragma unroll
+          for (int k = 0; k < 2; ++k) { ca[r8][k] = na[r8][k]; cbv[r8][k] = nbv[r8][k]; }
+      }
+      tmem_st_wait();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&a_ready[b])) : "memory");
+    }
+    if (!(omax < tc::ACT_LIMIT_H16) && a.status) atomicOr(a.status, 1);
   } else if (warp < PL::W_E2) {
     // ---- epilogue 1: h = SiLU(D1 * unscale + EA[src] + EB[dst]) -> fp16 (hi, lo) in place in tensor memory -------------------------------------
     const int q = warp & 3, row = q * 32 + lane;
@@ -400,6 +513,126 @@ k_egemm_c(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&a_ready[b])) : "memory");
+    }
+    if (!(omax < tc::ACT_LIMIT_H16) && a.status) atomicOr(a.status, 1);
+  } else if (QL) {
+    // ---- epilogue 2, four threads per row: warp (q, hf) owns output features [64 hf, 64 hf + 64) of rows [32 q, 32 q + 32); a thread
+    // holds 16 of them (its 8 features of both groups of 32) for each of its four rows -------------------------------------------------------------
+    const int q = warp & 3, hf = (warp - PL::W_E2) >> 2, tq = lane & 3, rq = lane >> 2;
+    const float unscale = a.g_units[(size_t)4 * (TC_UNIT / 4)];
+    float* xs = reinterpret_cast<float*>(smem_dyn + PL::OFF_XCH);
+    float* xq = xs + PL::NE2 * 32;
+    float omax = 0.f;
+    for (int it = 0; it < n_my; ++it) {
+      const int b = it & 1;
+      const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
+      if (q == 0 && hf == 0 && lane == 0 && it + 1 < n_my) prefetch_l2_bulk(a.in_s + (size_t)(tile + gridDim.x) * PL::T * F, PL::T * F * 4);
+      // row step rs = 2 half + r8 -> row 32 q + 16 half + lane / 4 + 8 r8; residual: 2 groups x 32 bytes per row step, two steps in flight
+      const size_t fo = (size_t)(hf * 64 + 8 * tq);              // this thread's first feature (group 0)
+      auto rowof = [&](int rs) { return q * 32 + 16 * (rs >> 1) + rq + 8 * (rs & 1); };
+      float4 rr[2][4];
+      auto resid = [&](int rs, float4 (&dst_)[4]) {
+        const float* rp = a.in_s + ((size_t)tile * PL::T + rowof(rs)) * F + fo;
+        ld_global_256_rw(rp, dst_[0], dst_[1]);
+        ld_global_256_rw(rp + 32, dst_[2], dst_[3]);
+      };
+      resid(0, rr[0]);
+      resid(1, rr[1]);
+      tc::mbar_wait(&d2_full[b], (it >> 1) & 1);
+      tc::tc_fence_after();
+      float y[2][32];                                          // [half][4 n + 2 r8 + c], n = 4 group + n4
+#pragma unroll
+      for (int half = 0; half < 2; ++half)
+        tmem_ld_16x256b_x8(tmem + ((uint32_t)(q * 32 + 16 * half) << 16) + (uint32_t)(b * 256 + 128 + hf * 64), y[half]);
+      tc::tmem_ld_wait();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&buf_empty[b])) : "memory");
+      float psum[4];
+#pragma unroll
+      for (int rs = 0; rs < 4; ++rs) {
+        const int half = rs >> 1, r8 = rs & 1;
+        const float4* rv = rr[rs & 1];
+        float sacc = 0.f;
+        if (!(a.dbg & 8)) {
+#pragma unroll
+          for (int gj = 0; gj < 2; ++gj) {
+            const float4 b0 = *reinterpret_cast<const float4*>(prm + fo + 32 * gj), b1 = *reinterpret_cast<const float4*>(prm + fo + 32 * gj + 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            const float rs8[8] = {rv[2 * gj].x, rv[2 * gj].y, rv[2 * gj].z, rv[2 * gj].w, rv[2 * gj + 1].x, rv[2 * gj + 1].y, rv[2 * gj + 1].z, rv[2 * gj + 1].w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {                       // feature fo + 32 gj + i = accumulator column 8 (4 gj + i / 2) + 2 t + i % 2
+              const int idx = 4 * (4 * gj + (i >> 1)) + 2 * r8 + (i & 1);
+              const float z = y[half][idx] * unscale + bb[i];
+              const float v = __fadd_rn(rs8[i], z * sigmoid_fast(z));
+              y[half][idx] = v;
+              sacc += v;
+            }
+          }
+        }
+        psum[rs] = sacc;
+        if (rs + 2 < 4) resid(rs + 2, rr[rs & 1]);
+      }
+      // LayerNorm statistics of a row: its quad (shuffles) x the two warps of the lane quarter (shared memory)
+      float mean[4], rstd[4];
+#pragma unroll
+      for (int rs = 0; rs < 4; ++rs) {
+        psum[rs] += __shfl_xor_sync(0xffffffffu, psum[rs], 1);
+        psum[rs] += __shfl_xor_sync(0xffffffffu, psum[rs], 2);
+        if (tq == 0) xs[(q * 2 + hf) * 32 + 16 * (rs >> 1) + rq + 8 * (rs & 1)] = psum[rs];
+      }
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+#pragma unroll
+      for (int rs = 0; rs < 4; ++rs) {
+        const float other = xs[(q * 2 + (hf ^ 1)) * 32 + 16 * (rs >> 1) + rq + 8 * (rs & 1)];
+        mean[rs] = (hf ? other + psum[rs] : psum[rs] + other) * (1.0f / 128.0f);
+        float sq = 0.f;
+#pragma unroll
+        for (int gj = 0; gj < 2; ++gj)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float dl = y[rs >> 1][4 * (4 * gj + (i >> 1)) + 2 * (rs & 1) + (i & 1)] - mean[rs];
+            sq += dl * dl;
+          }
+        sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+        sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+        psum[rs] = sq;
+        if (tq == 0) xq[(q * 2 + hf) * 32 + 16 * (rs >> 1) + rq + 8 * (rs & 1)] = sq;
+      }
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+#pragma unroll
+      for (int rs = 0; rs < 4; ++rs) {
+        const float other = xq[(q * 2 + (hf ^ 1)) * 32 + 16 * (rs >> 1) + rq + 8 * (rs & 1)];
+        rstd[rs] = rsqrtf((hf ? other + psum[rs] : psum[rs] + other) * (1.0f / 128.0f) + 1e-5f);
+      }
+      if (a.dbg & (8 | 32)) continue;
+#pragma unroll
+      for (int rs = 0; rs < 4; ++rs) {
+        const int r = rowof(rs);
+        float* op = a.out + ((size_t)tile * PL::T + r) * F + fo;
+        uint8_t* ib = reinterpret_cast<uint8_t*>(a.out_img) + ((size_t)tile * (F / 64) + hf) * PL::XSTAGE + (size_t)r * 128;
+#pragma unroll
+        for (int gj = 0; gj < 2; ++gj) {
+          const float4 g0 = *reinterpret_cast<const float4*>(prm + F + fo + 32 * gj), g1 = *reinterpret_cast<const float4*>(prm + F + fo + 32 * gj + 4);
+          const float4 t0 = *reinterpret_cast<const float4*>(prm + 2 * F + fo + 32 * gj), t1 = *reinterpret_cast<const float4*>(prm + 2 * F + fo + 32 * gj + 4);
+          const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, tt[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+          float o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            o[i] = (y[rs >> 1][4 * (4 * gj + (i >> 1)) + 2 * (rs & 1) + (i & 1)] - mean[rs]) * rstd[rs] * gg[i] + tt[i];
+            omax = fmaxf(omax, fabsf(o[i]));
+          }
+          st_global_256(op + 32 * gj, make_uint4(__float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3])),
+                        make_uint4(__float_as_uint(o[4]), __float_as_uint(o[5]), __float_as_uint(o[6]), __float_as_uint(o[7])));
+          uint32_t h4[4], l4[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc::split_h16x2(o[2 * k], o[2 * k + 1], h4[k], l4[k]);
+          // features 32 gj + 8 t .. + 7 of k-slab hf = its 16-byte piece 4 gj + t
+          uint8_t* pp = ib + ((((uint32_t)(4 * gj + tq)) ^ (uint32_t)(r & 7)) << 4);
+          *reinterpret_cast<uint4*>(pp) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+          *reinterpret_cast<uint4*>(pp + LO_OFF) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
+        }
+      }
     }
     if (!(omax < tc::ACT_LIMIT_H16) && a.status) atomicOr(a.status, 1);
   } else {

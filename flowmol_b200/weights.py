@@ -354,6 +354,15 @@ def feature_perm(n):
     return c32 + 8 * t + 2 * nn + c
 
 
+def quad_perm(n):
+    """perm[L] = physical feature held by accumulator column L when an epilogue reads tensor memory with the 16x256b shape (thread t of
+    a row's quad: columns 8 n + 2 t + c): 32 (n // 4) + 8 t + 2 (n % 4) + c -- the thread then owns 8 CONSECUTIVE features of every
+    group of 32 (csrc/egemm_c.cuh, QL)."""
+    L = np.arange(n)
+    nn, t, c = L // 8, (L % 8) // 2, L % 2
+    return 32 * (nn // 4) + 8 * t + 2 * (nn % 4) + c
+
+
 def _pack_gvp(P, base, sd, p, w_rows=None):
     """GVP under state_dict prefix `p` -> 6 consecutive entries starting at id `base`.
     [Wh | Wcp] are fused into one operand (they multiply the same input); `w_rows` selects/reorders the rows of the
@@ -471,7 +480,11 @@ def pack(cfg: ModelConfig, sd):
         P.vec(c("EUPD_LN_W"), _np(sd, p + ".edge_norm.weight")); P.vec(c("EUPD_LN_B"), _np(sd, p + ".edge_norm.bias"))
         if F == 128 and S % 128 == 0 and V <= 32:        # tensor-core images of the two EdgeUpdate linears (features on M)
             P.tc(c("EUPD_TC1"), c("EUPD_TC1_H"), w1[2 * S:].T, 128)                                  # [F, F + R], k order ef | d
-            P.tc(c("EUPD_TC2"), c("EUPD_TC2_H"), _np(sd, p + ".edge_update_fn.2.weight"), 128)       # [F, F]
+            w2 = _np(sd, p + ".edge_update_fn.2.weight")
+            P.tc(c("EUPD_TC2"), c("EUPD_TC2_H"), w2, 128)                                            # [F, F]
+            qp = quad_perm(F)
+            P.raw(c("EUPD_TC1_HP"), tc_units_h16(w1[2 * S:].T[qp, :], 128))                          # hidden features permuted
+            P.raw(c("EUPD_TC2_HP"), tc_units_h16(w2[qp, :][:, qp], 128))                             # k = permuted hidden, rows = permuted outputs
         if S % 128 == 0 and V <= 32 and 2 * F == S:
             for i in range(3):
                 q = f"node_position_updaters.{u}.gvps.{i}"

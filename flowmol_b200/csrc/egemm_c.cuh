@@ -338,6 +338,7 @@ k_egemm_c(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
         if (it + 1 < n_my) rowinfo(it + 1);
         // rbf(d): k values [0, 32) of the last k-slab; a load-free chunk: lanes 8 g .. 8 g + 7 cover the 32 centres of row 4 i + g
         uint8_t* hi = xst + st * PL::XSTAGE;
+        if (!(a.dbg & 512))
 #pragma unroll
         for (int k = 0; k < RPL; ++k) {
 #pragma unroll
@@ -392,6 +393,17 @@ k_egemm_c(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
           ld_global_256(pb[half][r8] + 32 * j, eb[r8][0], eb[r8][1]);
         }
       };
+      if (a.dbg & 128) {                                       // knock-out: barrier protocol only
+        tc::mbar_wait(&d1_full[b], (it >> 1) & 1);
+        tc::tc_fence_after();
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&a_ready[b])) : "memory");
+        continue;
+      }
+      // (Measured and dropped, profiles/r02_kprof_e1ring.txt: EB[dst] from the per-warp staging buffer of the one-thread-per-row path and
+      // the EA ring two steps deep -- this role alone is bound by the L2 round trip of its gathers, 362 us per launch in the knock-out
+      // timings, but with all roles running the change was neutral to slightly slower.)
       gather(0, ca, cbv);
       tc::mbar_wait(&d1_full[b], (it >> 1) & 1);
       tc::tc_fence_after();
@@ -536,6 +548,14 @@ k_egemm_c(const ModelRT m, const BatchRT bt, const EgArgs a, const int n_tiles) 
         ld_global_256_rw(rp, dst_[0], dst_[1]);
         ld_global_256_rw(rp + 32, dst_[2], dst_[3]);
       };
+      if (a.dbg & 256) {                                       // knock-out: barrier protocol only
+        tc::mbar_wait(&d2_full[b], (it >> 1) & 1);
+        tc::tc_fence_after();
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&buf_empty[b])) : "memory");
+        continue;
+      }
       resid(0, rr[0]);
       resid(1, rr[1]);
       tc::mbar_wait(&d2_full[b], (it >> 1) & 1);

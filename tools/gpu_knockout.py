@@ -2,7 +2,8 @@
 time (results are garbage, the barrier protocol is intact) and the in-situ per-launch times show which role paces the kernel.
     python tools/gpu_knockout.py
 bits: 1 no weight copies, 2 no main MMAs, 4 no activation-image copies, 8 no epilogue math / stores, 16 no gate MMAs,
-      32 no global stores of images / gates, 64 no segment sums"""
+      32 no global stores of images / gates, 64 no segment sums; k_egemm_c only: 128 epilogue 1 idle (barrier protocol only),
+      256 epilogue 2 idle, 512 no rbf conversion in the loader warps"""
 import os, sys, warnings
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

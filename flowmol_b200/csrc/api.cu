@@ -129,6 +129,8 @@ struct FmHandle {
   int eg_cluster = 1;          // k_egemm_p on edge rows: CTAs per thread-block cluster sharing one multicast weight stream (1, 2, 4)
   int eg_clusters_seen = 0;    // cudaOccupancyMaxActiveClusters of the last cluster kernel configured (diagnostics)
   int eu_quad = 1;             // k_egemm_c with four threads per row in the epilogues (permuted features)
+  int nemb_tc = 1;             // k_node_embed: its five 256-wide linears on mma.sync fp16x3 (tile_gemm_h16) in the fp16x3 tensor-core pipeline
+  int nemb_ok = 0;             // ... the five weight matrices fit the fixed 2^10 scale (checked at fm_create)
   int eg_perm = 1;             // k_egemm_h<MSG> with permuted output features: image stores re-read from tensor memory (16-byte pieces)
   int eg_epi12 = 1;            // gate-fused edge-row linears with twelve epilogue warps (k_egemm_h; needs sh_img)
   int sh_img = 1;              // norms of message GVPs 1 / 2 as operand images: every k-slab of k_egemm_g is a bulk copy
@@ -170,6 +172,8 @@ template <class D>
 int set_smem_attrs() {
   const int bytes = (int)D::SMEM_BYTES;
   CUDA_OK(cudaFuncSetAttribute(fm::k_node_embed<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  if constexpr (D::S == 256)
+    CUDA_OK(cudaFuncSetAttribute(fm::k_node_embed<D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::NodeEmbedMmaSmem<D>::BYTES));
   CUDA_OK(cudaFuncSetAttribute(fm::k_edge_init<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fm::EdgeSmem<D>::BYTES));
   CUDA_OK(cudaFuncSetAttribute(fm::k_conv_edge<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   CUDA_OK(cudaFuncSetAttribute(fm::k_node_update<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -549,7 +553,14 @@ int run_pass(FmHandle* h, void* ws, const Layout& L, const float* x_t, const uin
   float *s = at<float>(ws, L.s), *v = at<float>(ws, L.v), *x = at<float>(ws, L.x), *P = at<float>(ws, L.P);
   float *Q = at<float>(ws, L.Q), *vd = at<float>(ws, L.vd), *EAB = at<float>(ws, L.EAB), *M = at<float>(ws, L.M);
   float *partF = at<float>(ws, L.partF), *partL = at<float>(ws, L.partL), *ef = at<float>(ws, L.ef);
-  launch_k(h, fm::k_node_embed<D>, L.nNT, fm::NT, smem, st, m, bt, x_t, a_t, c_t, t, prev, has_prev, s, v, P);
+  bool embed_done = false;
+  if constexpr (D::S == 256) {
+    if (h->nemb_tc && h->nemb_ok && h->conv_impl == 2 && h->tc_prec == 1) {
+      launch_k(h, fm::k_node_embed<D, 1>, L.nNT, fm::NT, fm::NodeEmbedMmaSmem<D>::BYTES, st, m, bt, x_t, a_t, c_t, t, prev, has_prev, s, v, P, h->d_status);
+      embed_done = true;
+    }
+  }
+  if (!embed_done) launch_k(h, fm::k_node_embed<D>, L.nNT, fm::NT, smem, st, m, bt, x_t, a_t, c_t, t, prev, has_prev, s, v, P, (int*)nullptr);
   LAUNCH_OK(h);
   if (m.use_dst) { launch_k(h, fm::k_dst_proj<D>, L.nNT, fm::NT, smem, st, m, bt, 0, s, v, Q, vd); LAUNCH_OK(h); }
   bool edge_done = false;
@@ -770,6 +781,19 @@ int fm_create(const FmConfig* cfg, const float* w_host, size_t n_floats, const i
     return fail("fm_create: packed fp16 images were built for a different activation scale (weights.py vs csrc/tc.cuh)");
   }
   h->tc_prec = h->has_h16 ? 1 : 0;       // default: fp16x3 (same 22 significand bits as 3xTF32 at twice the MMA rate)
+  if (variant == 0) {                    // k_node_embed on mma.sync: fixed weight scale 2^10, every |w| of its five matrices must stay small
+    const int S = c.n_hidden_scalars, Ksc = ((S + c.n_atom_types + c.n_charges + c.rbf_dim + 3) / 4) * 4;
+    const int64_t ids[5] = {fm::G_SEMB0_W, fm::G_SEMB2_W, fm::G_SCN0_W, fm::G_SCN2_W, fm::G_COUNT + fm::C_WSRC};
+    const int64_t rows[5] = {2 * c.token_dim + c.time_embedding_dim, S, Ksc, S, S};
+    bool ok = true;
+    for (int i = 0; i < 5 && ok; ++i) {
+      const int64_t o = off_host[ids[i]];
+      if (o < 0) { ok = ok && (i == 2 || i == 3) && !c.self_conditioning; continue; }      // no self-conditioning: its MLP is absent
+      if (o + rows[i] * S > (int64_t)n_floats) { ok = false; break; }
+      for (int64_t k = 0; k < rows[i] * S; ++k) ok = ok && std::fabs(w_host[o + k]) < fm::NE_WMAX;
+    }
+    h->nemb_ok = ok ? 1 : 0;
+  }
   h->eg_nh = 1;
   h->dyn = Dyn{c.n_hidden_scalars, c.n_vec_channels, c.n_hidden_edge_feats, c.use_dst_feats ? c.s_dst : 0,
                c.use_dst_feats ? c.v_dst : 0, c.n_atom_types, c.n_charges, c.n_bond_types,
@@ -1155,6 +1179,7 @@ int fm_set_option(FmHandle* h, const char* name, int32_t value) {
   if (n == "eg_epi12") { h->eg_epi12 = value ? 1 : 0; return 0; }
   if (n == "eg_perm") { h->eg_perm = value ? 1 : 0; return 0; }
   if (n == "eu_quad") { h->eu_quad = value ? 1 : 0; return 0; }
+  if (n == "node_embed_tc") { h->nemb_tc = value ? 1 : 0; return 0; }
   if (n == "eg_cluster") {
     if (value != 1 && value != 2 && value != 4) return fail("fm_set_option: eg_cluster must be 1, 2 or 4");
     h->eg_cluster = value;
@@ -1227,6 +1252,7 @@ int fm_get_option(FmHandle* h, const char* name, int32_t* value) {
   if (std::string(name) == "eg_epi12") { *value = h->eg_epi12; return 0; }
   if (std::string(name) == "eg_perm") { *value = h->eg_perm; return 0; }
   if (std::string(name) == "eu_quad") { *value = h->eu_quad; return 0; }
+  if (std::string(name) == "node_embed_tc") { *value = h->nemb_tc && h->nemb_ok; return 0; }
   if (std::string(name) == "eg_cluster") { *value = h->eg_cluster; return 0; }
   if (std::string(name) == "eg_clusters_seen") { *value = h->eg_clusters_seen; return 0; }
   if (std::string(name) == "status") {      // synchronising read-and-clear of the device status word (see fm_check_status)

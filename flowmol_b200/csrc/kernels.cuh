@@ -15,6 +15,7 @@
 //   k_node_head / k_edge_head / k_com   output heads, softmax, COM removal (vector_field.py:336-367)
 #pragma once
 #include "gvp.cuh"
+#include "mma3.cuh"
 
 namespace fm {
 
@@ -90,22 +91,172 @@ __device__ __forceinline__ float pair_dist(const float* __restrict__ x, int a, i
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// tile_gemm_h16: the 64-row tile GEMM of tile_gemm.cuh, C = Xs[64][K] W[K][256], on mma.sync.m16n8k16 with the error-compensated
+// fp16 (hi, lo) operands of mma3.cuh (a_lo b_hi + a_hi b_lo + a_hi b_hi, fp32 accumulate) -- for k_node_embed, whose five
+// 256-wide linears were 0.62 ms of fp32 FFMA per evaluation (profiles/r02_kprof_last.txt).  The weights stay fp32 in global
+// memory: every CTA converts them on the fly, 32 k rows per chunk, into packed (k, k + 1) half2 words (double-buffered: the next
+// chunk's global loads are in flight during this chunk's MMAs).  Fixed power-of-two weight scale 2^10: lo parts are exact to
+// 2^-35 absolute, |w| must stay below 64 (fm_create checks the five matrices and keeps the fp32 path otherwise).
+// Warp w owns output columns [32 w, 32 w + 32) of all 64 rows (4 x 4 accumulator tiles); the result goes through shared memory
+// (Ys) into the caller's row-per-warp register layout (ColMap), so the epilogues are those of the fp32 path.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int NE_LDW = 264;                 // words per k-pair row of the converted weights (256 + 8: conflict-free B fragments)
+constexpr int NE_LDY = 264;                 // floats per row of the result tile
+constexpr int NE_WBUF = 2 * 16 * NE_LDW;    // one chunk: 16 k-pair rows of hi words | 16 of lo words
+constexpr float NE_WSCALE = 1024.0f;
+constexpr float NE_WMAX = 32.0f;            // fm_create: largest |w| the mma path accepts
+
+// not volatile: a pure function of its operands, ptxas may interleave it with the splits and loads around it
+__device__ __forceinline__ void ne_mma16(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// amax: running max |a| over the activation values this thread split into fp16 (hi, lo) -- the caller reports >= 65504 through the
+// status word like every other fp16x3 kernel (an overflowing hi part would turn into inf - inf = NaN inside the products)
+template <int S>
+__device__ __forceinline__ void tile_gemm_h16(const float* __restrict__ Xs, int lda, int K, const float* __restrict__ Wg,
+                                              uint32_t* __restrict__ wbuf, float* __restrict__ Ys, float (&acc)[1][RPW][S / 32],
+                                              float& amax) {
+  static_assert(S == 256 && NT == 256 && TM == 64, "8 warps x 32 columns, 4 m16 tiles");
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int n0 = warp * 32;
+  float c[4][4][4];
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) c[mt][nt][i] = 0.f;
+  // the next chunk's weights are fetched in two halves (k pairs 0-7 during k-step 0, 8-15 during k-step 1): 16 registers in flight
+  float4 wr[2][2];
+  auto wload = [&](int ch, int half) {       // item = (k pair, 4 columns): rows k, k + 1 of the chunk
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int item = tid + NT * (2 * half + j), kp = item >> 6, n4 = item & 63, k = ch * 32 + 2 * kp;
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      wr[j][0] = k < K ? __ldg(reinterpret_cast<const float4*>(Wg + (size_t)k * S) + n4) : z;
+      wr[j][1] = k + 1 < K ? __ldg(reinterpret_cast<const float4*>(Wg + (size_t)(k + 1) * S) + n4) : z;
+    }
+  };
+  auto wstore = [&](int buf, int half) {
+    uint32_t* hi = wbuf + buf * NE_WBUF;
+    uint32_t* lo = hi + 16 * NE_LDW;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int item = tid + NT * (2 * half + j), kp = item >> 6, n4 = item & 63;
+      uint4 h4, l4;
+      tc::split_h16x2(wr[j][0].x * NE_WSCALE, wr[j][1].x * NE_WSCALE, h4.x, l4.x);
+      tc::split_h16x2(wr[j][0].y * NE_WSCALE, wr[j][1].y * NE_WSCALE, h4.y, l4.y);
+      tc::split_h16x2(wr[j][0].z * NE_WSCALE, wr[j][1].z * NE_WSCALE, h4.z, l4.z);
+      tc::split_h16x2(wr[j][0].w * NE_WSCALE, wr[j][1].w * NE_WSCALE, h4.w, l4.w);
+      *reinterpret_cast<uint4*>(hi + kp * NE_LDW + 4 * n4) = h4;
+      *reinterpret_cast<uint4*>(lo + kp * NE_LDW + 4 * n4) = l4;
+    }
+  };
+  const int nch = (K + 31) / 32;
+  __syncthreads();                           // the A tile is complete; Ys / wbuf of a previous call have been read
+  wload(0, 0); wstore(0, 0);
+  wload(0, 1); wstore(0, 1);
+  __syncthreads();
+  for (int ch = 0; ch < nch; ++ch) {
+    const uint32_t* hi = wbuf + (ch & 1) * NE_WBUF;
+    const uint32_t* lo = hi + 16 * NE_LDW;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const int k0 = ch * 32 + 16 * ks;
+      if (ch + 1 < nch) wload(ch + 1, ks);
+      if (k0 < K) {
+        uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int w = (8 * ks + t + 4 * i) * NE_LDW + n0 + 8 * nt + g;
+            bh[nt][i] = hi[w]; bl[nt][i] = lo[w];
+          }
+        uint32_t ah[4][4], al[4][4];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {      // a0 (g, 2t)  a1 (g + 8, 2t)  a2 (g, 2t + 8)  a3 (g + 8, 2t + 8)
+            const int col = k0 + 2 * t + (i >> 1) * 8;
+            float2 v = make_float2(0.f, 0.f);
+            if (col < K) v = *reinterpret_cast<const float2*>(Xs + (16 * mt + g + (i & 1) * 8) * lda + col);
+            amax = fmaxf(amax, fmaxf(fabsf(v.x), fabsf(v.y)));
+            tc::split_h16x2(v.x, v.y, ah[mt][i], al[mt][i]);
+          }
+        // the three products of an accumulator are 16 instructions apart (same order per accumulator as mma3.cuh: a_lo b_hi, a_hi b_lo, a_hi b_hi)
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) ne_mma16(c[mt][nt], al[mt], bh[nt]);
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) ne_mma16(c[mt][nt], ah[mt], bl[nt]);
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) ne_mma16(c[mt][nt], ah[mt], bh[nt]);
+      }
+      if (ch + 1 < nch) wstore((ch + 1) & 1, ks);
+    }
+    __syncthreads();
+  }
+  constexpr float inv = 1.0f / NE_WSCALE;
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      float* yp = Ys + (16 * mt + g) * NE_LDY + n0 + 8 * nt + 2 * t;
+      *reinterpret_cast<float2*>(yp) = make_float2(c[mt][nt][0] * inv, c[mt][nt][1] * inv);
+      *reinterpret_cast<float2*>(yp + 8 * NE_LDY) = make_float2(c[mt][nt][2] * inv, c[mt][nt][3] * inv);
+    }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    const float* yr = Ys + (warp * RPW + r) * NE_LDY + lane * 4;
+    const float4 y0 = *reinterpret_cast<const float4*>(yr), y1 = *reinterpret_cast<const float4*>(yr + 128);
+    acc[0][r][0] = y0.x; acc[0][r][1] = y0.y; acc[0][r][2] = y0.z; acc[0][r][3] = y0.w;
+    acc[0][r][4] = y1.x; acc[0][r][5] = y1.y; acc[0][r][6] = y1.z; acc[0][r][7] = y1.w;
+  }
+}
+
+template <class D>
+struct NodeEmbedMmaSmem {                    // Xs | Ys | converted weight chunks (the fp32 path's vector planes / weight stage are unused)
+  static constexpr size_t BYTES = ((size_t)D::SM_XS + (size_t)TM * NE_LDY + 2 * NE_WBUF) * 4;
+  static_assert(BYTES <= 232448, "227 KB of shared memory per CTA");
+};
+
+// ------------------------------------------------------------------------------------------------------------------
 // k_node_embed
 // ------------------------------------------------------------------------------------------------------------------
 struct PredPtr {            // predicted endpoint ("dst_dict"): x [N,3], a [N,A], c [N,C], e [U,EB]   (device pointers)
   float *x, *a, *c, *e;
 };
 
-template <class D>
+// MMA = 1 (option node_embed_tc, S = 256): the five linears on mma.sync fp16x3 (tile_gemm_h16) instead of fp32 FFMA
+template <class D, int MMA = 0>
 __global__ void __launch_bounds__(NT, 1)
 k_node_embed(const ModelRT m, const BatchRT bt, const float* __restrict__ x_t, const uint8_t* __restrict__ a_t,
              const uint8_t* __restrict__ c_t, float t, const PredPtr prev, int has_prev,
-             float* __restrict__ s_out, float* __restrict__ v_out, float* __restrict__ P0) {
+             float* __restrict__ s_out, float* __restrict__ v_out, float* __restrict__ P0, int* __restrict__ status) {
   pdl_launch();
   pdl_wait();
   extern __shared__ __align__(16) float smem_raw[];
   Smem<D> sm(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float amax = 0.f;
+  auto gemm = [&](const float* __restrict__ W, int K, float (&out)[1][RPW][D::CPT_S]) {
+    if constexpr (MMA) {
+      float* Ys = smem_raw + D::SM_XS;
+      tile_gemm_h16<D::S>(sm.Xs, D::XLD, K, W, reinterpret_cast<uint32_t*>(Ys + TM * NE_LDY), Ys, out, amax);
+    } else {
+      tile_gemm<1, D::CPT_S>(sm.Xs, D::XLD, 0, K, W, sm.wstage, out);
+    }
+  };
   const int g0 = blockIdx.x * TM;
   // [Emb_a | Emb_c | time embedding]                                             (vector_field.py:232-243)
   const float* ea = m.g(G_EMB_A);
@@ -127,7 +278,7 @@ k_node_embed(const ModelRT m, const BatchRT bt, const float* __restrict__ x_t, c
     sm.Xs[row * D::XLD + c] = v;
   }
   float acc[1][RPW][D::CPT_S];
-  tile_gemm<1, D::CPT_S>(sm.Xs, D::XLD, 0, K0, m.g(G_SEMB0_W), sm.wstage, acc);
+  gemm(m.g(G_SEMB0_W), K0, acc);
   {
     const float* b = m.g(G_SEMB0_B);
 #pragma unroll
@@ -138,7 +289,7 @@ k_node_embed(const ModelRT m, const BatchRT bt, const float* __restrict__ x_t, c
         sm.Xs[(warp * RPW + r) * D::XLD + col] = silu_f(acc[0][r][c] + b[col]);
       }
   }
-  tile_gemm<1, D::CPT_S>(sm.Xs, D::XLD, 0, D::S, m.g(G_SEMB2_W), sm.wstage, acc);
+  gemm(m.g(G_SEMB2_W), D::S, acc);
   {
     const float* b = m.g(G_SEMB2_B);
 #pragma unroll
@@ -154,7 +305,13 @@ k_node_embed(const ModelRT m, const BatchRT bt, const float* __restrict__ x_t, c
 #pragma unroll
     for (int r = 0; r < RPW; ++r)
 #pragma unroll
-      for (int c = 0; c < D::CPT_S; ++c) sm.Xs[(warp * RPW + r) * D::XLD + ColMap<D::CPT_S>::col(lane, c)] = acc[0][r][c];
+      for (int c = 0; c < D::CPT_S; ++c) {
+        const int col = ColMap<D::CPT_S>::col(lane, c);
+        sm.Xs[(warp * RPW + r) * D::XLD + col] = acc[0][r][c];
+        // MMA: the 64 values of s are parked in s_out across the two linears (the mma path needs the registers: with them live the
+        // prefetched weight chunk was spilled, i.e. waited for, ahead of every MMA phase)
+        if (MMA && g0 + warp * RPW + r < bt.N) s_out[(size_t)(g0 + warp * RPW + r) * D::S + col] = acc[0][r][c];
+      }
     const float* mu = m.g(G_RBF_MU);
     const float sigma = m.rbf_dmax / (float)D::R;
     const int extra = KP - D::S;
@@ -173,7 +330,7 @@ k_node_embed(const ModelRT m, const BatchRT bt, const float* __restrict__ x_t, c
       sm.Xs[row * D::XLD + D::S + c] = v;
     }
     float acc2[1][RPW][D::CPT_S];
-    tile_gemm<1, D::CPT_S>(sm.Xs, D::XLD, 0, KP, m.g(G_SCN0_W), sm.wstage, acc2);
+    gemm(m.g(G_SCN0_W), KP, acc2);
     {
       const float* b = m.g(G_SCN0_B);
 #pragma unroll
@@ -184,14 +341,19 @@ k_node_embed(const ModelRT m, const BatchRT bt, const float* __restrict__ x_t, c
           sm.Xs[(warp * RPW + r) * D::XLD + col] = silu_f(acc2[0][r][c] + b[col]);
         }
     }
-    tile_gemm<1, D::CPT_S>(sm.Xs, D::XLD, 0, D::S, m.g(G_SCN2_W), sm.wstage, acc2);
+    gemm(m.g(G_SCN2_W), D::S, acc2);
     {
       const float* b = m.g(G_SCN2_B);
 #pragma unroll
       for (int r = 0; r < RPW; ++r)
 #pragma unroll
         for (int c = 0; c < D::CPT_S; ++c)
-          acc[0][r][c] = __fadd_rn(acc[0][r][c], silu_f(acc2[0][r][c] + b[ColMap<D::CPT_S>::col(lane, c)]));
+        {
+          const int col = ColMap<D::CPT_S>::col(lane, c);
+          float sv = acc[0][r][c];
+          if constexpr (MMA) sv = g0 + warp * RPW + r < bt.N ? s_out[(size_t)(g0 + warp * RPW + r) * D::S + col] : 0.f;
+          acc[0][r][c] = __fadd_rn(sv, silu_f(acc2[0][r][c] + b[col]));
+        }
     }
   }
   // store s, zero v (vector_field.py:251), and the per-node half of conv 0's first message linear
@@ -209,7 +371,7 @@ k_node_embed(const ModelRT m, const BatchRT bt, const float* __restrict__ x_t, c
     const int row = idx / (3 * D::V), g = g0 + row;
     if (g < bt.N) v_out[(size_t)g * 3 * D::V + (idx - row * 3 * D::V)] = 0.f;
   }
-  tile_gemm<1, D::CPT_S>(sm.Xs, D::XLD, 0, D::S, m.c(0, C_WSRC), sm.wstage, acc);
+  gemm(m.c(0, C_WSRC), D::S, acc);
   {
     const float* b = m.c(0, C_BSRC);
 #pragma unroll
@@ -223,6 +385,7 @@ k_node_embed(const ModelRT m, const BatchRT bt, const float* __restrict__ x_t, c
         }
     }
   }
+  if (MMA && !(amax < tc::ACT_LIMIT_H16) && status) atomicOr(status, 1);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

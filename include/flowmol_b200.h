@@ -174,6 +174,8 @@ int fm_time_egemm_msg(FmHandle* h, void* workspace, int32_t layer, int32_t iters
  *          warps (bit-identical to k_egemm_g); "eg_perm" = 1 (default): k_egemm_h<MSG> with permuted output features (image stores
  *          from tensor memory, 16 bytes per lane); "eu_quad" = 1 (default): k_egemm_c with four threads per row in both epilogues
  *          (tcgen05.ld 16x256b / st 16x128b, permuted hidden / output features; 0: one / two threads per row, agrees to 1e-6);
+ *          "node_embed_tc" = 1 (default): the five 256-wide linears of k_node_embed on mma.sync fp16x3 instead of fp32 FFMA (active in
+ *          the fp16x3 pipeline when every |w| of those matrices is below 32; fm_get_option reports whether it is in effect);
  *          fm_get_option(h, "status", &v) synchronises the device and reads-and-clears the status word: bit 0 = an activation
  *          left the fp16 operand range since the last read (results invalid; switch to tc_prec 0).  fm_sample_host checks it. */
 int fm_set_option(FmHandle* h, const char* name, int32_t value);

@@ -358,3 +358,66 @@ def test_cli_prior_is_drawn_once_per_batch_and_sliced_per_rank():
         assert (pr['a_0'].argmax(-1) == 6).all() and (pr['e_0'].argmax(-1) == 4).all() and pr['fake_atoms'] is True
         parts.append(pr['x_0'])
     assert torch.equal(torch.cat(parts), x0)
+
+
+def test_permuted_feature_layouts_match_the_epilogue_index_algebra():
+    """weights.quad_perm / feature_perm (packed entries EUPD_TC1_HP / EUPD_TC2_HP, MSG1_TCW_HP / MSG1_TCG_HP / MSG1_BP) against the
+    register <-> accumulator-column maps of the tcgen05.ld / st shapes the epilogues use (csrc/egemm_c.cuh QL, csrc/egemm_h.cuh PERM;
+    the maps themselves were measured on the GPU: tools/gpu_tmem_shapes.py)."""
+    qp, fp = WT.quad_perm(128), WT.feature_perm(256)
+    assert sorted(qp) == list(range(128)) and sorted(fp) == list(range(256))
+    # 16x256b.x4 load of column group j: thread t of a row's quad receives accumulator columns 32 j + 8 n + 2 t + c (n < 4, c < 2) -- under
+    # quad_perm these are 8 CONSECUTIVE features, the 32 bytes of EA[src] / EB[dst] / the residual row the thread fetches with one load
+    for j in range(4):
+        for t in range(4):
+            cols = [32 * j + 8 * n + 2 * t + c for n in range(4) for c in range(2)]
+            assert [int(qp[L]) for L in cols] == list(range(32 * j + 8 * t, 32 * j + 8 * t + 8))
+    # epilogue 2: warp half hf, group gj, register i of thread t = accumulator column 64 hf + 8 (4 gj + i // 2) + 2 t + i % 2 is stored
+    # to feature 64 hf + 32 gj + 8 t + i (fp32 row) = fp16 elements of 16-byte piece 4 gj + t of k-slab hf (operand image)
+    for hf in range(2):
+        for gj in range(2):
+            for t in range(4):
+                for i in range(8):
+                    M = 64 * hf + 8 * (4 * gj + i // 2) + 2 * t + i % 2
+                    f = 64 * hf + 32 * gj + 8 * t + i
+                    assert int(qp[M]) == f and (f % 64) // 8 == 4 * gj + t
+    # k_egemm_h<MSG, PERM>: the packed (hi | lo) words of a 32-feature chunk are re-read with 16x128b.x4 -- thread t receives word
+    # 4 n + t (n < 4) = accumulator columns 8 n + 2 t, 8 n + 2 t + 1 -- and must hold the physical fp16 pairs 4 t .. 4 t + 3 in order
+    for chunk in range(8):
+        for t in range(4):
+            feats = [int(fp[32 * chunk + 2 * (4 * n + t) + c]) for n in range(4) for c in range(2)]
+            assert feats == list(range(32 * chunk + 8 * t, 32 * chunk + 8 * t + 8))
+    # the algebra the packed entries rely on: permuting the hidden features of linear 1 and BOTH sides of linear 2 yields the permuted output
+    rng = np.random.default_rng(3)
+    W1, W2 = rng.standard_normal((128, 160)), rng.standard_normal((128, 128))
+    x, ea, b2 = rng.standard_normal(160), rng.standard_normal(128), rng.standard_normal(128)
+    silu = lambda z: z / (1.0 + np.exp(-z))
+    y = W2 @ silu(W1 @ x + ea) + b2
+    h_log = silu(W1[qp] @ x + ea[qp])                       # accumulator column L holds hidden feature qp[L]; the thread adds EA at qp[L]
+    y_log = W2[qp][:, qp] @ h_log + b2[qp]                  # k order of linear 2 = logical hidden order (in-place write-back), rows permuted
+    assert np.allclose(y_log, y[qp], rtol=1e-12, atol=1e-12)
+    # message GVP 1: permuted output features, the gate linear contracts over them in the permuted k order
+    Wm, Wg, bm = rng.standard_normal((256, 292)), rng.standard_normal((32, 256)), rng.standard_normal(256)
+    xm = rng.standard_normal(292)
+    s1 = silu(Wm @ xm + bm)
+    s1_log = silu(Wm[fp] @ xm + bm[fp])
+    assert np.allclose(s1_log, s1[fp]) and np.allclose(Wg[:, fp] @ s1_log, Wg @ s1)
+
+
+def test_packer_builds_the_permuted_entries_from_the_natural_ones():
+    """The permuted twins the default kernels read are the natural entries with rows / k columns permuted: same unit builder, same
+    scale rule (checked on the bias vector and on the first hi unit of the EdgeUpdate linears)."""
+    cfg = ModelConfig.named("flowmol3", 11)
+    sd = WT.init_state_dict(cfg, 5)
+    blob, off = WT.pack(cfg, sd)
+    fp, qp = WT.feature_perm(256), WT.quad_perm(128)
+    b = sd["conv_layers.2.edge_message.1.to_feats_out.0.bias"].numpy()
+    o = off[WL.cid(2, "MSG1_BP")]
+    assert o >= 0 and np.array_equal(blob[o:o + 256], b[fp])
+    S, F = cfg.n_hidden_scalars, cfg.n_hidden_edge_feats
+    w1 = sd["edge_updaters.0.edge_update_fn.0.weight"].numpy().T         # [in, out]
+    w2 = sd["edge_updaters.0.edge_update_fn.2.weight"].numpy()           # [out, in]
+    for name, w in (("EUPD_TC1_HP", w1[2 * S:].T[qp, :]), ("EUPD_TC2_HP", w2[qp, :][:, qp])):
+        want = WT.tc_units_h16(w, 128)
+        o = off[WL.uid(cfg.n_convs, 0, name)]
+        assert o >= 0 and np.array_equal(blob[o:o + want.size].view(np.uint32), want.view(np.uint32)), name

@@ -421,3 +421,56 @@ def test_packer_builds_the_permuted_entries_from_the_natural_ones():
         want = WT.tc_units_h16(w, 128)
         o = off[WL.uid(cfg.n_convs, 0, name)]
         assert o >= 0 and np.array_equal(blob[o:o + want.size].view(np.uint32), want.view(np.uint32)), name
+
+
+def test_node_embed_mma_tile_gemm_index_algebra_emulated():
+    """csrc/kernels.cuh:tile_gemm_h16 in numpy: weight chunks as packed (k, k + 1) half2 words [16 k pairs][264], the m16n8k16 fragment
+    ownership (A: rows g / g + 8, k 2t / 2t + 8; B: k pairs t / t + 4, column g; C: rows g / g + 8, columns 2t, 2t + 1), warp w = output
+    columns [32 w, 32 w + 32), the result tile Ys [64][264] and its read-back into the row-per-warp register layout (ColMap) --
+    with K = 308 (ragged last chunk, as the self-conditioning linear) the emulation must reproduce the fp16x3 product sum."""
+    rng = np.random.default_rng(11)
+    K, S, LDW, LDA = 308, 256, 264, 316
+    X = np.zeros((64, LDA), np.float32); X[:, :K] = rng.standard_normal((64, K)).astype(np.float32)
+    W = (rng.standard_normal((K, S)) * 0.06).astype(np.float32)
+    xh, xl = WT.split_h16(X)
+    wh, wl = WT.split_h16(W * np.float32(1024.0))
+    xh, xl, wh, wl = (a.astype(np.float64) for a in (xh, xl, wh, wl))
+    Ys = np.zeros((64, 264))
+    for ch in range((K + 31) // 32):
+        hi, lo = np.zeros((16, LDW, 2)), np.zeros((16, LDW, 2))          # converted chunk: word (kp, n) = (W[k][n], W[k + 1][n])
+        for item in range(1024):
+            kp, n4 = item >> 6, item & 63
+            for r in range(2):
+                k = ch * 32 + 2 * kp + r
+                if k < K:
+                    hi[kp, 4 * n4:4 * n4 + 4, r], lo[kp, 4 * n4:4 * n4 + 4, r] = wh[k, 4 * n4:4 * n4 + 4], wl[k, 4 * n4:4 * n4 + 4]
+        for ks in range(2):
+            k0 = ch * 32 + 16 * ks
+            if k0 >= K:
+                continue
+            # operand coverage: A registers a_i <-> (row g + 8 (i & 1), k 2t + 8 (i >> 1) + {0, 1}); B b_i <-> (k pair t + 4 i, column g)
+            A_h = np.zeros((64, 16)); A_l = np.zeros((64, 16))
+            for lane in range(32):
+                g, t = lane >> 2, lane & 3
+                for mt in range(4):
+                    for i in range(4):
+                        col = k0 + 2 * t + (i >> 1) * 8
+                        row = 16 * mt + g + (i & 1) * 8
+                        if col < K:
+                            A_h[row, col - k0:col - k0 + 2], A_l[row, col - k0:col - k0 + 2] = xh[row, col:col + 2], xl[row, col:col + 2]
+            B_h = np.zeros((16, S)); B_l = np.zeros((16, S))
+            for warp in range(8):
+                for lane in range(32):
+                    g, t = lane >> 2, lane & 3
+                    for nt in range(4):
+                        for i in range(2):
+                            kp, n = 8 * ks + t + 4 * i, 32 * warp + 8 * nt + g
+                            B_h[2 * (t + 4 * i):2 * (t + 4 * i) + 2, n], B_l[2 * (t + 4 * i):2 * (t + 4 * i) + 2, n] = hi[kp, n], lo[kp, n]
+            Ys[:, :S] += A_l @ B_h + A_h @ B_l + A_h @ B_h
+    Ys[:, :S] /= 1024.0
+    want = (xl[:, :K] @ wh + xh[:, :K] @ wl + xh[:, :K] @ wh) / 1024.0
+    assert np.allclose(Ys[:, :S], want, rtol=0, atol=1e-9)
+    assert np.abs(want - X[:, :K].astype(np.float64) @ W.astype(np.float64)).max() < 2e-5 * np.abs(want).max()      # fp16x3 ~ 2^-22 relative per product
+    # read-back: warp w, row r, register c <- Ys[8 w + r][ColMap<8>::col(lane, c)], col = (c // 4) * 128 + lane * 4 + c % 4: every column once
+    cols = sorted((c // 4) * 128 + lane * 4 + c % 4 for lane in range(32) for c in range(8))
+    assert cols == list(range(256))
